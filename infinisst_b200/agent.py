@@ -1,0 +1,399 @@
+"""SimulEval agent mirror of agents/infinisst.py (class InfiniSST, S2TAgentStates) on the B200 engine.
+
+Same class / method / flag names (agents/infinisst.py:69-72,115-128,185-198,270-394;
+agents/options.py:1-125).  Differences, each deliberate:
+  * greedy decoding (`--beam 1`) instead of the reference's asserted beam > 1: beam search is §8f "next";
+  * `cache_checkpoints` and `system_prompt_size` live on the per-stream states (quirk Q3) so several
+    streams can share one agent/engine;
+  * `policy_batch` advances many independent streams in lock-step (the reference can only tile one
+    stream, agents/infinisst.py:291-301).
+SimulEval is imported when present; otherwise light stand-ins keep the agent usable and testable.
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass, field
+from time import perf_counter
+from typing import List, Optional, Sequence
+
+import torch
+
+from .config import InfiniSSTConfig, production_config, tiny_config
+from .model import SpeechLlamaForCausalLM
+
+try:  # pragma: no cover - simuleval is not installed in the build image
+    from simuleval.agents import SpeechToTextAgent
+    from simuleval.agents.actions import ReadAction, WriteAction
+    from simuleval.agents.states import AgentStates
+    from simuleval.utils import entrypoint
+except Exception:  # minimal stand-ins with the attributes the agent touches
+    class ReadAction:
+        def is_read(self):
+            return True
+
+    @dataclass
+    class WriteAction:
+        content: str = ""
+        finished: bool = False
+
+        def is_read(self):
+            return False
+
+    class AgentStates:
+        def __init__(self):
+            self.reset()
+
+        def reset(self):
+            self.source: list = []
+            self.target: list = []
+            self.source_finished = False
+            self.target_finished = False
+            self.source_sample_rate = 0
+
+    class SpeechToTextAgent:
+        def __init__(self, args):
+            self.args = args
+            self.states = self.build_states()
+
+    def entrypoint(cls):
+        return cls
+
+
+DEFAULT_SPEECH_PATCH_TOKEN = "<sp_patch>"      # train/dataset.py:52
+DEFAULT_LATENCY_TOKEN = "<latency_{}>"         # train/dataset.py:56
+
+
+def synchronized_timer(description: str, sink: Optional[list] = None):
+    """agents/infinisst.py:37-48: device-synchronised wall time of one policy step."""
+    @contextlib.contextmanager
+    def timer():
+        torch.cuda.synchronize()
+        t0 = perf_counter()
+        yield
+        torch.cuda.synchronize()
+        dt = perf_counter() - t0
+        if sink is not None:
+            sink.append(dt)
+    return timer()
+
+
+class S2TAgentStates(AgentStates):
+    """agents/infinisst.py:50-67 plus the per-stream eviction bookkeeping (quirk Q3)."""
+    MAX_SRC_LEN = 1600000
+
+    def __init__(self, src_len=0, speech_cache=None, past_key_values=None, target_ids=None, segment_idx=0,
+                 translations_list=None):
+        super().__init__()
+        self.src_len = src_len
+        self.speech_cache = speech_cache
+        self.past_key_values = past_key_values
+        self.target_ids = target_ids if target_ids is not None else []
+        self.segment_idx = segment_idx
+        self.translations_list = translations_list if translations_list is not None else []
+        self.cache_checkpoints: List[int] = []
+        self.system_prompt_size = 0
+
+    def reset(self):
+        super().reset()
+        if getattr(self, "speech_cache", None) is not None:
+            self.speech_cache.close()        # give the stream slot and its KV pages back
+        self.src_len = 0
+        self.speech_cache = None
+        self.past_key_values = None
+        self.target_ids = []
+        self.segment_idx = 0
+        self.translations_list = []
+        self.cache_checkpoints = []
+        self.system_prompt_size = 0
+
+
+class TemplateTokenizer:
+    """Stand-in for the Llama-3.1 tokenizer + chat template when no tokenizer files are available:
+    reproduces the turn layout of agents/infinisst.py:225-268 from a TemplateConfig."""
+
+    def __init__(self, cfg: InfiniSSTConfig):
+        self.tpl = cfg.tpl
+        self.pad_token_id = cfg.gen.pad_token_id
+
+    def system_ids(self) -> List[int]:
+        return list(self.tpl.system_ids)
+
+    def turn_ids(self, n_speech: int) -> List[int]:
+        t = self.tpl
+        return [t.start_header_id, t.user_token_id, t.end_header_id, t.nl_id] + [t.sp_patch_id] * n_speech + \
+               [t.eot_id, t.start_header_id, t.assist_token_id, t.end_header_id, t.nl_id]
+
+    def decode(self, ids: Sequence[int], skip_special_tokens: bool = True) -> str:
+        return " ".join(f"t{i}" for i in ids)
+
+
+def evict_plan(states: S2TAgentStates, cur: int, max_llm_cache_size: int, always_cache_system_prompt: bool):
+    """Integer part of agents/infinisst.py:337-352.  Returns None or (keep_prefix, drop_upto): the
+    logical KV tokens [keep_prefix, drop_upto) are evicted."""
+    states.cache_checkpoints.append(cur)
+    if cur <= max_llm_cache_size:
+        return None
+    new = 0
+    for i, ckpt in enumerate(states.cache_checkpoints):
+        new = cur - ckpt
+        if new <= max_llm_cache_size:
+            rest = states.cache_checkpoints[i + 1:]
+            trimmed = ckpt - (states.system_prompt_size if always_cache_system_prompt else 0)
+            states.cache_checkpoints = [c - trimmed for c in rest]
+            break
+    if new == 0:
+        # a single turn longer than the window: the reference's `k[:, :, -0:]` keeps everything (:355)
+        # (and would duplicate the system prompt); nothing is evicted here.
+        return None
+    return (states.system_prompt_size if always_cache_system_prompt else 0, cur - new)
+
+
+@entrypoint
+class InfiniSST(SpeechToTextAgent):
+    def __init__(self, args):
+        self.min_start_sec = args.min_start_sec
+        self.latency_multiplier = args.latency_multiplier
+        self.source_segment_size = getattr(args, "source_segment_size", 960 * args.latency_multiplier)
+        self.max_latency_multiplier = args.max_latency_multiplier
+        self.source_lang = args.source_lang
+        self.target_lang = args.target_lang
+        self.beam = args.beam
+        if self.beam != 1:
+            raise NotImplementedError("infinisst_b200 runs the greedy path (--beam 1); beam search is §8f next")
+        self.no_repeat_ngram_lookback = args.no_repeat_ngram_lookback
+        self.no_repeat_ngram_size = args.no_repeat_ngram_size
+        self.repetition_penalty = args.repetition_penalty
+        self.suppress_non_language = args.suppress_non_language
+        self.max_new_tokens = args.max_new_tokens
+        self.pseudo_batch_size = getattr(args, "pseudo_batch_size", 1)
+        self.max_llm_cache_size = args.max_llm_cache_size
+        self.always_cache_system_prompt = args.always_cache_system_prompt
+        self.chunk_latencies: List[float] = []
+        self.args = args
+        self.load_model(args)
+        super().__init__(args)
+
+    def build_states(self):
+        return S2TAgentStates()
+
+    def update_multiplier(self, multiplier):
+        self.latency_multiplier = multiplier
+        self.max_new_tokens = 10 * multiplier
+
+    def load_model(self, args):
+        """agents/infinisst.py:130-183.  `args.model_config` is an InfiniSSTConfig (or 'tiny' /
+        'production'); `args.state_dict` a reference-layout state dict (or `args.state_dict_path`)."""
+        cfg = getattr(args, "model_config", None) or "production"
+        if isinstance(cfg, str):
+            cfg = tiny_config() if cfg == "tiny" else production_config()
+        cfg.enc.block_size = args.block_size
+        cfg.enc.max_cache_size = args.max_cache_size
+        cfg.enc.rope, cfg.enc.xpos = bool(args.rope), bool(args.xpos)
+        if cfg.enc.xpos or not cfg.enc.rope:
+            raise NotImplementedError("--xpos 1 / --rope 0 encoder variants are §8f next")
+        if args.w2v2_type != "w2v2":
+            raise ValueError(f"Unsupported type: {args.w2v2_type}")            # agents/infinisst.py:171
+        self.cfg = cfg
+        self.tokenizer = getattr(args, "tokenizer", None) or TemplateTokenizer(cfg)
+        self.bad_words_ids = list(getattr(args, "bad_words_ids", []) or [])
+        self.model = SpeechLlamaForCausalLM(
+            cfg, engine=getattr(args, "engine", None), max_streams=getattr(args, "max_streams", 8),
+            max_multiplier=self.max_latency_multiplier)
+        sd = getattr(args, "state_dict", None)
+        if sd is None and getattr(args, "state_dict_path", None):
+            sd = torch.load(args.state_dict_path, map_location="cpu", weights_only=True)
+        if sd is not None:
+            self.model.load_state_dict(sd)
+        self.model.model.inference = True
+
+    @staticmethod
+    def add_args(parser):
+        # agents/options.py:1-125 + agents/infinisst.py:185-198
+        parser.add_argument("--source-lang", type=str, default="English")
+        parser.add_argument("--target-lang", type=str, default="German")
+        parser.add_argument("--min-start-sec", default=0.32, type=float)
+        parser.add_argument("--w2v2-path", type=str, default=None)
+        parser.add_argument("--w2v2-type", type=str, default=None)
+        parser.add_argument("--ctc-finetuned", type=lambda x: (str(x).lower() == "true"), default=False)
+        parser.add_argument("--length-shrink-cfg", type=str, default=None)
+        parser.add_argument("--block-size", type=int, default=12)
+        parser.add_argument("--max-cache-size", type=int, default=125)
+        parser.add_argument("--xpos", type=int, default=1)
+        parser.add_argument("--rope", type=int, default=1)
+        parser.add_argument("--max-len-a", type=int, default=5)
+        parser.add_argument("--max-len-b", type=int, default=20)
+        parser.add_argument("--beam", type=int, default=1)
+        parser.add_argument("--no-repeat-ngram-lookback", type=int, default=100)
+        parser.add_argument("--no-repeat-ngram-size", type=int, default=3)
+        parser.add_argument("--repetition-penalty", type=float, default=1.2)
+        parser.add_argument("--suppress-non-language", action="store_true")
+        parser.add_argument("--max-new-tokens", type=int, default=1000)
+        parser.add_argument("--do-sample", action="store_true")
+        parser.add_argument("--top-p", type=float, default=1.0)
+        parser.add_argument("--top-k", type=int, default=0)
+        parser.add_argument("--epsilon-cutoff", type=float, default=0.0)
+        parser.add_argument("--temperature", type=float, default=1.0)
+        parser.add_argument("--model-name", type=str, default="facebook/opt-350m")
+        parser.add_argument("--state-dict-path", type=str, default=None)
+        parser.add_argument("--latency-multiplier", type=int, default=4)
+        parser.add_argument("--max-latency-multiplier", type=int, default=4)
+        parser.add_argument("--max-llm-cache-size", type=int, default=10000)
+        parser.add_argument("--always-cache-system-prompt", action="store_true")
+        parser.add_argument("--dpo-sampling", action="store_true")
+        parser.add_argument("--output-file", type=str, default="translations.json")
+        parser.add_argument("--pseudo-batch-size", type=int, default=1)
+
+    # ---------------------------------------------------------------- per-chunk pieces
+    def _prepare_speech(self, states) -> torch.Tensor:
+        """agents/infinisst.py:200-223; returns float32 [1, n] on the host (the bf16 cast of :222
+        happens on the device inside conv0)."""
+        sp_seg_frame = int(self.args.block_size // 4 * 0.08 * 16000)
+        if len(states.source) > states.MAX_SRC_LEN:
+            states.src_len -= len(states.source) - states.MAX_SRC_LEN
+            states.source = states.source[-states.MAX_SRC_LEN:]
+        src = states.source[states.src_len:]
+        source = src.float() if isinstance(src, torch.Tensor) else torch.tensor(src, dtype=torch.float32)
+        seg = sp_seg_frame * self.latency_multiplier
+        if source.size(0) % seg != 0:
+            n_pad = seg - source.size(0) % seg
+            source = torch.cat([source, torch.zeros(n_pad)], dim=0)
+        if states.src_len == 0:
+            source = torch.cat([torch.zeros(79 + 320), source], dim=0)
+        states.src_len = len(states.source)
+        return source.unsqueeze(0)
+
+    def _prepare_inputs(self, states) -> torch.Tensor:
+        """agents/infinisst.py:225-268.  With a HF tokenizer the chat template is applied exactly as
+        the reference does; with the TemplateTokenizer the same layout is built from the template ids."""
+        n_speech = self.args.block_size // 4 * self.latency_multiplier
+        tok = self.tokenizer
+        if isinstance(tok, TemplateTokenizer):
+            ids: List[int] = []
+            if states.speech_cache is None:
+                ids += tok.system_ids()
+                states.system_prompt_size = len(ids)
+                ids += tok.turn_ids(n_speech)
+            else:
+                ids = [self.cfg.tpl.eot_id] + tok.turn_ids(n_speech)
+            return torch.tensor([ids], dtype=torch.long)
+        messages = []
+        if states.speech_cache is None:
+            latency_token = DEFAULT_LATENCY_TOKEN.format(self.latency_multiplier)
+            messages.append({"role": "system", "content": f"Translate the following speech from {self.source_lang} "
+                                                          f"to {self.target_lang} with latency {latency_token}."})
+            states.system_prompt_size = tok.apply_chat_template([messages], return_tensors="pt", padding=True,
+                                                                truncation=False, add_special_tokens=False).size(1)
+        messages.append({"role": "user", "content": n_speech * DEFAULT_SPEECH_PATCH_TOKEN})
+        messages.append({"role": "assistant", "content": ""})
+        input_ids = tok.apply_chat_template([messages], return_tensors="pt", padding=True, truncation=False,
+                                            add_special_tokens=False)[:, :-1]
+        if states.speech_cache is not None:
+            input_ids = input_ids[:, 25:]          # Llama-3.1 default system header (agents/infinisst.py:262-264)
+        return input_ids
+
+    def _evict(self, states) -> None:
+        cur = states.past_key_values[0][0].size(2)
+        plan = evict_plan(states, cur, self.max_llm_cache_size, self.always_cache_system_prompt)
+        if plan is not None:
+            states.past_key_values.engine.kv_evict(states.past_key_values.sid, plan[0], plan[1])
+
+    def _finish(self, states, input_len: int, sequence: List[int]):
+        output_ids = sequence[input_len:-1]                                   # agents/infinisst.py:363
+        states.target_ids.extend(output_ids)
+        translation = self.tokenizer.decode(output_ids, skip_special_tokens=True).strip().replace("�", "")
+        states.segment_idx += 1
+        if translation != "" or states.source_finished:
+            return WriteAction(content=translation, finished=states.source_finished)
+        return ReadAction()
+
+    @torch.inference_mode()
+    def policy(self, states: Optional[S2TAgentStates] = None):
+        if states is None:
+            states = self.states
+        return self.policy_batch([states])[0]
+
+    @torch.inference_mode()
+    def policy_batch(self, states_list: Sequence[S2TAgentStates]):
+        """agents/infinisst.py:270-394 for several independent streams in lock-step."""
+        actions: List[object] = [None] * len(states_list)
+        run = []
+        for i, st in enumerate(states_list):
+            secs = float(len(st.source)) / st.source_sample_rate if st.source_sample_rate else 0.0
+            if not st.source_finished and secs < self.min_start_sec:
+                actions[i] = ReadAction()
+            elif st.source_finished and secs < 0.32:
+                actions[i] = WriteAction(content="", finished=True)
+            else:
+                run.append(i)
+        if not run:
+            return actions
+        with synchronized_timer("generate", self.chunk_latencies):
+            sts = [states_list[i] for i in run]
+            first = [st.speech_cache is None for st in sts]
+            if any(first) != all(first):
+                raise ValueError("a lock-step batch must not mix first chunks with later chunks")
+            speech = torch.cat([self._prepare_speech(st) for st in sts], dim=0)
+            ids = torch.cat([self._prepare_inputs(st) for st in sts], dim=0)
+            enc = [st.target_ids[-self.no_repeat_ngram_lookback:] for st in sts]
+            pin = sts[0].system_prompt_size if self.always_cache_system_prompt else 0
+            outputs = self._generate(sts, ids, speech, enc, pin)
+            for st in sts:
+                st.past_key_values = st.speech_cache
+                self._evict(st)
+        for j, i in enumerate(run):
+            seq = [t for t in outputs.sequences[j].tolist()]
+            n_gen = self._n_generated[j]
+            seq = seq[: ids.shape[1] + n_gen]
+            actions[i] = self._finish(states_list[i], ids.shape[1], seq)
+        return actions
+
+    def _generate(self, sts, ids, speech, enc, pin):
+        """model.generate with the kwargs of agents/infinisst.py:307-332 (ragged `encoder_input_ids`
+        are passed per stream instead of one padded tensor)."""
+        width = max((len(e) for e in enc), default=0)
+        enc_t = None
+        if width > 0 and all(len(e) == width for e in enc):
+            enc_t = torch.tensor(enc, dtype=torch.long)
+        if enc_t is None and width > 0:
+            # ragged histories: run the engine directly (same path the shim takes)
+            handles = self.model._handles(sts if len(sts) > 1 else sts[0], None, len(sts))
+            self.model.engine.encode_chunk([h.sid for h in handles], speech, self.latency_multiplier)
+            rows = [ids[b].tolist() for b in range(len(sts))]
+            g = self._gen_cfg()
+            toks = self.model.engine.generate([h.sid for h in handles], rows, [self.model._slot_map(r) for r in rows],
+                                              enc, g, pin_prefix=pin)
+            self._n_generated = [len(t) for t in toks]
+            from .model import GenerateOutput
+            w = max(len(r) + len(t) for r, t in zip(rows, toks))
+            seqs = torch.full((len(sts), w), self.tokenizer.pad_token_id, dtype=torch.long)
+            for b, (r, t) in enumerate(zip(rows, toks)):
+                seqs[b, :len(r) + len(t)] = torch.tensor(r + t)
+            return GenerateOutput(seqs, handles[0] if len(sts) == 1 else handles)
+        out = self.model.generate(
+            attention_mask=None, input_ids=ids, speech_batch=speech, do_sample=False, top_p=1.0, top_k=0,
+            epsilon_cutoff=0.0, temperature=1.0, num_beams=self.beam, max_new_tokens=self.max_new_tokens,
+            num_return_sequences=1, encoder_input_ids=enc_t, encoder_no_repeat_ngram_size=self.no_repeat_ngram_size,
+            no_repeat_ngram_size=self.no_repeat_ngram_size, repetition_penalty=self.repetition_penalty,
+            pad_token_id=self.tokenizer.pad_token_id, return_dict_in_generate=True, return_legacy_cache=False,
+            use_cache=True, past_key_values=None, suppress_tokens=self.bad_words_ids,
+            states=sts if len(sts) > 1 else sts[0], multiplier=self.latency_multiplier, pin_prefix=pin)
+        pad = self.tokenizer.pad_token_id
+        self._n_generated = []
+        for b in range(len(sts)):
+            row = out.sequences[b, ids.shape[1]:].tolist()
+            n = len(row)
+            while n > 0 and row[n - 1] == pad and pad not in self.cfg.gen.eos_token_ids:
+                n -= 1
+            self._n_generated.append(n)
+        return out
+
+    def _gen_cfg(self):
+        class _G:
+            pass
+        g = _G()
+        g.max_new_tokens = self.max_new_tokens
+        g.no_repeat_ngram_size = self.no_repeat_ngram_size
+        g.repetition_penalty = float(self.repetition_penalty)
+        g.eos_token_ids = list(self.cfg.gen.eos_token_ids)
+        g.suppress_tokens = list(self.bad_words_ids)
+        return g

@@ -1,0 +1,408 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  out[tok, feat] = act[tok, K] . W[feat, K]^T  (+ fused epilogue)
+//
+// Replaces the cuBLAS Linear / cuDNN Conv1d call sites of the reference's per-chunk step
+// (E1 conv1-6, E3, E6, E10, E11, E13, E14, L2, L7, L8, L9).
+//
+// Both operands are K-major (activations [tok, K] row-major, nn.Linear weights [feat, K]
+// row-major), staged by TMA into 128B-swizzled shared memory and consumed by
+// tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM).
+//
+//   kSwap = false : UMMA M (128 TMEM lanes) = tokens,   UMMA N = kBN features   (prefill / batched / encoder)
+//   kSwap = true  : UMMA M (128 TMEM lanes) = features, UMMA N = kBN tokens     (few tokens: weight streaming,
+//                   HBM-bound; the 128-row operand is the weight so no tensor-core rows are wasted on padding)
+//   kDual         : two weight tiles per k-block (rows f and f + dual_off) -> two accumulators;
+//                   epilogue writes silu(acc0) * acc1  (Llama gate/up)
+//
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).  Split-K: grid.z = batch * splits;
+// partials go to an fp32 workspace and the last-arriving CTA of a tile reduces them in split order
+// (deterministic) and applies the epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace isst {
+namespace tc {
+
+constexpr int kBM = 128;       // rows of the 128-lane operand
+constexpr int kBK = 64;        // bf16 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+  int M_tok;        // token rows per batch
+  int N_out;        // output features (per half when dual)
+  int K;
+  int batch;        // activation batches (dim 2 of the activation tensor map)
+  int splits;       // split-K factor
+  int dual_off;     // row offset of the second weight block (dual)
+  int conv_c;       // activation view: K index = tap * conv_c + c  (plain matrices: conv_c = K, conv_s = 1)
+  int conv_s;       //   row r, tap t lives at time index r * conv_s + t  (im2col-free strided Conv1d)
+  void* out;
+  long long ldo;                // elements
+  long long out_batch_stride;   // elements
+  int out_f32;
+  const float* bias;            // [N_out] or null
+  const bf16* resid;            // may alias out (same element read then written by the same thread)
+  long long ldr;
+  long long resid_batch_stride;
+  int act;                      // 0 none, 1 gelu(erf)
+  float* ws;                    // split-K workspace
+  int* counters;                // one per output tile, zero on entry, zero on exit
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, set 1) | SBO>>4 [32,46) = 1024 B (8 rows x 128 B)
+// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(umma_n >> 3) << 17) |
+         (static_cast<uint32_t>(umma_m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int kBN, bool kDual, bool kSwap>
+struct Cfg {
+  static constexpr int kActRows = kSwap ? kBN : kBM;
+  static constexpr int kWRows = kSwap ? kBM : kBN;
+  static constexpr int kNW = kDual ? 2 : 1;
+  static constexpr int kActBytes = kActRows * kBK * 2;
+  static constexpr int kWBytes = kWRows * kBK * 2;
+  static constexpr int kStageBytes = kActBytes + kNW * kWBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kAccCols = kBN * kNW;
+  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
+  static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
+};
+
+// Final epilogue for 16 consecutive columns of one TMEM lane.
+//   normal: lane = token row, columns = features;  swap: lane = feature, columns = tokens.
+template <bool kDual, bool kSwap>
+__device__ __forceinline__ void epilogue_store16(const GemmParams& p, int b, int lane_idx, int col0,
+                                                 const float* v0, const float* v1) {
+  const long long obase = static_cast<long long>(b) * p.out_batch_stride;
+  const long long rbase = static_cast<long long>(b) * p.resid_batch_stride;
+  if (!kSwap) {
+    const int tok = lane_idx;
+    if (tok >= p.M_tok) return;
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int f = col0 + i;
+      float x = v0[i];
+      if (f < p.N_out) {
+        if (p.bias) x += p.bias[f];
+        if (kDual) x = silu(x) * v1[i];
+        if (p.act == 1) x = gelu_erf(x);
+      }
+      y[i] = x;
+    }
+    const bool full = (col0 + 16 <= p.N_out);
+    if (p.resid) {
+      const bf16* r = p.resid + rbase + static_cast<long long>(tok) * p.ldr + col0;
+      if (full && ((p.ldr & 7) == 0)) {
+        uint4 r0 = *reinterpret_cast<const uint4*>(r);
+        uint4 r1 = *reinterpret_cast<const uint4*>(r + 8);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float2 f2 = unpack_bf16(rr[i]);
+          y[2 * i] += f2.x;
+          y[2 * i + 1] += f2.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + i < p.N_out) y[i] += __bfloat162float(r[i]);
+      }
+    }
+    if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + obase + static_cast<long long>(tok) * p.ldo + col0;
+      if (full && ((p.ldo & 3) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(o + 4 * i) = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + i < p.N_out) o[i] = y[i];
+      }
+    } else {
+      bf16* o = reinterpret_cast<bf16*>(p.out) + obase + static_cast<long long>(tok) * p.ldo + col0;
+      if (full && ((p.ldo & 7) == 0)) {
+        uint4 s0, s1;
+        s0.x = pack_bf16(y[0], y[1]);   s0.y = pack_bf16(y[2], y[3]);
+        s0.z = pack_bf16(y[4], y[5]);   s0.w = pack_bf16(y[6], y[7]);
+        s1.x = pack_bf16(y[8], y[9]);   s1.y = pack_bf16(y[10], y[11]);
+        s1.z = pack_bf16(y[12], y[13]); s1.w = pack_bf16(y[14], y[15]);
+        *reinterpret_cast<uint4*>(o) = s0;
+        *reinterpret_cast<uint4*>(o + 8) = s1;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + i < p.N_out) o[i] = __float2bfloat16_rn(y[i]);
+      }
+    }
+  } else {
+    const int f = lane_idx;
+    if (f >= p.N_out) return;
+    const float bias = p.bias ? p.bias[f] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int tok = col0 + i;
+      if (tok >= p.M_tok) break;
+      float x = v0[i] + bias;
+      if (kDual) x = silu(x) * v1[i];
+      if (p.act == 1) x = gelu_erf(x);
+      if (p.resid) x += __bfloat162float(p.resid[rbase + static_cast<long long>(tok) * p.ldr + f]);
+      const long long oi = obase + static_cast<long long>(tok) * p.ldo + f;
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = x;
+      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+template <int kBN, bool kDual, bool kSwap>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
+                    const GemmParams p) {
+  using C = Cfg<kBN, kDual, kSwap>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full_bar = empty_bar + C::kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  int* flag_smem = reinterpret_cast<int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_tok = blockIdx.x;    // token tile (128 rows normal, kBN rows swap)
+  const int tile_feat = blockIdx.y;   // feature tile (kBN normal, 128 swap)
+  const int b = blockIdx.z / p.splits;
+  const int split = blockIdx.z % p.splits;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int kb0 = static_cast<int>((static_cast<long long>(num_kb) * split) / p.splits);
+  const int kb1 = static_cast<int>((static_cast<long long>(num_kb) * (split + 1)) / p.splits);
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_act)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(static_cast<uint32_t>(C::kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int act_row0 = tile_tok * C::kActRows;
+  const int w_row0 = tile_feat * C::kWRows;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::kStageBytes;
+        uint8_t* sw = sa + C::kActBytes;
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        // activation tensor map is 4-D {conv_c, conv_s, row_group, batch}: tap t of row r = (t % s, r + t / s)
+        const int k0 = kb * kBK;
+        const int tap = k0 / p.conv_c;
+        tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, b);
+        tma_load_2d(sw, &tm_w, &full_bar[stage], kb * kBK, w_row0);
+        if (kDual) tma_load_2d(sw + C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, w_row0 + p.dual_off);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+        const uint32_t sw = sa + C::kActBytes;
+        const uint64_t d_act = make_smem_desc(sa);
+        const uint64_t d_w0 = make_smem_desc(sw);
+        const uint64_t d_w1 = make_smem_desc(sw + C::kWBytes);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+          const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+          if (!kSwap) {
+            umma_bf16(tmem_base, d_act + koff, d_w0 + koff, idesc, acc);
+            if (kDual) umma_bf16(tmem_base + kBN, d_act + koff, d_w1 + koff, idesc, acc);
+          } else {
+            umma_bf16(tmem_base, d_w0 + koff, d_act + koff, idesc, acc);
+            if (kDual) umma_bf16(tmem_base + kBN, d_w1 + koff, d_act + koff, idesc, acc);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == kb1 - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
+    const int r = q * 32 + lane;                  // TMEM lane == row of the 128-row operand
+    const int et = threadIdx.x - 128;             // 0..127 epilogue thread id
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int lane_idx = (kSwap ? tile_feat : tile_tok) * kBM + r;
+    const int col_base = (kSwap ? tile_tok : tile_feat) * kBN;
+    if (p.splits == 1) {
+#pragma unroll 1
+      for (int c = 0; c < kBN; c += 16) {
+        float v0[16], v1[16];
+        tmem_ld16(taddr + c, v0);
+        if (kDual) tmem_ld16(taddr + kBN + c, v1);
+        epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
+      }
+    } else {
+      const int tiles_per_b = gridDim.x * gridDim.y;
+      const int tile_lin = (b * gridDim.y + tile_feat) * gridDim.x + tile_tok;
+      (void)tiles_per_b;
+      float* ws_tile = p.ws + static_cast<size_t>(tile_lin) * p.splits * (C::kAccCols * kBM);
+      float* mine = ws_tile + static_cast<size_t>(split) * (C::kAccCols * kBM);
+#pragma unroll 1
+      for (int c = 0; c < C::kAccCols; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mine[(c + i) * kBM + r] = v[i];
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const int prev = atomicAdd(&p.counters[tile_lin], 1);
+        *flag_smem = (prev == p.splits - 1) ? 1 : 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*flag_smem) {
+        __threadfence();
+#pragma unroll 1
+        for (int c = 0; c < kBN; c += 16) {
+          float v0[16], v1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
+          for (int s = 0; s < p.splits; ++s) {
+            const float* src = ws_tile + static_cast<size_t>(s) * (C::kAccCols * kBM);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v0[i] += __ldcg(&src[(c + i) * kBM + r]);
+              if (kDual) v1[i] += __ldcg(&src[(kBN + c + i) * kBM + r]);
+            }
+          }
+          epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
+        }
+        if (et == 0) p.counters[tile_lin] = 0;
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(C::kTmemCols))
+                 : "memory");
+  }
+}
+
+}  // namespace tc
+}  // namespace isst

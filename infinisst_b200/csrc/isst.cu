@@ -1,0 +1,1468 @@
+// infinisst_b200: context, weight ingestion, stream/KV management and the per-chunk step
+// (encoder -> adapter -> chunk-prefill -> greedy decode) behind the C-ABI of include/infinisst_b200.h.
+//
+// Reference call stack being replaced:
+//   InfiniSST.policy (agents/infinisst.py:270-394) -> model.generate -> SpeechLlamaModel.forward
+//   (model/llm.py:51-126) -> encode_speech (model/speech_encoder.py:219-236) -> uni_w2v2_forward /
+//   uni_mha_forward (model/patches/patch_speech_encoder.py) and llama_sdpa_attention_new_forward
+//   (model/patches/patch_llm.py:231-336).
+#include "../../include/infinisst_b200.h"
+
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include "rowops.cuh"
+
+namespace isst {
+thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+
+static int load_driver_api() {
+  if (g_encode_tiled) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  ISST_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  ISST_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) return 0;
+  ISST_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+
+struct Weight2D {
+  bf16* ptr = nullptr;
+  int rows = 0, K = 0;
+  CUtensorMap map;
+};
+
+static int make_weight_map(Weight2D& w) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(w.K), static_cast<cuuint64_t>(w.rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(w.K) * 2};
+  cuuint32_t box[2] = {tc::kBK, tc::kBM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&w.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.ptr, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ISST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: " + std::to_string(static_cast<int>(r)));
+  return 0;
+}
+
+// Activation view: element (row, kidx) of batch b lives at
+//   ptr + b * batch_stride + ((row * conv_s + kidx / conv_c) * conv_c + kidx % conv_c)
+// (plain [rows, K] matrices have conv_c = K, conv_s = 1).  4-D tensor map {conv_c, conv_s, row_groups, batch}.
+struct ActView {
+  const bf16* ptr;
+  int rows;               // logical rows per batch (M_tok)
+  int K;
+  int conv_c, conv_s;
+  int row_groups;         // extent of the row-group dimension (>= rows + (k-1)/s)
+  long long batch_stride; // elements
+  int batch;
+};
+static ActView plain_view(const bf16* p, int rows, int K) { return ActView{p, rows, K, K, 1, rows, 0, 1}; }
+
+static int make_act_map(CUtensorMap* map, const ActView& v, int box_rows) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(v.conv_c), static_cast<cuuint64_t>(v.conv_s),
+                        static_cast<cuuint64_t>(v.row_groups), static_cast<cuuint64_t>(v.batch)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(v.conv_c) * 2,
+                           static_cast<cuuint64_t>(v.conv_c) * v.conv_s * 2,
+                           static_cast<cuuint64_t>(v.batch > 1 ? v.batch_stride : static_cast<long long>(v.conv_c) * v.conv_s * v.row_groups) * 2};
+  cuuint32_t box[4] = {tc::kBK, 1, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(v.ptr), dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ISST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: " + std::to_string(static_cast<int>(r)));
+  return 0;
+}
+
+struct EncLayerW {
+  float *ln1_w = nullptr, *ln1_b = nullptr, *bqkv = nullptr, *bo = nullptr, *ln2_w = nullptr, *ln2_b = nullptr,
+        *b1 = nullptr, *b2 = nullptr;
+  Weight2D wqkv, wo, w1, w2;
+};
+struct LlmLayerW {
+  float *rms1 = nullptr, *rms2 = nullptr;
+  Weight2D wqkv, wo, wgu, wd;
+};
+struct ConvW {
+  Weight2D w;                       // conv j >= 1 and adapter: [C_out, k*C_in], K index = tap * C_in + c
+  float *w0_t = nullptr;            // conv0 only: [k][C] fp32
+  float *bias = nullptr, *ln_w = nullptr, *ln_b = nullptr;
+};
+
+struct StreamHost {
+  bool open = false;
+  int enc_prefix = 0;               // W2V2RoPECache.n_steps
+  int kv_len = 0, sys_len = 0, ring_start = 0;
+  bool prefilled = false;
+  std::vector<int> pages;           // page table entries (sys pages first, then ring pages)
+};
+
+}  // namespace isst
+
+using namespace isst;
+
+struct isst_ctx {
+  isst_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  bool finalized = false;
+  bool simple_gemm = false;
+  int64_t launches = 0;
+  bool debug = false;
+  std::map<std::string, std::pair<void*, size_t>> taps;   // name -> (device buffer, bytes)
+  std::map<std::string, bool> loaded;
+
+  // geometry
+  int C = 0, n_tail = 0, rf = 0, total_stride = 0, frames_max = 0, samples_max = 0, enc_cap = 0;
+  int speech_per_block = 0;   // LLM tokens per block of frames
+  int pages_per_stream = 0;
+
+  // weights
+  std::vector<ConvW> conv, adapter;
+  float *feat_ln_w = nullptr, *feat_ln_b = nullptr, *post_b = nullptr, *enc_ln_w = nullptr, *enc_ln_b = nullptr,
+        *proj_b = nullptr, *final_norm = nullptr;
+  Weight2D post_proj, proj, lm_head;
+  std::vector<EncLayerW> enc;
+  std::vector<LlmLayerW> llm;
+  bf16* embed = nullptr;
+  float *enc_rope_cos = nullptr, *enc_rope_sin = nullptr;
+  int enc_rope_npos = 0;
+  float *llm_rope_cos_f = nullptr, *llm_rope_sin_f = nullptr;
+  bf162* llm_rope = nullptr;
+  int llm_rope_npos = 0;
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
+
+  // stream state
+  std::vector<StreamHost> streams;
+  std::vector<int> free_pages;
+  float* tail = nullptr;
+  bf16 *enc_k = nullptr, *enc_v = nullptr;
+  int *d_enc_prefix = nullptr, *d_page_table = nullptr, *d_kv_len = nullptr, *d_sys_len = nullptr,
+      *d_ring_start = nullptr;
+  bf16* kv_pool = nullptr;
+  size_t kv_layer_elems = 0, enc_layer_elems = 0;
+
+  // workspaces
+  float* d_pcm = nullptr;
+  bf16 *conv_a = nullptr, *conv_b = nullptr;
+  bf16 *ex = nullptr, *eh = nullptr, *eqkv = nullptr, *eattn = nullptr, *effn = nullptr, *ead0 = nullptr,
+       *ead1 = nullptr, *speech = nullptr;
+  int speech_rows_per_stream = 0;
+  bf16 *lx = nullptr, *lh = nullptr, *lqkv = nullptr, *lattn = nullptr, *lgu = nullptr, *llast = nullptr;
+  float* logits = nullptr;
+  float *part_o = nullptr, *part_ml = nullptr;
+  int decode_splits = 1;
+  float* gemm_ws = nullptr;
+  size_t gemm_ws_floats = 0;
+  int* gemm_counters = nullptr;
+  int n_counters = 0;
+  // batch metadata (device) + pinned host staging
+  int* d_meta = nullptr;
+  int* h_meta = nullptr;
+  size_t meta_ints = 0;
+  int* d_step_logits_dummy = nullptr;
+};
+
+namespace isst {
+
+#define LAUNCH_CHECK(ctx)                                                                   \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) +     \
+                       " at " + __FILE__ + ":" + std::to_string(__LINE__));                 \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------------
+struct Epilogue {
+  const float* bias = nullptr;
+  int act = 0;
+  const bf16* resid = nullptr;
+  long long ldr = 0;
+  long long resid_batch_stride = 0;
+  int out_f32 = 0;
+  int dual = 0;   // 1: weights hold [gate; up] stacked, rows N_out and dual_off + N_out
+  int dual_off = 0;
+};
+
+template <int kBN, bool kDual, bool kSwap>
+static int launch_tc(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
+                     dim3 grid) {
+  using C = tc::Cfg<kBN, kDual, kSwap>;
+  static bool attr_set = false;
+  auto kern = tc::gemm_tcgen05_kernel<kBN, kDual, kSwap>;
+  if (!attr_set) {
+    ISST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap amap;
+  ISST_TRY(make_act_map(&amap, v, C::kActRows));
+  kern<<<grid, tc::kThreads, C::kSmemBytes, st>>>(amap, w.map, p);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, int n_out, void* out,
+                long long ldo, long long out_batch_stride, const Epilogue& e, int force_swap = -1,
+                int force_splits = 0, int force_simple = -1) {
+  tc::GemmParams p{};
+  p.M_tok = v.rows;
+  p.N_out = n_out;
+  p.K = v.K;
+  p.batch = v.batch;
+  p.splits = 1;
+  p.dual_off = e.dual_off;
+  p.conv_c = v.conv_c;
+  p.conv_s = v.conv_s;
+  p.out = out;
+  p.ldo = ldo;
+  p.out_batch_stride = out_batch_stride;
+  p.out_f32 = e.out_f32;
+  p.bias = e.bias;
+  p.resid = e.resid;
+  p.ldr = e.ldr;
+  p.resid_batch_stride = e.resid_batch_stride;
+  p.act = e.act;
+  p.ws = ctx->gemm_ws;
+  p.counters = ctx->gemm_counters;
+  ISST_CHECK(v.K == w.K, "gemm: K mismatch");
+  const bool simple = force_simple >= 0 ? (force_simple != 0) : ctx->simple_gemm;
+  if (simple) {
+    SimpleGemmExtra x{v.ptr, v.batch_stride, v.conv_c, v.conv_s, w.ptr, e.dual};
+    dim3 grid(ceil_div(n_out, 8), ceil_div(v.rows, 8), v.batch);
+    gemm_simple_kernel<<<grid, 256, 0, st>>>(p, x);
+    LAUNCH_CHECK(ctx);
+    return 0;
+  }
+  ISST_CHECK(v.conv_c % tc::kBK == 0, "gemm: conv_c must be a multiple of 64");
+  bool swap = (v.rows <= 64 && v.batch == 1);
+  if (force_swap >= 0) swap = force_swap != 0;
+  ISST_CHECK(!(swap && v.batch != 1), "gemm: swap mode needs batch == 1");
+  const int num_kb = ceil_div(v.K, tc::kBK);
+  int bn = 128;
+  if (swap) bn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
+  const int tok_tiles = swap ? ceil_div(v.rows, bn) : ceil_div(v.rows, tc::kBM);
+  const int feat_tiles = swap ? ceil_div(n_out, tc::kBM) : ceil_div(n_out, bn);
+  const int tiles = tok_tiles * feat_tiles * v.batch;
+  int splits = 1;
+  if (tiles < ctx->sm_count) {
+    splits = std::max(1, ctx->sm_count / tiles);
+    splits = std::min(splits, std::max(1, num_kb / 4));
+    splits = std::min(splits, 16);
+  }
+  if (force_splits > 0) splits = std::min(force_splits, num_kb);
+  const size_t acc_cols = static_cast<size_t>(bn) * (e.dual ? 2 : 1);
+  if (splits > 1) {
+    const size_t need = static_cast<size_t>(tiles) * splits * acc_cols * tc::kBM;
+    if (need > ctx->gemm_ws_floats || tiles > ctx->n_counters) splits = 1;
+  }
+  p.splits = splits;
+  dim3 grid(tok_tiles, feat_tiles, v.batch * splits);
+#define ISST_TC(BN, DUAL, SWAP) return launch_tc<BN, DUAL, SWAP>(ctx, st, v, w, p, grid)
+  if (!swap) {
+    if (e.dual) ISST_TC(128, true, false);
+    ISST_TC(128, false, false);
+  }
+  if (e.dual) {
+    switch (bn) {
+      case 16: ISST_TC(16, true, true);
+      case 32: ISST_TC(32, true, true);
+      case 64: ISST_TC(64, true, true);
+      default: ISST_TC(128, true, true);
+    }
+  }
+  switch (bn) {
+    case 16: ISST_TC(16, false, true);
+    case 32: ISST_TC(32, false, true);
+    case 64: ISST_TC(64, false, true);
+    default: ISST_TC(128, false, true);
+  }
+#undef ISST_TC
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight ingestion helpers
+// ------------------------------------------------------------------------------------------------
+template <typename Src>
+__global__ void cvt_rows_kernel(const Src* __restrict__ src, bf16* __restrict__ dst, long long rows, long long cols,
+                                float scale) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16_rn(static_cast<float>(src[i]) * scale);
+}
+template <typename Src>
+__global__ void cvt_vec_kernel(const Src* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = bf16_round(static_cast<float>(src[i])) * scale;   // parameters live in the model dtype (bf16)
+}
+// conv weight [Co][Ci][k] -> [Co][k][Ci]
+template <typename Src>
+__global__ void cvt_conv_kernel(const Src* __restrict__ src, bf16* __restrict__ dst, int Co, int Ci, int k) {
+  const long long n = static_cast<long long>(Co) * Ci * k;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kk = i % k;
+    const int ci = (i / k) % Ci;
+    const int co = i / (static_cast<long long>(k) * Ci);
+    dst[(static_cast<long long>(co) * k + kk) * Ci + ci] = __float2bfloat16_rn(static_cast<float>(src[i]));
+  }
+}
+// conv0 weight [C][1][k] -> fp32 [k][C]
+template <typename Src>
+__global__ void cvt_conv0_kernel(const Src* __restrict__ src, float* __restrict__ dst, int C, int k) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * k; i += gridDim.x * blockDim.x) {
+    const int kk = i % k, c = i / k;
+    dst[kk * C + c] = bf16_round(static_cast<float>(src[i]));
+  }
+}
+__global__ void build_llm_rope_kernel(const float* __restrict__ c, const float* __restrict__ s, bf162* out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __floats2bfloat162_rn(c[i], s[i]);
+}
+__global__ void fill_pattern_kernel(bf16* p, long long n, uint32_t seed) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t h = static_cast<uint32_t>(i) * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    p[i] = __float2bfloat16_rn((static_cast<float>(h & 0xffff) / 65536.f - 0.5f));
+  }
+}
+
+static int numel(const int64_t* shape, int ndim, long long* out) {
+  long long n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  *out = n;
+  return 0;
+}
+
+// returns a device pointer to the source data (copying host data into the staging buffer)
+static int stage_source(isst_ctx* ctx, const void* data, size_t bytes, const void** dev) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, data);
+  if (e == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+    *dev = data;
+    return 0;
+  }
+  cudaGetLastError();
+  if (bytes > ctx->staging_bytes) {
+    if (ctx->staging) cudaFree(ctx->staging);
+    ctx->staging = nullptr;
+    ctx->staging_bytes = 0;
+    ISST_CUDA(cudaMalloc(&ctx->staging, bytes));
+    ctx->staging_bytes = bytes;
+  }
+  ISST_CUDA(cudaMemcpy(ctx->staging, data, bytes, cudaMemcpyHostToDevice));
+  *dev = ctx->staging;
+  return 0;
+}
+
+static int load_matrix(isst_ctx* ctx, bf16* dst, long long rows, long long cols, const void* data, const int64_t* shape,
+                       int ndim, int dtype, float scale = 1.f) {
+  long long n;
+  numel(shape, ndim, &n);
+  ISST_CHECK(n == rows * cols, "weight has the wrong number of elements");
+  const void* src;
+  ISST_TRY(stage_source(ctx, data, static_cast<size_t>(n) * (dtype == ISST_DTYPE_F32 ? 4 : 2), &src));
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  if (dtype == ISST_DTYPE_F32) cvt_rows_kernel<float><<<blocks, 256>>>(static_cast<const float*>(src), dst, rows, cols, scale);
+  else cvt_rows_kernel<bf16><<<blocks, 256>>>(static_cast<const bf16*>(src), dst, rows, cols, scale);
+  ISST_CUDA(cudaGetLastError());
+  ISST_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+static int load_vector(isst_ctx* ctx, float* dst, long long n_expect, const void* data, const int64_t* shape, int ndim,
+                       int dtype, float scale = 1.f) {
+  long long n;
+  numel(shape, ndim, &n);
+  ISST_CHECK(n == n_expect, "vector weight has the wrong number of elements");
+  const void* src;
+  ISST_TRY(stage_source(ctx, data, static_cast<size_t>(n) * (dtype == ISST_DTYPE_F32 ? 4 : 2), &src));
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 1024));
+  if (dtype == ISST_DTYPE_F32) cvt_vec_kernel<float><<<blocks, 256>>>(static_cast<const float*>(src), dst, n, scale);
+  else cvt_vec_kernel<bf16><<<blocks, 256>>>(static_cast<const bf16*>(src), dst, n, scale);
+  ISST_CUDA(cudaGetLastError());
+  ISST_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+static int load_conv(isst_ctx* ctx, bf16* dst, int Co, int Ci, int k, const void* data, const int64_t* shape, int ndim,
+                     int dtype) {
+  long long n;
+  numel(shape, ndim, &n);
+  ISST_CHECK(n == static_cast<long long>(Co) * Ci * k, "conv weight has the wrong number of elements");
+  const void* src;
+  ISST_TRY(stage_source(ctx, data, static_cast<size_t>(n) * (dtype == ISST_DTYPE_F32 ? 4 : 2), &src));
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  if (dtype == ISST_DTYPE_F32) cvt_conv_kernel<float><<<blocks, 256>>>(static_cast<const float*>(src), dst, Co, Ci, k);
+  else cvt_conv_kernel<bf16><<<blocks, 256>>>(static_cast<const bf16*>(src), dst, Co, Ci, k);
+  ISST_CUDA(cudaGetLastError());
+  ISST_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+static int alloc_w2d(Weight2D& w, int rows, int K) {
+  w.rows = rows;
+  w.K = K;
+  return dev_alloc(&w.ptr, static_cast<size_t>(rows) * K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug taps
+// ------------------------------------------------------------------------------------------------
+static int tap(isst_ctx* ctx, cudaStream_t st, const std::string& name, const void* src, size_t bytes,
+               size_t offset = 0, size_t total = 0) {
+  if (!ctx->debug) return 0;
+  if (total == 0) total = bytes;
+  auto it = ctx->taps.find(name);
+  if (it == ctx->taps.end() || it->second.second != total) {
+    if (it != ctx->taps.end()) cudaFree(it->second.first);
+    void* p = nullptr;
+    ISST_CUDA(cudaMalloc(&p, total));
+    ISST_CUDA(cudaMemsetAsync(p, 0, total, st));
+    ctx->taps[name] = {p, total};
+    it = ctx->taps.find(name);
+  }
+  ISST_CUDA(cudaMemcpyAsync(static_cast<char*>(it->second.first) + offset, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch metadata: a handful of int arrays packed into one pinned buffer and copied once per call
+// ------------------------------------------------------------------------------------------------
+constexpr size_t kEncMetaInts = 2048;   // region reserved for isst_encode_chunk
+struct MetaBuilder {
+  isst_ctx* ctx;
+  size_t used = 0;
+  int* host(size_t off) { return ctx->h_meta + off; }
+  int* dev(size_t off) { return ctx->d_meta + off; }
+  size_t alloc(size_t n) {
+    size_t o = used;
+    used += (n + 3) & ~size_t(3);
+    return o;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// encoder
+// ------------------------------------------------------------------------------------------------
+static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const bf16* in, bf16* out, const float* w,
+                     const float* b, const int* gather, int rows, int C, float eps) {
+  ISST_CHECK(C % 8 == 0 && C <= 4096, "norm_rows: unsupported width");
+  if (rows == 0) return 0;
+  if (rms) norm_rows_kernel<true, false><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
+  else if (gelu) norm_rows_kernel<false, true><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
+  else norm_rows_kernel<false, false><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+static int conv_len(int n, int k, int s) { return (n - k) / s + 1; }
+
+static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_h, const int* d_slots, int n_new,
+                        int multiplier) {
+  const isst_config& c = ctx->cfg;
+  const int C = ctx->C;
+  const int window = ctx->n_tail + n_new;
+  // ---- conv feature extractor (E1) ----
+  int T = conv_len(window, c.conv_k[0], c.conv_s[0]);
+  {
+    dim3 grid(ceil_div(T, kConv0FramesPerCta), n);
+    const size_t smem = (static_cast<size_t>(c.conv_k[0]) * C + kConv0FramesPerCta * c.conv_s[0] + c.conv_k[0]) * 4;
+    conv0_ln_gelu_kernel<<<grid, 256, smem, st>>>(ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail, ctx->conv[0].w0_t,
+                                                  ctx->conv[0].bias, ctx->conv[0].ln_w, ctx->conv[0].ln_b, ctx->conv_a,
+                                                  C, c.conv_k[0], c.conv_s[0], T);
+    LAUNCH_CHECK(ctx);
+    update_tail_kernel<<<n, 128, 0, st>>>(ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail);
+    LAUNCH_CHECK(ctx);
+  }
+  bf16* cur = ctx->conv_a;
+  bf16* nxt = ctx->conv_b;
+  for (int j = 1; j < c.n_conv; ++j) {
+    const int k = c.conv_k[j], s = c.conv_s[j];
+    const int To = conv_len(T, k, s);
+    ActView v{cur, To, k * C, C, s, ceil_div(T, s) + (k - 1) / s, static_cast<long long>(T) * C, n};
+    // keep the row-group extent inside the batch stride (the last group of an odd T spills one row
+    // into the next batch / the buffer's pad row; those elements are never multiplied into valid rows)
+    v.row_groups = ceil_div(T, s);
+    Epilogue e;
+    e.bias = ctx->conv[j].bias;
+    ISST_TRY(gemm(ctx, st, v, ctx->conv[j].w, C, nxt, C, static_cast<long long>(To) * C, e));
+    ISST_TRY(norm_rows(ctx, st, false, true, nxt, nxt, ctx->conv[j].ln_w, ctx->conv[j].ln_b, nullptr, n * To, C, 1e-5f));
+    std::swap(cur, nxt);
+    T = To;
+  }
+  const int frames = T;   // new frames per stream
+  ISST_CHECK(frames == c.block_size * multiplier, "chunk does not produce block_size*multiplier frames");
+  const int M = n * frames;
+  ISST_TRY(tap(ctx, st, "enc_conv", cur, static_cast<size_t>(M) * C * 2));
+  // ---- LayerNorm(C) + post_extract_proj (E3) ----
+  ISST_TRY(norm_rows(ctx, st, false, false, cur, nxt, ctx->feat_ln_w, ctx->feat_ln_b, nullptr, M, C, 1e-5f));
+  const int D = c.enc_dim, F = c.enc_ffn, H = c.enc_heads, HD = D / H;
+  {
+    Epilogue e;
+    e.bias = ctx->post_b;
+    ISST_TRY(gemm(ctx, st, plain_view(nxt, M, C), ctx->post_proj, D, ctx->ex, D, 0, e));
+  }
+  ISST_TRY(tap(ctx, st, "enc_post_proj", ctx->ex, static_cast<size_t>(M) * D * 2));
+  // ---- 24 pre-LN layers (E4-E11) ----
+  const int blocksize = c.block_size * multiplier;
+  for (int l = 0; l < c.enc_layers; ++l) {
+    EncLayerW& w = ctx->enc[l];
+    ISST_TRY(norm_rows(ctx, st, false, false, ctx->ex, ctx->eh, w.ln1_w, w.ln1_b, nullptr, M, D, 1e-5f));
+    {
+      Epilogue e;
+      e.bias = w.bqkv;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->eh, M, D), w.wqkv, 3 * D, ctx->eqkv, 3 * D, 0, e));
+    }
+    bf16* kr = ctx->enc_k + static_cast<size_t>(l) * ctx->enc_layer_elems;
+    bf16* vr = ctx->enc_v + static_cast<size_t>(l) * ctx->enc_layer_elems;
+    {
+      dim3 grid(ceil_div(frames * D / 8, 256), n);
+      enc_kv_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, ctx->d_enc_prefix, frames, H, HD, ctx->enc_cap);
+      LAUNCH_CHECK(ctx);
+    }
+    {
+      EncAttnParams ep{};
+      ep.qkv = ctx->eqkv; ep.out = ctx->eattn; ep.k_ring = kr; ep.v_ring = vr; ep.slots = d_slots;
+      ep.prefix = ctx->d_enc_prefix; ep.rope_cos = ctx->enc_rope_cos; ep.rope_sin = ctx->enc_rope_sin;
+      ep.T = frames; ep.H = H; ep.cap = ctx->enc_cap; ep.max_cache = c.max_cache_size; ep.blocksize = blocksize;
+      LlmAttnParams lp{};
+      constexpr int NW = 4;
+      dim3 grid(ceil_div(frames, NW * 16), H, n);
+      const size_t smem = static_cast<size_t>(NW * 16 + 2 * 64) * (64 + 8) * 2;
+      ISST_CHECK(HD == 64, "encoder attention kernel is built for head_dim 64");
+      chunk_attention_kernel<64, true, NW><<<grid, NW * 32, smem, st>>>(ep, lp);
+      LAUNCH_CHECK(ctx);
+    }
+    {
+      Epilogue e;
+      e.bias = w.bo; e.resid = ctx->ex; e.ldr = D;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->eattn, M, D), w.wo, D, ctx->ex, D, 0, e));
+    }
+    ISST_TRY(norm_rows(ctx, st, false, false, ctx->ex, ctx->eh, w.ln2_w, w.ln2_b, nullptr, M, D, 1e-5f));
+    {
+      Epilogue e;
+      e.bias = w.b1; e.act = 1;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->eh, M, D), w.w1, F, ctx->effn, F, 0, e));
+    }
+    {
+      Epilogue e;
+      e.bias = w.b2; e.resid = ctx->ex; e.ldr = D;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->effn, M, F), w.w2, D, ctx->ex, D, 0, e));
+    }
+    if (ctx->debug) ISST_TRY(tap(ctx, st, "enc_layer_" + std::to_string(l), ctx->ex, static_cast<size_t>(M) * D * 2));
+  }
+  ISST_TRY(norm_rows(ctx, st, false, false, ctx->ex, ctx->eh, ctx->enc_ln_w, ctx->enc_ln_b, nullptr, M, D, 1e-5f));
+  ISST_TRY(tap(ctx, st, "enc_out", ctx->eh, static_cast<size_t>(M) * D * 2));
+  // ---- length adapter (E13): k == s strided convs are reshapes + GEMMs ----
+  const bf16* a_in = ctx->eh;
+  int rows = M, width = D;
+  bf16* bufs[2] = {ctx->ead0, ctx->ead1};
+  for (int j = 0; j < c.n_adapter; ++j) {
+    const int k = c.adapter_k[j], s = c.adapter_s[j];
+    ISST_CHECK(k == s && (rows / n) % s == 0, "length adapter needs kernel == stride and divisible frame count");
+    rows /= s;
+    Epilogue e;
+    ISST_TRY(gemm(ctx, st, plain_view(a_in, rows, k * width), ctx->adapter[j].w, c.adapter_dim[j], bufs[j & 1],
+                  c.adapter_dim[j], 0, e));
+    ISST_TRY(norm_rows(ctx, st, false, true, bufs[j & 1], bufs[j & 1], ctx->adapter[j].ln_w, ctx->adapter[j].ln_b,
+                       nullptr, rows, c.adapter_dim[j], 1e-5f));
+    a_in = bufs[j & 1];
+    width = c.adapter_dim[j];
+  }
+  {
+    Epilogue e;
+    e.bias = ctx->proj_b;
+    ISST_TRY(gemm(ctx, st, plain_view(a_in, rows, width), ctx->proj, c.hidden, ctx->speech, c.hidden, 0, e));
+  }
+  ctx->speech_rows_per_stream = rows / n;
+  ISST_TRY(tap(ctx, st, "speech_feats", ctx->speech, static_cast<size_t>(rows) * c.hidden * 2));
+  // cache.n_steps += T  (patch_speech_encoder.py:533)
+  for (int b = 0; b < n; ++b) ctx->streams[slots_h[b]].enc_prefix += frames;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LLM forward over packed new tokens (prefill: T_b >= 1; decode: T_b == 1)
+// ------------------------------------------------------------------------------------------------
+struct LlmBatch {
+  int n = 0, M = 0, max_T = 0;
+  const int* d_slots = nullptr;
+  const int* d_tok_base = nullptr;
+  const int* d_T = nullptr;
+  const int* d_last_row = nullptr;
+  const int* d_active = nullptr;   // may be null
+  bool decode = false;
+};
+
+static PagedKV paged_kv(isst_ctx* ctx, int layer) {
+  PagedKV kv;
+  kv.pool = ctx->kv_pool + static_cast<size_t>(layer) * ctx->kv_layer_elems;
+  kv.page_table = ctx->d_page_table;
+  kv.kv_len = ctx->d_kv_len;
+  kv.sys_len = ctx->d_sys_len;
+  kv.ring_start = ctx->d_ring_start;
+  kv.pages_per_stream = ctx->pages_per_stream;
+  kv.kv_heads = ctx->cfg.kv_heads;
+  kv.head_dim = ctx->cfg.head_dim;
+  return kv;
+}
+
+static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool tap_layers) {
+  const isst_config& c = ctx->cfg;
+  const int D = c.hidden, H = c.heads, Hkv = c.kv_heads, HD = c.head_dim, F = c.ffn;
+  const int QKV = (H + 2 * Hkv) * HD;
+  const int M = lb.M;
+  const float scale_log2 = 1.4426950408889634f / std::sqrt(static_cast<float>(HD));
+  ISST_CHECK(HD == 128 && H / Hkv == 4, "LLM attention kernels are built for head_dim 128 and 4:1 GQA");
+  for (int l = 0; l < c.layers; ++l) {
+    LlmLayerW& w = ctx->llm[l];
+    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms1, nullptr, nullptr, M, D, c.rms_eps));
+    {
+      Epilogue e;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->lh, M, D), w.wqkv, QKV, ctx->lqkv, QKV, 0, e));
+    }
+    PagedKV kv = paged_kv(ctx, l);
+    {
+      dim3 grid(ceil_div(lb.max_T * Hkv * HD / 8, 128), lb.n);
+      llm_kv_append_kernel<<<grid, 128, 0, st>>>(ctx->lqkv, kv, lb.d_slots, lb.d_tok_base, lb.d_T, lb.d_active, H);
+      LAUNCH_CHECK(ctx);
+    }
+    if (!lb.decode) {
+      LlmAttnParams lp{};
+      lp.qkv = ctx->lqkv; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
+      lp.T = lb.d_T; lp.rope = ctx->llm_rope; lp.H = H; lp.scale_log2 = scale_log2;
+      EncAttnParams ep{};
+      constexpr int NW = 8;
+      dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
+      const size_t smem = static_cast<size_t>(NW * 16 + 2 * 64) * (128 + 8) * 2;
+      static bool attr_set = false;
+      if (!attr_set) {
+        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<128, false, NW>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+      }
+      chunk_attention_kernel<128, false, NW><<<grid, NW * 32, smem, st>>>(ep, lp);
+      LAUNCH_CHECK(ctx);
+    } else {
+      DecodeParams dp{};
+      dp.qkv = ctx->lqkv; dp.kv = kv; dp.slots = lb.d_slots; dp.rope = ctx->llm_rope; dp.part_o = ctx->part_o;
+      dp.part_ml = ctx->part_ml; dp.H = H; dp.splits = ctx->decode_splits; dp.scale_log2 = scale_log2;
+      // fill the machine: n * Hkv * splits CTAs
+      int splits = std::max(1, std::min(ctx->decode_splits, ceil_div(2 * ctx->sm_count, lb.n * Hkv)));
+      dp.splits = splits;
+      dim3 grid(splits, Hkv, lb.n);
+      decode_attention_kernel<128, 4><<<grid, 128, 0, st>>>(dp);
+      LAUNCH_CHECK(ctx);
+      decode_combine_kernel<<<lb.n * H, 128, 0, st>>>(ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits);
+      LAUNCH_CHECK(ctx);
+    }
+    {
+      Epilogue e;
+      e.resid = ctx->lx; e.ldr = D;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->lattn, M, H * HD), w.wo, D, ctx->lx, D, 0, e));
+    }
+    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms2, nullptr, nullptr, M, D, c.rms_eps));
+    {
+      Epilogue e;
+      e.dual = 1; e.dual_off = F;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->lh, M, D), w.wgu, F, ctx->lgu, F, 0, e));
+    }
+    {
+      Epilogue e;
+      e.resid = ctx->lx; e.ldr = D;
+      ISST_TRY(gemm(ctx, st, plain_view(ctx->lgu, M, F), w.wd, D, ctx->lx, D, 0, e));
+    }
+    if (tap_layers && ctx->debug)
+      ISST_TRY(tap(ctx, st, "llm_layer_" + std::to_string(l), ctx->lx, static_cast<size_t>(M) * D * 2));
+  }
+  advance_kv_len_kernel<<<ceil_div(lb.n, 128), 128, 0, st>>>(ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n);
+  LAUNCH_CHECK(ctx);
+  // final norm + lm_head on the LAST position of each stream only (the reference computes and discards
+  // the other T-1 rows, llm.py:236-237 / SURVEY §2.3 L9)
+  ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->llast, ctx->final_norm, nullptr, lb.d_last_row, lb.n, D, c.rms_eps));
+  {
+    Epilogue e;
+    e.out_f32 = 1;
+    ISST_TRY(gemm(ctx, st, plain_view(ctx->llast, lb.n, D), ctx->lm_head, c.vocab, ctx->logits, c.vocab, 0, e));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV page management (host side; device tables are refreshed before every forward)
+// ------------------------------------------------------------------------------------------------
+static int ensure_capacity(isst_ctx* ctx, int slot, int extra_tokens, int pin_prefix) {
+  StreamHost& s = ctx->streams[slot];
+  if (!s.prefilled) {
+    s.sys_len = pin_prefix;
+    const int sys_pages = ceil_div(pin_prefix, kPageTokens);
+    s.ring_start = sys_pages * kPageTokens;
+    s.prefilled = true;
+  }
+  const int need_len = s.kv_len + extra_tokens;
+  ISST_CHECK(need_len <= ctx->cfg.max_kv_len, "stream KV length would exceed max_kv_len");
+  // highest slot index needed
+  const int last_slot = need_len <= s.sys_len ? need_len - 1 : need_len - 1 - s.sys_len + s.ring_start;
+  const int need_pages = last_slot / kPageTokens + 1;
+  ISST_CHECK(need_pages <= ctx->pages_per_stream, "stream needs more pages than pages_per_stream");
+  while (static_cast<int>(s.pages.size()) < need_pages) {
+    ISST_CHECK(!ctx->free_pages.empty(), "KV page pool exhausted");
+    s.pages.push_back(ctx->free_pages.back());
+    ctx->free_pages.pop_back();
+  }
+  return 0;
+}
+
+static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int* slots) {
+  // h_meta tail region is used as pinned staging for the per-stream tables
+  for (int b = 0; b < n; ++b) {
+    const int slot = slots[b];
+    StreamHost& s = ctx->streams[slot];
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_page_table + static_cast<size_t>(slot) * ctx->pages_per_stream, s.pages.data(),
+                              s.pages.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    int vals[3] = {s.kv_len, s.sys_len, s.ring_start};
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_kv_len + slot, &vals[0], sizeof(int), cudaMemcpyHostToDevice, st));
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_sys_len + slot, &vals[1], sizeof(int), cudaMemcpyHostToDevice, st));
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_ring_start + slot, &vals[2], sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  return 0;
+}
+
+static int check_batch(isst_ctx* ctx, int n, const int* ids) {
+  ISST_CHECK(ctx && ctx->finalized, "context not finalized (call isst_finalize_weights)");
+  ISST_CHECK(n >= 1 && n <= ctx->cfg.max_batch, "batch size out of range");
+  for (int b = 0; b < n; ++b) {
+    ISST_CHECK(ids[b] >= 0 && ids[b] < ctx->cfg.max_streams && ctx->streams[ids[b]].open, "bad stream id");
+    for (int a = 0; a < b; ++a) ISST_CHECK(ids[a] != ids[b], "duplicate stream id in batch");
+  }
+  return 0;
+}
+
+}  // namespace isst
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+const char* isst_last_error(void) { return g_last_error.c_str(); }
+
+int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
+  ISST_CHECK(cfg && out, "null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_error("no CUDA device: infinisst_b200 has no CPU fallback");
+  ISST_CHECK(device >= 0 && device < ndev, "bad device index");
+  ISST_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ISST_CUDA(cudaGetDeviceProperties(&prop, device));
+  ISST_CHECK(prop.major == 10, "infinisst_b200 kernels are built for sm_100a only");
+  ISST_TRY(load_driver_api());
+  isst_ctx* ctx = new isst_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  const char* g = getenv("ISST_GEMM");
+  ctx->simple_gemm = g && std::string(g) == "simple";
+  const isst_config& c = ctx->cfg;
+  ISST_CHECK(c.n_conv >= 2 && c.n_conv <= ISST_MAX_CONV && c.n_adapter >= 0 && c.n_adapter <= ISST_MAX_CONV, "bad conv config");
+  ctx->C = c.conv_dim[0];
+  for (int j = 0; j < c.n_conv; ++j) ISST_CHECK(c.conv_dim[j] == ctx->C, "all conv blocks must share one width");
+  ISST_CHECK(ctx->C % 64 == 0 && ctx->C <= 512 && c.conv_k[0] <= kConv0MaxK, "unsupported conv width / kernel");
+  // receptive field and total stride of the conv stack
+  int rf = 1, stride = 1;
+  for (int j = 0; j < c.n_conv; ++j) { rf += (c.conv_k[j] - 1) * stride; stride *= c.conv_s[j]; }
+  ctx->rf = rf;
+  ctx->total_stride = stride;
+  ctx->n_tail = rf - 1;   // 79 + 320 for wav2vec2 (agents/infinisst.py:216-218)
+  ctx->frames_max = c.block_size * c.max_multiplier;
+  ctx->samples_max = ctx->frames_max * stride;
+  ctx->enc_cap = c.max_cache_size + ctx->frames_max;
+  ctx->pages_per_stream = ceil_div(c.max_kv_len, kPageTokens) + 2;
+  const int D = c.enc_dim, F = c.enc_ffn, C = ctx->C, HID = c.hidden;
+  ISST_CHECK(D % 64 == 0 && F % 64 == 0 && HID % 64 == 0 && c.ffn % 64 == 0, "model widths must be multiples of 64");
+
+  // ---- weights ----
+  ctx->conv.resize(c.n_conv);
+  for (int j = 0; j < c.n_conv; ++j) {
+    ConvW& w = ctx->conv[j];
+    if (j == 0) ISST_TRY(dev_alloc(&w.w0_t, static_cast<size_t>(c.conv_k[0]) * C));
+    else ISST_TRY(alloc_w2d(w.w, C, c.conv_k[j] * C));
+    ISST_TRY(dev_alloc(&w.bias, C)); ISST_TRY(dev_alloc(&w.ln_w, C)); ISST_TRY(dev_alloc(&w.ln_b, C));
+  }
+  ISST_TRY(dev_alloc(&ctx->feat_ln_w, C)); ISST_TRY(dev_alloc(&ctx->feat_ln_b, C));
+  ISST_TRY(alloc_w2d(ctx->post_proj, D, C)); ISST_TRY(dev_alloc(&ctx->post_b, D));
+  ctx->enc.resize(c.enc_layers);
+  for (auto& w : ctx->enc) {
+    ISST_TRY(dev_alloc(&w.ln1_w, D)); ISST_TRY(dev_alloc(&w.ln1_b, D)); ISST_TRY(dev_alloc(&w.ln2_w, D));
+    ISST_TRY(dev_alloc(&w.ln2_b, D)); ISST_TRY(dev_alloc(&w.bqkv, 3 * D)); ISST_TRY(dev_alloc(&w.bo, D));
+    ISST_TRY(dev_alloc(&w.b1, F)); ISST_TRY(dev_alloc(&w.b2, D));
+    ISST_TRY(alloc_w2d(w.wqkv, 3 * D, D)); ISST_TRY(alloc_w2d(w.wo, D, D));
+    ISST_TRY(alloc_w2d(w.w1, F, D)); ISST_TRY(alloc_w2d(w.w2, D, F));
+  }
+  ISST_TRY(dev_alloc(&ctx->enc_ln_w, D)); ISST_TRY(dev_alloc(&ctx->enc_ln_b, D));
+  ctx->adapter.resize(c.n_adapter);
+  int width = D;
+  for (int j = 0; j < c.n_adapter; ++j) {
+    ISST_TRY(alloc_w2d(ctx->adapter[j].w, c.adapter_dim[j], c.adapter_k[j] * width));
+    ISST_TRY(dev_alloc(&ctx->adapter[j].ln_w, c.adapter_dim[j])); ISST_TRY(dev_alloc(&ctx->adapter[j].ln_b, c.adapter_dim[j]));
+    width = c.adapter_dim[j];
+  }
+  ISST_TRY(alloc_w2d(ctx->proj, HID, width)); ISST_TRY(dev_alloc(&ctx->proj_b, HID));
+  const int QKV = (c.heads + 2 * c.kv_heads) * c.head_dim;
+  ctx->llm.resize(c.layers);
+  for (auto& w : ctx->llm) {
+    ISST_TRY(dev_alloc(&w.rms1, HID)); ISST_TRY(dev_alloc(&w.rms2, HID));
+    ISST_TRY(alloc_w2d(w.wqkv, QKV, HID)); ISST_TRY(alloc_w2d(w.wo, HID, c.heads * c.head_dim));
+    ISST_TRY(alloc_w2d(w.wgu, 2 * c.ffn, HID)); ISST_TRY(alloc_w2d(w.wd, HID, c.ffn));
+  }
+  ISST_TRY(dev_alloc(&ctx->final_norm, HID));
+  ISST_TRY(alloc_w2d(ctx->lm_head, c.vocab, HID));
+  ISST_TRY(dev_alloc(&ctx->embed, static_cast<size_t>(c.vocab) * HID));
+  ctx->enc_rope_npos = ctx->enc_cap;
+  ISST_TRY(dev_alloc(&ctx->enc_rope_cos, static_cast<size_t>(ctx->enc_rope_npos) * (D / c.enc_heads / 2)));
+  ISST_TRY(dev_alloc(&ctx->enc_rope_sin, static_cast<size_t>(ctx->enc_rope_npos) * (D / c.enc_heads / 2)));
+  ctx->llm_rope_npos = c.max_kv_len;
+  ISST_TRY(dev_alloc(&ctx->llm_rope_cos_f, static_cast<size_t>(c.max_kv_len) * (c.head_dim / 2)));
+  ISST_TRY(dev_alloc(&ctx->llm_rope_sin_f, static_cast<size_t>(c.max_kv_len) * (c.head_dim / 2)));
+  ISST_TRY(dev_alloc(&ctx->llm_rope, static_cast<size_t>(c.max_kv_len) * (c.head_dim / 2)));
+
+  // ---- stream state ----
+  ctx->streams.resize(c.max_streams);
+  ISST_TRY(dev_alloc(&ctx->tail, static_cast<size_t>(c.max_streams) * ctx->n_tail));
+  ctx->enc_layer_elems = static_cast<size_t>(c.max_streams) * D * ctx->enc_cap;
+  ISST_TRY(dev_alloc(&ctx->enc_k, ctx->enc_layer_elems * c.enc_layers));
+  ISST_TRY(dev_alloc(&ctx->enc_v, ctx->enc_layer_elems * c.enc_layers));
+  ISST_TRY(dev_alloc(&ctx->d_enc_prefix, c.max_streams));
+  ISST_TRY(dev_alloc(&ctx->d_page_table, static_cast<size_t>(c.max_streams) * ctx->pages_per_stream));
+  ISST_TRY(dev_alloc(&ctx->d_kv_len, c.max_streams)); ISST_TRY(dev_alloc(&ctx->d_sys_len, c.max_streams));
+  ISST_TRY(dev_alloc(&ctx->d_ring_start, c.max_streams));
+  ISST_CUDA(cudaMemset(ctx->d_page_table, 0, static_cast<size_t>(c.max_streams) * ctx->pages_per_stream * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_kv_len, 0, c.max_streams * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_sys_len, 0, c.max_streams * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_ring_start, 0, c.max_streams * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_enc_prefix, 0, c.max_streams * sizeof(int)));
+  ctx->kv_layer_elems = static_cast<size_t>(c.kv_pages) * 2 * c.kv_heads * kPageTokens * c.head_dim;
+  ISST_TRY(dev_alloc(&ctx->kv_pool, ctx->kv_layer_elems * c.layers));
+  for (int p = c.kv_pages - 1; p >= 0; --p) ctx->free_pages.push_back(p);
+
+  // ---- workspaces ----
+  const int nb = c.max_batch;
+  ISST_TRY(dev_alloc(&ctx->d_pcm, static_cast<size_t>(nb) * (ctx->samples_max + ctx->n_tail)));
+  const int T0 = conv_len(ctx->n_tail + ctx->samples_max, c.conv_k[0], c.conv_s[0]);
+  ISST_TRY(dev_alloc(&ctx->conv_a, static_cast<size_t>(nb) * T0 * C + 2 * C));
+  ISST_TRY(dev_alloc(&ctx->conv_b, static_cast<size_t>(nb) * T0 * C + 2 * C));
+  ISST_CUDA(cudaMemset(ctx->conv_a, 0, (static_cast<size_t>(nb) * T0 * C + 2 * C) * 2));
+  ISST_CUDA(cudaMemset(ctx->conv_b, 0, (static_cast<size_t>(nb) * T0 * C + 2 * C) * 2));
+  const size_t ME = static_cast<size_t>(nb) * ctx->frames_max;
+  ISST_TRY(dev_alloc(&ctx->ex, ME * D)); ISST_TRY(dev_alloc(&ctx->eh, ME * D)); ISST_TRY(dev_alloc(&ctx->eqkv, ME * 3 * D));
+  ISST_TRY(dev_alloc(&ctx->eattn, ME * D)); ISST_TRY(dev_alloc(&ctx->effn, ME * F));
+  int maxw = D;
+  for (int j = 0; j < c.n_adapter; ++j) maxw = std::max(maxw, c.adapter_dim[j]);
+  ISST_TRY(dev_alloc(&ctx->ead0, ME * maxw)); ISST_TRY(dev_alloc(&ctx->ead1, ME * maxw));
+  ISST_TRY(dev_alloc(&ctx->speech, ME * HID));
+  const size_t ML = static_cast<size_t>(nb) * std::max(c.max_prompt, 1);
+  ISST_TRY(dev_alloc(&ctx->lx, ML * HID)); ISST_TRY(dev_alloc(&ctx->lh, ML * HID)); ISST_TRY(dev_alloc(&ctx->lqkv, ML * QKV));
+  ISST_TRY(dev_alloc(&ctx->lattn, ML * c.heads * c.head_dim)); ISST_TRY(dev_alloc(&ctx->lgu, ML * c.ffn));
+  ISST_TRY(dev_alloc(&ctx->llast, static_cast<size_t>(nb) * HID));
+  ISST_TRY(dev_alloc(&ctx->logits, static_cast<size_t>(nb) * c.vocab));
+  ctx->decode_splits = 32;
+  ISST_TRY(dev_alloc(&ctx->part_o, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * c.head_dim));
+  ISST_TRY(dev_alloc(&ctx->part_ml, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * 2));
+  ctx->gemm_ws_floats = static_cast<size_t>(16) << 20;   // 64 MB
+  ISST_TRY(dev_alloc(&ctx->gemm_ws, ctx->gemm_ws_floats));
+  ctx->n_counters = 4096;
+  ISST_TRY(dev_alloc(&ctx->gemm_counters, ctx->n_counters));
+  ISST_CUDA(cudaMemset(ctx->gemm_counters, 0, ctx->n_counters * sizeof(int)));
+  ctx->meta_ints = kEncMetaInts + static_cast<size_t>(nb) * (c.max_prompt * 4 + 256 + c.max_new_tokens * 4) + 4096;
+  ISST_TRY(dev_alloc(&ctx->d_meta, ctx->meta_ints));
+  ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_meta), ctx->meta_ints * sizeof(int)));
+  ISST_CUDA(cudaDeviceSynchronize());
+  *out = ctx;
+  return 0;
+}
+
+void isst_destroy(isst_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  // the context owns every device allocation it made; release the big pools explicitly
+  cudaFree(ctx->kv_pool); cudaFree(ctx->enc_k); cudaFree(ctx->enc_v); cudaFree(ctx->embed);
+  for (auto& w : ctx->llm) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.wgu.ptr); cudaFree(w.wd.ptr); cudaFree(w.rms1); cudaFree(w.rms2); }
+  for (auto& w : ctx->enc) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.w1.ptr); cudaFree(w.w2.ptr);
+    cudaFree(w.ln1_w); cudaFree(w.ln1_b); cudaFree(w.ln2_w); cudaFree(w.ln2_b); cudaFree(w.bqkv); cudaFree(w.bo); cudaFree(w.b1); cudaFree(w.b2); }
+  for (auto& w : ctx->conv) { cudaFree(w.w.ptr); cudaFree(w.w0_t); cudaFree(w.bias); cudaFree(w.ln_w); cudaFree(w.ln_b); }
+  for (auto& w : ctx->adapter) { cudaFree(w.w.ptr); cudaFree(w.ln_w); cudaFree(w.ln_b); }
+  cudaFree(ctx->lm_head.ptr); cudaFree(ctx->post_proj.ptr); cudaFree(ctx->proj.ptr);
+  void* misc[] = {ctx->feat_ln_w, ctx->feat_ln_b, ctx->post_b, ctx->enc_ln_w, ctx->enc_ln_b, ctx->proj_b, ctx->final_norm,
+                  ctx->enc_rope_cos, ctx->enc_rope_sin, ctx->llm_rope_cos_f, ctx->llm_rope_sin_f, ctx->llm_rope, ctx->staging,
+                  ctx->tail, ctx->d_enc_prefix, ctx->d_page_table, ctx->d_kv_len, ctx->d_sys_len, ctx->d_ring_start,
+                  ctx->d_pcm, ctx->conv_a, ctx->conv_b, ctx->ex, ctx->eh, ctx->eqkv, ctx->eattn, ctx->effn, ctx->ead0,
+                  ctx->ead1, ctx->speech, ctx->lx, ctx->lh, ctx->lqkv, ctx->lattn, ctx->lgu, ctx->llast, ctx->logits,
+                  ctx->part_o, ctx->part_ml, ctx->gemm_ws, ctx->gemm_counters, ctx->d_meta};
+  for (void* p : misc) cudaFree(p);
+  for (auto& t : ctx->taps) cudaFree(t.second.first);
+  cudaFreeHost(ctx->h_meta);
+  delete ctx;
+}
+
+static bool starts_with(const std::string& s, const std::string& p) { return s.compare(0, p.size(), p) == 0; }
+
+int isst_load_weight(isst_ctx* ctx, const char* name_c, const void* data, const int64_t* shape, int ndim, int dtype) {
+  ISST_CHECK(ctx && name_c && data && shape, "null argument");
+  ISST_CHECK(dtype == ISST_DTYPE_F32 || dtype == ISST_DTYPE_BF16, "dtype must be f32 or bf16");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  const isst_config& c = ctx->cfg;
+  const std::string name(name_c);
+  const int D = c.enc_dim, F = c.enc_ffn, C = ctx->C, HID = c.hidden, HD = c.head_dim;
+  const std::string ENC = "model.speech_encoder.speech_encoder.";
+  const std::string SPE = "model.speech_encoder.";
+  ctx->finalized = false;
+  auto done = [&]() { ctx->loaded[name] = true; return 0; };
+#define LM(dst, rows, cols) do { ISST_TRY(load_matrix(ctx, dst, rows, cols, data, shape, ndim, dtype)); return done(); } while (0)
+#define LV(dst, n) do { ISST_TRY(load_vector(ctx, dst, n, data, shape, ndim, dtype)); return done(); } while (0)
+  if (name == "rope.enc.cos" || name == "rope.enc.sin" || name == "rope.llm.cos" || name == "rope.llm.sin") {
+    const bool enc = name[5] == 'e';
+    const int half = enc ? (D / c.enc_heads / 2) : HD / 2;
+    const int npos = enc ? ctx->enc_rope_npos : ctx->llm_rope_npos;
+    ISST_CHECK(ndim == 2 && shape[1] == half && shape[0] >= npos, "rope table must be [>= n_pos, head_dim/2]");
+    ISST_CHECK(dtype == ISST_DTYPE_F32, "rope tables are f32");
+    float* dst = enc ? (name[9] == 'c' ? ctx->enc_rope_cos : ctx->enc_rope_sin)
+                     : (name[9] == 'c' ? ctx->llm_rope_cos_f : ctx->llm_rope_sin_f);
+    ISST_CUDA(cudaMemcpy(dst, data, static_cast<size_t>(npos) * half * 4, cudaMemcpyDefault));
+    return done();
+  }
+  if (starts_with(name, ENC + "feature_extractor.conv_layers.")) {
+    const std::string rest = name.substr((ENC + "feature_extractor.conv_layers.").size());
+    const int j = atoi(rest.c_str());
+    ISST_CHECK(j >= 0 && j < c.n_conv, "conv layer index out of range");
+    const std::string leaf = rest.substr(rest.find('.') + 1);
+    ConvW& w = ctx->conv[j];
+    if (leaf == "0.weight") {
+      if (j == 0) {
+        long long n; numel(shape, ndim, &n);
+        ISST_CHECK(n == static_cast<long long>(C) * c.conv_k[0], "conv0 weight size");
+        const void* src;
+        ISST_TRY(stage_source(ctx, data, static_cast<size_t>(n) * (dtype == ISST_DTYPE_F32 ? 4 : 2), &src));
+        if (dtype == ISST_DTYPE_F32) cvt_conv0_kernel<float><<<32, 256>>>(static_cast<const float*>(src), w.w0_t, C, c.conv_k[0]);
+        else cvt_conv0_kernel<bf16><<<32, 256>>>(static_cast<const bf16*>(src), w.w0_t, C, c.conv_k[0]);
+        ISST_CUDA(cudaDeviceSynchronize());
+        return done();
+      }
+      ISST_TRY(load_conv(ctx, w.w.ptr, C, C, c.conv_k[j], data, shape, ndim, dtype));
+      return done();
+    }
+    if (leaf == "0.bias") LV(w.bias, C);
+    if (leaf == "2.1.weight") LV(w.ln_w, C);
+    if (leaf == "2.1.bias") LV(w.ln_b, C);
+    return set_error("unknown conv key: " + name);
+  }
+  if (name == ENC + "layer_norm.weight") LV(ctx->feat_ln_w, C);
+  if (name == ENC + "layer_norm.bias") LV(ctx->feat_ln_b, C);
+  if (name == ENC + "post_extract_proj.weight") LM(ctx->post_proj.ptr, D, C);
+  if (name == ENC + "post_extract_proj.bias") LV(ctx->post_b, D);
+  if (name == ENC + "encoder.layer_norm.weight") LV(ctx->enc_ln_w, D);
+  if (name == ENC + "encoder.layer_norm.bias") LV(ctx->enc_ln_b, D);
+  if (starts_with(name, ENC + "encoder.layers.")) {
+    const std::string rest = name.substr((ENC + "encoder.layers.").size());
+    const int i = atoi(rest.c_str());
+    ISST_CHECK(i >= 0 && i < c.enc_layers, "encoder layer index out of range");
+    const std::string leaf = rest.substr(rest.find('.') + 1);
+    EncLayerW& w = ctx->enc[i];
+    // q is pre-scaled by head_dim^-0.5 (patch_speech_encoder.py:768); exact for head_dim 64 (power of two)
+    const float qs = 1.0f / std::sqrt(static_cast<float>(D / c.enc_heads));
+    if (leaf == "self_attn.q_proj.weight") { ISST_TRY(load_matrix(ctx, w.wqkv.ptr, D, D, data, shape, ndim, dtype, qs)); return done(); }
+    if (leaf == "self_attn.k_proj.weight") LM(w.wqkv.ptr + static_cast<size_t>(D) * D, D, D);
+    if (leaf == "self_attn.v_proj.weight") LM(w.wqkv.ptr + static_cast<size_t>(2) * D * D, D, D);
+    if (leaf == "self_attn.q_proj.bias") { ISST_TRY(load_vector(ctx, w.bqkv, D, data, shape, ndim, dtype, qs)); return done(); }
+    if (leaf == "self_attn.k_proj.bias") LV(w.bqkv + D, D);
+    if (leaf == "self_attn.v_proj.bias") LV(w.bqkv + 2 * D, D);
+    if (leaf == "self_attn.out_proj.weight") LM(w.wo.ptr, D, D);
+    if (leaf == "self_attn.out_proj.bias") LV(w.bo, D);
+    if (leaf == "self_attn_layer_norm.weight") LV(w.ln1_w, D);
+    if (leaf == "self_attn_layer_norm.bias") LV(w.ln1_b, D);
+    if (leaf == "final_layer_norm.weight") LV(w.ln2_w, D);
+    if (leaf == "final_layer_norm.bias") LV(w.ln2_b, D);
+    if (leaf == "fc1.weight") LM(w.w1.ptr, F, D);
+    if (leaf == "fc1.bias") LV(w.b1, F);
+    if (leaf == "fc2.weight") LM(w.w2.ptr, D, F);
+    if (leaf == "fc2.bias") LV(w.b2, D);
+    if (leaf == "self_attn.rotary_emb.freqs") return 0;   // consumed on the host to build rope.enc.*
+    return set_error("unknown encoder layer key: " + name);
+  }
+  if (starts_with(name, SPE + "length_shrink.conv_layers.")) {
+    const std::string rest = name.substr((SPE + "length_shrink.conv_layers.").size());
+    const int j = atoi(rest.c_str());
+    ISST_CHECK(j >= 0 && j < c.n_adapter, "adapter layer index out of range");
+    const std::string leaf = rest.substr(rest.find('.') + 1);
+    const int cin = j == 0 ? D : c.adapter_dim[j - 1];
+    if (leaf == "0.weight") { ISST_TRY(load_conv(ctx, ctx->adapter[j].w.ptr, c.adapter_dim[j], cin, c.adapter_k[j], data, shape, ndim, dtype)); return done(); }
+    if (leaf == "2.1.weight") LV(ctx->adapter[j].ln_w, c.adapter_dim[j]);
+    if (leaf == "2.1.bias") LV(ctx->adapter[j].ln_b, c.adapter_dim[j]);
+    return set_error("unknown adapter key: " + name);
+  }
+  if (name == SPE + "proj.weight") LM(ctx->proj.ptr, HID, ctx->proj.K);
+  if (name == SPE + "proj.bias") LV(ctx->proj_b, HID);
+  if (name == "model.embed_tokens.weight") LM(ctx->embed, c.vocab, HID);
+  if (name == "model.norm.weight") LV(ctx->final_norm, HID);
+  if (name == "lm_head.weight") LM(ctx->lm_head.ptr, c.vocab, HID);
+  if (starts_with(name, "model.layers.")) {
+    const std::string rest = name.substr(std::string("model.layers.").size());
+    const int i = atoi(rest.c_str());
+    ISST_CHECK(i >= 0 && i < c.layers, "LLM layer index out of range");
+    const std::string leaf = rest.substr(rest.find('.') + 1);
+    LlmLayerW& w = ctx->llm[i];
+    const size_t qrows = static_cast<size_t>(c.heads) * HD, kvrows = static_cast<size_t>(c.kv_heads) * HD;
+    if (leaf == "self_attn.q_proj.weight") LM(w.wqkv.ptr, qrows, HID);
+    if (leaf == "self_attn.k_proj.weight") LM(w.wqkv.ptr + qrows * HID, kvrows, HID);
+    if (leaf == "self_attn.v_proj.weight") LM(w.wqkv.ptr + (qrows + kvrows) * HID, kvrows, HID);
+    if (leaf == "self_attn.o_proj.weight") LM(w.wo.ptr, HID, qrows);
+    if (leaf == "mlp.gate_proj.weight") LM(w.wgu.ptr, c.ffn, HID);
+    if (leaf == "mlp.up_proj.weight") LM(w.wgu.ptr + static_cast<size_t>(c.ffn) * HID, c.ffn, HID);
+    if (leaf == "mlp.down_proj.weight") LM(w.wd.ptr, HID, c.ffn);
+    if (leaf == "input_layernorm.weight") LV(w.rms1, HID);
+    if (leaf == "post_attention_layernorm.weight") LV(w.rms2, HID);
+    return set_error("unknown LLM layer key: " + name);
+  }
+#undef LM
+#undef LV
+  return 0;   // unused module (encoder.pos_conv.*, mask_emb, ...): ignored like load_state_dict on dead weights
+}
+
+int isst_finalize_weights(isst_ctx* ctx) {
+  ISST_CHECK(ctx, "null ctx");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  const isst_config& c = ctx->cfg;
+  // every tensor of the hot path must have been loaded
+  std::vector<std::string> need = {"rope.enc.cos", "rope.enc.sin", "rope.llm.cos", "rope.llm.sin",
+                                   "model.embed_tokens.weight", "model.norm.weight", "lm_head.weight",
+                                   "model.speech_encoder.proj.weight", "model.speech_encoder.proj.bias"};
+  const std::string ENC = "model.speech_encoder.speech_encoder.";
+  for (int j = 0; j < c.n_conv; ++j)
+    for (const char* leaf : {"0.weight", "0.bias", "2.1.weight", "2.1.bias"})
+      need.push_back(ENC + "feature_extractor.conv_layers." + std::to_string(j) + "." + leaf);
+  for (const char* leaf : {"layer_norm.weight", "layer_norm.bias", "post_extract_proj.weight", "post_extract_proj.bias",
+                           "encoder.layer_norm.weight", "encoder.layer_norm.bias"})
+    need.push_back(ENC + leaf);
+  for (int i = 0; i < c.enc_layers; ++i)
+    for (const char* leaf : {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
+                             "self_attn.out_proj.weight", "self_attn.q_proj.bias", "self_attn.k_proj.bias",
+                             "self_attn.v_proj.bias", "self_attn.out_proj.bias", "self_attn_layer_norm.weight",
+                             "self_attn_layer_norm.bias", "final_layer_norm.weight", "final_layer_norm.bias",
+                             "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"})
+      need.push_back(ENC + "encoder.layers." + std::to_string(i) + "." + leaf);
+  for (int j = 0; j < c.n_adapter; ++j)
+    for (const char* leaf : {"0.weight", "2.1.weight", "2.1.bias"})
+      need.push_back("model.speech_encoder.length_shrink.conv_layers." + std::to_string(j) + "." + leaf);
+  for (int i = 0; i < c.layers; ++i)
+    for (const char* leaf : {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
+                             "self_attn.o_proj.weight", "mlp.gate_proj.weight", "mlp.up_proj.weight",
+                             "mlp.down_proj.weight", "input_layernorm.weight", "post_attention_layernorm.weight"})
+      need.push_back("model.layers." + std::to_string(i) + "." + leaf);
+  for (const auto& k : need)
+    if (!ctx->loaded.count(k)) return set_error("missing weight: " + k);
+  // tensor maps
+  for (int j = 1; j < c.n_conv; ++j) ISST_TRY(make_weight_map(ctx->conv[j].w));
+  for (auto& a : ctx->adapter) ISST_TRY(make_weight_map(a.w));
+  ISST_TRY(make_weight_map(ctx->post_proj)); ISST_TRY(make_weight_map(ctx->proj)); ISST_TRY(make_weight_map(ctx->lm_head));
+  for (auto& w : ctx->enc) { ISST_TRY(make_weight_map(w.wqkv)); ISST_TRY(make_weight_map(w.wo)); ISST_TRY(make_weight_map(w.w1)); ISST_TRY(make_weight_map(w.w2)); }
+  for (auto& w : ctx->llm) { ISST_TRY(make_weight_map(w.wqkv)); ISST_TRY(make_weight_map(w.wo)); ISST_TRY(make_weight_map(w.wgu)); ISST_TRY(make_weight_map(w.wd)); }
+  const long long nr = static_cast<long long>(ctx->llm_rope_npos) * (c.head_dim / 2);
+  build_llm_rope_kernel<<<256, 256>>>(ctx->llm_rope_cos_f, ctx->llm_rope_sin_f, ctx->llm_rope, nr);
+  ISST_CUDA(cudaGetLastError());
+  ISST_CUDA(cudaDeviceSynchronize());
+  if (ctx->staging) { cudaFree(ctx->staging); ctx->staging = nullptr; ctx->staging_bytes = 0; }
+  ctx->finalized = true;
+  return 0;
+}
+
+int isst_stream_open(isst_ctx* ctx, int* stream_id) {
+  ISST_CHECK(ctx && stream_id, "null argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  for (int s = 0; s < ctx->cfg.max_streams; ++s) {
+    if (!ctx->streams[s].open) {
+      ctx->streams[s] = StreamHost();
+      ctx->streams[s].open = true;
+      // zero carried samples == the 79+320 zero offset of the first chunk (agents/infinisst.py:216-218)
+      ISST_CUDA(cudaMemset(ctx->tail + static_cast<size_t>(s) * ctx->n_tail, 0, ctx->n_tail * sizeof(float)));
+      int zero = 0;
+      ISST_CUDA(cudaMemcpy(ctx->d_enc_prefix + s, &zero, sizeof(int), cudaMemcpyHostToDevice));
+      *stream_id = s;
+      return 0;
+    }
+  }
+  return set_error("no free stream slot (max_streams reached)");
+}
+
+int isst_stream_close(isst_ctx* ctx, int stream_id) {
+  ISST_CHECK(ctx && stream_id >= 0 && stream_id < ctx->cfg.max_streams && ctx->streams[stream_id].open, "bad stream id");
+  StreamHost& s = ctx->streams[stream_id];
+  for (int p : s.pages) ctx->free_pages.push_back(p);
+  s = StreamHost();
+  return 0;
+}
+
+int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* pcm, int n_samples, int multiplier,
+                      void* out_feats, void* cuda_stream) {
+  ISST_TRY(check_batch(ctx, n, stream_ids));
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ISST_CHECK(multiplier >= 1 && multiplier <= ctx->cfg.max_multiplier, "multiplier out of range");
+  const int n_new = ctx->cfg.block_size * multiplier * ctx->total_stride;
+  bool fresh = ctx->streams[stream_ids[0]].enc_prefix == 0;
+  for (int b = 0; b < n; ++b)
+    ISST_CHECK((ctx->streams[stream_ids[b]].enc_prefix == 0) == fresh, "batch mixes fresh and running streams");
+  const bool with_offset = fresh && n_samples == n_new + ctx->n_tail;
+  ISST_CHECK(n_samples == n_new || with_offset,
+             "n_samples must be block_size*multiplier*320 (+ 79+320 on the first chunk of a stream)");
+  ISST_CUDA(cudaStreamSynchronize(st));   // the pinned metadata region below may still be in flight from a previous call
+  MetaBuilder mb{ctx};
+  const size_t o_slots = mb.alloc(n), o_prefix = mb.alloc(n);
+  ISST_CHECK(mb.used <= kEncMetaInts, "max_batch too large for the encoder metadata region");
+  for (int b = 0; b < n; ++b) {
+    mb.host(o_slots)[b] = stream_ids[b];
+    mb.host(o_prefix)[b] = ctx->streams[stream_ids[b]].enc_prefix;
+  }
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_meta, ctx->h_meta, mb.used * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int b = 0; b < n; ++b)
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_enc_prefix + stream_ids[b], mb.host(o_prefix) + b, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (with_offset) {
+    // explicit 79+320 leading samples: they become the carried tail (zeros in the reference)
+    ISST_CUDA(cudaMemcpy2DAsync(ctx->d_pcm, static_cast<size_t>(n_samples) * 4, pcm, static_cast<size_t>(n_samples) * 4,
+                                static_cast<size_t>(n_samples) * 4, n, cudaMemcpyDefault, st));
+    // tail <- first n_tail samples (rounded like the cast at agents/infinisst.py:222), new <- rest, compacted
+    // done with two strided copies on the stream
+    for (int b = 0; b < n; ++b) {
+      update_tail_kernel<<<1, 128, 0, st>>>(ctx->d_pcm + static_cast<size_t>(b) * n_samples, ctx->tail, mb.dev(o_slots) + b,
+                                            ctx->n_tail, ctx->n_tail);
+      LAUNCH_CHECK(ctx);
+    }
+    float* tmp = reinterpret_cast<float*>(ctx->conv_b);   // scratch, large enough (n * T0 * C bf16 >> n * n_new floats)
+    ISST_CUDA(cudaMemcpy2DAsync(tmp, static_cast<size_t>(n_new) * 4, ctx->d_pcm + ctx->n_tail, static_cast<size_t>(n_samples) * 4,
+                                static_cast<size_t>(n_new) * 4, n, cudaMemcpyDeviceToDevice, st));
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_pcm, tmp, static_cast<size_t>(n) * n_new * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_pcm, pcm, static_cast<size_t>(n) * n_new * 4, cudaMemcpyDefault, st));
+  }
+  ISST_TRY(encode_chunk(ctx, st, n, stream_ids, mb.dev(o_slots), n_new, multiplier));
+  if (out_feats) {
+    ISST_CUDA(cudaMemcpyAsync(out_feats, ctx->speech, static_cast<size_t>(n) * ctx->speech_rows_per_stream * ctx->cfg.hidden * 2,
+                              cudaMemcpyDefault, st));
+    ISST_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// Builds the packed batch description shared by isst_forward / isst_generate.
+static int setup_llm_batch(isst_ctx* ctx, cudaStream_t st, MetaBuilder& mb, int n, const int* stream_ids, const int* lens,
+                           const int32_t* ids, const int32_t* speech_slot, int extra_decode, int pin_prefix, LlmBatch* lb,
+                           size_t* o_ids_out, size_t* o_srow_out) {
+  int M = 0, maxT = 0;
+  for (int b = 0; b < n; ++b) {
+    ISST_CHECK(lens[b] >= 1 && lens[b] <= ctx->cfg.max_prompt, "prompt length out of range");
+    M += lens[b];
+    maxT = std::max(maxT, lens[b]);
+  }
+  for (int b = 0; b < n; ++b) ISST_TRY(ensure_capacity(ctx, stream_ids[b], lens[b] + extra_decode, pin_prefix));
+  ISST_TRY(upload_stream_tables(ctx, st, n, stream_ids));
+  const size_t o_slots = mb.alloc(n), o_base = mb.alloc(n), o_T = mb.alloc(n), o_last = mb.alloc(n);
+  const size_t o_ids = mb.alloc(M), o_srow = mb.alloc(M);
+  int row = 0;
+  for (int b = 0; b < n; ++b) {
+    mb.host(o_slots)[b] = stream_ids[b];
+    mb.host(o_base)[b] = row;
+    mb.host(o_T)[b] = lens[b];
+    mb.host(o_last)[b] = row + lens[b] - 1;
+    for (int t = 0; t < lens[b]; ++t) {
+      mb.host(o_ids)[row + t] = ids ? ids[row + t] : 0;
+      const int ss = speech_slot ? speech_slot[row + t] : -1;
+      if (ss >= 0) ISST_CHECK(ss < ctx->speech_rows_per_stream, "speech slot index beyond the encoded features");
+      mb.host(o_srow)[row + t] = ss >= 0 ? b * ctx->speech_rows_per_stream + ss : -1;
+      if (ids) ISST_CHECK(ids[row + t] >= 0 && ids[row + t] < ctx->cfg.vocab, "token id out of range");
+    }
+    row += lens[b];
+  }
+  lb->n = n; lb->M = M; lb->max_T = maxT;
+  lb->d_slots = mb.dev(o_slots); lb->d_tok_base = mb.dev(o_base); lb->d_T = mb.dev(o_T); lb->d_last_row = mb.dev(o_last);
+  lb->d_active = nullptr; lb->decode = false;
+  *o_ids_out = o_ids; *o_srow_out = o_srow;
+  return 0;
+}
+
+int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                 const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
+                 void* cuda_stream) {
+  ISST_TRY(check_batch(ctx, n, stream_ids));
+  ISST_CHECK(lens && (ids || embeds_override), "null argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  MetaBuilder mb{ctx, kEncMetaInts};
+  LlmBatch lb;
+  size_t o_ids, o_srow;
+  ISST_TRY(setup_llm_batch(ctx, st, mb, n, stream_ids, lens, ids, speech_slot, 0, pin_prefix, &lb, &o_ids, &o_srow));
+  ISST_CHECK(mb.used <= ctx->meta_ints, "metadata buffer too small");
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_meta + kEncMetaInts, ctx->h_meta + kEncMetaInts, (mb.used - kEncMetaInts) * sizeof(int),
+                            cudaMemcpyHostToDevice, st));
+  if (embeds_override) {
+    ISST_CUDA(cudaMemcpyAsync(ctx->lx, embeds_override, static_cast<size_t>(lb.M) * ctx->cfg.hidden * 2, cudaMemcpyDefault, st));
+  } else {
+    embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, ctx->cfg.hidden);
+    LAUNCH_CHECK(ctx);
+  }
+  ISST_TRY(tap(ctx, st, "prompt_embeds", ctx->lx, static_cast<size_t>(lb.M) * ctx->cfg.hidden * 2));
+  ISST_TRY(llm_forward(ctx, st, lb, true));
+  if (out_logits) ISST_CUDA(cudaMemcpyAsync(out_logits, ctx->logits, static_cast<size_t>(n) * ctx->cfg.vocab * 4, cudaMemcpyDefault, st));
+  ISST_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < n; ++b) ctx->streams[stream_ids[b]].kv_len += lens[b];
+  return 0;
+}
+
+int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                  const int32_t* speech_slot, const int32_t* enc_ids, const int* enc_lens,
+                  const isst_gen_params* gen, const int32_t* forced, int32_t* out_tokens, int* out_counts,
+                  void* cuda_stream) {
+  ISST_TRY(check_batch(ctx, n, stream_ids));
+  ISST_CHECK(ids && lens && gen && out_tokens && out_counts, "null argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const isst_config& c = ctx->cfg;
+  const int max_new = gen->max_new_tokens;
+  ISST_CHECK(max_new >= 1 && max_new <= c.max_new_tokens, "max_new_tokens out of range");
+  ISST_CHECK(gen->n_eos >= 0 && gen->n_eos <= 8, "too many eos ids");
+  MetaBuilder mb{ctx, kEncMetaInts};
+  LlmBatch lb;
+  size_t o_ids, o_srow;
+  ISST_TRY(setup_llm_batch(ctx, st, mb, n, stream_ids, lens, ids, speech_slot, max_new - 1, gen->pin_prefix, &lb, &o_ids, &o_srow));
+  // generation state
+  const int ctx_cap = c.max_prompt + max_new;
+  const int enc_cap = 128;
+  const size_t o_ctx = mb.alloc(static_cast<size_t>(n) * ctx_cap), o_ctxlen = mb.alloc(n);
+  const size_t o_enc = mb.alloc(static_cast<size_t>(n) * enc_cap), o_enclen = mb.alloc(n);
+  const size_t o_active = mb.alloc(n), o_out = mb.alloc(static_cast<size_t>(n) * max_new), o_cnt = mb.alloc(n);
+  const size_t o_next = mb.alloc(n), o_forced = mb.alloc(forced ? static_cast<size_t>(n) * max_new : 0);
+  const size_t o_sup = mb.alloc(gen->n_suppress), o_eos = mb.alloc(8);
+  const size_t o_ones = mb.alloc(n), o_iota = mb.alloc(n);
+  ISST_CHECK(mb.used <= ctx->meta_ints, "metadata buffer too small");
+  int row = 0, eoff = 0;
+  for (int b = 0; b < n; ++b) {
+    for (int t = 0; t < lens[b]; ++t) mb.host(o_ctx)[static_cast<size_t>(b) * ctx_cap + t] = ids[row + t];
+    mb.host(o_ctxlen)[b] = lens[b];
+    const int el = enc_lens ? enc_lens[b] : 0;
+    ISST_CHECK(el >= 0 && el <= enc_cap, "encoder id history longer than 128");
+    for (int t = 0; t < el; ++t) mb.host(o_enc)[static_cast<size_t>(b) * enc_cap + t] = enc_ids[eoff + t];
+    mb.host(o_enclen)[b] = el;
+    mb.host(o_active)[b] = 1;
+    mb.host(o_cnt)[b] = 0;
+    mb.host(o_next)[b] = 0;
+    mb.host(o_ones)[b] = 1;
+    mb.host(o_iota)[b] = b;
+    for (int s = 0; s < max_new; ++s) {
+      mb.host(o_out)[static_cast<size_t>(b) * max_new + s] = -1;
+      if (forced) mb.host(o_forced)[static_cast<size_t>(b) * max_new + s] = forced[static_cast<size_t>(b) * max_new + s];
+    }
+    row += lens[b];
+    eoff += el;
+  }
+  for (int i = 0; i < gen->n_suppress; ++i) mb.host(o_sup)[i] = gen->suppress_tokens[i];
+  for (int i = 0; i < gen->n_eos; ++i) mb.host(o_eos)[i] = gen->eos_token_ids[i];
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_meta + kEncMetaInts, ctx->h_meta + kEncMetaInts, (mb.used - kEncMetaInts) * sizeof(int),
+                            cudaMemcpyHostToDevice, st));
+
+  GenState g{};
+  g.ctx_ids = mb.dev(o_ctx); g.ctx_len = mb.dev(o_ctxlen); g.enc_ids = mb.dev(o_enc); g.enc_len = mb.dev(o_enclen);
+  g.active = mb.dev(o_active); g.out_tokens = mb.dev(o_out); g.out_count = mb.dev(o_cnt); g.next_token = mb.dev(o_next);
+  g.forced = forced ? mb.dev(o_forced) : nullptr; g.suppress = mb.dev(o_sup); g.eos = mb.dev(o_eos);
+  g.ctx_cap = ctx_cap; g.enc_cap = enc_cap; g.max_new = max_new; g.n_suppress = gen->n_suppress; g.n_eos = gen->n_eos;
+  g.ngram = gen->no_repeat_ngram_size; g.penalty = gen->repetition_penalty;
+
+  // ---- step 0: splice + chunk prefill ----
+  embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, c.hidden);
+  LAUNCH_CHECK(ctx);
+  ISST_TRY(tap(ctx, st, "prompt_embeds", ctx->lx, static_cast<size_t>(lb.M) * c.hidden * 2));
+  ISST_TRY(llm_forward(ctx, st, lb, true));
+  const size_t lbytes = static_cast<size_t>(n) * c.vocab * 4;
+  ISST_TRY(tap(ctx, st, "step_logits", ctx->logits, lbytes, 0, lbytes * max_new));
+  g.step = 0;
+  greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
+  LAUNCH_CHECK(ctx);
+  // ---- decode steps ----
+  LlmBatch db = lb;
+  db.M = n; db.max_T = 1; db.d_T = mb.dev(o_ones); db.d_tok_base = mb.dev(o_iota); db.d_last_row = mb.dev(o_iota);
+  db.d_active = mb.dev(o_active); db.decode = true;
+  int* h_active = ctx->h_meta + o_active;
+  for (int step = 1; step < max_new; ++step) {
+    // early exit when every stream hit EOS (one small D2H + sync per step; a step is >= 2 ms of weight streaming)
+    ISST_CUDA(cudaMemcpyAsync(h_active, mb.dev(o_active), n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ISST_CUDA(cudaStreamSynchronize(st));
+    bool any = false;
+    for (int b = 0; b < n; ++b) any = any || h_active[b];
+    if (!any) break;
+    embed_splice_kernel<<<n, 128, 0, st>>>(mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden);
+    LAUNCH_CHECK(ctx);
+    ISST_TRY(llm_forward(ctx, st, db, false));
+    ISST_TRY(tap(ctx, st, "step_logits", ctx->logits, lbytes, lbytes * step, lbytes * max_new));
+    g.step = step;
+    greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
+    LAUNCH_CHECK(ctx);
+  }
+  ISST_CUDA(cudaMemcpyAsync(ctx->h_meta + o_out, mb.dev(o_out), static_cast<size_t>(n) * max_new * sizeof(int), cudaMemcpyDeviceToHost, st));
+  ISST_CUDA(cudaMemcpyAsync(ctx->h_meta + o_cnt, mb.dev(o_cnt), n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  ISST_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < n; ++b) {
+    const int cnt = ctx->h_meta[o_cnt + b];
+    out_counts[b] = cnt;
+    for (int s = 0; s < max_new; ++s) out_tokens[static_cast<size_t>(b) * max_new + s] = ctx->h_meta[o_out + static_cast<size_t>(b) * max_new + s];
+    // KV holds the prompt and every chosen token except the last (drop-last rule)
+    ctx->streams[stream_ids[b]].kv_len += lens[b] + std::max(0, cnt - 1);
+  }
+  return 0;
+}
+
+int isst_kv_len(isst_ctx* ctx, int stream_id, int* len) {
+  ISST_CHECK(ctx && len && stream_id >= 0 && stream_id < ctx->cfg.max_streams && ctx->streams[stream_id].open, "bad stream id");
+  *len = ctx->streams[stream_id].kv_len;
+  return 0;
+}
+
+int isst_enc_steps(isst_ctx* ctx, int stream_id, int* n_steps) {
+  ISST_CHECK(ctx && n_steps && stream_id >= 0 && stream_id < ctx->cfg.max_streams && ctx->streams[stream_id].open, "bad stream id");
+  *n_steps = ctx->streams[stream_id].enc_prefix;
+  return 0;
+}
+
+int isst_kv_evict(isst_ctx* ctx, int stream_id, int keep_prefix, int drop_upto) {
+  ISST_CHECK(ctx && stream_id >= 0 && stream_id < ctx->cfg.max_streams && ctx->streams[stream_id].open, "bad stream id");
+  StreamHost& s = ctx->streams[stream_id];
+  ISST_CHECK(keep_prefix == s.sys_len, "keep_prefix must equal the stream's pinned prefix (gen.pin_prefix of its first prefill)");
+  ISST_CHECK(drop_upto >= keep_prefix && drop_upto <= s.kv_len, "drop range out of bounds");
+  const int n_drop = drop_upto - keep_prefix;
+  if (n_drop == 0) return 0;
+  s.ring_start += n_drop;
+  s.kv_len -= n_drop;
+  // release ring pages that fell completely behind ring_start
+  const int sys_pages = ceil_div(s.sys_len, kPageTokens);
+  int freeable = s.ring_start / kPageTokens - sys_pages;
+  freeable = std::min(freeable, static_cast<int>(s.pages.size()) - sys_pages);
+  if (freeable > 0) {
+    for (int i = 0; i < freeable; ++i) ctx->free_pages.push_back(s.pages[sys_pages + i]);
+    s.pages.erase(s.pages.begin() + sys_pages, s.pages.begin() + sys_pages + freeable);
+    s.ring_start -= freeable * kPageTokens;
+  }
+  return 0;
+}
+
+int isst_debug_enable(isst_ctx* ctx, int on) {
+  ISST_CHECK(ctx, "null ctx");
+  ctx->debug = on != 0;
+  return 0;
+}
+
+int isst_debug_read(isst_ctx* ctx, const char* name, void* dst_host, int64_t max_bytes, int64_t* n_bytes) {
+  ISST_CHECK(ctx && name && n_bytes, "null argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  auto it = ctx->taps.find(name);
+  if (it == ctx->taps.end()) return set_error(std::string("no such tap: ") + name);
+  *n_bytes = static_cast<int64_t>(it->second.second);
+  if (dst_host) {
+    ISST_CHECK(max_bytes >= *n_bytes, "destination too small");
+    ISST_CUDA(cudaDeviceSynchronize());
+    ISST_CUDA(cudaMemcpy(dst_host, it->second.first, it->second.second, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int64_t isst_launch_count(isst_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int isst_pages_free(isst_ctx* ctx) { return ctx ? static_cast<int>(ctx->free_pages.size()) : -1; }
+
+int isst_op_gemm(isst_ctx* ctx, const void* act_bf16, const void* w_bf16, int M, int N, int K, const float* bias,
+                 int act_gelu, const void* resid_bf16, int dual, void* out, int out_f32, int impl, int force_swap,
+                 int force_splits, void* cuda_stream) {
+  ISST_CHECK(ctx && act_bf16 && w_bf16 && out, "null argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  Weight2D w;
+  w.ptr = const_cast<bf16*>(static_cast<const bf16*>(w_bf16));
+  w.rows = dual ? 2 * N : N;
+  w.K = K;
+  ISST_TRY(make_weight_map(w));
+  Epilogue e;
+  e.bias = bias; e.act = act_gelu; e.resid = static_cast<const bf16*>(resid_bf16); e.ldr = N; e.out_f32 = out_f32;
+  e.dual = dual; e.dual_off = dual ? N : 0;
+  return gemm(ctx, st, plain_view(static_cast<const bf16*>(act_bf16), M, K), w, N, out, N, 0, e, force_swap, force_splits, impl);
+}
+
+int isst_op_decode_attention_bench(isst_ctx* ctx, int n, int L, int iters, float* ms_per_iter, void* cuda_stream) {
+  ISST_CHECK(ctx && ms_per_iter && n >= 1 && n <= ctx->cfg.max_batch && iters >= 1, "bad argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const isst_config& c = ctx->cfg;
+  ISST_CHECK(L + 1 <= c.max_kv_len, "L too large");
+  // temporary streams with L tokens of pseudo-random KV in layer 0..layers-1 pools
+  std::vector<int> slots(n);
+  for (int b = 0; b < n; ++b) {
+    ISST_TRY(isst_stream_open(ctx, &slots[b]));
+    ISST_TRY(ensure_capacity(ctx, slots[b], L + 1, 0));
+    ctx->streams[slots[b]].kv_len = L;
+  }
+  ISST_TRY(upload_stream_tables(ctx, st, n, slots.data()));
+  fill_pattern_kernel<<<1024, 256, 0, st>>>(ctx->kv_pool, static_cast<long long>(ctx->kv_layer_elems) * c.layers, 17u);
+  const int QKV = (c.heads + 2 * c.kv_heads) * c.head_dim;
+  fill_pattern_kernel<<<64, 256, 0, st>>>(ctx->lqkv, static_cast<long long>(n) * QKV, 3u);
+  MetaBuilder mb{ctx};
+  const size_t o_slots = mb.alloc(n);
+  for (int b = 0; b < n; ++b) mb.host(o_slots)[b] = slots[b];
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_meta, ctx->h_meta, mb.used * sizeof(int), cudaMemcpyHostToDevice, st));
+  const float scale_log2 = 1.4426950408889634f / std::sqrt(static_cast<float>(c.head_dim));
+  cudaEvent_t e0, e1;
+  ISST_CUDA(cudaEventCreate(&e0)); ISST_CUDA(cudaEventCreate(&e1));
+  const int splits = std::max(1, std::min(ctx->decode_splits, ceil_div(2 * ctx->sm_count, n * c.kv_heads)));
+  for (int it = -2; it < iters; ++it) {
+    if (it == 0) ISST_CUDA(cudaEventRecord(e0, st));
+    // walk the layers so consecutive launches read different (cold) KV: total footprint = layers * n * L * 4 KB
+    const int layer = ((it % c.layers) + c.layers) % c.layers;
+    DecodeParams dp{};
+    dp.qkv = ctx->lqkv; dp.kv = paged_kv(ctx, layer); dp.slots = mb.dev(o_slots); dp.rope = ctx->llm_rope;
+    dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = c.heads; dp.splits = splits; dp.scale_log2 = scale_log2;
+    decode_attention_kernel<128, 4><<<dim3(splits, c.kv_heads, n), 128, 0, st>>>(dp);
+    LAUNCH_CHECK(ctx);
+  }
+  ISST_CUDA(cudaEventRecord(e1, st));
+  ISST_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  ISST_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_iter = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (int b = 0; b < n; ++b) ISST_TRY(isst_stream_close(ctx, slots[b]));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// Memory-bound row kernels: conv0 + LayerNorm + GELU, LayerNorm / RMSNorm rows, embedding gather +
+// speech splice, logits processors + arg-max, and the CUDA-core validation GEMM.
+#pragma once
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace isst {
+
+// ----------------------------------------------------------------------------------------------
+// conv0: Conv1d(1 -> C, k, stride, bias) -> Fp32LayerNorm(C) -> GELU on the window [tail | new samples].
+// fairseq ConvFeatureExtractionModel block 0, layer_norm mode (call site
+// patch_speech_encoder.py:245-251).  Only the minimal window (RF-1 carried samples + the new chunk) is
+// convolved instead of the reference's two-chunk ring: identical frames, half the work.
+// One warp per output frame; weights transposed [k][C] in shared memory.
+// ----------------------------------------------------------------------------------------------
+constexpr int kConv0FramesPerCta = 64;
+constexpr int kConv0MaxK = 16;
+
+__global__ void __launch_bounds__(256)
+conv0_ln_gelu_kernel(const float* __restrict__ pcm,      // [n][n_new] new samples (fp32, rounded to bf16 here
+                                                         //  like `.to(dtype=bf16)`, agents/infinisst.py:222)
+                     const float* __restrict__ tail,     // [max_streams][n_tail] carried samples (already rounded)
+                     const int* __restrict__ slots, int n_new, int n_tail,
+                     const float* __restrict__ w_t,      // [k][C]
+                     const float* __restrict__ bias, const float* __restrict__ ln_w,
+                     const float* __restrict__ ln_b, bf16* __restrict__ out,   // [n][T0][C]
+                     int C, int k, int stride, int T0) {
+  extern __shared__ float c0_smem[];
+  float* s_w = c0_smem;                 // k*C
+  float* s_x = s_w + k * C;             // window span of this CTA
+  const int b = blockIdx.y;
+  const int slot = slots[b];
+  const int f0 = blockIdx.x * kConv0FramesPerCta;
+  const int nf = min(kConv0FramesPerCta, T0 - f0);
+  const int span = (nf - 1) * stride + k;
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) s_w[i] = w_t[i];
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int idx = f0 * stride + i;
+    s_x[i] = idx < n_tail ? tail[static_cast<size_t>(slot) * n_tail + idx]
+                          : bf16_round(pcm[static_cast<size_t>(b) * n_new + (idx - n_tail)]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int per = C / 32;               // channels per lane (C % 32 == 0, <= 16)
+  for (int f = warp; f < nf; f += nwarps) {
+    float x[kConv0MaxK];
+#pragma unroll
+    for (int j = 0; j < kConv0MaxK; ++j) x[j] = j < k ? s_x[f * stride + j] : 0.f;
+    float y[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < per) {
+        const int ch = lane + 32 * i;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < kConv0MaxK; ++j)
+          if (j < k) acc += s_w[j * C + ch] * x[j];
+        y[i] = bf16_round(acc + bias[ch]);        // conv output in the model dtype
+        sum += y[i];
+      }
+    }
+    const float mean = warp_sum(sum) / C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < per) { const float d = y[i] - mean; var += d * d; }
+    const float rstd = rsqrtf(warp_sum(var) / C + 1e-5f);
+    bf16* o = out + (static_cast<size_t>(b) * T0 + f0 + f) * C;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < per) {
+        const int ch = lane + 32 * i;
+        const float z = bf16_round((y[i] - mean) * rstd * ln_w[ch] + ln_b[ch]);   // Fp32LayerNorm(...).type_as(x)
+        o[ch] = __float2bfloat16_rn(gelu_erf(z));
+      }
+    }
+  }
+}
+
+// tail <- last n_tail samples of [tail | new]
+__global__ void update_tail_kernel(const float* __restrict__ pcm, float* tail, const int* __restrict__ slots,
+                                   int n_new, int n_tail) {
+  const int b = blockIdx.x;
+  const int slot = slots[b];
+  float* t = tail + static_cast<size_t>(slot) * n_tail;
+  // n_new >= n_tail in every supported configuration (chunk of 15360 samples vs 399 carried)
+  for (int i = threadIdx.x; i < n_tail; i += blockDim.x)
+    t[i] = bf16_round(pcm[static_cast<size_t>(b) * n_new + (n_new - n_tail + i)]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Row normalisation: one CTA (128 threads) per row, up to 4096 columns held in registers.
+//   kRms = false: LayerNorm(w, b);  kRms = true: LlamaRMSNorm (fp32 normalise -> round -> * w)
+//   kGelu: GELU(erf) after the norm (conv feature extractor / length adapter blocks)
+//   gather: optional row indices into `in` (last-token gather before the final norm + lm_head)
+// ----------------------------------------------------------------------------------------------
+template <bool kRms, bool kGelu>
+__global__ void __launch_bounds__(128)
+norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const float* __restrict__ bvec,
+                 const int* __restrict__ gather, int C, float eps) {
+  const int row = blockIdx.x;
+  const bf16* x = in + static_cast<size_t>(gather ? gather[row] : row) * C;
+  bf16* o = out + static_cast<size_t>(row) * C;
+  const int tid = threadIdx.x;
+  float v[4][8];
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c0 = (it * 128 + tid) * 8;
+    if (c0 < C) {
+      uint4 raw = *reinterpret_cast<const uint4*>(x + c0);
+      const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16(u[j]);
+        v[it][2 * j] = f.x; v[it][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+        sq += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  __shared__ float red[2][4];
+  __shared__ float stat[2];
+  sum = warp_sum(sum); sq = warp_sum(sq);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = sum; red[1][tid >> 5] = sq; }
+  __syncthreads();
+  if (tid == 0) {
+    const float s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    const float q = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    if (kRms) { stat[0] = 0.f; stat[1] = rsqrtf(q / C + eps); }
+    else {
+      const float mean = s / C;
+      stat[0] = mean;
+      stat[1] = -1.f;   // second pass below
+    }
+  }
+  __syncthreads();
+  float mean = stat[0], rstd = stat[1];
+  if (!kRms) {
+    float var = 0.f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int c0 = (it * 128 + tid) * 8;
+      if (c0 < C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mean; var += d * d; }
+      }
+    }
+    var = warp_sum(var);
+    __syncthreads();
+    if ((tid & 31) == 0) red[0][tid >> 5] = var;
+    __syncthreads();
+    rstd = rsqrtf((red[0][0] + red[0][1] + red[0][2] + red[0][3]) / C + eps);
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c0 = (it * 128 + tid) * 8;
+    if (c0 < C) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = c0 + 2 * j + e;
+          float t;
+          if (kRms) t = w[c] * bf16_round(v[it][2 * j + e] * rstd);
+          else t = (v[it][2 * j + e] - mean) * rstd * w[c] + bvec[c];
+          if (kGelu) t = gelu_erf(bf16_round(t));
+          y[e] = t;
+        }
+        pk[j] = pack_bf16(y[0], y[1]);
+      }
+      *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Embedding gather + speech splice (SpeechLlamaModel.forward, llm.py:86-115): row r takes
+// speech[speech_row[r]] when speech_row[r] >= 0 (the <sp_patch> slots), else embed[ids[r]].
+// ----------------------------------------------------------------------------------------------
+__global__ void embed_splice_kernel(const int* __restrict__ ids, const int* __restrict__ speech_row,
+                                    const bf16* __restrict__ embed, const bf16* __restrict__ speech,
+                                    bf16* __restrict__ out, int D) {
+  const int r = blockIdx.x;
+  const int sr = speech_row ? speech_row[r] : -1;
+  const bf16* src = sr >= 0 ? speech + static_cast<size_t>(sr) * D : embed + static_cast<size_t>(ids[r]) * D;
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * D + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Device-side greedy step: HF processor order RepetitionPenalty ->
+// NoRepeatNGram -> EncoderNoRepeatNGram -> SuppressTokens, then arg-max (lowest index wins ties),
+// EOS / max-length bookkeeping.  One CTA per stream; the host only ever sees token ids.
+// ----------------------------------------------------------------------------------------------
+struct GenState {
+  int* ctx_ids;        // [n][ctx_cap]  prompt of this call + generated tokens
+  int* ctx_len;        // [n]
+  const int* enc_ids;  // [n][enc_cap]  last `lookback` emitted target ids
+  const int* enc_len;  // [n]
+  int* active;         // [n] 1 while the stream is still generating
+  int* out_tokens;     // [n][max_new]
+  int* out_count;      // [n]
+  int* next_token;     // [n] token to forward at the next decode step
+  const int* forced;   // [n][max_new] or null (teacher forcing for parity tests)
+  const int* suppress; // [n_suppress]
+  const int* eos;      // [n_eos]
+  int ctx_cap, enc_cap, max_new, n_suppress, n_eos;
+  int ngram;
+  float penalty;
+  int step;
+};
+
+__global__ void __launch_bounds__(1024)
+greedy_select_kernel(float* logits, int V, GenState g) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (!g.active[b]) return;
+  float* lg = logits + static_cast<size_t>(b) * V;
+  const int* ctx = g.ctx_ids + static_cast<size_t>(b) * g.ctx_cap;
+  const int n_ctx = g.ctx_len[b];
+  const int* enc = g.enc_ids + static_cast<size_t>(b) * g.enc_cap;
+  const int n_enc = g.enc_len[b];
+  // (1) repetition penalty, once per distinct id
+  if (g.penalty != 1.0f) {
+    for (int i = tid; i < n_ctx; i += blockDim.x) {
+      const int id = ctx[i];
+      bool first = true;
+      for (int j = 0; j < i; ++j) if (ctx[j] == id) { first = false; break; }
+      if (first) { const float s = lg[id]; lg[id] = s < 0.f ? s * g.penalty : s / g.penalty; }
+    }
+  }
+  __syncthreads();
+  // (2)+(3) n-gram bans: tail = last ngram-1 ids of ctx
+  if (g.ngram > 0 && n_ctx + 1 >= g.ngram) {
+    const int m = g.ngram - 1;
+    const int* tail = ctx + n_ctx - m;
+    for (int t = tid; t + g.ngram <= n_ctx; t += blockDim.x) {
+      bool eq = true;
+      for (int j = 0; j < m; ++j) if (ctx[t + j] != tail[j]) { eq = false; break; }
+      if (eq) lg[ctx[t + m]] = -INFINITY;
+    }
+    for (int t = tid; t + g.ngram <= n_enc; t += blockDim.x) {
+      bool eq = true;
+      for (int j = 0; j < m; ++j) if (enc[t + j] != tail[j]) { eq = false; break; }
+      if (eq) lg[enc[t + m]] = -INFINITY;
+    }
+  }
+  // (4) suppress tokens
+  for (int i = tid; i < g.n_suppress; i += blockDim.x) lg[g.suppress[i]] = -INFINITY;
+  __syncthreads();
+  // (5) arg-max
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const float s = lg[i];
+    if (s > best || (s == best && i < bi)) { best = s; bi = i; }
+  }
+  __shared__ float sb[32];
+  __shared__ int si[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((tid & 31) == 0) { sb[tid >> 5] = best; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w)
+      if (sb[w] > best || (sb[w] == best && si[w] < bi)) { best = sb[w]; bi = si[w]; }
+    int tok = (bi == 0x7fffffff) ? 0 : bi;
+    if (g.forced) tok = g.forced[static_cast<size_t>(b) * g.max_new + g.step];
+    g.out_tokens[static_cast<size_t>(b) * g.max_new + g.step] = tok;
+    g.out_count[b] = g.step + 1;
+    g.next_token[b] = tok;
+    if (n_ctx < g.ctx_cap) g.ctx_ids[static_cast<size_t>(b) * g.ctx_cap + n_ctx] = tok;
+    g.ctx_len[b] = n_ctx + 1;
+    bool stop = false;
+    for (int e = 0; e < g.n_eos; ++e) if (tok == g.eos[e]) stop = true;
+    if (stop) g.active[b] = 0;
+  }
+}
+
+// kv_len[slot] += T[b] for active streams (after all layers appended their K/V)
+__global__ void advance_kv_len_kernel(int* kv_len, const int* __restrict__ slots, const int* __restrict__ Tn,
+                                      const int* __restrict__ active, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n && (!active || active[b])) kv_len[slots[b]] += Tn[b];
+}
+
+// ----------------------------------------------------------------------------------------------
+// CUDA-core validation GEMM (same contract as tc::gemm_tcgen05_kernel; selected with ISST_GEMM=simple).
+// It exists to separate "tcgen05 kernel wrong" from "everything else wrong" on the GPU box; the product
+// default is the tcgen05 kernel.  One warp = one output feature x 8 tokens.
+// Activation addressing covers the im2col-free conv view: element (tok, kidx) lives at
+//   act + b*act_batch_stride + ((tok*conv_s + kidx / conv_c) * conv_c + kidx % conv_c).
+// ----------------------------------------------------------------------------------------------
+struct SimpleGemmExtra {
+  const bf16* act;
+  long long act_batch_stride;
+  int conv_c, conv_s;
+  const bf16* w;     // [rows, K] row-major
+  int dual;
+};
+
+__global__ void __launch_bounds__(256)
+gemm_simple_kernel(const tc::GemmParams p, const SimpleGemmExtra x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 8 + warp;
+  const int t0 = blockIdx.y * 8;
+  const int b = blockIdx.z;
+  if (f >= p.N_out) return;
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+  const bf16* w0 = x.w + static_cast<size_t>(f) * p.K;
+  const bf16* w1 = x.w + static_cast<size_t>(f + p.dual_off) * p.K;
+  const bf16* a = x.act + static_cast<size_t>(b) * x.act_batch_stride;
+  for (int k = lane * 2; k < p.K; k += 64) {
+    const float2 wv = __bfloat1622float2(*reinterpret_cast<const bf162*>(w0 + k));
+    float2 uv = make_float2(0.f, 0.f);
+    if (x.dual) uv = __bfloat1622float2(*reinterpret_cast<const bf162*>(w1 + k));
+    const int kk = k / x.conv_c, c = k % x.conv_c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int tok = t0 + i;
+      if (tok < p.M_tok) {
+        const float2 av = __bfloat1622float2(*reinterpret_cast<const bf162*>(
+            a + (static_cast<size_t>(tok) * x.conv_s + kk) * x.conv_c + c));
+        acc0[i] += av.x * wv.x + av.y * wv.y;
+        if (x.dual) acc1[i] += av.x * uv.x + av.y * uv.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc0[i] = warp_sum(acc0[i]);
+    if (x.dual) acc1[i] = warp_sum(acc1[i]);
+  }
+  if (lane == 0) {
+    for (int i = 0; i < 8; ++i) {
+      const int tok = t0 + i;
+      if (tok >= p.M_tok) break;
+      float v = acc0[i] + (p.bias ? p.bias[f] : 0.f);
+      if (x.dual) v = silu(v) * acc1[i];
+      if (p.act == 1) v = gelu_erf(v);
+      if (p.resid) v += __bfloat162float(p.resid[b * p.resid_batch_stride + static_cast<long long>(tok) * p.ldr + f]);
+      const long long oi = b * p.out_batch_stride + static_cast<long long>(tok) * p.ldo + f;
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = v;
+      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+}  // namespace isst
