@@ -123,6 +123,15 @@ int isst_enc_steps(isst_ctx* ctx, int stream_id, int* n_steps);   /* W2V2RoPECac
 int isst_debug_enable(isst_ctx* ctx, int on);   /* keep per-step raw logits + encoder taps */
 int isst_debug_read(isst_ctx* ctx, const char* name, void* dst_host, int64_t max_bytes, int64_t* n_bytes);
 int64_t isst_launch_count(isst_ctx* ctx);       /* kernels launched so far */
+/* Per-kernel-class device timing for the roofline leg of bench.py: while enabled every launch is
+ * bracketed by CUDA events on the caller's stream.  isst_profile_read walks the classes by index
+ * (returns 1 past the last one): launches, summed event time, and the ALGORITHMIC flops / bytes
+ * of those launches (DESIGN.md states the per-unit figures; the reference's own probe is the
+ * whole-step synchronized_timer, agents/infinisst.py:37-48). */
+int isst_profile_enable(isst_ctx* ctx, int on);
+int isst_profile_reset(isst_ctx* ctx);
+int isst_profile_read(isst_ctx* ctx, int index, char* name, int name_cap, int64_t* launches, double* ms,
+                      double* flops, double* bytes);
 int isst_pages_free(isst_ctx* ctx);
 
 /* Stand-alone operator entry points (device pointers) used by the parity tests and bench.py:

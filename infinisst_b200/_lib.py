@@ -61,6 +61,10 @@ SYMBOLS = {
     "isst_debug_read": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "isst_launch_count": (C.c_int64, [_P]),
     "isst_pages_free": (_I, [_P]),
+    "isst_profile_enable": (_I, [_P, _I]),
+    "isst_profile_reset": (_I, [_P]),
+    "isst_profile_read": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                               C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "isst_op_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "isst_op_decode_attention_bench": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), _P]),
 }

@@ -350,25 +350,7 @@ class InfiniSST(SpeechToTextAgent):
     def _generate(self, sts, ids, speech, enc, pin):
         """model.generate with the kwargs of agents/infinisst.py:307-332 (ragged `encoder_input_ids`
         are passed per stream instead of one padded tensor)."""
-        width = max((len(e) for e in enc), default=0)
-        enc_t = None
-        if width > 0 and all(len(e) == width for e in enc):
-            enc_t = torch.tensor(enc, dtype=torch.long)
-        if enc_t is None and width > 0:
-            # ragged histories: run the engine directly (same path the shim takes)
-            handles = self.model._handles(sts if len(sts) > 1 else sts[0], None, len(sts))
-            self.model.engine.encode_chunk([h.sid for h in handles], speech, self.latency_multiplier)
-            rows = [ids[b].tolist() for b in range(len(sts))]
-            g = self._gen_cfg()
-            toks = self.model.engine.generate([h.sid for h in handles], rows, [self.model._slot_map(r) for r in rows],
-                                              enc, g, pin_prefix=pin)
-            self._n_generated = [len(t) for t in toks]
-            from .model import GenerateOutput
-            w = max(len(r) + len(t) for r, t in zip(rows, toks))
-            seqs = torch.full((len(sts), w), self.tokenizer.pad_token_id, dtype=torch.long)
-            for b, (r, t) in enumerate(zip(rows, toks)):
-                seqs[b, :len(r) + len(t)] = torch.tensor(r + t)
-            return GenerateOutput(seqs, handles[0] if len(sts) == 1 else handles)
+        enc_t = enc if any(len(e) for e in enc) else None
         out = self.model.generate(
             attention_mask=None, input_ids=ids, speech_batch=speech, do_sample=False, top_p=1.0, top_k=0,
             epsilon_cutoff=0.0, temperature=1.0, num_beams=self.beam, max_new_tokens=self.max_new_tokens,
@@ -377,14 +359,7 @@ class InfiniSST(SpeechToTextAgent):
             pad_token_id=self.tokenizer.pad_token_id, return_dict_in_generate=True, return_legacy_cache=False,
             use_cache=True, past_key_values=None, suppress_tokens=self.bad_words_ids,
             states=sts if len(sts) > 1 else sts[0], multiplier=self.latency_multiplier, pin_prefix=pin)
-        pad = self.tokenizer.pad_token_id
-        self._n_generated = []
-        for b in range(len(sts)):
-            row = out.sequences[b, ids.shape[1]:].tolist()
-            n = len(row)
-            while n > 0 and row[n - 1] == pad and pad not in self.cfg.gen.eos_token_ids:
-                n -= 1
-            self._n_generated.append(n)
+        self._n_generated = [len(t) for t in out.generated]
         return out
 
     def _gen_cfg(self):

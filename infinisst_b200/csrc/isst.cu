@@ -110,6 +110,25 @@ struct ConvW {
   float *bias = nullptr, *ln_w = nullptr, *ln_b = nullptr;
 };
 
+// ---- per-kernel-class device timing (bench.py roofline leg): CUDA events around every launch ----
+enum ProfCat { P_GEMM_TENSOR = 0, P_GEMM_STREAM, P_ATTN_ENC, P_ATTN_PREFILL, P_ATTN_DECODE, P_NORM, P_CONV0, P_APPEND,
+               P_EMBED, P_SELECT, P_NCAT };
+static const char* kProfNames[P_NCAT] = {"gemm_tensor", "gemm_stream", "attn_encoder", "attn_prefill", "attn_decode",
+                                         "norm", "conv0", "kv_append", "embed_splice", "greedy_select"};
+struct ProfRec { int cat; cudaEvent_t e0, e1; double flops, bytes; };
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<ProfRec> recs;
+  double ms[P_NCAT] = {0}, flops[P_NCAT] = {0}, bytes[P_NCAT] = {0};
+  long long n[P_NCAT] = {0};
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+};
+
 struct StreamHost {
   bool open = false;
   int enc_prefix = 0;               // W2V2RoPECache.n_steps
@@ -130,6 +149,7 @@ struct isst_ctx {
   bool simple_gemm = false;
   int64_t launches = 0;
   bool debug = false;
+  Prof prof;
   std::map<std::string, std::pair<void*, size_t>> taps;   // name -> (device buffer, bytes)
   std::map<std::string, bool> loaded;
 
@@ -196,6 +216,35 @@ namespace isst {
                        " at " + __FILE__ + ":" + std::to_string(__LINE__));                 \
   } while (0)
 
+// Scope that brackets the launches inside it with two events when profiling is on.
+struct ProfScope {
+  isst_ctx* ctx; cudaStream_t st; ProfRec r; bool live;
+  ProfScope(isst_ctx* c, cudaStream_t s, int cat, double flops, double bytes) : ctx(c), st(s), live(c->prof.on) {
+    if (!live) return;
+    r.cat = cat; r.flops = flops; r.bytes = bytes;
+    r.e0 = ctx->prof.get(); r.e1 = ctx->prof.get();
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!live) return;
+    cudaEventRecord(r.e1, st);
+    ctx->prof.recs.push_back(r);
+  }
+};
+// Folds finished records into the per-class totals (the caller has synchronised the stream).
+static void prof_flush(isst_ctx* ctx) {
+  Prof& p = ctx->prof;
+  for (const ProfRec& r : p.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      p.ms[r.cat] += ms; p.flops[r.cat] += r.flops; p.bytes[r.cat] += r.bytes; p.n[r.cat]++;
+    }
+  }
+  p.recs.clear();
+  p.used = 0;
+  cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // GEMM dispatch
 // ------------------------------------------------------------------------------------------------
@@ -252,6 +301,15 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
   p.counters = ctx->gemm_counters;
   ISST_CHECK(v.K == w.K, "gemm: K mismatch");
   const bool simple = force_simple >= 0 ? (force_simple != 0) : ctx->simple_gemm;
+  // algorithmic work: every operand touched once (weights dominate when few tokens stream them)
+  const double nw = e.dual ? 2.0 : 1.0;
+  const double g_flops = 2.0 * v.rows * v.batch * static_cast<double>(n_out) * v.K * nw;
+  const double act_elems = (v.conv_c == v.K) ? static_cast<double>(v.rows) * v.K
+                                             : static_cast<double>(v.rows) * v.conv_s * v.conv_c;   // strided conv: input once
+  const double g_bytes = nw * n_out * static_cast<double>(v.K) * 2 + act_elems * v.batch * 2 +
+                         static_cast<double>(v.rows) * v.batch * n_out * (e.out_f32 ? 4 : 2) * (e.resid ? 2 : 1);
+  // M <= 128 tokens: weight streaming (HBM roofline); more: tensor-pipe roofline
+  ProfScope ps(ctx, st, v.rows * v.batch <= 128 ? P_GEMM_STREAM : P_GEMM_TENSOR, g_flops, g_bytes);
   if (simple) {
     SimpleGemmExtra x{v.ptr, v.batch_stride, v.conv_c, v.conv_s, w.ptr, e.dual};
     dim3 grid(ceil_div(n_out, 8), ceil_div(v.rows, 8), v.batch);
@@ -476,6 +534,7 @@ static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const 
                      const float* b, const int* gather, int rows, int C, float eps) {
   ISST_CHECK(C % 8 == 0 && C <= 4096, "norm_rows: unsupported width");
   if (rows == 0) return 0;
+  ProfScope ps(ctx, st, P_NORM, 0.0, static_cast<double>(rows) * C * 4);
   if (rms) norm_rows_kernel<true, false><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
   else if (gelu) norm_rows_kernel<false, true><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
   else norm_rows_kernel<false, false><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
@@ -493,6 +552,7 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
   // ---- conv feature extractor (E1) ----
   int T = conv_len(window, c.conv_k[0], c.conv_s[0]);
   {
+    ProfScope ps(ctx, st, P_CONV0, 2.0 * n * T * C * c.conv_k[0], static_cast<double>(n) * (window * 4 + static_cast<double>(T) * C * 2));
     dim3 grid(ceil_div(T, kConv0FramesPerCta), n);
     const size_t smem = (static_cast<size_t>(c.conv_k[0]) * C + kConv0FramesPerCta * c.conv_s[0] + c.conv_k[0]) * 4;
     conv0_ln_gelu_kernel<<<grid, 256, smem, st>>>(ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail, ctx->conv[0].w0_t,
@@ -544,6 +604,7 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     bf16* kr = ctx->enc_k + static_cast<size_t>(l) * ctx->enc_layer_elems;
     bf16* vr = ctx->enc_v + static_cast<size_t>(l) * ctx->enc_layer_elems;
     {
+      ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(n) * frames * D * 2 * 4);
       dim3 grid(ceil_div(frames * D / 8, 256), n);
       enc_kv_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, ctx->d_enc_prefix, frames, H, HD, ctx->enc_cap);
       LAUNCH_CHECK(ctx);
@@ -555,6 +616,9 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
       ep.T = frames; ep.H = H; ep.cap = ctx->enc_cap; ep.max_cache = c.max_cache_size; ep.blocksize = blocksize;
       LlmAttnParams lp{};
       constexpr int NW = 4;
+      double keys = 0;
+      for (int b = 0; b < n; ++b) keys += std::min(ctx->streams[slots_h[b]].enc_prefix, c.max_cache_size) + frames;
+      ProfScope ps(ctx, st, P_ATTN_ENC, 4.0 * frames * keys * D, keys * D * 2 * 2 + static_cast<double>(M) * D * 2 * 2);
       dim3 grid(ceil_div(frames, NW * 16), H, n);
       const size_t smem = static_cast<size_t>(NW * 16 + 2 * 64) * (64 + 8) * 2;
       ISST_CHECK(HD == 64, "encoder attention kernel is built for head_dim 64");
@@ -620,6 +684,8 @@ struct LlmBatch {
   const int* d_last_row = nullptr;
   const int* d_active = nullptr;   // may be null
   bool decode = false;
+  double kv_tokens = 0;            // sum over streams of the KV length attended to (profiling only)
+  double qk_pairs = 0;             // sum over streams of T_b * L_b (profiling only)
 };
 
 static PagedKV paged_kv(isst_ctx* ctx, int layer) {
@@ -651,6 +717,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
     }
     PagedKV kv = paged_kv(ctx, l);
     {
+      ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * Hkv * HD * 2 * 2 * 2);
       dim3 grid(ceil_div(lb.max_T * Hkv * HD / 8, 128), lb.n);
       llm_kv_append_kernel<<<grid, 128, 0, st>>>(ctx->lqkv, kv, lb.d_slots, lb.d_tok_base, lb.d_T, lb.d_active, H);
       LAUNCH_CHECK(ctx);
@@ -661,6 +728,8 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       lp.T = lb.d_T; lp.rope = ctx->llm_rope; lp.H = H; lp.scale_log2 = scale_log2;
       EncAttnParams ep{};
       constexpr int NW = 8;
+      ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
+                   lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
       dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
       const size_t smem = static_cast<size_t>(NW * 16 + 2 * 64) * (128 + 8) * 2;
       static bool attr_set = false;
@@ -675,6 +744,8 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       DecodeParams dp{};
       dp.qkv = ctx->lqkv; dp.kv = kv; dp.slots = lb.d_slots; dp.rope = ctx->llm_rope; dp.part_o = ctx->part_o;
       dp.part_ml = ctx->part_ml; dp.H = H; dp.splits = ctx->decode_splits; dp.scale_log2 = scale_log2;
+      // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
+      ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
       // fill the machine: n * Hkv * splits CTAs
       int splits = std::max(1, std::min(ctx->decode_splits, ceil_div(2 * ctx->sm_count, lb.n * Hkv)));
       dp.splits = splits;
@@ -1211,6 +1282,12 @@ static int setup_llm_batch(isst_ctx* ctx, cudaStream_t st, MetaBuilder& mb, int 
     }
     row += lens[b];
   }
+  lb->kv_tokens = 0; lb->qk_pairs = 0;
+  for (int b = 0; b < n; ++b) {
+    const double L = ctx->streams[stream_ids[b]].kv_len + lens[b];
+    lb->kv_tokens += L;
+    lb->qk_pairs += L * lens[b];
+  }
   lb->n = n; lb->M = M; lb->max_T = maxT;
   lb->d_slots = mb.dev(o_slots); lb->d_tok_base = mb.dev(o_base); lb->d_T = mb.dev(o_T); lb->d_last_row = mb.dev(o_last);
   lb->d_active = nullptr; lb->decode = false;
@@ -1235,6 +1312,7 @@ int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids
   if (embeds_override) {
     ISST_CUDA(cudaMemcpyAsync(ctx->lx, embeds_override, static_cast<size_t>(lb.M) * ctx->cfg.hidden * 2, cudaMemcpyDefault, st));
   } else {
+    ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(lb.M) * ctx->cfg.hidden * 4);
     embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, ctx->cfg.hidden);
     LAUNCH_CHECK(ctx);
   }
@@ -1242,6 +1320,7 @@ int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids
   ISST_TRY(llm_forward(ctx, st, lb, true));
   if (out_logits) ISST_CUDA(cudaMemcpyAsync(out_logits, ctx->logits, static_cast<size_t>(n) * ctx->cfg.vocab * 4, cudaMemcpyDefault, st));
   ISST_CUDA(cudaStreamSynchronize(st));
+  prof_flush(ctx);
   for (int b = 0; b < n; ++b) ctx->streams[stream_ids[b]].kv_len += lens[b];
   return 0;
 }
@@ -1305,15 +1384,21 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   g.ngram = gen->no_repeat_ngram_size; g.penalty = gen->repetition_penalty;
 
   // ---- step 0: splice + chunk prefill ----
-  embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, c.hidden);
-  LAUNCH_CHECK(ctx);
+  {
+    ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(lb.M) * c.hidden * 4);
+    embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, c.hidden);
+    LAUNCH_CHECK(ctx);
+  }
   ISST_TRY(tap(ctx, st, "prompt_embeds", ctx->lx, static_cast<size_t>(lb.M) * c.hidden * 2));
   ISST_TRY(llm_forward(ctx, st, lb, true));
   const size_t lbytes = static_cast<size_t>(n) * c.vocab * 4;
   ISST_TRY(tap(ctx, st, "step_logits", ctx->logits, lbytes, 0, lbytes * max_new));
   g.step = 0;
-  greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
-  LAUNCH_CHECK(ctx);
+  {
+    ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(lbytes));
+    greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
+    LAUNCH_CHECK(ctx);
+  }
   // ---- decode steps ----
   LlmBatch db = lb;
   db.M = n; db.max_T = 1; db.d_T = mb.dev(o_ones); db.d_tok_base = mb.dev(o_iota); db.d_last_row = mb.dev(o_iota);
@@ -1326,17 +1411,27 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     bool any = false;
     for (int b = 0; b < n; ++b) any = any || h_active[b];
     if (!any) break;
-    embed_splice_kernel<<<n, 128, 0, st>>>(mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden);
-    LAUNCH_CHECK(ctx);
+    {
+      ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(n) * c.hidden * 4);
+      embed_splice_kernel<<<n, 128, 0, st>>>(mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden);
+      LAUNCH_CHECK(ctx);
+    }
+    db.kv_tokens = 0;
+    for (int b = 0; b < n; ++b)
+      if (h_active[b]) db.kv_tokens += ctx->streams[stream_ids[b]].kv_len + lens[b] + step;
     ISST_TRY(llm_forward(ctx, st, db, false));
     ISST_TRY(tap(ctx, st, "step_logits", ctx->logits, lbytes, lbytes * step, lbytes * max_new));
     g.step = step;
-    greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
-    LAUNCH_CHECK(ctx);
+    {
+      ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(lbytes));
+      greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
+      LAUNCH_CHECK(ctx);
+    }
   }
   ISST_CUDA(cudaMemcpyAsync(ctx->h_meta + o_out, mb.dev(o_out), static_cast<size_t>(n) * max_new * sizeof(int), cudaMemcpyDeviceToHost, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->h_meta + o_cnt, mb.dev(o_cnt), n * sizeof(int), cudaMemcpyDeviceToHost, st));
   ISST_CUDA(cudaStreamSynchronize(st));
+  prof_flush(ctx);
   for (int b = 0; b < n; ++b) {
     const int cnt = ctx->h_meta[o_cnt + b];
     out_counts[b] = cnt;
@@ -1397,6 +1492,36 @@ int isst_debug_read(isst_ctx* ctx, const char* name, void* dst_host, int64_t max
     ISST_CUDA(cudaDeviceSynchronize());
     ISST_CUDA(cudaMemcpy(dst_host, it->second.first, it->second.second, cudaMemcpyDeviceToHost));
   }
+  return 0;
+}
+
+int isst_profile_enable(isst_ctx* ctx, int on) {
+  ISST_CHECK(ctx, "null ctx");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  ISST_CUDA(cudaDeviceSynchronize());
+  prof_flush(ctx);
+  ctx->prof.on = on != 0;
+  return 0;
+}
+
+int isst_profile_reset(isst_ctx* ctx) {
+  ISST_CHECK(ctx, "null ctx");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  ISST_CUDA(cudaDeviceSynchronize());
+  prof_flush(ctx);
+  for (int i = 0; i < P_NCAT; ++i) { ctx->prof.ms[i] = 0; ctx->prof.flops[i] = 0; ctx->prof.bytes[i] = 0; ctx->prof.n[i] = 0; }
+  return 0;
+}
+
+int isst_profile_read(isst_ctx* ctx, int index, char* name, int name_cap, int64_t* launches, double* ms, double* flops,
+                      double* bytes) {
+  ISST_CHECK(ctx && name && launches && ms && flops && bytes, "null argument");
+  if (index < 0 || index >= P_NCAT) return 1;   // end of list
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  ISST_CUDA(cudaDeviceSynchronize());
+  prof_flush(ctx);
+  snprintf(name, name_cap, "%s", kProfNames[index]);
+  *launches = ctx->prof.n[index]; *ms = ctx->prof.ms[index]; *flops = ctx->prof.flops[index]; *bytes = ctx->prof.bytes[index];
   return 0;
 }
 

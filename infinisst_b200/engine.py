@@ -235,6 +235,27 @@ class Engine:
                                          C.c_void_p(out.data_ptr()), self._stream_ptr()))
         return out
 
+    # ------------------------------------------------------------------ per-kernel-class timing
+    def profile(self, on: bool = True) -> None:
+        _lib.check(self.lib.isst_profile_enable(self.h, int(on)))
+
+    def profile_reset(self) -> None:
+        _lib.check(self.lib.isst_profile_reset(self.h))
+
+    def profile_read(self) -> Dict[str, dict]:
+        """{class: {launches, ms, flops, bytes}} - event time and algorithmic work per kernel class."""
+        out, i = {}, 0
+        name = C.create_string_buffer(64)
+        n, ms, fl, by = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
+        while True:
+            st = self.lib.isst_profile_read(self.h, i, name, 64, C.byref(n), C.byref(ms), C.byref(fl), C.byref(by))
+            if st == 1:
+                break
+            _lib.check(st)
+            out[name.value.decode()] = {"launches": n.value, "ms": ms.value, "flops": fl.value, "bytes": by.value}
+            i += 1
+        return out
+
     # ------------------------------------------------------------------ debug taps
     def debug(self, on: bool = True) -> None:
         _lib.check(self.lib.isst_debug_enable(self.h, int(on)))

@@ -67,8 +67,9 @@ class StreamHandle:
 
 @dataclass
 class GenerateOutput:
-    sequences: torch.Tensor            # int64 [B, prompt + generated]
+    sequences: torch.Tensor            # int64 [B, prompt + generated], right-padded with pad_token_id
     past_key_values: object            # StreamHandle (B == 1) or list of StreamHandle
+    generated: Optional[List[List[int]]] = None   # extension: chosen tokens per row without padding
 
 
 @dataclass
@@ -188,7 +189,9 @@ class SpeechLlamaForCausalLM:
         self.model.speech_encoder.set_blocksize(multiplier)
         self.engine.encode_chunk([h.sid for h in handles], speech_batch.float(), multiplier)
         enc = [[] for _ in range(B)]
-        if encoder_input_ids is not None and encoder_input_ids.numel() > 0:
+        if isinstance(encoder_input_ids, (list, tuple)):      # extension: ragged per-stream histories
+            enc = [[int(t) for t in row] for row in encoder_input_ids]
+        elif encoder_input_ids is not None and encoder_input_ids.numel() > 0:
             enc = [[int(t) for t in encoder_input_ids[b].tolist()] for b in range(B)]
 
         class _G:
@@ -208,7 +211,7 @@ class SpeechLlamaForCausalLM:
             row = ids[b] + toks[b]
             seqs[b, :len(row)] = torch.tensor(row, dtype=torch.long)
         pkv = handles[0] if B == 1 else handles
-        return GenerateOutput(sequences=seqs, past_key_values=pkv)
+        return GenerateOutput(sequences=seqs, past_key_values=pkv, generated=toks)
 
     @torch.inference_mode()
     def forward(self, input_ids=None, text_input_ids=None, attention_mask=None, text_attention_mask=None,

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One gpurun call: smoke, GPU parity tests, bench line, ncu launch list + full captures of the top kernels.
+# Every stage runs under its own timeout so one hung kernel cannot eat the lease.
+mkdir -p gpurun_out
+O=gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $O/gpu.txt 2>&1
+nproc >> $O/gpu.txt; free -g | head -2 >> $O/gpu.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit=$?" | tee -a $O/smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q -s > $O/pytest_gpu.log 2>&1; echo "pytest exit=$?" | tee -a $O/pytest_gpu.log
+tail -5 $O/pytest_gpu.log
+timeout 600 python bench.py --steps ${STEPS:-6} --warmup 3 > $O/bench.json 2> $O/bench.err; echo "bench exit=$?" | tee -a $O/bench.err
+tail -3 $O/bench.err; cat $O/bench.json
+if [ "${NCU:-1}" = "1" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file $O/launches.csv python bench.py --ncu-step --warmup 1 > $O/ncu_launches.log 2>&1; echo "ncu launches exit=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:gemm_tcgen05 -s 300 -c 8 -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:decode_attention -s 32 -c 2 -o $O/prof_decode_attn python bench.py --ncu-step --warmup 1 > $O/ncu_attn.log 2>&1; echo "ncu attn exit=$?"
+fi
+ls -la $O

@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle on the same seeded
+inputs, against the committed golden vectors, and - at production widths - against the oracle
+executed in fp32 on the same device.
+
+Tolerances (north_star: "encoder outputs and logits within a stated bf16 tolerance"):
+  * encoder taps / speech features: rel-L2 <= 3e-2 against the fp32 oracle;
+  * last-position logits:           rel-L2 <= 5e-2 against the fp32 oracle, and never worse than
+    2x the error of the oracle itself run in bf16 eager (the reference's own numerics) + 1e-2;
+  * greedy tokens: identical under teacher forcing except at near-ties (oracle margin < TIE_EPS);
+  * KV lengths and eviction ranges: bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from infinisst_b200 import production_config, tiny_config
+from infinisst_b200.synthetic import make_audio, make_state_dict
+from oracle import infinisst_oracle as O
+from parity_utils import OracleStream, bf16_weights, max_abs, rel_l2, slot_map
+
+pytestmark = pytest.mark.gpu
+
+# the oracle also runs on the GPU as an fp32 checker at production widths: keep it true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+ENC_TOL, LOGIT_TOL, TIE_EPS = 3e-2, 5e-2, 0.35
+SEG = 15360
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_stream.npz")
+
+
+def _engine(cfg, sd, **kw):
+    from infinisst_b200.engine import Engine
+    eng = Engine(cfg, device=0, **kw)
+    eng.load_state_dict(sd)
+    return eng
+
+
+def _chunk_pcm(audio, c):
+    pcm = audio[c * SEG:(c + 1) * SEG][None].clone()
+    if c == 0:
+        pcm = torch.cat([torch.zeros(1, 399), pcm], 1)
+    return pcm
+
+
+# ----------------------------------------------------------------------------------------------
+# operators
+# ----------------------------------------------------------------------------------------------
+GEMM_CASES = [
+    (128, 128, 64, {}), (128, 128, 256, {}), (256, 384, 512, {}), (100, 200, 192, {}),
+    (3072, 1024, 1024, {}), (1408, 4096, 4096, {}),
+    (1, 128, 64, {}), (1, 4096, 4096, {}), (16, 256, 512, {}), (22, 6144, 4096, {}), (48, 3072, 1024, {}),
+    (64, 1024, 4096, {}), (12, 519, 512, {"out_f32": True}), (1, 128263, 4096, {"out_f32": True}),
+    (64, 128263, 4096, {"out_f32": True}),
+    (22, 4096, 4096, {"force_splits": 4}), (1, 4096, 14336, {"force_splits": 8}), (300, 512, 1024, {"force_splits": 3}),
+    (48, 1024, 1024, {"bias": True, "resid": True}), (48, 4096, 1024, {"bias": True, "gelu": True}),
+    (3072, 4096, 1024, {"bias": True, "gelu": True}), (3072, 1024, 4096, {"bias": True, "resid": True}),
+    (22, 768, 512, {"dual": True}), (1, 14336, 4096, {"dual": True}), (1408, 14336, 4096, {"dual": True}),
+    (64, 14336, 4096, {"dual": True, "force_splits": 2}), (100, 256, 512, {"force_swap": 1}),
+    (30, 256, 512, {"force_swap": 0}),
+]
+
+
+@pytest.fixture(scope="module")
+def op_engine():
+    from infinisst_b200.engine import Engine
+    eng = Engine(tiny_config(), device=0, max_streams=2)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "cuda_core"])
+def test_gemm_vs_torch_fp32(op_engine, impl):
+    """out = act . W^T with every fused epilogue, against a plain PyTorch fp32 reference of the op.
+    Inputs are bf16, accumulation fp32: the only error is the bf16 rounding of the output."""
+    torch.manual_seed(0)
+    dev = "cuda:0"
+    for (M, N, K, kw) in GEMM_CASES:
+        a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        dual = kw.get("dual", False)
+        w = (torch.randn(N * (2 if dual else 1), K, device=dev) * (K ** -0.5)).bfloat16()
+        bias = torch.randn(N, device=dev) if kw.get("bias") else None
+        resid = torch.randn(M, N, device=dev).bfloat16() if kw.get("resid") else None
+        ref = a.float() @ w.float().t()
+        if dual:
+            ref = torch.nn.functional.silu(ref[:, :N]) * ref[:, N:]
+        if bias is not None:
+            ref = ref + bias
+        if kw.get("gelu"):
+            ref = torch.nn.functional.gelu(ref)
+        if resid is not None:
+            ref = ref + resid.float()
+        out = op_engine.op_gemm(a, w, bias=bias, gelu=kw.get("gelu", False), resid=resid, dual=dual,
+                                out_f32=kw.get("out_f32", False), impl=impl, force_swap=kw.get("force_swap", -1),
+                                force_splits=kw.get("force_splits", 0))
+        torch.cuda.synchronize()
+        tol = 2e-5 if kw.get("out_f32") else 4e-3            # fp32 out: accumulation order only; bf16 out: 2^-8 rounding
+        assert rel_l2(out, ref) < tol, (M, N, K, kw, rel_l2(out, ref))
+
+
+# ----------------------------------------------------------------------------------------------
+# the per-chunk step, tiny config (production head sizes -> production kernels)
+# ----------------------------------------------------------------------------------------------
+def _run_stream(cfg, n_chunks, check_taps=True, yardstick=False):
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=2)
+    eng.debug(True)
+    audio = make_audio(n_chunks * SEG / 16000.0)
+    orc = OracleStream(cfg, sd)
+    orc16 = OracleStream(cfg, sd, torch.bfloat16) if yardstick else None
+    sid = eng.open_stream()
+    target, ck = [], O.EvictionState()
+    stats = {"near_ties": 0, "steps": 0, "evictions": 0, "worst_logit": 0.0}
+    for c in range(n_chunks):
+        out_o, rec, taps = orc.chunk(audio[: (c + 1) * SEG].tolist())
+        ids = O.build_prompt(cfg.tpl, c == 0)
+        forced = rec.sequences[0][len(ids):]
+        if yardstick:
+            _, rec16, taps16 = orc16.chunk(audio[: (c + 1) * SEG].tolist(), forced=forced)
+        feats = eng.encode_chunk([sid], _chunk_pcm(audio, c), 1, return_feats=True)
+        torch.cuda.synchronize()
+        if check_taps:
+            for name, okey in [("enc_conv", "conv"), ("enc_post_proj", "post_proj"), ("enc_layer_0", "enc_layer_0"),
+                               ("enc_layer_1", "enc_layer_1"), ("enc_out", "enc_out"), ("speech_feats", "speech_feats")]:
+                got = eng.read_tap(name).float()
+                ref = taps[okey].flatten()
+                e = rel_l2(got[: ref.numel()], ref)
+                assert e < ENC_TOL, (c, name, e)
+                if yardstick:
+                    e16 = rel_l2(taps16[okey].flatten(), ref)
+                    assert e <= 2 * e16 + 1e-2, (c, name, e, e16)
+        assert rel_l2(feats.cpu(), taps["speech_feats"]) < ENC_TOL
+        toks = eng.generate([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen,
+                            pin_prefix=len(cfg.tpl.system_ids), forced=[forced])[0]
+        logits = eng.read_tap("step_logits", torch.float32).view(cfg.gen.max_new_tokens, 1, cfg.llm.vocab)
+        assert toks == forced, (c, toks, forced)
+        for s in range(len(rec.step_logits)):
+            e = rel_l2(logits[s, 0], rec.step_logits[s][0])
+            stats["worst_logit"] = max(stats["worst_logit"], e)
+            assert e < LOGIT_TOL, (c, s, e)
+            if yardstick:
+                e16 = rel_l2(rec16.step_logits[s][0], rec.step_logits[s][0])
+                assert e <= 2 * e16 + 1e-2, (c, s, e, e16)
+            # the token the CUDA path would pick on its own (same processors, applied by the oracle code to
+            # the CUDA logits) must be the oracle's token, or the oracle itself must be at a near-tie
+            call_ids = ids + forced[:s]
+            sc_gpu = O.process_logits(logits[s, 0], call_ids, target[-100:], cfg.gen)
+            pick = int(sc_gpu.argmax())
+            stats["steps"] += 1
+            if pick != forced[s]:
+                sc_o = rec.step_scores[s][0]
+                assert sc_o[pick] >= sc_o.max() - TIE_EPS, (c, s, pick, forced[s], float(sc_o.max() - sc_o[pick]))
+                stats["near_ties"] += 1
+        assert eng.kv_len(sid) == orc.st.kv_log[-1]["cur"]
+        target.extend(out_o)
+        cur = eng.kv_len(sid)
+        kept = O.evict(ck, cur, cfg.gen.max_llm_cache_size, True, len(cfg.tpl.system_ids))
+        if kept is not None:
+            eng.kv_evict(sid, kept[0], cur - kept[1])
+            stats["evictions"] += 1
+        assert eng.kv_len(sid) == orc.st.llm_cache.length()          # eviction bit-exact
+        assert eng.enc_steps(sid) == orc.st.enc_cache.n_steps
+    eng.close()
+    return stats
+
+
+def test_stream_vs_oracle_tiny():
+    st = _run_stream(tiny_config(), 4, yardstick=True)
+    assert st["near_ties"] <= 0.01 * st["steps"] + 1
+
+
+def test_stream_with_both_windows_sliding():
+    """Encoder window 96 frames and LLM window 150 tokens: ring wrap-around, page recycling and
+    position shifts after eviction are all exercised within 12 chunks."""
+    st = _run_stream(tiny_config(max_cache_size=96, max_llm_cache_size=150), 12, check_taps=True)
+    assert st["evictions"] >= 6
+    assert st["near_ties"] <= 0.01 * st["steps"] + 1
+
+
+def test_long_stream_no_drift():
+    """BASELINE.json configs[3] scaled down: 60 chunks, ~55 evictions; the logits error must not grow."""
+    st = _run_stream(tiny_config(max_cache_size=96, max_llm_cache_size=150), 60, check_taps=False)
+    assert st["evictions"] >= 50 and st["worst_logit"] < LOGIT_TOL
+
+
+def test_golden_stream():
+    """Committed golden vectors (tests/golden/make_golden.py): features, logits, tokens, KV log."""
+    gold = np.load(GOLD)
+    n = int(gold["n_chunks"])
+    cfg = tiny_config(max_cache_size=int(gold["max_cache"]), max_llm_cache_size=int(gold["max_llm"]))
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=2)
+    eng.debug(True)
+    audio = make_audio(n * SEG / 16000.0)
+    sid = eng.open_stream()
+    from infinisst_b200.agent import S2TAgentStates, evict_plan
+    st = S2TAgentStates()
+    st.system_prompt_size = len(cfg.tpl.system_ids)
+    target = []
+    for c in range(n):
+        feats = eng.encode_chunk([sid], _chunk_pcm(audio, c), 1, return_feats=True)
+        assert rel_l2(feats[0].cpu(), torch.from_numpy(gold[f"c{c}_speech_feats"])) < ENC_TOL
+        ids = O.build_prompt(cfg.tpl, c == 0)
+        seq = gold[f"c{c}_sequence"].tolist()
+        assert seq[:len(ids)] == ids
+        forced = seq[len(ids):]
+        toks = eng.generate([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen,
+                            pin_prefix=len(cfg.tpl.system_ids), forced=[forced])[0]
+        assert toks == forced
+        logits = eng.read_tap("step_logits", torch.float32).view(cfg.gen.max_new_tokens, cfg.llm.vocab)
+        g = torch.from_numpy(gold[f"c{c}_step_logits"])
+        for s in range(g.shape[0]):
+            assert rel_l2(logits[s], g[s]) < LOGIT_TOL
+        target.extend(gold[f"c{c}_output_ids"].tolist())
+        cur, kp, kt, after = gold[f"c{c}_kv"].tolist()
+        assert eng.kv_len(sid) == cur
+        plan = evict_plan(st, cur, cfg.gen.max_llm_cache_size, True)
+        if kp < 0:
+            assert plan is None
+        else:
+            assert plan == (kp, cur - kt)                    # kept = [0, kp) U [cur - kt, cur): bit-exact
+            eng.kv_evict(sid, plan[0], plan[1])
+        assert eng.kv_len(sid) == after
+    eng.close()
+
+
+def test_batched_streams_equal_independent_streams():
+    """BASELINE.json configs[2] scaled down: 5 distinct streams in lock-step through one batched call
+    each chunk == the same streams run one by one (oracle = loop of B=1 oracles)."""
+    from infinisst_b200.engine import Engine
+    from infinisst_b200.runner import LockstepRunner
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    B, n_chunks = 5, 7
+    audios = [make_audio(n_chunks * SEG / 16000.0, seed=100 + b) for b in range(B)]
+    eng = _engine(cfg, sd, max_streams=B)
+    eng.debug(True)
+    run = LockstepRunner(eng, cfg, B)
+    orcs = [OracleStream(cfg, sd) for _ in range(B)]
+    for c in range(n_chunks):
+        recs = [o.chunk(a[: (c + 1) * SEG].tolist()) for o, a in zip(orcs, audios)]
+        ids = O.build_prompt(cfg.tpl, c == 0)
+        forced = [r[1].sequences[0][len(ids):] for r in recs]
+        pcm = torch.cat([_chunk_pcm(a, c) for a in audios], 0)
+        outs = run.step_device(pcm, forced=forced)
+        logits = eng.read_tap("step_logits", torch.float32).view(cfg.gen.max_new_tokens, B, cfg.llm.vocab)
+        for b in range(B):
+            assert run.last_tokens[b] == forced[b]
+            assert outs[b] == recs[b][0]
+            for s in range(len(recs[b][1].step_logits)):
+                assert rel_l2(logits[s, b], recs[b][1].step_logits[s][0]) < LOGIT_TOL, (c, b, s)
+            assert eng.kv_len(run.sids[b]) == orcs[b].st.llm_cache.length()
+            log = orcs[b].st.kv_log[-1]
+            mine = run.evict_log[-1][b]
+            if log["kept"] is None:
+                assert mine is None
+            else:
+                assert mine == (log["kept"][0], log["cur"] - log["kept"][1], log["cur"])
+    assert run.evictions >= B
+    run.close()
+    eng.close()
+
+
+def test_agent_drop_in_api():
+    """The SimulEval-facing agent (same class/method names as agents/infinisst.py): audio arrives as
+    growing Python lists on `states.source`; tokens equal the oracle's free-running greedy tokens up
+    to the first near-tie; KV lengths follow the integer eviction model."""
+    import argparse
+    from infinisst_b200.agent import InfiniSST
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    p = argparse.ArgumentParser()
+    InfiniSST.add_args(p)
+    args = p.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", "96", "--xpos", "0",
+                         "--latency-multiplier", "1", "--max-latency-multiplier", "1", "--max-new-tokens", "10",
+                         "--no-repeat-ngram-size", "5", "--max-llm-cache-size", "150", "--always-cache-system-prompt",
+                         "--beam", "1"])
+    args.model_config, args.state_dict = cfg, sd
+    agent = InfiniSST(args)
+    states = agent.build_states()
+    states.source_sample_rate = 16000
+    n_chunks = 8
+    audio = make_audio(n_chunks * SEG / 16000.0)
+    orc = OracleStream(cfg, sd)
+    agree = True
+    for c in range(n_chunks):
+        states.source = audio[: (c + 1) * SEG].tolist()
+        states.source_finished = c == n_chunks - 1
+        n_before = len(states.target_ids)
+        act = agent.policy(states)
+        out_o, rec, _ = orc.chunk(audio[: (c + 1) * SEG].tolist())
+        assert not act.is_read()
+        if agree and states.target_ids[n_before:] != out_o:
+            agree = False                                  # a near-tie flipped: later chunks legitimately differ
+            margins = [float(s[0].max() - s[0].topk(2).values[1]) for s in rec.step_scores]
+            assert min(margins) < TIE_EPS, (c, margins)
+        if agree:
+            assert states.past_key_values[0][0].size(2) == orc.st.llm_cache.length()
+    assert states.past_key_values[0][0].size(2) <= 150 + 40
+    assert len(agent.chunk_latencies) == n_chunks
+    assert act.finished
+    states.reset()
+    agent.model.engine.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# production widths
+# ----------------------------------------------------------------------------------------------
+def _production(enc_layers, llm_layers):
+    cfg = production_config()
+    cfg.enc.layers, cfg.llm.layers = enc_layers, llm_layers
+    return cfg
+
+
+def _oracle_on_gpu_stream(cfg, sd_dev):
+    """The oracle is plain PyTorch: at production widths it runs in fp32 on the GPU as the checker."""
+    class _S:
+        pass
+    s = _S()
+    s.cfg, s.sd, s.st = cfg, sd_dev, O.StreamState()
+    return s
+
+
+@pytest.mark.parametrize("layers", [(2, 2), (24, 32)], ids=["slice_2+2_layers", "full_24+32_layers"])
+def test_production_widths_vs_oracle(layers):
+    """wav2vec2-large widths (512-ch extractor, d=1024, ffn 4096, 16x64 heads) and Llama-3.1-8B widths
+    (4096, 32/8x128, ffn 14336, vocab 128263); `full` is the whole BASELINE.json configs[1] model."""
+    cfg = _production(*layers)
+    dev = "cuda:0"
+    sd16 = make_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16)
+    eng = _engine(cfg, sd16, max_streams=2)
+    eng.debug(True)
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    del sd16
+    n_chunks = 3
+    audio = make_audio(n_chunks * SEG / 16000.0)
+    st = O.StreamState()
+    sid = eng.open_stream()
+    target = []
+    worst = {"feat": 0.0, "logit": 0.0}
+    flips = steps = 0
+    with torch.inference_mode():
+        for c in range(n_chunks):
+            taps = {}
+            out_o, rec = O.policy_chunk(sd32, cfg, st, audio[: (c + 1) * SEG].tolist(), torch.float32, taps)
+            ids = O.build_prompt(cfg.tpl, c == 0)
+            forced = rec.sequences[0][len(ids):]
+            feats = eng.encode_chunk([sid], _chunk_pcm(audio, c), 1, return_feats=True)
+            e = rel_l2(feats, taps["speech_feats"])
+            worst["feat"] = max(worst["feat"], e)
+            assert e < ENC_TOL, (c, e)
+            toks = eng.generate([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen,
+                                pin_prefix=len(cfg.tpl.system_ids), forced=[forced])[0]
+            assert toks == forced
+            logits = eng.read_tap("step_logits", torch.float32).view(cfg.gen.max_new_tokens, cfg.llm.vocab)
+            for s in range(len(rec.step_logits)):
+                ref = rec.step_logits[s][0].cpu()
+                e = rel_l2(logits[s], ref)
+                worst["logit"] = max(worst["logit"], e)
+                assert e < LOGIT_TOL, (c, s, e)
+                sc = O.process_logits(logits[s], ids + forced[:s], target[-100:], cfg.gen)
+                steps += 1
+                if int(sc.argmax()) != forced[s]:
+                    so = rec.step_scores[s][0].cpu()
+                    assert so[int(sc.argmax())] >= so.max() - TIE_EPS
+                    flips += 1
+            assert eng.kv_len(sid) == st.llm_cache.length()
+            target.extend(out_o)
+    print(f"production {layers}: worst feat rel_l2 {worst['feat']:.3e}, worst logit rel_l2 {worst['logit']:.3e}, "
+          f"near-tie flips {flips}/{steps}")
+    assert flips <= 0.01 * steps + 1
+    eng.close()
+
+
+def test_decode_attention_bench_runs(op_engine):
+    ms = op_engine.decode_attention_bench(2, 500, 4)
+    assert ms > 0
+
+
+def test_profile_counters(op_engine):
+    """The roofline leg of bench.py: per-class launches and algorithmic work are recorded."""
+    cfg = tiny_config()
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=2)
+    eng.profile(True)
+    eng.profile_reset()
+    sid = eng.open_stream()
+    audio = make_audio(SEG / 16000.0)
+    eng.encode_chunk([sid], _chunk_pcm(audio, 0), 1)
+    ids = O.build_prompt(cfg.tpl, True)
+    eng.generate([sid], [ids], [slot_map(cfg, ids)], [[]], cfg.gen, pin_prefix=40)
+    prof = eng.profile_read()
+    assert prof["gemm_stream"]["launches"] > 0 and prof["gemm_stream"]["bytes"] > 0
+    assert prof["attn_decode"]["launches"] == cfg.llm.layers * (cfg.gen.max_new_tokens - 1)
+    assert prof["attn_encoder"]["launches"] == cfg.enc.layers and prof["attn_prefill"]["launches"] == cfg.llm.layers
+    assert all(v["ms"] >= 0 for v in prof.values())
+    eng.close()
