@@ -248,7 +248,7 @@ def main_native(args, env):
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
     t0 = time.perf_counter()
-    eng = Engine(cfg, device=dev, max_streams=S + 1, max_batch=S, max_prompt=64)
+    eng = Engine(cfg, device=dev, max_streams=2 * S + 2, max_batch=S, max_prompt=64)   # + scratch streams of the stand-alone kernel bench and the latency stream
     sd = make_state_dict(cfg, seed=0, device=f"cuda:{dev}", dtype=torch.bfloat16)
     eng.load_state_dict(sd)
     del sd

@@ -155,6 +155,37 @@ struct Cfg {
 
 // Final epilogue for 16 consecutive columns of one TMEM lane.
 //   normal: lane = token row, columns = features;  swap: lane = feature, columns = tokens.
+// Swap-mode epilogue for NC consecutive token columns of one TMEM lane (= one output feature).
+template <bool kDual, int NC>
+__device__ __forceinline__ void epilogue_store_swap(const GemmParams& p, int b, int f, int col0,
+                                                    const float* v0, const float* v1) {
+  if (f >= p.N_out) return;
+  const long long obase = static_cast<long long>(b) * p.out_batch_stride;
+  const long long rbase = static_cast<long long>(b) * p.resid_batch_stride;
+  const float bias = p.bias ? p.bias[f] : 0.f;
+  // Residual values are read up front: `resid` may alias `out` (x += ...), so a load issued after a store
+  // is serialised behind it (one dependent L2 round trip per token otherwise).
+  float rv[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int tok = col0 + i;
+    rv[i] = (p.resid && tok < p.M_tok) ? __bfloat162float(p.resid[rbase + static_cast<long long>(tok) * p.ldr + f]) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int tok = col0 + i;
+    if (tok < p.M_tok) {
+      float x = v0[i] + bias;
+      if (kDual) x = silu(x) * v1[i];
+      if (p.act == 1) x = gelu_erf(x);
+      x += rv[i];
+      const long long oi = obase + static_cast<long long>(tok) * p.ldo + f;
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = x;
+      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
 template <bool kDual, bool kSwap>
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, int b, int lane_idx, int col0,
                                                  const float* v0, const float* v1) {
@@ -222,21 +253,7 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, int b, int
       }
     }
   } else {
-    const int f = lane_idx;
-    if (f >= p.N_out) return;
-    const float bias = p.bias ? p.bias[f] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int tok = col0 + i;
-      if (tok >= p.M_tok) break;
-      float x = v0[i] + bias;
-      if (kDual) x = silu(x) * v1[i];
-      if (p.act == 1) x = gelu_erf(x);
-      if (p.resid) x += __bfloat162float(p.resid[rbase + static_cast<long long>(tok) * p.ldr + f]);
-      const long long oi = obase + static_cast<long long>(tok) * p.ldo + f;
-      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = x;
-      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
-    }
+    epilogue_store_swap<kDual, 16>(p, b, lane_idx, col0, v0, v1);
   }
 }
 
@@ -346,12 +363,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const int lane_idx = (kSwap ? tile_feat : tile_tok) * kBM + r;
     const int col_base = (kSwap ? tile_tok : tile_feat) * kBN;
     if (p.splits == 1) {
+      if (kSwap && kBN >= 32) {
 #pragma unroll 1
-      for (int c = 0; c < kBN; c += 16) {
-        float v0[16], v1[16];
-        tmem_ld16(taddr + c, v0);
-        if (kDual) tmem_ld16(taddr + kBN + c, v1);
-        epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
+        for (int c = 0; c < kBN; c += 32) {
+          float v0[32], v1[32];
+          tmem_ld16(taddr + c, v0);
+          tmem_ld16(taddr + c + 16, v0 + 16);
+          if (kDual) { tmem_ld16(taddr + kBN + c, v1); tmem_ld16(taddr + kBN + c + 16, v1 + 16); }
+          epilogue_store_swap<kDual, 32>(p, b, lane_idx, col_base + c, v0, v1);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < kBN; c += 16) {
+          float v0[16], v1[16];
+          tmem_ld16(taddr + c, v0);
+          if (kDual) tmem_ld16(taddr + kBN + c, v1);
+          epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
+        }
       }
     } else {
       const int tiles_per_b = gridDim.x * gridDim.y;
@@ -375,20 +403,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*flag_smem) {
         __threadfence();
+        constexpr int NC = (kSwap && kBN >= 32) ? 32 : 16;
 #pragma unroll 1
-        for (int c = 0; c < kBN; c += 16) {
-          float v0[16], v1[16];
+        for (int c = 0; c < kBN; c += NC) {
+          float v0[NC], v1[NC];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
+          for (int i = 0; i < NC; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
+#pragma unroll 2
           for (int s = 0; s < p.splits; ++s) {
             const float* src = ws_tile + static_cast<size_t>(s) * (C::kAccCols * kBM);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < NC; ++i) {
               v0[i] += __ldcg(&src[(c + i) * kBM + r]);
               if (kDual) v1[i] += __ldcg(&src[(kBN + c + i) * kBM + r]);
             }
           }
-          epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
+          if (kSwap && kBN >= 32) epilogue_store_swap<kDual, NC>(p, b, lane_idx, col_base + c, v0, v1);
+          else epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
         }
         if (et == 0) p.counters[tile_lin] = 0;
       }

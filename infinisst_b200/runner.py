@@ -57,7 +57,7 @@ class LockstepRunner:
             if plan is not None:
                 self.engine.kv_evict(st.speech_cache.sid, plan[0], plan[1])
                 self.evictions += 1
-            log.append(None if plan is None else (plan[0], cur - plan[1], cur))
+            log.append(None if plan is None else (plan[0], plan[1], cur))   # (keep_prefix, drop_upto, cur)
             outs.append(out_ids)
         self.evict_log.append(log)
         self.chunk += 1
