@@ -86,17 +86,35 @@ struct LlmAttnParams {
   float scale_log2;       // HD^-0.5 * log2(e)
 };
 
-// One CTA = NW warps x 16 query rows; streams over 64-key tiles.
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Shared-memory bytes of chunk_attention_kernel<HD, *, NW>: [Q staging | rotated K] (aliased) + 2 raw (K, V) stages.
+template <int HD, int NW>
+constexpr int chunk_attn_smem_bytes() {
+  return ((NW * 16 > 64 ? NW * 16 : 64) + 4 * 64) * (HD + 8) * 2;
+}
+
+// One CTA = NW warps x 16 query rows, walking the keys in 64-key tiles.  Raw (un-rotated) K and V tiles
+// stream global -> shared memory with cp.async through two stages, so the next tile is in flight while the
+// current one is rotated (cooperative pass: raw K -> rotated K, window-relative positions) and consumed by
+// the tensor cores.  2 CTAs per SM (HD 128) keep a second pipeline running on the same SM.
 template <int HD, bool ENC, int NW>
 __global__ void __launch_bounds__(NW * 32)
 chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   constexpr int KT = 64;             // keys per tile
   constexpr int LDS = HD + 8;        // padded smem row (elements)
   constexpr int NTHREADS = NW * 32;
+  constexpr int QROWS = NW * 16 > KT ? NW * 16 : KT;
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(attn_smem);            // [NW*16][LDS]
-  bf16* sK = sQ + NW * 16 * LDS;                            // [KT][LDS] rotated keys
-  bf16* sV = sK + KT * LDS;                                 // [KT][LDS]
+  bf16* sQ = reinterpret_cast<bf16*>(attn_smem);            // [NW*16][LDS] rotated queries (start only)
+  bf16* sK = sQ;                                            // [KT][LDS] rotated keys of the current tile (aliases sQ)
+  bf16* sRaw = sQ + QROWS * LDS;                            // [2 stages][K | V][KT][LDS] raw tiles
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -129,6 +147,45 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     table = lp.kv.page_table + static_cast<size_t>(slot) * lp.kv.pages_per_stream;
   }
   if (row0 >= n_rows) return;
+
+  // keys needed by this CTA: up to the largest visible index over its rows
+  int key_end;
+  if (ENC) key_end = L;
+  else {
+    const int rmax = min(row0 + NW * 16, n_rows) - 1;
+    // rows are hq * T + i: a tile may span several heads, so the largest i is T-1 unless the tile is inside one head
+    const int i_hi = (row0 / T == rmax / T) ? (rmax % T) : (T - 1);
+    key_end = L - T + i_hi + 1;
+  }
+  const int n_tiles = (key_end + KT - 1) / KT;
+
+  // ---- raw tile loader (cp.async, zero fill beyond L) ----
+  auto load_tile = [&](int t, int stage) {
+    constexpr int CH = HD / 8;
+    bf16* dK = sRaw + stage * 2 * KT * LDS;
+    bf16* dV = dK + KT * LDS;
+    for (int u = tid; u < KT * CH; u += NTHREADS) {
+      const int kl = u / CH, c = u % CH;
+      const int j = t * KT + kl;
+      const bool ok = j < L;
+      const bf16* ks;
+      const bf16* vs;
+      if (ENC) {
+        const int rs = ok ? (ring0 + j) % ep.cap : 0;
+        const size_t off = ((static_cast<size_t>(slot) * ep.H + head) * ep.cap + rs) * HD + c * 8;
+        ks = ep.k_ring + off;
+        vs = ep.v_ring + off;
+      } else {
+        const int sl = ok ? kv_slot(j, sys_len, ring_start) : 0;
+        ks = lp.kv.pool + (ok ? kv_offset(lp.kv, table, sl, 0, head) : 0) + c * 8;
+        vs = ks + static_cast<size_t>(lp.kv.kv_heads) * kPageTokens * HD;
+      }
+      cpa16(dK + kl * LDS + c * 8, ks, ok ? 16 : 0);
+      cpa16(dV + kl * LDS + c * 8, vs, ok ? 16 : 0);
+    }
+  };
+  load_tile(0, 0);
+  cpa_commit();
 
   // ---- stage rotated Q: rows r = hq * T + i ----
   {
@@ -220,58 +277,51 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
       qhi[h] = L - T + i + 1;                         // causal, bottom-right aligned
     }
   }
-  // keys needed by this CTA: up to the max qhi over its rows (uniform bound: all rows' max)
-  int key_end;
-  if (ENC) key_end = L;
-  else {
-    const int rmax = min(row0 + NW * 16, n_rows) - 1;
-    // rows are hq * T + i: a tile may span several heads, so the largest i is T-1 unless the tile is inside one head
-    const int i_hi = (row0 / T == rmax / T) ? (rmax % T) : (T - 1);
-    key_end = L - T + i_hi + 1;
-  }
   const float sl2 = ENC ? 1.4426950408889634f : lp.scale_log2;
+  const bool warp_live = row0 + warp * 16 < n_rows;
 
-  for (int k0 = 0; k0 < key_end; k0 += KT) {
-    __syncthreads();   // previous tile fully consumed
-    // ---- stage K (rotated) and V ----
+  for (int t = 0; t < n_tiles; ++t) {
+    const int k0 = t * KT;
+    cpa_wait<0>();
+    __syncthreads();   // raw tile t landed; every warp is done with rotated tile t-1 (and with the Q staging)
+    if (t + 1 < n_tiles) load_tile(t + 1, (t + 1) & 1);
+    cpa_commit();
+    const bf16* rK = sRaw + (t & 1) * 2 * KT * LDS;
+    const bf16* sV = rK + KT * LDS;
+    // ---- rotate raw K -> sK (window-relative positions: key j of the window sits at position j) ----
     {
       constexpr int CH = HD / 8;
       constexpr int UNITS = ENC ? CH : CH / 2;
       for (int u = tid; u < KT * UNITS; u += NTHREADS) {
         const int kl = u / UNITS, c = u % UNITS;
-        const int j = k0 + kl;
+        const int j = min(k0 + kl, L - 1);            // rows beyond L are zero: any valid table row will do
+        const bf16* src = rK + kl * LDS;
         bf16* dst = sK + kl * LDS;
-        if (j >= L) {
-          *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
-          if (!ENC) *reinterpret_cast<uint4*>(dst + (c + CH / 2) * 8) = make_uint4(0, 0, 0, 0);
-          continue;
-        }
         if (ENC) {
-          const int rs = (ring0 + j) % ep.cap;
-          const bf16* src = ep.k_ring + ((static_cast<size_t>(slot) * ep.H + head) * ep.cap + rs) * HD + c * 8;
-          uint4 raw = ld_nc_u4(src);
+          uint4 raw = *reinterpret_cast<const uint4*>(src + c * 8);
           const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-          const float* cs = ep.rope_cos + static_cast<size_t>(j) * (HD / 2) + c * 4;
-          const float* sn = ep.rope_sin + static_cast<size_t>(j) * (HD / 2) + c * 4;
+          const float4 cs = *reinterpret_cast<const float4*>(ep.rope_cos + static_cast<size_t>(j) * (HD / 2) + c * 4);
+          const float4 sn = *reinterpret_cast<const float4*>(ep.rope_sin + static_cast<size_t>(j) * (HD / 2) + c * 4);
+          const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
           uint32_t o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float2 x = unpack_bf16(w[q]);
-            o[q] = pack_bf16(x.x * cs[q] - x.y * sn[q], x.y * cs[q] + x.x * sn[q]);
+            o[q] = pack_bf16(x.x * cc[q] - x.y * ss[q], x.y * cc[q] + x.x * ss[q]);
           }
           *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         } else {
-          const int sl = kv_slot(j, sys_len, ring_start);
-          const bf16* src = lp.kv.pool + kv_offset(lp.kv, table, sl, 0, head);
-          uint4 lo = ld_nc_u4(src + c * 8);
-          uint4 hi = ld_nc_u4(src + (c + CH / 2) * 8);
+          uint4 lo = *reinterpret_cast<const uint4*>(src + c * 8);
+          uint4 hi = *reinterpret_cast<const uint4*>(src + (c + CH / 2) * 8);
           const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
-          const bf162* rp = lp.rope + static_cast<size_t>(j) * (HD / 2) + c * 8;
+          const uint4* rp4 = reinterpret_cast<const uint4*>(lp.rope + static_cast<size_t>(j) * (HD / 2) + c * 8);
+          const uint4 r0 = __ldg(rp4), r1 = __ldg(rp4 + 1);
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
           uint32_t ol[4], oh[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float2 a = unpack_bf16(wl[q]), bb = unpack_bf16(wh[q]);
-            float2 cs0 = __bfloat1622float2(rp[2 * q]), cs1 = __bfloat1622float2(rp[2 * q + 1]);
+            float2 cs0 = unpack_bf16(rr[2 * q]), cs1 = unpack_bf16(rr[2 * q + 1]);
             ol[q] = pack_bf16(a.x * cs0.x - bb.x * cs0.y, a.y * cs1.x - bb.y * cs1.y);
             oh[q] = pack_bf16(bb.x * cs0.x + a.x * cs0.y, bb.y * cs1.x + a.y * cs1.y);
           }
@@ -279,24 +329,9 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
           *reinterpret_cast<uint4*>(dst + (c + CH / 2) * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
         }
       }
-      for (int u = tid; u < KT * CH; u += NTHREADS) {
-        const int kl = u / CH, c = u % CH;
-        const int j = k0 + kl;
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (j < L) {
-          if (ENC) {
-            const int rs = (ring0 + j) % ep.cap;
-            raw = ld_nc_u4(ep.v_ring + ((static_cast<size_t>(slot) * ep.H + head) * ep.cap + rs) * HD + c * 8);
-          } else {
-            const int sl = kv_slot(j, sys_len, ring_start);
-            raw = ld_nc_u4(lp.kv.pool + kv_offset(lp.kv, table, sl, 1, head) + c * 8);
-          }
-        }
-        *reinterpret_cast<uint4*>(sV + kl * LDS + c * 8) = raw;
-      }
     }
     __syncthreads();
-    if (row0 + warp * 16 >= n_rows) continue;   // warp has no valid rows (still took part in staging)
+    if (!warp_live) continue;   // warp has no valid rows (still took part in staging)
 
     // ---- S = Q K^T ----
     float s[KT / 8][4];
@@ -369,9 +404,10 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
       }
     }
   }
+  cpa_wait<0>();
 
   // ---- normalise + store ----
-  if (row0 + warp * 16 >= n_rows) return;
+  if (!warp_live) return;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float l = l_run[h];

@@ -19,6 +19,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "decode_attention.cuh"
 #include "gemm_tcgen05.cuh"
 #include "rowops.cuh"
 
@@ -147,6 +148,7 @@ struct isst_ctx {
   int sm_count = 148;
   bool finalized = false;
   bool simple_gemm = false;
+  bool decode_v1 = false;   // ISST_DECODE=v1: CUDA-core validation kernel
   int64_t launches = 0;
   bool debug = false;
   Prof prof;
@@ -620,8 +622,13 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
       for (int b = 0; b < n; ++b) keys += std::min(ctx->streams[slots_h[b]].enc_prefix, c.max_cache_size) + frames;
       ProfScope ps(ctx, st, P_ATTN_ENC, 4.0 * frames * keys * D, keys * D * 2 * 2 + static_cast<double>(M) * D * 2 * 2);
       dim3 grid(ceil_div(frames, NW * 16), H, n);
-      const size_t smem = static_cast<size_t>(NW * 16 + 2 * 64) * (64 + 8) * 2;
+      constexpr int smem = chunk_attn_smem_bytes<64, NW>();
       ISST_CHECK(HD == 64, "encoder attention kernel is built for head_dim 64");
+      static bool enc_attr_set = false;
+      if (!enc_attr_set) {
+        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<64, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        enc_attr_set = true;
+      }
       chunk_attention_kernel<64, true, NW><<<grid, NW * 32, smem, st>>>(ep, lp);
       LAUNCH_CHECK(ctx);
     }
@@ -686,6 +693,7 @@ struct LlmBatch {
   bool decode = false;
   double kv_tokens = 0;            // sum over streams of the KV length attended to (profiling only)
   double qk_pairs = 0;             // sum over streams of T_b * L_b (profiling only)
+  int max_L = 0;                   // longest KV length attended to in this batch (grid sizing)
 };
 
 static PagedKV paged_kv(isst_ctx* ctx, int layer) {
@@ -699,6 +707,30 @@ static PagedKV paged_kv(isst_ctx* ctx, int layer) {
   kv.kv_heads = ctx->cfg.kv_heads;
   kv.head_dim = ctx->cfg.head_dim;
   return kv;
+}
+
+// Decode attention launch: split count from the longest stream so that the grid is a few waves of
+// 2 CTAs per SM; every split is a whole number of 64-key tiles.
+static int decode_splits_for(isst_ctx* ctx, int n, int max_L) {
+  const int tiles_total = std::max(1, ceil_div(max_L, kDecTile));
+  const int target = std::max(1, std::min(ctx->decode_splits, ceil_div(8 * ctx->sm_count, n * ctx->cfg.kv_heads)));
+  const int tiles_per = ceil_div(tiles_total, target);
+  return ceil_div(tiles_total, tiles_per);
+}
+static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* qkv, const PagedKV& kv, const int* d_slots,
+                                   int n, int splits, float scale_log2) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ISST_CUDA(cudaFuncSetAttribute(decode_attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes));
+    attr_set = true;
+  }
+  DecodeParams2 dp{};
+  dp.qkv = qkv; dp.kv = kv; dp.slots = d_slots; dp.rope_cos = ctx->llm_rope_cos_f; dp.rope_sin = ctx->llm_rope_sin_f;
+  dp.rope_tile = ctx->llm_rope; dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
+  dp.splits = splits; dp.scale_log2 = scale_log2;
+  decode_attention_mma_kernel<4><<<dim3(splits, ctx->cfg.kv_heads, n), 128, kDecSmemBytes, st>>>(dp);
+  LAUNCH_CHECK(ctx);
+  return 0;
 }
 
 static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool tap_layers) {
@@ -727,31 +759,32 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       lp.qkv = ctx->lqkv; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
       lp.T = lb.d_T; lp.rope = ctx->llm_rope; lp.H = H; lp.scale_log2 = scale_log2;
       EncAttnParams ep{};
-      constexpr int NW = 8;
+      constexpr int NW = 6;   // 96 query rows per CTA: the 4 x 22 rows of a steady-state turn in one CTA, 2 CTAs per SM
       ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
                    lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
       dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
-      const size_t smem = static_cast<size_t>(NW * 16 + 2 * 64) * (128 + 8) * 2;
+      constexpr int smem = chunk_attn_smem_bytes<128, NW>();
       static bool attr_set = false;
       if (!attr_set) {
         ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<128, false, NW>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
       }
       chunk_attention_kernel<128, false, NW><<<grid, NW * 32, smem, st>>>(ep, lp);
       LAUNCH_CHECK(ctx);
     } else {
-      DecodeParams dp{};
-      dp.qkv = ctx->lqkv; dp.kv = kv; dp.slots = lb.d_slots; dp.rope = ctx->llm_rope; dp.part_o = ctx->part_o;
-      dp.part_ml = ctx->part_ml; dp.H = H; dp.splits = ctx->decode_splits; dp.scale_log2 = scale_log2;
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
-      // fill the machine: n * Hkv * splits CTAs
-      int splits = std::max(1, std::min(ctx->decode_splits, ceil_div(2 * ctx->sm_count, lb.n * Hkv)));
-      dp.splits = splits;
-      dim3 grid(splits, Hkv, lb.n);
-      decode_attention_kernel<128, 4><<<grid, 128, 0, st>>>(dp);
-      LAUNCH_CHECK(ctx);
+      const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
+      if (ctx->decode_v1) {
+        DecodeParams dp{};
+        dp.qkv = ctx->lqkv; dp.kv = kv; dp.slots = lb.d_slots; dp.rope = ctx->llm_rope; dp.part_o = ctx->part_o;
+        dp.part_ml = ctx->part_ml; dp.H = H; dp.splits = splits; dp.scale_log2 = scale_log2;
+        decode_attention_kernel<128, 4><<<dim3(splits, Hkv, lb.n), 128, 0, st>>>(dp);
+        LAUNCH_CHECK(ctx);
+      } else {
+        ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2));
+      }
       decode_combine_kernel<<<lb.n * H, 128, 0, st>>>(ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits);
       LAUNCH_CHECK(ctx);
     }
@@ -864,6 +897,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   const char* g = getenv("ISST_GEMM");
   ctx->simple_gemm = g && std::string(g) == "simple";
+  const char* dv = getenv("ISST_DECODE");
+  ctx->decode_v1 = dv && std::string(dv) == "v1";
   const isst_config& c = ctx->cfg;
   ISST_CHECK(c.n_conv >= 2 && c.n_conv <= ISST_MAX_CONV && c.n_adapter >= 0 && c.n_adapter <= ISST_MAX_CONV, "bad conv config");
   ctx->C = c.conv_dim[0];
@@ -1287,6 +1322,7 @@ static int setup_llm_batch(isst_ctx* ctx, cudaStream_t st, MetaBuilder& mb, int 
     const double L = ctx->streams[stream_ids[b]].kv_len + lens[b];
     lb->kv_tokens += L;
     lb->qk_pairs += L * lens[b];
+    lb->max_L = std::max(lb->max_L, static_cast<int>(L));
   }
   lb->n = n; lb->M = M; lb->max_T = maxT;
   lb->d_slots = mb.dev(o_slots); lb->d_tok_base = mb.dev(o_base); lb->d_T = mb.dev(o_T); lb->d_last_row = mb.dev(o_last);
@@ -1417,8 +1453,12 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
       LAUNCH_CHECK(ctx);
     }
     db.kv_tokens = 0;
-    for (int b = 0; b < n; ++b)
-      if (h_active[b]) db.kv_tokens += ctx->streams[stream_ids[b]].kv_len + lens[b] + step;
+    db.max_L = 1;
+    for (int b = 0; b < n; ++b) {
+      const int Lb = ctx->streams[stream_ids[b]].kv_len + lens[b] + step;
+      if (h_active[b]) db.kv_tokens += Lb;
+      db.max_L = std::max(db.max_L, Lb);
+    }
     ISST_TRY(llm_forward(ctx, st, db, false));
     ISST_TRY(tap(ctx, st, "step_logits", ctx->logits, lbytes, lbytes * step, lbytes * max_new));
     g.step = step;
@@ -1569,16 +1609,12 @@ int isst_op_decode_attention_bench(isst_ctx* ctx, int n, int L, int iters, float
   const float scale_log2 = 1.4426950408889634f / std::sqrt(static_cast<float>(c.head_dim));
   cudaEvent_t e0, e1;
   ISST_CUDA(cudaEventCreate(&e0)); ISST_CUDA(cudaEventCreate(&e1));
-  const int splits = std::max(1, std::min(ctx->decode_splits, ceil_div(2 * ctx->sm_count, n * c.kv_heads)));
+  const int splits = decode_splits_for(ctx, n, L + 1);
   for (int it = -2; it < iters; ++it) {
     if (it == 0) ISST_CUDA(cudaEventRecord(e0, st));
     // walk the layers so consecutive launches read different (cold) KV: total footprint = layers * n * L * 4 KB
     const int layer = ((it % c.layers) + c.layers) % c.layers;
-    DecodeParams dp{};
-    dp.qkv = ctx->lqkv; dp.kv = paged_kv(ctx, layer); dp.slots = mb.dev(o_slots); dp.rope = ctx->llm_rope;
-    dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = c.heads; dp.splits = splits; dp.scale_log2 = scale_log2;
-    decode_attention_kernel<128, 4><<<dim3(splits, c.kv_heads, n), 128, 0, st>>>(dp);
-    LAUNCH_CHECK(ctx);
+    ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, paged_kv(ctx, layer), mb.dev(o_slots), n, splits, scale_log2));
   }
   ISST_CUDA(cudaEventRecord(e1, st));
   ISST_CUDA(cudaStreamSynchronize(st));
