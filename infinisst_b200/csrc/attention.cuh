@@ -64,7 +64,7 @@ struct EncAttnParams {
   bf16* k_ring;           // this layer: [stream_slot][H][cap][HD]
   bf16* v_ring;
   const int* slots;       // [n] stream slot per batch entry
-  const int* prefix;      // [max_streams] frames encoded before this chunk (cache.n_steps)
+  const int* prefix;      // [n] frames encoded before this chunk (cache.n_steps), per batch entry
   const float* rope_cos;  // [n_pos][HD/2]
   const float* rope_sin;
   int T;                  // new frames per stream
@@ -128,7 +128,7 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   if (ENC) {
     slot = ep.slots[b];
     T = ep.T;
-    prefix = ep.prefix[slot];
+    prefix = ep.prefix[b];
     kept = min(prefix, ep.max_cache);
     L = kept + T;
     n_rows = T;
@@ -438,7 +438,7 @@ __global__ void enc_kv_append_kernel(const bf16* __restrict__ qkv, bf16* k_ring,
                                      int HD, int cap) {
   const int b = blockIdx.y;
   const int slot = slots[b];
-  const int pre = prefix[slot];
+  const int pre = prefix[b];   // per batch entry
   const int chunks = H * HD / 8;
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * chunks; u += gridDim.x * blockDim.x) {
     const int i = u / chunks, c = u % chunks;

@@ -203,6 +203,8 @@ struct isst_ctx {
   // batch metadata (device) + pinned host staging
   int* d_meta = nullptr;
   int* h_meta = nullptr;
+  cudaEvent_t ev_active = nullptr;
+  int* h_tables = nullptr;   // pinned staging of the per-batch page tables / lengths
   size_t meta_ints = 0;
   int* d_step_logits_dummy = nullptr;
 };
@@ -546,8 +548,8 @@ static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const 
 
 static int conv_len(int n, int k, int s) { return (n - k) / s + 1; }
 
-static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_h, const int* d_slots, int n_new,
-                        int multiplier) {
+static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_h, const int* d_slots,
+                        const int* d_prefix, int n_new, int multiplier) {
   const isst_config& c = ctx->cfg;
   const int C = ctx->C;
   const int window = ctx->n_tail + n_new;
@@ -608,13 +610,13 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(n) * frames * D * 2 * 4);
       dim3 grid(ceil_div(frames * D / 8, 256), n);
-      enc_kv_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, ctx->d_enc_prefix, frames, H, HD, ctx->enc_cap);
+      enc_kv_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, d_prefix, frames, H, HD, ctx->enc_cap);
       LAUNCH_CHECK(ctx);
     }
     {
       EncAttnParams ep{};
       ep.qkv = ctx->eqkv; ep.out = ctx->eattn; ep.k_ring = kr; ep.v_ring = vr; ep.slots = d_slots;
-      ep.prefix = ctx->d_enc_prefix; ep.rope_cos = ctx->enc_rope_cos; ep.rope_sin = ctx->enc_rope_sin;
+      ep.prefix = d_prefix; ep.rope_cos = ctx->enc_rope_cos; ep.rope_sin = ctx->enc_rope_sin;
       ep.T = frames; ep.H = H; ep.cap = ctx->enc_cap; ep.max_cache = c.max_cache_size; ep.blocksize = blocksize;
       LlmAttnParams lp{};
       constexpr int NW = 4;
@@ -845,18 +847,23 @@ static int ensure_capacity(isst_ctx* ctx, int slot, int extra_tokens, int pin_pr
   return 0;
 }
 
+// The LLM kernels index the per-stream tables by BATCH entry (their `slots` argument is the identity), so one
+// call's tables are four contiguous uploads from pinned memory instead of four small copies per stream.
 static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int* slots) {
-  // h_meta tail region is used as pinned staging for the per-stream tables
+  const int pps = ctx->pages_per_stream;
+  int* h = ctx->h_tables;
+  int* h_len = h + static_cast<size_t>(ctx->cfg.max_batch) * pps;
+  int* h_sys = h_len + ctx->cfg.max_batch;
+  int* h_ring = h_sys + ctx->cfg.max_batch;
   for (int b = 0; b < n; ++b) {
-    const int slot = slots[b];
-    StreamHost& s = ctx->streams[slot];
-    ISST_CUDA(cudaMemcpyAsync(ctx->d_page_table + static_cast<size_t>(slot) * ctx->pages_per_stream, s.pages.data(),
-                              s.pages.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    int vals[3] = {s.kv_len, s.sys_len, s.ring_start};
-    ISST_CUDA(cudaMemcpyAsync(ctx->d_kv_len + slot, &vals[0], sizeof(int), cudaMemcpyHostToDevice, st));
-    ISST_CUDA(cudaMemcpyAsync(ctx->d_sys_len + slot, &vals[1], sizeof(int), cudaMemcpyHostToDevice, st));
-    ISST_CUDA(cudaMemcpyAsync(ctx->d_ring_start + slot, &vals[2], sizeof(int), cudaMemcpyHostToDevice, st));
+    const StreamHost& s = ctx->streams[slots[b]];
+    std::copy(s.pages.begin(), s.pages.end(), h + static_cast<size_t>(b) * pps);
+    h_len[b] = s.kv_len; h_sys[b] = s.sys_len; h_ring[b] = s.ring_start;
   }
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_page_table, h, static_cast<size_t>(n) * pps * sizeof(int), cudaMemcpyHostToDevice, st));
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_kv_len, h_len, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_sys_len, h_sys, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_ring_start, h_ring, n * sizeof(int), cudaMemcpyHostToDevice, st));
   return 0;
 }
 
@@ -1012,6 +1019,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->meta_ints = kEncMetaInts + static_cast<size_t>(nb) * (c.max_prompt * 4 + 256 + c.max_new_tokens * 4) + 4096;
   ISST_TRY(dev_alloc(&ctx->d_meta, ctx->meta_ints));
   ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_meta), ctx->meta_ints * sizeof(int)));
+  ISST_CUDA(cudaEventCreateWithFlags(&ctx->ev_active, cudaEventDisableTiming));
+  ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_tables), (static_cast<size_t>(nb) * (ctx->pages_per_stream + 3) + 16) * sizeof(int)));
   ISST_CUDA(cudaDeviceSynchronize());
   *out = ctx;
   return 0;
@@ -1038,6 +1047,8 @@ void isst_destroy(isst_ctx* ctx) {
   for (void* p : misc) cudaFree(p);
   for (auto& t : ctx->taps) cudaFree(t.second.first);
   cudaFreeHost(ctx->h_meta);
+  cudaFreeHost(ctx->h_tables);
+  if (ctx->ev_active) cudaEventDestroy(ctx->ev_active);
   delete ctx;
 }
 
@@ -1220,8 +1231,6 @@ int isst_stream_open(isst_ctx* ctx, int* stream_id) {
       ctx->streams[s].open = true;
       // zero carried samples == the 79+320 zero offset of the first chunk (agents/infinisst.py:216-218)
       ISST_CUDA(cudaMemset(ctx->tail + static_cast<size_t>(s) * ctx->n_tail, 0, ctx->n_tail * sizeof(float)));
-      int zero = 0;
-      ISST_CUDA(cudaMemcpy(ctx->d_enc_prefix + s, &zero, sizeof(int), cudaMemcpyHostToDevice));
       *stream_id = s;
       return 0;
     }
@@ -1259,8 +1268,6 @@ int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* 
     mb.host(o_prefix)[b] = ctx->streams[stream_ids[b]].enc_prefix;
   }
   ISST_CUDA(cudaMemcpyAsync(ctx->d_meta, ctx->h_meta, mb.used * sizeof(int), cudaMemcpyHostToDevice, st));
-  for (int b = 0; b < n; ++b)
-    ISST_CUDA(cudaMemcpyAsync(ctx->d_enc_prefix + stream_ids[b], mb.host(o_prefix) + b, sizeof(int), cudaMemcpyHostToDevice, st));
   if (with_offset) {
     // explicit 79+320 leading samples: they become the carried tail (zeros in the reference)
     ISST_CUDA(cudaMemcpy2DAsync(ctx->d_pcm, static_cast<size_t>(n_samples) * 4, pcm, static_cast<size_t>(n_samples) * 4,
@@ -1279,7 +1286,7 @@ int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* 
   } else {
     ISST_CUDA(cudaMemcpyAsync(ctx->d_pcm, pcm, static_cast<size_t>(n) * n_new * 4, cudaMemcpyDefault, st));
   }
-  ISST_TRY(encode_chunk(ctx, st, n, stream_ids, mb.dev(o_slots), n_new, multiplier));
+  ISST_TRY(encode_chunk(ctx, st, n, stream_ids, mb.dev(o_slots), mb.dev(o_prefix), n_new, multiplier));
   if (out_feats) {
     ISST_CUDA(cudaMemcpyAsync(out_feats, ctx->speech, static_cast<size_t>(n) * ctx->speech_rows_per_stream * ctx->cfg.hidden * 2,
                               cudaMemcpyDefault, st));
@@ -1304,7 +1311,7 @@ static int setup_llm_batch(isst_ctx* ctx, cudaStream_t st, MetaBuilder& mb, int 
   const size_t o_ids = mb.alloc(M), o_srow = mb.alloc(M);
   int row = 0;
   for (int b = 0; b < n; ++b) {
-    mb.host(o_slots)[b] = stream_ids[b];
+    mb.host(o_slots)[b] = b;   // tables are uploaded per batch entry (upload_stream_tables)
     mb.host(o_base)[b] = row;
     mb.host(o_T)[b] = lens[b];
     mb.host(o_last)[b] = row + lens[b] - 1;
@@ -1441,12 +1448,16 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   db.d_active = mb.dev(o_active); db.decode = true;
   int* h_active = ctx->h_meta + o_active;
   for (int step = 1; step < max_new; ++step) {
-    // early exit when every stream hit EOS (one small D2H + sync per step; a step is >= 2 ms of weight streaming)
+    // Early exit when every stream hit EOS, without stalling the launch queue: the flags of the previous step
+    // are copied to pinned memory behind an event; the host only polls it (at most one surplus step is launched,
+    // and a finished stream appends nothing: llm_kv_append_kernel / advance_kv_len_kernel check `active`).
+    if (step >= 2 && cudaEventQuery(ctx->ev_active) == cudaSuccess) {
+      bool any = false;
+      for (int b = 0; b < n; ++b) any = any || h_active[b];
+      if (!any) break;
+    }
     ISST_CUDA(cudaMemcpyAsync(h_active, mb.dev(o_active), n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    ISST_CUDA(cudaStreamSynchronize(st));
-    bool any = false;
-    for (int b = 0; b < n; ++b) any = any || h_active[b];
-    if (!any) break;
+    ISST_CUDA(cudaEventRecord(ctx->ev_active, st));
     {
       ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(n) * c.hidden * 4);
       embed_splice_kernel<<<n, 128, 0, st>>>(mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden);
@@ -1604,7 +1615,7 @@ int isst_op_decode_attention_bench(isst_ctx* ctx, int n, int L, int iters, float
   fill_pattern_kernel<<<64, 256, 0, st>>>(ctx->lqkv, static_cast<long long>(n) * QKV, 3u);
   MetaBuilder mb{ctx};
   const size_t o_slots = mb.alloc(n);
-  for (int b = 0; b < n; ++b) mb.host(o_slots)[b] = slots[b];
+  for (int b = 0; b < n; ++b) mb.host(o_slots)[b] = b;
   ISST_CUDA(cudaMemcpyAsync(ctx->d_meta, ctx->h_meta, mb.used * sizeof(int), cudaMemcpyHostToDevice, st));
   const float scale_log2 = 1.4426950408889634f / std::sqrt(static_cast<float>(c.head_dim));
   cudaEvent_t e0, e1;
