@@ -435,5 +435,288 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
   }
 }
 
+
+// =================================================================================================
+// Persistent stream-K variant (the product default).
+//
+// The work of one GEMM is the linear sequence of "units" (tile, k-block), tile-major with the token
+// tile fastest (consecutive tiles share a weight tile, which therefore leaves HBM once).  CTA c of G
+// (G <= #SMs, one CTA per SM) owns the contiguous unit range [U*c/G, U*(c+1)/G): every SM streams the
+// same number of bytes whatever the tile count, the TMA ring never drains at tile boundaries, and the
+// accumulator is double-buffered in TMEM so the epilogue of one segment overlaps the MMAs of the next.
+// A tile whose k-range is split between CTAs is reduced through an fp32 workspace by its last-arriving
+// contributor, in contributor order (deterministic).
+// =================================================================================================
+struct SkParams {
+  int tiles_tok, tiles_feat;   // tiles per batch entry
+  int num_kb;                  // k-blocks per tile
+  long long units;             // batch * tiles_tok * tiles_feat * num_kb
+  unsigned long long* dbg;     // optional [grid][8] globaltimer stamps (phase analysis), may be null
+};
+
+template <int kBN, bool kDual, bool kSwap>
+struct SkCfg {
+  static constexpr int kActRows = kSwap ? kBN : kBM;
+  static constexpr int kWRows = kSwap ? kBM : kBN;
+  static constexpr int kNW = kDual ? 2 : 1;
+  static constexpr int kActBytes = kActRows * kBK * 2;
+  static constexpr int kWBytes = kWRows * kBK * 2;
+  static constexpr int kStageBytes = kActBytes + kNW * kWBytes;
+  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 10 ? 10 : kStagesRaw;
+  static constexpr int kAccCols = kBN * kNW;
+  static constexpr int kTmemColsRaw = 2 * kAccCols;
+  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
+  static_assert(kTmemColsRaw <= 512, "two accumulators must fit TMEM");
+  static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct SkTile { int b, tf, tt; };
+__device__ __forceinline__ SkTile sk_tile(long long tile, const SkParams& sk) {
+  SkTile t;
+  t.tt = static_cast<int>(tile % sk.tiles_tok);
+  const long long rest = tile / sk.tiles_tok;
+  t.tf = static_cast<int>(rest % sk.tiles_feat);
+  t.b = static_cast<int>(rest / sk.tiles_feat);
+  return t;
+}
+// CTA that owns unit u when CTA c starts at floor(U * c / G)
+__device__ __forceinline__ int sk_cta_of(long long u, long long U, int G) {
+  return static_cast<int>(((u + 1) * G - 1) / U);
+}
+
+template <int kBN, bool kDual, bool kSwap>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
+               const GemmParams p, const SkParams sk) {
+  using C = SkCfg<kBN, kDual, kSwap>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  int* flag_smem = reinterpret_cast<int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const long long U = sk.units;
+  const long long u0 = U * cta / G, u1 = U * (cta + 1) / G;
+  const int nkb = sk.num_kb;
+  if (sk.dbg && threadIdx.x == 0) sk.dbg[cta * 8 + 0] = gtimer();
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_act)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(static_cast<uint32_t>(C::kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long tile = u0 / nkb;
+      int kb = static_cast<int>(u0 % nkb);
+      SkTile t = sk_tile(tile, sk);
+      for (long long u = u0; u < u1; ++u) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::kStageBytes;
+        uint8_t* sw = sa + C::kActBytes;
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        const int act_row0 = t.tt * C::kActRows;
+        const int w_row0 = t.tf * C::kWRows;
+        const int k0 = kb * kBK;
+        const int tap = k0 / p.conv_c;
+        tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, t.b);
+#pragma unroll
+        for (int h = 0; h < C::kWRows / kBM; ++h)      // the weight map's box is 128 rows
+          tma_load_2d(sw + h * (kBM * kBK * 2), &tm_w, &full_bar[stage], k0, w_row0 + h * kBM);
+        if (kDual) tma_load_2d(sw + C::kWBytes, &tm_w, &full_bar[stage], k0, w_row0 + p.dual_off);
+        if (u == u0 && sk.dbg) sk.dbg[cta * 8 + 1] = gtimer();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (++kb == nkb) { kb = 0; ++tile; t = sk_tile(tile, sk); }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long u = u0;
+    while (u < u1) {
+      const int kb_begin = static_cast<int>(u % nkb);
+      const int kb_end = static_cast<int>(min(static_cast<long long>(nkb), kb_begin + (u1 - u)));
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + acc * C::kAccCols;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sw = sa + C::kActBytes;
+          const uint64_t d_act = make_smem_desc(sa);
+          const uint64_t d_w0 = make_smem_desc(sw);
+          const uint64_t d_w1 = make_smem_desc(sw + C::kWBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+            if (!kSwap) {
+              umma_bf16(tacc, d_act + koff, d_w0 + koff, idesc, accum);
+              if (kDual) umma_bf16(tacc + kBN, d_act + koff, d_w1 + koff, idesc, accum);
+            } else {
+              umma_bf16(tacc, d_w0 + koff, d_act + koff, idesc, accum);
+              if (kDual) umma_bf16(tacc + kBN, d_w1 + koff, d_act + koff, idesc, accum);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb_end - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      u += kb_end - kb_begin;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
+    const int r = q * 32 + lane;                  // TMEM lane == row of the 128-row operand
+    const int et = threadIdx.x - 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long u = u0;
+    bool first_seg = true;
+    while (u < u1) {
+      const long long tile = u / nkb;
+      const int kb_begin = static_cast<int>(u % nkb);
+      const int kb_end = static_cast<int>(min(static_cast<long long>(nkb), kb_begin + (u1 - u)));
+      const SkTile t = sk_tile(tile, sk);
+      const int lane_idx = (kSwap ? t.tf : t.tt) * kBM + r;
+      const int col_base = (kSwap ? t.tt : t.tf) * kBN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      if (first_seg && sk.dbg && et == 0) sk.dbg[cta * 8 + 2] = gtimer();
+      const uint32_t taddr = tmem_base + acc * C::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      if (kb_begin == 0 && kb_end == nkb) {
+        // ---- the whole k-range of this tile was accumulated here: final epilogue straight from TMEM ----
+        if (kSwap && kBN >= 32) {
+#pragma unroll 1
+          for (int c = 0; c < kBN; c += 32) {
+            float v0[32], v1[32];
+            tmem_ld16(taddr + c, v0);
+            tmem_ld16(taddr + c + 16, v0 + 16);
+            if (kDual) { tmem_ld16(taddr + kBN + c, v1); tmem_ld16(taddr + kBN + c + 16, v1 + 16); }
+            epilogue_store_swap<kDual, 32>(p, t.b, lane_idx, col_base + c, v0, v1);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kBN; c += 16) {
+            float v0[16], v1[16];
+            tmem_ld16(taddr + c, v0);
+            if (kDual) tmem_ld16(taddr + kBN + c, v1);
+            epilogue_store16<kDual, kSwap>(p, t.b, lane_idx, col_base + c, v0, v1);
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      } else {
+        // ---- partial tile: park the fp32 partial, the last contributor reduces ----
+        const int c_first = sk_cta_of(tile * nkb, U, G);
+        const int c_last = sk_cta_of((tile + 1) * nkb - 1, U, G);
+        constexpr size_t kSlot = static_cast<size_t>(C::kAccCols) * kBM;
+        float* mine = p.ws + static_cast<size_t>(cta == c_first ? G + cta : cta) * kSlot;
+#pragma unroll 1
+        for (int c = 0; c < C::kAccCols; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mine[(c + i) * kBM + r] = v[i];
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&tempty_bar[acc]);            // the accumulator is free again: MMAs of the next segment go on
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int prev = atomicAdd(&p.counters[c_first], 1);
+          *flag_smem = (prev == c_last - c_first) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*flag_smem) {
+          __threadfence();
+          constexpr int NC = (kSwap && kBN >= 32) ? 32 : 16;
+#pragma unroll 1
+          for (int c = 0; c < kBN; c += NC) {
+            float v0[NC], v1[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
+#pragma unroll 1
+            for (int cc = c_first; cc <= c_last; ++cc) {
+              const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot;
+#pragma unroll
+              for (int i = 0; i < NC; ++i) {
+                v0[i] += __ldcg(&src[(c + i) * kBM + r]);
+                if (kDual) v1[i] += __ldcg(&src[(kBN + c + i) * kBM + r]);
+              }
+            }
+            if (kSwap && kBN >= 32) epilogue_store_swap<kDual, NC>(p, t.b, lane_idx, col_base + c, v0, v1);
+            else epilogue_store16<kDual, kSwap>(p, t.b, lane_idx, col_base + c, v0, v1);
+          }
+          if (et == 0) p.counters[c_first] = 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // flag_smem is reused by the next segment
+      }
+      first_seg = false;
+      u += kb_end - kb_begin;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (sk.dbg && et == 0) sk.dbg[cta * 8 + 3] = gtimer();
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(C::kTmemCols))
+                 : "memory");
+  }
+  if (sk.dbg && threadIdx.x == 0) sk.dbg[cta * 8 + 4] = gtimer();
+}
+
 }  // namespace tc
 }  // namespace isst

@@ -149,6 +149,8 @@ struct isst_ctx {
   bool finalized = false;
   bool simple_gemm = false;
   bool decode_v1 = false;   // ISST_DECODE=v1: CUDA-core validation kernel
+  bool gemm_v1 = false;     // ISST_GEMM=v1: one-tile-per-CTA tcgen05 kernel (previous generation, kept for A/B runs)
+  unsigned long long* gemm_dbg = nullptr;   // optional phase stamps of the last stream-K launch
   int64_t launches = 0;
   bool debug = false;
   Prof prof;
@@ -280,6 +282,35 @@ static int launch_tc(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   return 0;
 }
 
+template <int kBN, bool kDual, bool kSwap>
+static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
+                     int force_splits) {
+  using C = tc::SkCfg<kBN, kDual, kSwap>;
+  static bool attr_set = false;
+  auto kern = tc::gemm_sk_kernel<kBN, kDual, kSwap>;
+  if (!attr_set) {
+    ISST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  tc::SkParams sk{};
+  sk.tiles_tok = ceil_div(p.M_tok, C::kActRows);
+  sk.tiles_feat = ceil_div(p.N_out, C::kWRows);
+  sk.num_kb = ceil_div(p.K, tc::kBK);
+  const long long tiles = static_cast<long long>(sk.tiles_tok) * sk.tiles_feat * p.batch;
+  sk.units = tiles * sk.num_kb;
+  sk.dbg = ctx->gemm_dbg;
+  long long G = std::min<long long>(ctx->sm_count, sk.units);
+  if (force_splits > 0) G = std::min<long long>(sk.units, tiles * force_splits);
+  const size_t slot = static_cast<size_t>(C::kAccCols) * tc::kBM;
+  ISST_CHECK(2 * static_cast<size_t>(G) * slot <= ctx->gemm_ws_floats && G <= ctx->n_counters,
+             "gemm: stream-K workspace too small");
+  CUtensorMap amap;
+  ISST_TRY(make_act_map(&amap, v, C::kActRows));
+  kern<<<static_cast<unsigned>(G), tc::kThreads, C::kSmemBytes, st>>>(amap, w.map, p, sk);
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, int n_out, void* out,
                 long long ldo, long long out_batch_stride, const Epilogue& e, int force_swap = -1,
                 int force_splits = 0, int force_simple = -1) {
@@ -325,6 +356,31 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
   bool swap = (v.rows <= 64 && v.batch == 1);
   if (force_swap >= 0) swap = force_swap != 0;
   ISST_CHECK(!(swap && v.batch != 1), "gemm: swap mode needs batch == 1");
+  if (!ctx->gemm_v1) {
+    // persistent stream-K kernel: tile shape by mode, CTA count = SM count whatever the tile count
+    const int sbn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
+#define ISST_SK(BN, DUAL, SWAP) return launch_sk<BN, DUAL, SWAP>(ctx, st, v, w, p, force_splits)
+    if (!swap) {
+      if (e.dual) ISST_SK(128, true, false);
+      if (n_out >= 256) ISST_SK(256, false, false);
+      ISST_SK(128, false, false);
+    }
+    if (e.dual) {
+      switch (sbn) {
+        case 16: ISST_SK(16, true, true);
+        case 32: ISST_SK(32, true, true);
+        case 64: ISST_SK(64, true, true);
+        default: ISST_SK(128, true, true);
+      }
+    }
+    switch (sbn) {
+      case 16: ISST_SK(16, false, true);
+      case 32: ISST_SK(32, false, true);
+      case 64: ISST_SK(64, false, true);
+      default: ISST_SK(128, false, true);
+    }
+#undef ISST_SK
+  }
   const int num_kb = ceil_div(v.K, tc::kBK);
   int bn = 128;
   if (swap) bn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
@@ -904,6 +960,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   const char* g = getenv("ISST_GEMM");
   ctx->simple_gemm = g && std::string(g) == "simple";
+  ctx->gemm_v1 = g && std::string(g) == "v1";
   const char* dv = getenv("ISST_DECODE");
   ctx->decode_v1 = dv && std::string(dv) == "v1";
   const isst_config& c = ctx->cfg;
@@ -1528,13 +1585,28 @@ int isst_kv_evict(isst_ctx* ctx, int stream_id, int keep_prefix, int drop_upto) 
 
 int isst_debug_enable(isst_ctx* ctx, int on) {
   ISST_CHECK(ctx, "null ctx");
-  ctx->debug = on != 0;
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  ctx->debug = (on & 1) != 0;
+  if ((on & 2) && !ctx->gemm_dbg) {           // bit 1: per-CTA phase stamps of stream-K GEMM launches ("gemm_stamps" tap)
+    ISST_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_dbg), 4096 * 8 * sizeof(unsigned long long)));
+    ISST_CUDA(cudaMemset(ctx->gemm_dbg, 0, 4096 * 8 * sizeof(unsigned long long)));
+  }
+  if (!(on & 2) && ctx->gemm_dbg) { cudaFree(ctx->gemm_dbg); ctx->gemm_dbg = nullptr; }
   return 0;
 }
 
 int isst_debug_read(isst_ctx* ctx, const char* name, void* dst_host, int64_t max_bytes, int64_t* n_bytes) {
   ISST_CHECK(ctx && name && n_bytes, "null argument");
   ISST_CUDA(cudaSetDevice(ctx->device));
+  if (std::string(name) == "gemm_stamps" && ctx->gemm_dbg) {
+    *n_bytes = 4096 * 8 * sizeof(unsigned long long);
+    if (dst_host) {
+      ISST_CHECK(max_bytes >= *n_bytes, "destination too small");
+      ISST_CUDA(cudaDeviceSynchronize());
+      ISST_CUDA(cudaMemcpy(dst_host, ctx->gemm_dbg, *n_bytes, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
   auto it = ctx->taps.find(name);
   if (it == ctx->taps.end()) return set_error(std::string("no such tap: ") + name);
   *n_bytes = static_cast<int64_t>(it->second.second);

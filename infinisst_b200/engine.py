@@ -257,7 +257,8 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ debug taps
-    def debug(self, on: bool = True) -> None:
+    def debug(self, on=True) -> None:
+        """bit 0: keep taps (per-step logits, encoder stages); bit 1: per-CTA phase stamps of GEMM launches."""
         _lib.check(self.lib.isst_debug_enable(self.h, int(on)))
 
     def read_tap(self, name: str, dtype=torch.bfloat16) -> torch.Tensor:

