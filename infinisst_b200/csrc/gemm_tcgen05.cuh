@@ -437,22 +437,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
 
 
 // =================================================================================================
-// Persistent stream-K variant (the product default).
+// Persistent data-parallel + stream-K variant (the product default).
 //
-// The work of one GEMM is the linear sequence of "units" (tile, k-block), tile-major with the token
-// tile fastest (consecutive tiles share a weight tile, which therefore leaves HBM once).  CTA c of G
-// (G <= #SMs, one CTA per SM) owns the contiguous unit range [U*c/G, U*(c+1)/G): every SM streams the
-// same number of bytes whatever the tile count, the TMA ring never drains at tile boundaries, and the
-// accumulator is double-buffered in TMEM so the epilogue of one segment overlaps the MMAs of the next.
-// A tile whose k-range is split between CTAs is reduced through an fp32 workspace by its last-arriving
-// contributor, in contributor order (deterministic).
+// G CTAs (G <= #SMs, one per SM) stay resident for the whole GEMM:
+//   * data-parallel part: the first floor(tiles / G) * G tiles are dealt round-robin (CTA c takes tiles
+//     c, c + G, ...), whole k-range each, so the tiles in flight at any moment are neighbours (token
+//     tile fastest) that share weight / activation tiles in L2;
+//   * stream-K part: the remaining tiles (all of them when tiles < G, the weight-streaming decode
+//     case) form a linear sequence of (tile, k-block) units cut into G equal contiguous ranges, so
+//     every SM streams the same number of bytes whatever the tile count.
+// The TMA ring never drains at tile boundaries and the accumulator is double-buffered in TMEM: the
+// epilogue of one segment (8 warps) overlaps the MMAs of the next.  A tile whose k-range is shared by
+// several CTAs is reduced through an fp32 workspace: every contributor parks its partial and bumps
+// the tile's counter; once all have arrived (all CTAs are co-resident, so waiting cannot deadlock)
+// each contributor reduces its own share of the columns in contributor order (deterministic).
 // =================================================================================================
 struct SkParams {
   int tiles_tok, tiles_feat;   // tiles per batch entry
   int num_kb;                  // k-blocks per tile
-  long long units;             // batch * tiles_tok * tiles_feat * num_kb
+  long long tiles;             // batch * tiles_tok * tiles_feat
+  long long tiles_dp;          // tiles handled data-parallel (multiple of the grid size)
+  long long units_sk;          // (tiles - tiles_dp) * num_kb
+  int g_sk;                    // CTAs taking part in the stream-K part (<= grid, <= units_sk)
   unsigned long long* dbg;     // optional [grid][8] globaltimer stamps (phase analysis), may be null
 };
+
+constexpr int kSkThreads = 384;      // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
 
 template <int kBN, bool kDual, bool kSwap>
 struct SkCfg {
@@ -468,6 +478,9 @@ struct SkCfg {
   static constexpr int kTmemColsRaw = 2 * kAccCols;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kEpiHalves = kBN >= 32 ? 2 : 1;     // column halves handled by warps 4-7 / 8-11
+  static constexpr int kHalfCols = kBN / kEpiHalves;
+  static constexpr int kNC = (kSwap && kHalfCols >= 32) ? 32 : 16;   // columns per epilogue step
   static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
   static_assert(kTmemColsRaw <= 512, "two accumulators must fit TMEM");
   static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
@@ -481,6 +494,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 struct SkTile { int b, tf, tt; };
 __device__ __forceinline__ SkTile sk_tile(long long tile, const SkParams& sk) {
@@ -491,13 +509,45 @@ __device__ __forceinline__ SkTile sk_tile(long long tile, const SkParams& sk) {
   t.b = static_cast<int>(rest / sk.tiles_feat);
   return t;
 }
-// CTA that owns unit u when CTA c starts at floor(U * c / G)
+// CTA that owns stream-K unit u when CTA c starts at floor(U * c / G)
 __device__ __forceinline__ int sk_cta_of(long long u, long long U, int G) {
   return static_cast<int>(((u + 1) * G - 1) / U);
 }
 
+// Walks the work of one CTA: first its data-parallel tiles (whole k-range), then its stream-K range.
+// All three roles (producer, MMA, epilogue) iterate the same sequence of segments.
+struct SkWalker {
+  const SkParams& sk;
+  int G, cta;
+  long long dp_i, dp_n;        // data-parallel tiles done / total for this CTA
+  long long u, u1;             // stream-K unit cursor / end (units are relative to tile tiles_dp)
+  __device__ SkWalker(const SkParams& s, int G_, int cta_) : sk(s), G(G_), cta(cta_) {
+    dp_i = 0;
+    dp_n = sk.tiles_dp / G;
+    if (cta < sk.g_sk) { u = sk.units_sk * cta / sk.g_sk; u1 = sk.units_sk * (cta + 1) / sk.g_sk; }
+    else { u = 0; u1 = 0; }
+  }
+  // next segment: tile, [kb_begin, kb_end); returns false when the CTA is done
+  __device__ bool next(long long& tile, int& kb_begin, int& kb_end) {
+    if (dp_i < dp_n) {
+      tile = dp_i * G + cta;
+      kb_begin = 0; kb_end = sk.num_kb;
+      ++dp_i;
+      return true;
+    }
+    if (u < u1) {
+      tile = sk.tiles_dp + u / sk.num_kb;
+      kb_begin = static_cast<int>(u % sk.num_kb);
+      kb_end = static_cast<int>(min(static_cast<long long>(sk.num_kb), kb_begin + (u1 - u)));
+      u += kb_end - kb_begin;
+      return true;
+    }
+    return false;
+  }
+};
+
 template <int kBN, bool kDual, bool kSwap>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kSkThreads, 1)
 gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const GemmParams p, const SkParams sk) {
   using C = SkCfg<kBN, kDual, kSwap>;
@@ -508,13 +558,10 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
   uint64_t* tfull_bar = empty_bar + C::kStages;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  int* flag_smem = reinterpret_cast<int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
-  const long long U = sk.units;
-  const long long u0 = U * cta / G, u1 = U * (cta + 1) / G;
   const int nkb = sk.num_kb;
   if (sk.dbg && threadIdx.x == 0) sk.dbg[cta * 8 + 0] = gtimer();
 
@@ -527,7 +574,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -547,26 +594,30 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      long long tile = u0 / nkb;
-      int kb = static_cast<int>(u0 % nkb);
-      SkTile t = sk_tile(tile, sk);
-      for (long long u = u0; u < u1; ++u) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * C::kStageBytes;
-        uint8_t* sw = sa + C::kActBytes;
-        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+      SkWalker w(sk, G, cta);
+      long long tile;
+      int kb_begin, kb_end;
+      bool first = true;
+      while (w.next(tile, kb_begin, kb_end)) {
+        const SkTile t = sk_tile(tile, sk);
         const int act_row0 = t.tt * C::kActRows;
         const int w_row0 = t.tf * C::kWRows;
-        const int k0 = kb * kBK;
-        const int tap = k0 / p.conv_c;
-        tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, t.b);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sw = sa + C::kActBytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          const int k0 = kb * kBK;
+          const int tap = k0 / p.conv_c;
+          tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, t.b);
 #pragma unroll
-        for (int h = 0; h < C::kWRows / kBM; ++h)      // the weight map's box is 128 rows
-          tma_load_2d(sw + h * (kBM * kBK * 2), &tm_w, &full_bar[stage], k0, w_row0 + h * kBM);
-        if (kDual) tma_load_2d(sw + C::kWBytes, &tm_w, &full_bar[stage], k0, w_row0 + p.dual_off);
-        if (u == u0 && sk.dbg) sk.dbg[cta * 8 + 1] = gtimer();
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-        if (++kb == nkb) { kb = 0; ++tile; t = sk_tile(tile, sk); }
+          for (int h = 0; h < C::kWRows / kBM; ++h)      // the weight map's box is 128 rows
+            tma_load_2d(sw + h * (kBM * kBK * 2), &tm_w, &full_bar[stage], k0, w_row0 + h * kBM);
+          if (kDual) tma_load_2d(sw + C::kWBytes, &tm_w, &full_bar[stage], k0, w_row0 + p.dual_off);
+          if (first && sk.dbg) sk.dbg[cta * 8 + 1] = gtimer();
+          first = false;
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -576,10 +627,10 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    long long u = u0;
-    while (u < u1) {
-      const int kb_begin = static_cast<int>(u % nkb);
-      const int kb_end = static_cast<int>(min(static_cast<long long>(nkb), kb_begin + (u1 - u)));
+    SkWalker w(sk, G, cta);
+    long long tile;
+    int kb_begin, kb_end;
+    while (w.next(tile, kb_begin, kb_end)) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + acc * C::kAccCols;
@@ -610,102 +661,124 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
-      u += kb_end - kb_begin;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
+    // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
     const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
+    const int half = (warp - 4) >> 2;             // column half of the tile
     const int r = q * 32 + lane;                  // TMEM lane == row of the 128-row operand
-    const int et = threadIdx.x - 128;
+    const int et = threadIdx.x - 128;             // 0..255
+    const bool works = half < C::kEpiHalves;
+    const int hc0 = half * C::kHalfCols;          // first column of this warp's half
+    constexpr int NC = C::kNC;
+    constexpr size_t kSlot = static_cast<size_t>(C::kAccCols) * kBM;
     int acc = 0;
     uint32_t acc_phase = 0;
-    long long u = u0;
+    SkWalker w(sk, G, cta);
+    long long tile;
+    int kb_begin, kb_end;
+    long long part_tile[2];                       // partial tiles of this CTA (at most its first and last stream-K tile)
+    int n_part = 0;
     bool first_seg = true;
-    while (u < u1) {
-      const long long tile = u / nkb;
-      const int kb_begin = static_cast<int>(u % nkb);
-      const int kb_end = static_cast<int>(min(static_cast<long long>(nkb), kb_begin + (u1 - u)));
+    while (w.next(tile, kb_begin, kb_end)) {
       const SkTile t = sk_tile(tile, sk);
       const int lane_idx = (kSwap ? t.tf : t.tt) * kBM + r;
       const int col_base = (kSwap ? t.tt : t.tf) * kBN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       if (first_seg && sk.dbg && et == 0) sk.dbg[cta * 8 + 2] = gtimer();
+      first_seg = false;
       const uint32_t taddr = tmem_base + acc * C::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
       if (kb_begin == 0 && kb_end == nkb) {
         // ---- the whole k-range of this tile was accumulated here: final epilogue straight from TMEM ----
-        if (kSwap && kBN >= 32) {
+        if (works) {
 #pragma unroll 1
-          for (int c = 0; c < kBN; c += 32) {
-            float v0[32], v1[32];
-            tmem_ld16(taddr + c, v0);
-            tmem_ld16(taddr + c + 16, v0 + 16);
-            if (kDual) { tmem_ld16(taddr + kBN + c, v1); tmem_ld16(taddr + kBN + c + 16, v1 + 16); }
-            epilogue_store_swap<kDual, 32>(p, t.b, lane_idx, col_base + c, v0, v1);
-          }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < kBN; c += 16) {
-            float v0[16], v1[16];
-            tmem_ld16(taddr + c, v0);
-            if (kDual) tmem_ld16(taddr + kBN + c, v1);
-            epilogue_store16<kDual, kSwap>(p, t.b, lane_idx, col_base + c, v0, v1);
+          for (int c = hc0; c < hc0 + C::kHalfCols; c += NC) {
+            float v0[NC], v1[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j += 16) {
+              tmem_ld16(taddr + c + j, v0 + j);
+              if (kDual) tmem_ld16(taddr + kBN + c + j, v1 + j);
+            }
+            if (kSwap) epilogue_store_swap<kDual, NC>(p, t.b, lane_idx, col_base + c, v0, v1);
+            else epilogue_store16<kDual, false>(p, t.b, lane_idx, col_base + c, v0, v1);
           }
         }
         tcgen05_fence_before();
         mbar_arrive(&tempty_bar[acc]);
       } else {
-        // ---- partial tile: park the fp32 partial, the last contributor reduces ----
-        const int c_first = sk_cta_of(tile * nkb, U, G);
-        const int c_last = sk_cta_of((tile + 1) * nkb - 1, U, G);
-        constexpr size_t kSlot = static_cast<size_t>(C::kAccCols) * kBM;
+        // ---- partial tile: park the fp32 partial and announce it; the reduction happens after the walk ----
+        const long long ut = (tile - sk.tiles_dp) * nkb;
+        const int c_first = sk_cta_of(ut, sk.units_sk, sk.g_sk);
         float* mine = p.ws + static_cast<size_t>(cta == c_first ? G + cta : cta) * kSlot;
+        if (works) {
 #pragma unroll 1
-        for (int c = 0; c < C::kAccCols; c += 16) {
-          float v[16];
-          tmem_ld16(taddr + c, v);
+          for (int cc = 0; cc < C::kNW; ++cc)
+#pragma unroll 1
+            for (int c = hc0; c < hc0 + C::kHalfCols; c += 16) {
+              float v[16];
+              tmem_ld16(taddr + cc * kBN + c, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mine[(c + i) * kBM + r] = v[i];
+              for (int i = 0; i < 16; ++i) mine[(cc * kBN + c + i) * kBM + r] = v[i];
+            }
         }
         tcgen05_fence_before();
         mbar_arrive(&tempty_bar[acc]);            // the accumulator is free again: MMAs of the next segment go on
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          const int prev = atomicAdd(&p.counters[c_first], 1);
-          *flag_smem = (prev == c_last - c_first) ? 1 : 0;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*flag_smem) {
-          __threadfence();
-          constexpr int NC = (kSwap && kBN >= 32) ? 32 : 16;
-#pragma unroll 1
-          for (int c = 0; c < kBN; c += NC) {
-            float v0[NC], v1[NC];
-#pragma unroll
-            for (int i = 0; i < NC; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
-#pragma unroll 1
-            for (int cc = c_first; cc <= c_last; ++cc) {
-              const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot;
-#pragma unroll
-              for (int i = 0; i < NC; ++i) {
-                v0[i] += __ldcg(&src[(c + i) * kBM + r]);
-                if (kDual) v1[i] += __ldcg(&src[(kBN + c + i) * kBM + r]);
-              }
-            }
-            if (kSwap && kBN >= 32) epilogue_store_swap<kDual, NC>(p, t.b, lane_idx, col_base + c, v0, v1);
-            else epilogue_store16<kDual, kSwap>(p, t.b, lane_idx, col_base + c, v0, v1);
-          }
-          if (et == 0) p.counters[c_first] = 0;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // flag_smem is reused by the next segment
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) atomicAdd(&p.counters[c_first], 1);
+        part_tile[n_part++] = tile;
       }
-      first_seg = false;
-      u += kb_end - kb_begin;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (sk.dbg && et == 0) sk.dbg[cta * 8 + 3] = gtimer();
+    // ---- reduce the shared tiles: every contributor takes its share of the 16-column chunks ----
+    for (int pi = 0; pi < n_part; ++pi) {
+      const long long tl = part_tile[pi];
+      const long long ut = (tl - sk.tiles_dp) * nkb;
+      const int c_first = sk_cta_of(ut, sk.units_sk, sk.g_sk);
+      const int c_last = sk_cta_of(ut + nkb - 1, sk.units_sk, sk.g_sk);
+      const int nc = c_last - c_first + 1;
+      if (et == 0) {
+        while (ld_acquire(&p.counters[c_first]) < nc) __nanosleep(64);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      __threadfence();
+      const SkTile t = sk_tile(tl, sk);
+      const int lane_idx = (kSwap ? t.tf : t.tt) * kBM + r;
+      const int col_base = (kSwap ? t.tt : t.tf) * kBN;
+      // chunk list: kBN / 16 chunks dealt to (contributor, half) pairs
+      constexpr int kChunks = kBN / 16;
+      const int workers = nc * 2;
+      const int me = (cta - c_first) * 2 + half;
+      const int ch0 = kChunks * me / workers, ch1 = kChunks * (me + 1) / workers;
+#pragma unroll 1
+      for (int ch = ch0; ch < ch1; ++ch) {
+        const int c = ch * 16;
+        float v0[16], v1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
+#pragma unroll 4
+        for (int cc = c_first; cc <= c_last; ++cc) {
+          const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v0[i] += __ldcg(&src[(c + i) * kBM + r]);
+            if (kDual) v1[i] += __ldcg(&src[(kBN + c + i) * kBM + r]);
+          }
+        }
+        if (kSwap) epilogue_store_swap<kDual, 16>(p, t.b, lane_idx, col_base + c, v0, v1);
+        else epilogue_store16<kDual, false>(p, t.b, lane_idx, col_base + c, v0, v1);
+      }
+      // second phase of the counter: the last contributor to finish re-arms it for the next launch
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        const int prev = atomicAdd(&p.counters[c_first], 1);
+        if (prev == 2 * nc - 1) p.counters[c_first] = 0;
+      }
+    }
+    if (sk.dbg && et == 0) sk.dbg[cta * 8 + 5] = gtimer();
     tcgen05_fence_before();
   }
   __syncthreads();

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "attention.cuh"
@@ -96,6 +97,15 @@ static int make_act_map(CUtensorMap* map, const ActView& v, int box_rows) {
   return 0;
 }
 
+// Activation tensor maps are pure functions of (pointer, geometry): encode once, reuse on every launch.
+struct ActMapKey {
+  const void* ptr; int rows, K, conv_c, conv_s, row_groups, batch, box_rows; long long batch_stride;
+  bool operator<(const ActMapKey& o) const {
+    return std::tie(ptr, rows, K, conv_c, conv_s, row_groups, batch, box_rows, batch_stride) <
+           std::tie(o.ptr, o.rows, o.K, o.conv_c, o.conv_s, o.row_groups, o.batch, o.box_rows, o.batch_stride);
+  }
+};
+
 struct EncLayerW {
   float *ln1_w = nullptr, *ln1_b = nullptr, *bqkv = nullptr, *bo = nullptr, *ln2_w = nullptr, *ln2_b = nullptr,
         *b1 = nullptr, *b2 = nullptr;
@@ -156,6 +166,7 @@ struct isst_ctx {
   Prof prof;
   std::map<std::string, std::pair<void*, size_t>> taps;   // name -> (device buffer, bytes)
   std::map<std::string, bool> loaded;
+  std::map<ActMapKey, CUtensorMap> act_maps;
 
   // geometry
   int C = 0, n_tail = 0, rf = 0, total_stride = 0, frames_max = 0, samples_max = 0, enc_cap = 0;
@@ -282,6 +293,19 @@ static int launch_tc(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   return 0;
 }
 
+static int get_act_map(isst_ctx* ctx, CUtensorMap* map, const ActView& v, int box_rows) {
+  const ActMapKey key{v.ptr, v.rows, v.K, v.conv_c, v.conv_s, v.row_groups, v.batch, box_rows, v.batch_stride};
+  auto it = ctx->act_maps.find(key);
+  if (it == ctx->act_maps.end()) {
+    CUtensorMap m;
+    ISST_TRY(make_act_map(&m, v, box_rows));
+    if (ctx->act_maps.size() > 4096) ctx->act_maps.clear();      // caller-owned pointers (isst_op_gemm) may churn
+    it = ctx->act_maps.emplace(key, m).first;
+  }
+  *map = it->second;
+  return 0;
+}
+
 template <int kBN, bool kDual, bool kSwap>
 static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
                      int force_splits) {
@@ -296,17 +320,19 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   sk.tiles_tok = ceil_div(p.M_tok, C::kActRows);
   sk.tiles_feat = ceil_div(p.N_out, C::kWRows);
   sk.num_kb = ceil_div(p.K, tc::kBK);
-  const long long tiles = static_cast<long long>(sk.tiles_tok) * sk.tiles_feat * p.batch;
-  sk.units = tiles * sk.num_kb;
+  sk.tiles = static_cast<long long>(sk.tiles_tok) * sk.tiles_feat * p.batch;
   sk.dbg = ctx->gemm_dbg;
-  long long G = std::min<long long>(ctx->sm_count, sk.units);
-  if (force_splits > 0) G = std::min<long long>(sk.units, tiles * force_splits);
+  long long G = std::min<long long>(ctx->sm_count, sk.tiles * sk.num_kb);
+  if (force_splits > 0) G = std::min<long long>(G, sk.tiles * force_splits);
+  sk.tiles_dp = (sk.tiles / G) * G;
+  sk.units_sk = (sk.tiles - sk.tiles_dp) * sk.num_kb;
+  sk.g_sk = static_cast<int>(std::min<long long>(G, sk.units_sk));
   const size_t slot = static_cast<size_t>(C::kAccCols) * tc::kBM;
   ISST_CHECK(2 * static_cast<size_t>(G) * slot <= ctx->gemm_ws_floats && G <= ctx->n_counters,
              "gemm: stream-K workspace too small");
   CUtensorMap amap;
-  ISST_TRY(make_act_map(&amap, v, C::kActRows));
-  kern<<<static_cast<unsigned>(G), tc::kThreads, C::kSmemBytes, st>>>(amap, w.map, p, sk);
+  ISST_TRY(get_act_map(ctx, &amap, v, C::kActRows));
+  kern<<<static_cast<unsigned>(G), tc::kSkThreads, C::kSmemBytes, st>>>(amap, w.map, p, sk);
   LAUNCH_CHECK(ctx);
   return 0;
 }

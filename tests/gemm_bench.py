@@ -63,8 +63,9 @@ def stamps(eng, M, N, K, kw):
     t = eng.read_tap("gemm_stamps", torch.int64).view(4096, 8)[:148].double()
     eng.debug(0)
     t0 = t[:, 0].min()
-    rel = (t[:, :5] - t0) / 1e3
-    return [f"{rel[:, i].mean():.1f}/{rel[:, i].max():.1f}" for i in range(5)]
+    n = int((t[:, 0] > 0).sum())
+    rel = (t[:n, :6] - t0) / 1e3
+    return [f"{rel[:, i].mean():.1f}/{rel[:, i].max():.1f}" for i in (0, 1, 2, 3, 5, 4)]
 
 
 def main():
@@ -79,7 +80,7 @@ def main():
             us, tf, gbs = bench(eng, name, M, N, K, kw)
             line = f"[{mode}] {name:12s} M={M:5d} N={N:6d} K={K:5d}  {us:8.1f} us  {tf:7.1f} TFLOP/s  {gbs:7.1f} GB/s"
             if mode == "sk" and M <= 64:
-                line += "  stamps(start, first_tma, first_acc, epi_done, exit) mean/max us: " + " ".join(stamps(eng, M, N, K, kw))
+                line += "  stamps(start, first_tma, first_acc, walk_done, reduce_done, exit) mean/max us: " + " ".join(stamps(eng, M, N, K, kw))
             print(line, flush=True)
         eng.close()
 

@@ -2,7 +2,7 @@
 # Quick GPU iteration: parity tests + GEMM micro-benchmark + short bench.
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest exit=$?" | tee -a $O/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q -s > $O/pytest_gpu.log 2>&1; echo "pytest exit=$?" | tee -a $O/pytest_gpu.log
 tail -4 $O/pytest_gpu.log
 timeout 600 python tests/gemm_bench.py ${GEMM_ARGS:---ab} > $O/gemm_bench.log 2>&1; echo "gemm_bench exit=$?"; cat $O/gemm_bench.log | tail -40
 timeout 600 python bench.py --steps 4 --warmup 3 --latency-chunks 10 --cpu-baseline-chunks 0 > $O/bench.json 2> $O/bench.err; echo "bench exit=$?"; tail -2 $O/bench.err

@@ -333,10 +333,10 @@ def test_production_widths_vs_oracle(layers):
     eng = _engine(cfg, sd16, max_streams=2)
     eng.debug(True)
     sd32 = {k: v.float() for k, v in sd16.items()}
-    del sd16
     n_chunks = 3
     audio = make_audio(n_chunks * SEG / 16000.0)
     st = O.StreamState()
+    st16 = O.StreamState()      # the oracle in bf16 eager on the GPU = the reference's own numerics (yardstick)
     sid = eng.open_stream()
     target = []
     worst = {"feat": 0.0, "logit": 0.0}
@@ -347,10 +347,14 @@ def test_production_widths_vs_oracle(layers):
             out_o, rec = O.policy_chunk(sd32, cfg, st, audio[: (c + 1) * SEG].tolist(), torch.float32, taps)
             ids = O.build_prompt(cfg.tpl, c == 0)
             forced = rec.sequences[0][len(ids):]
+            taps16 = {}
+            _, rec16 = O.policy_chunk(sd16, cfg, st16, audio[: (c + 1) * SEG].tolist(), torch.bfloat16, taps16, forced)
             feats = eng.encode_chunk([sid], _chunk_pcm(audio, c), 1, return_feats=True)
             e = rel_l2(feats, taps["speech_feats"])
+            e16 = rel_l2(taps16["speech_feats"], taps["speech_feats"])
             worst["feat"] = max(worst["feat"], e)
-            assert e < ENC_TOL, (c, e)
+            worst["feat16"] = max(worst.get("feat16", 0.0), e16)
+            assert e < ENC_TOL and e <= 2 * e16 + 1e-2, (c, e, e16)
             toks = eng.generate([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen,
                                 pin_prefix=len(cfg.tpl.system_ids), forced=[forced])[0]
             assert toks == forced
@@ -358,18 +362,21 @@ def test_production_widths_vs_oracle(layers):
             for s in range(len(rec.step_logits)):
                 ref = rec.step_logits[s][0].cpu()
                 e = rel_l2(logits[s], ref)
+                e16 = rel_l2(rec16.step_logits[s][0].cpu(), ref)
                 worst["logit"] = max(worst["logit"], e)
-                assert e < LOGIT_TOL, (c, s, e)
+                worst["logit16"] = max(worst.get("logit16", 0.0), e16)
+                assert e < LOGIT_TOL and e <= 2 * e16 + 1e-2, (c, s, e, e16)
                 sc = O.process_logits(logits[s], ids + forced[:s], target[-100:], cfg.gen)
                 steps += 1
                 if int(sc.argmax()) != forced[s]:
                     so = rec.step_scores[s][0].cpu()
-                    assert so[int(sc.argmax())] >= so.max() - TIE_EPS
+                    # a flip is a near-tie when the oracle margin is below a tenth of the logit spread
+                    assert so[int(sc.argmax())] >= so.max() - max(TIE_EPS, 0.1 * float(ref.std()))
                     flips += 1
             assert eng.kv_len(sid) == st.llm_cache.length()
             target.extend(out_o)
-    print(f"production {layers}: worst feat rel_l2 {worst['feat']:.3e}, worst logit rel_l2 {worst['logit']:.3e}, "
-          f"near-tie flips {flips}/{steps}")
+    print(f"production {layers}: worst feat rel_l2 {worst['feat']:.3e} (bf16-eager oracle {worst['feat16']:.3e}), "
+          f"worst logit rel_l2 {worst['logit']:.3e} (bf16-eager oracle {worst['logit16']:.3e}), near-tie flips {flips}/{steps}")
     # 128 263 near-iid random logits: the top-2 gap is below the bf16 error for a few percent of the steps
     # (SURVEY §7 hard part 2); every flip was checked above to be such a near-tie
     assert flips <= 0.1 * steps + 1
