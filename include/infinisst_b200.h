@@ -72,8 +72,8 @@ void isst_destroy(isst_ctx* ctx);
 
 /* Weight ingestion, keyed by the reference's state-dict names (`pytorch_model.bin`,
  * agents/infinisst.py:179-180; key layout SURVEY §8b).  `data` may be a host or a device pointer.
- * Extra keys: "rope.enc.cos"/"rope.enc.sin" [n_pos, head_dim/2] f32 (rotary_embedding_torch tables,
- * patch_speech_encoder.py:631,823-824) and "rope.llm.cos"/"rope.llm.sin" [n_pos, head_dim/2] f32
+ * Extra keys: "rope.enc.inv_freq" [enc_head_dim/2] f32 (rotary_embedding_torch `freqs`,
+ * patch_speech_encoder.py:631,823-824) and "rope.llm.inv_freq" [head_dim/2] f32
  * (HF LlamaRotaryEmbedding, patch_llm.py:287-299).  Unknown keys (e.g. encoder.pos_conv.*, mask_emb)
  * are accepted and ignored, like load_state_dict on unused modules. */
 int isst_load_weight(isst_ctx* ctx, const char* name, const void* data, const int64_t* shape, int ndim,
@@ -122,6 +122,10 @@ int isst_enc_steps(isst_ctx* ctx, int stream_id, int* n_steps);   /* W2V2RoPECac
 /* Introspection for tests / bench. */
 int isst_debug_enable(isst_ctx* ctx, int on);   /* keep per-step raw logits + encoder taps */
 int isst_debug_read(isst_ctx* ctx, const char* name, void* dst_host, int64_t max_bytes, int64_t* n_bytes);
+/* Test hook: pretend `delta` more ring tokens were appended and evicted before now, i.e. move the stream's
+ * absolute RoPE positions (a one-hour stream reaches ~1e5).  Scores only depend on position differences
+ * (patch_llm.py:287-299), so results must not change. */
+int isst_debug_shift_positions(isst_ctx* ctx, int stream_id, int64_t delta);
 int64_t isst_launch_count(isst_ctx* ctx);       /* kernels launched so far */
 /* Per-kernel-class device timing for the roofline leg of bench.py: while enabled every launch is
  * bracketed by CUDA events on the caller's stream.  isst_profile_read walks the classes by index

@@ -61,6 +61,7 @@ SYMBOLS = {
     "isst_debug_read": (_I, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "isst_launch_count": (C.c_int64, [_P]),
     "isst_pages_free": (_I, [_P]),
+    "isst_debug_shift_positions": (_I, [_P, _I, C.c_int64]),
     "isst_profile_enable": (_I, [_P, _I]),
     "isst_profile_reset": (_I, [_P]),
     "isst_profile_read": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64), C.POINTER(C.c_double),

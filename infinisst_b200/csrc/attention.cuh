@@ -1,18 +1,26 @@
-// Attention kernels with RoPE-on-read over un-rotated KV caches.
+// Attention kernels over position-stable rotated KV caches.
 //
+// The reference keeps K UN-rotated and re-applies RoPE to every cached key at its index in the current
+// cache on every call (patch_llm.py:280-299, patch_speech_encoder.py:797-824), so that sliding-window
+// eviction shifts all positions consistently.  A score only depends on the DIFFERENCE of the two
+// positions, so the same scores are obtained with keys rotated ONCE, when they are appended, at their
+// ABSOLUTE index a (tokens / frames ever appended to the stream), and queries rotated at their absolute
+// index: the difference a_q - a_k equals the reference's pos_q - pos_k for every key that slid with the
+// window.  The pinned system prompt does not slide: its keys keep absolute index == reference position,
+// and the reference distance to them is (a_q - evicted) - a_k, so a second copy of the query rotated at
+// a_q - evicted is used for the system-prompt keys (two query variants per turn instead of re-rotating
+// ~1000 keys per layer per step).  Angles are formed in fp64 and reduced mod 2 pi before sin/cos, so an
+// unbounded stream (absolute indices ~1e5-1e6) keeps fp32-accurate rotations.  Eviction stays a
+// page-table edit with no data movement, and the kept index sets are exactly the reference's.
+//
+//  * rope_table_kernel: (cos, sin) of the new tokens' / frames' absolute positions
+//  * llm_rope_append_kernel / enc_rope_append_kernel: rotate q in place, append rotated K and V
 //  * chunk_attention_kernel<HD, ENC>: tensor-core (mma.sync m16n8k16 bf16) flash-style kernel for
 //      ENC = true : wav2vec2 block-causal sliding-window attention over the per-layer KV ring
-//                   (uni_mha_forward, patch_speech_encoder.py:692-933; mask closed form SURVEY §4.4;
-//                   interleaved-pair RoPE, rotate_queries_with_cached_keys :823-824)
+//                   (uni_mha_forward, patch_speech_encoder.py:692-933; mask closed form SURVEY §4.4)
 //      ENC = false: Llama chunk-prefill over the paged KV with GQA row packing
-//                   (llama_sdpa_attention_new_forward, patch_llm.py:231-336; half-split RoPE at
-//                   positions 0..L-1 of the *current* cache, :287-299)
-//  * decode_attention_kernel / decode_combine_kernel: single-token split-K decode over the paged KV
-//    (HBM-bound).
-//
-// Keys are stored UN-rotated (patch_llm.py:280-284, patch_speech_encoder.py:797-821) and rotated while
-// they are staged into shared memory, with window-relative positions, exactly like the reference
-// re-rotates the whole cache on every call -- so sliding-window eviction needs no data movement.
+//                   (llama_sdpa_attention_new_forward, patch_llm.py:231-336)
+//  * decode attention lives in decode_attention.cuh; decode_combine_kernel merges its split partials.
 #pragma once
 #include "common.cuh"
 
@@ -59,14 +67,12 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 }
 
 struct EncAttnParams {
-  const bf16* qkv;        // [tok, 3*H*HD]  (q pre-scaled by HD^-0.5 through the folded weights)
+  const bf16* qkv;        // [tok, 3*H*HD]  q (pre-scaled by HD^-0.5 through the folded weights) rotated in place
   bf16* out;              // [tok, H*HD]
-  bf16* k_ring;           // this layer: [stream_slot][H][cap][HD]
+  bf16* k_ring;           // this layer: [stream_slot][H][cap][HD], keys rotated at their absolute frame index
   bf16* v_ring;
   const int* slots;       // [n] stream slot per batch entry
   const int* prefix;      // [n] frames encoded before this chunk (cache.n_steps), per batch entry
-  const float* rope_cos;  // [n_pos][HD/2]
-  const float* rope_sin;
   int T;                  // new frames per stream
   int H;
   int cap;                // ring capacity (>= max_cache + T)
@@ -75,13 +81,13 @@ struct EncAttnParams {
 };
 
 struct LlmAttnParams {
-  const bf16* qkv;        // [tok, (H + 2*Hkv) * HD]
+  const bf16* qkv;        // [tok, (H + 2*Hkv) * HD]; q rotated in place at the absolute index (ring variant)
+  const bf16* q_sys;      // [tok, H * HD]: q rotated at (absolute index - evicted), used against the pinned prefix
   bf16* out;              // [tok, H*HD]
   PagedKV kv;
   const int* slots;       // [n]
   const int* tok_base;    // [n] first packed row of this stream
   const int* T;           // [n] new tokens of this stream
-  const bf162* rope;      // [max_pos][HD/2] (cos, sin) bf16-rounded like HF (cos/sin cast to the model dtype)
   int H;                  // q heads
   float scale_log2;       // HD^-0.5 * log2(e)
 };
@@ -93,28 +99,73 @@ __device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, int src_
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Shared-memory bytes of chunk_attention_kernel<HD, *, NW>: [Q staging | rotated K] (aliased) + 2 raw (K, V) stages.
-template <int HD, int NW>
-constexpr int chunk_attn_smem_bytes() {
-  return ((NW * 16 > 64 ? NW * 16 : 64) + 4 * 64) * (HD + 8) * 2;
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
-// One CTA = NW warps x 16 query rows, walking the keys in 64-key tiles.  Raw (un-rotated) K and V tiles
-// stream global -> shared memory with cp.async through two stages, so the next tile is in flight while the
-// current one is rotated (cooperative pass: raw K -> rotated K, window-relative positions) and consumed by
-// the tensor cores.  2 CTAs per SM (HD 128) keep a second pipeline running on the same SM.
+// ----------------------------------------------------------------------------------------------
+// (cos, sin) of absolute positions, fp64 angle reduced mod 2 pi.
+//   LLM (ENC = false): token i of batch entry b sits at logical index kv_len[b] + i; ring table at
+//     kv_len + i + evicted (absolute), sys table at kv_len + i (reference position, see header).
+//   ENC: frame i of batch entry b sits at absolute frame prefix[b] + i.
+// ----------------------------------------------------------------------------------------------
+template <bool ENC>
+__global__ void rope_table_kernel(float2* __restrict__ tab_ring, float2* __restrict__ tab_sys,
+                                  const int* __restrict__ tok_base, const int* __restrict__ Tn,
+                                  const int* __restrict__ base_pos, const int* __restrict__ evicted,
+                                  const int* __restrict__ active, const float* __restrict__ inv_freq, int n_freq,
+                                  int T_fixed) {
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;
+  const int T = ENC ? T_fixed : Tn[b];
+  const int row0 = ENC ? b * T_fixed : tok_base[b];
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * n_freq; u += gridDim.x * blockDim.x) {
+    const int i = u / n_freq, d = u % n_freq;
+    const double f = static_cast<double>(inv_freq[d]);
+    const long long a_sys = static_cast<long long>(base_pos[b]) + i;
+    const long long a_ring = a_sys + (ENC ? 0 : evicted[b]);
+    double ang = static_cast<double>(a_ring) * f;
+    ang -= two_pi * floor(ang / two_pi);
+    float sn, cs;
+    sincosf(static_cast<float>(ang), &sn, &cs);
+    tab_ring[static_cast<size_t>(row0 + i) * n_freq + d] = make_float2(cs, sn);
+    if (!ENC) {
+      double as = static_cast<double>(a_sys) * f;
+      as -= two_pi * floor(as / two_pi);
+      sincosf(static_cast<float>(as), &sn, &cs);
+      tab_sys[static_cast<size_t>(row0 + i) * n_freq + d] = make_float2(cs, sn);
+    }
+  }
+}
+
+// Shared-memory bytes of chunk_attention_kernel<HD, *, NW>: Q staging + 2 (K, V) stages.
+template <int HD, int NW>
+constexpr int chunk_attn_smem_bytes() {
+  return (NW * 16 + 4 * 64) * (HD + 8) * 2;
+}
+
+// One CTA = NW warps x 16 query rows, walking the keys in 64-key tiles.  K (already rotated) and V tiles
+// stream global -> shared memory with cp.async through two stages, so the next tile is in flight while
+// the current one is consumed by the tensor cores; 2+ CTAs per SM keep further pipelines running.
+// LLM: the pinned system-prompt keys [0, sys_len) are visited first with the q_sys query variant, then the
+// query fragments are reloaded from the ring variant for the sliding part (see the header).
 template <int HD, bool ENC, int NW>
 __global__ void __launch_bounds__(NW * 32)
 chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   constexpr int KT = 64;             // keys per tile
   constexpr int LDS = HD + 8;        // padded smem row (elements)
   constexpr int NTHREADS = NW * 32;
-  constexpr int QROWS = NW * 16 > KT ? NW * 16 : KT;
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(attn_smem);            // [NW*16][LDS] rotated queries (start only)
-  bf16* sK = sQ;                                            // [KT][LDS] rotated keys of the current tile (aliases sQ)
-  bf16* sRaw = sQ + QROWS * LDS;                            // [2 stages][K | V][KT][LDS] raw tiles
+  bf16* sQ = reinterpret_cast<bf16*>(attn_smem);            // [NW*16][LDS] queries of the current variant
+  bf16* sRaw = sQ + NW * 16 * LDS;                          // [2 stages][K | V][KT][LDS]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -133,8 +184,7 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     L = kept + T;
     n_rows = T;
     tok0 = b * T;
-    // ring slot of window index 0: frame f lives in slot f % cap
-    ring0 = (prefix - kept) % ep.cap;
+    ring0 = (prefix - kept) % ep.cap;   // ring slot of window index 0: frame f lives in slot f % cap
   } else {
     slot = lp.slots[b];
     T = lp.T[b];
@@ -142,7 +192,7 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     group = lp.H / lp.kv.kv_heads;
     n_rows = group * T;
     L = lp.kv.kv_len[slot] + T;
-    sys_len = lp.kv.sys_len[slot];
+    sys_len = min(lp.kv.sys_len[slot], L);
     ring_start = lp.kv.ring_start[slot];
     table = lp.kv.page_table + static_cast<size_t>(slot) * lp.kv.pages_per_stream;
   }
@@ -157,17 +207,23 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     const int i_hi = (row0 / T == rmax / T) ? (rmax % T) : (T - 1);
     key_end = L - T + i_hi + 1;
   }
-  const int n_tiles = (key_end + KT - 1) / KT;
+  // tile list: [0, sys_end) in 64-key tiles (query variant q_sys), then [sys_end, key_end)
+  const int sys_end = ENC ? 0 : min(sys_len, key_end);
+  const int n_sys_tiles = (sys_end + KT - 1) / KT;
+  const int n_tiles = n_sys_tiles + (key_end - sys_end + KT - 1) / KT;
+  auto tile_k0 = [&](int t) { return t < n_sys_tiles ? t * KT : sys_end + (t - n_sys_tiles) * KT; };
+  auto tile_k1 = [&](int t) { return t < n_sys_tiles ? min(sys_end, t * KT + KT) : min(key_end, sys_end + (t - n_sys_tiles + 1) * KT); };
 
-  // ---- raw tile loader (cp.async, zero fill beyond L) ----
+  // ---- tile loader (cp.async, zero fill beyond the tile's key range) ----
   auto load_tile = [&](int t, int stage) {
     constexpr int CH = HD / 8;
     bf16* dK = sRaw + stage * 2 * KT * LDS;
     bf16* dV = dK + KT * LDS;
+    const int k0 = tile_k0(t), k1 = tile_k1(t);
     for (int u = tid; u < KT * CH; u += NTHREADS) {
       const int kl = u / CH, c = u % CH;
-      const int j = t * KT + kl;
-      const bool ok = j < L;
+      const int j = k0 + kl;
+      const bool ok = j < k1;
       const bf16* ks;
       const bf16* vs;
       if (ENC) {
@@ -184,65 +240,31 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
       cpa16(dV + kl * LDS + c * 8, vs, ok ? 16 : 0);
     }
   };
-  load_tile(0, 0);
+  if (n_tiles > 0) load_tile(0, 0);
   cpa_commit();
 
-  // ---- stage rotated Q: rows r = hq * T + i ----
-  {
-    constexpr int CH = HD / 8;                 // 16-byte chunks per row
-    constexpr int UNITS = ENC ? CH : CH / 2;   // LLM handles chunk c together with c + CH/2
-    for (int u = tid; u < NW * 16 * UNITS; u += NTHREADS) {
-      const int rl = u / UNITS, c = u % UNITS;
+  // ---- query staging: rows r = hq * T + i ----
+  auto stage_q = [&](bool sys_variant) {
+    constexpr int CH = HD / 8;
+    for (int u = tid; u < NW * 16 * CH; u += NTHREADS) {
+      const int rl = u / CH, c = u % CH;
       const int r = row0 + rl;
-      bf16* dst = sQ + rl * LDS;
-      if (r >= n_rows) {
-        *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
-        if (!ENC) *reinterpret_cast<uint4*>(dst + (c + CH / 2) * 8) = make_uint4(0, 0, 0, 0);
-        continue;
-      }
-      if (ENC) {
-        const int i = r;
-        const bf16* src = ep.qkv + static_cast<size_t>(tok0 + i) * (3 * ep.H * HD) + head * HD + c * 8;
-        uint4 raw = *reinterpret_cast<const uint4*>(src);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        const int pos = kept + i;
-        const float* cs = ep.rope_cos + static_cast<size_t>(pos) * (HD / 2) + c * 4;
-        const float* sn = ep.rope_sin + static_cast<size_t>(pos) * (HD / 2) + c * 4;
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 x = unpack_bf16(w[j]);
-          o[j] = pack_bf16(x.x * cs[j] - x.y * sn[j], x.y * cs[j] + x.x * sn[j]);
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (r < n_rows) {
+        if (ENC) {
+          val = *reinterpret_cast<const uint4*>(ep.qkv + static_cast<size_t>(tok0 + r) * (3 * ep.H * HD) + head * HD + c * 8);
+        } else {
+          const int hq = r / T, i = r % T;
+          const int qh = head * group + hq;
+          if (sys_variant) val = *reinterpret_cast<const uint4*>(lp.q_sys + static_cast<size_t>(tok0 + i) * (lp.H * HD) + qh * HD + c * 8);
+          else val = *reinterpret_cast<const uint4*>(lp.qkv + static_cast<size_t>(tok0 + i) * ((lp.H + 2 * lp.kv.kv_heads) * HD) + qh * HD + c * 8);
         }
-        *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-      } else {
-        const int hq = r / T, i = r % T;
-        const int qh = head * group + hq;
-        const int ldq = (lp.H + 2 * lp.kv.kv_heads) * HD;
-        const bf16* src = lp.qkv + static_cast<size_t>(tok0 + i) * ldq + qh * HD;
-        uint4 lo = *reinterpret_cast<const uint4*>(src + c * 8);
-        uint4 hi = *reinterpret_cast<const uint4*>(src + (c + CH / 2) * 8);
-        const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
-        const int pos = L - T + i;
-        const bf162* rp = lp.rope + static_cast<size_t>(pos) * (HD / 2) + c * 8;
-        uint32_t ol[4], oh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 a = unpack_bf16(wl[j]), bb = unpack_bf16(wh[j]);
-          float2 cs0 = __bfloat1622float2(rp[2 * j]), cs1 = __bfloat1622float2(rp[2 * j + 1]);
-          ol[j] = pack_bf16(a.x * cs0.x - bb.x * cs0.y, a.y * cs1.x - bb.y * cs1.y);
-          oh[j] = pack_bf16(bb.x * cs0.x + a.x * cs0.y, bb.y * cs1.x + a.y * cs1.y);
-        }
-        *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-        *reinterpret_cast<uint4*>(dst + (c + CH / 2) * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
       }
+      *reinterpret_cast<uint4*>(sQ + rl * LDS + c * 8) = val;
     }
-  }
-  __syncthreads();
-
-  // ---- Q fragments (A operand) ----
+  };
   uint32_t qf[HD / 16][4];
-  {
+  auto load_qf = [&]() {
     const bf16* q0 = sQ + (warp * 16 + g) * LDS;
     const bf16* q1 = q0 + 8 * LDS;
 #pragma unroll
@@ -252,7 +274,11 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
       qf[kk][2] = *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + 2 * t4);
       qf[kk][3] = *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + 2 * t4);
     }
-  }
+  };
+  stage_q(n_sys_tiles > 0);
+  __syncthreads();
+  load_qf();
+
   float o_acc[HD / 8][4];
 #pragma unroll
   for (int n = 0; n < HD / 8; ++n) { o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f; }
@@ -281,72 +307,42 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   const bool warp_live = row0 + warp * 16 < n_rows;
 
   for (int t = 0; t < n_tiles; ++t) {
-    const int k0 = t * KT;
+    const int k0 = tile_k0(t);
+    if (!ENC && t == n_sys_tiles && n_sys_tiles > 0) {
+      // switch from the system-prompt segment to the sliding segment: reload the ring query variant
+      __syncthreads();
+      stage_q(false);
+      __syncthreads();
+      load_qf();
+    }
     cpa_wait<0>();
-    __syncthreads();   // raw tile t landed; every warp is done with rotated tile t-1 (and with the Q staging)
+    __syncthreads();   // tile t landed; every warp is done with tile t-1
     if (t + 1 < n_tiles) load_tile(t + 1, (t + 1) & 1);
     cpa_commit();
-    const bf16* rK = sRaw + (t & 1) * 2 * KT * LDS;
-    const bf16* sV = rK + KT * LDS;
-    // ---- rotate raw K -> sK (window-relative positions: key j of the window sits at position j) ----
-    {
-      constexpr int CH = HD / 8;
-      constexpr int UNITS = ENC ? CH : CH / 2;
-      for (int u = tid; u < KT * UNITS; u += NTHREADS) {
-        const int kl = u / UNITS, c = u % UNITS;
-        const int j = min(k0 + kl, L - 1);            // rows beyond L are zero: any valid table row will do
-        const bf16* src = rK + kl * LDS;
-        bf16* dst = sK + kl * LDS;
-        if (ENC) {
-          uint4 raw = *reinterpret_cast<const uint4*>(src + c * 8);
-          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-          const float4 cs = *reinterpret_cast<const float4*>(ep.rope_cos + static_cast<size_t>(j) * (HD / 2) + c * 4);
-          const float4 sn = *reinterpret_cast<const float4*>(ep.rope_sin + static_cast<size_t>(j) * (HD / 2) + c * 4);
-          const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 x = unpack_bf16(w[q]);
-            o[q] = pack_bf16(x.x * cc[q] - x.y * ss[q], x.y * cc[q] + x.x * ss[q]);
-          }
-          *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-          uint4 lo = *reinterpret_cast<const uint4*>(src + c * 8);
-          uint4 hi = *reinterpret_cast<const uint4*>(src + (c + CH / 2) * 8);
-          const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
-          const uint4* rp4 = reinterpret_cast<const uint4*>(lp.rope + static_cast<size_t>(j) * (HD / 2) + c * 8);
-          const uint4 r0 = __ldg(rp4), r1 = __ldg(rp4 + 1);
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          uint32_t ol[4], oh[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 a = unpack_bf16(wl[q]), bb = unpack_bf16(wh[q]);
-            float2 cs0 = unpack_bf16(rr[2 * q]), cs1 = unpack_bf16(rr[2 * q + 1]);
-            ol[q] = pack_bf16(a.x * cs0.x - bb.x * cs0.y, a.y * cs1.x - bb.y * cs1.y);
-            oh[q] = pack_bf16(bb.x * cs0.x + a.x * cs0.y, bb.y * cs1.x + a.y * cs1.y);
-          }
-          *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-          *reinterpret_cast<uint4*>(dst + (c + CH / 2) * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-        }
-      }
-    }
-    __syncthreads();
-    if (!warp_live) continue;   // warp has no valid rows (still took part in staging)
+    if (!warp_live) continue;   // warp has no valid rows (still takes part in loading)
+    const bf16* sK = sRaw + (t & 1) * 2 * KT * LDS;
+    const bf16* sV = sK + KT * LDS;
 
     // ---- S = Q K^T ----
     float s[KT / 8][4];
 #pragma unroll
-    for (int n = 0; n < KT / 8; ++n) {
-      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-      const bf16* kr = sK + (n * 8 + g) * LDS + 2 * t4;
+    for (int n = 0; n < KT / 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+    {
+      // ldmatrix.x4 over a 16-key x 16-dim block: (keys 0-7, lo) (keys 0-7, hi) (keys 8-15, lo) (keys 8-15, hi)
+      const bf16* krow = sK + (((lane >> 4) << 3) + (lane & 7)) * LDS + (((lane >> 3) & 1) << 3);
 #pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kk * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8);
-        mma_bf16_16816(s[n], qf[kk], b0, b1);
+      for (int n2 = 0; n2 < KT / 16; ++n2) {
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          uint32_t kf[4];
+          ldsm_x4(kf, krow + n2 * 16 * LDS + kk * 16);
+          mma_bf16_16816(s[2 * n2], qf[kk], kf[0], kf[1]);
+          mma_bf16_16816(s[2 * n2 + 1], qf[kk], kf[2], kf[3]);
+        }
       }
     }
     // ---- mask + online softmax (rows g, g+8; cols n*8 + 2*t4 + {0,1}) ----
+    const int k1 = tile_k1(t);
     float mx[2] = {m_run[0], m_run[1]};
 #pragma unroll
     for (int n = 0; n < KT / 8; ++n) {
@@ -354,8 +350,7 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
       for (int e = 0; e < 4; ++e) {
         const int h = e >> 1;
         const int j = k0 + n * 8 + 2 * t4 + (e & 1);
-        const bool ok = (j >= qlo[h]) && (j < qhi[h]);
-        // the reference forms scores in the model dtype before the fp32 softmax (patch_speech_encoder.py:853-890)
+        const bool ok = (j >= qlo[h]) && (j < qhi[h]) && (j < k1);
         s[n][e] = ok ? s[n][e] * sl2 : -INFINITY;
         mx[h] = fmaxf(mx[h], s[n][e]);
       }
@@ -392,15 +387,20 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     }
     l_run[0] += ls[0];
     l_run[1] += ls[1];
-    // ---- O += P V ----
+    // ---- O += P V : ldmatrix.x4.trans over a 16-key x 16-dim block of V ----
+    {
+      // matrices (keys 0-7, dims lo) (keys 8-15, dims lo) (keys 0-7, dims hi) (keys 8-15, dims hi)
+      // = B fragments (b0, b1) of the dim-lo n-tile and (b0, b1) of the dim-hi n-tile
+      const bf16* vrow = sV + ((((lane >> 3) & 1) << 3) + (lane & 7)) * LDS + ((lane >> 4) << 3);
 #pragma unroll
-    for (int kk = 0; kk < KT / 16; ++kk) {
-      const bf16* vrow = sV + (kk * 16 + (lane & 15)) * LDS;
+      for (int kk = 0; kk < KT / 16; ++kk) {
 #pragma unroll
-      for (int n = 0; n < HD / 8; ++n) {
-        uint32_t b0, b1;
-        ldmatrix_x2_trans(b0, b1, vrow + n * 8);
-        mma_bf16_16816(o_acc[n], pf[kk], b0, b1);
+        for (int n2 = 0; n2 < HD / 16; ++n2) {
+          uint32_t vf[4];
+          ldsm_x4_trans(vf, vrow + kk * 16 * LDS + n2 * 16);
+          mma_bf16_16816(o_acc[2 * n2], pf[kk], vf[0], vf[1]);
+          mma_bf16_16816(o_acc[2 * n2 + 1], pf[kk], vf[2], vf[3]);
+        }
       }
     }
   }
@@ -431,11 +431,13 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Encoder KV ring append: K/V of the T new frames -> slots (prefix + i) % cap.  (patch_speech_encoder.py:797-821)
+// Encoder: rotate q in place and append rotated K / plain V of the T new frames to the ring slots
+// (prefix + i) % cap.  Interleaved-pair RoPE (rotary_embedding_torch, patch_speech_encoder.py:823-824) at
+// the absolute frame index; `tab` = rope_table_kernel<true> output [n*T][HD/2] (cos, sin).
 // ----------------------------------------------------------------------------------------------
-__global__ void enc_kv_append_kernel(const bf16* __restrict__ qkv, bf16* k_ring, bf16* v_ring,
-                                     const int* __restrict__ slots, const int* __restrict__ prefix, int T, int H,
-                                     int HD, int cap) {
+__global__ void enc_rope_append_kernel(bf16* __restrict__ qkv, bf16* k_ring, bf16* v_ring,
+                                       const int* __restrict__ slots, const int* __restrict__ prefix,
+                                       const float2* __restrict__ tab, int T, int H, int HD, int cap) {
   const int b = blockIdx.y;
   const int slot = slots[b];
   const int pre = prefix[b];   // per batch entry
@@ -443,192 +445,100 @@ __global__ void enc_kv_append_kernel(const bf16* __restrict__ qkv, bf16* k_ring,
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * chunks; u += gridDim.x * blockDim.x) {
     const int i = u / chunks, c = u % chunks;
     const int head = (c * 8) / HD, d = (c * 8) % HD;
-    const bf16* src = qkv + static_cast<size_t>(b * T + i) * (3 * H * HD);
+    bf16* row = qkv + static_cast<size_t>(b * T + i) * (3 * H * HD);
+    const float2* cs = tab + static_cast<size_t>(b * T + i) * (HD / 2) + d / 2;
+    const float2 c0 = cs[0], c1 = cs[1], c2 = cs[2], c3 = cs[3];
+    const float cc[4] = {c0.x, c1.x, c2.x, c3.x}, ss[4] = {c0.y, c1.y, c2.y, c3.y};
+    uint4 q = *reinterpret_cast<const uint4*>(row + c * 8);
+    uint4 k = *reinterpret_cast<const uint4*>(row + H * HD + c * 8);
+    uint32_t qw[4] = {q.x, q.y, q.z, q.w}, kw[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 x = unpack_bf16(qw[j]);
+      qw[j] = pack_bf16(x.x * cc[j] - x.y * ss[j], x.y * cc[j] + x.x * ss[j]);
+      x = unpack_bf16(kw[j]);
+      kw[j] = pack_bf16(x.x * cc[j] - x.y * ss[j], x.y * cc[j] + x.x * ss[j]);
+    }
+    *reinterpret_cast<uint4*>(row + c * 8) = make_uint4(qw[0], qw[1], qw[2], qw[3]);
     const size_t dst = ((static_cast<size_t>(slot) * H + head) * cap + (pre + i) % cap) * HD + d;
-    *reinterpret_cast<uint4*>(k_ring + dst) = *reinterpret_cast<const uint4*>(src + H * HD + c * 8);
-    *reinterpret_cast<uint4*>(v_ring + dst) = *reinterpret_cast<const uint4*>(src + 2 * H * HD + c * 8);
+    *reinterpret_cast<uint4*>(k_ring + dst) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+    *reinterpret_cast<uint4*>(v_ring + dst) = *reinterpret_cast<const uint4*>(row + 2 * H * HD + c * 8);
   }
 }
 
 // ----------------------------------------------------------------------------------------------
-// LLM paged KV append (un-rotated K, V) for packed new tokens.  (patch_llm.py:280-284)
-// active[b] == 0 -> stream finished (EOS): nothing is appended.
+// LLM: rotate the q heads in place (ring variant), write the q_sys variant, and append rotated K and
+// plain V of the packed new tokens to the paged cache.  Half-split RoPE (HF apply_rotary_pos_emb,
+// patch_llm.py:294-299).  active[b] == 0 -> stream finished (EOS): nothing is appended.
+// One unit = 8 elements d..d+7 of the first half of a head together with d+64..d+71.
 // ----------------------------------------------------------------------------------------------
-__global__ void llm_kv_append_kernel(const bf16* __restrict__ qkv, PagedKV kv, const int* __restrict__ slots,
-                                     const int* __restrict__ tok_base, const int* __restrict__ Tn,
-                                     const int* __restrict__ active, int H) {
+__global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ q_sys, PagedKV kv,
+                                       const int* __restrict__ slots, const int* __restrict__ tok_base,
+                                       const int* __restrict__ Tn, const int* __restrict__ active,
+                                       const float2* __restrict__ tab_ring, const float2* __restrict__ tab_sys, int H) {
   const int b = blockIdx.y;
   if (active && !active[b]) return;
   const int slot = slots[b];
   const int T = Tn[b];
-  const int HD = kv.head_dim;
-  const int chunks = kv.kv_heads * HD / 8;
+  const int HD = kv.head_dim, HALF = HD / 2;
+  const int upr = HALF / 8;                              // units per head
+  const int heads_all = H + 2 * kv.kv_heads;
   const int base = kv.kv_len[slot];
   const int sys_len = kv.sys_len[slot], ring_start = kv.ring_start[slot];
   const int* table = kv.page_table + static_cast<size_t>(slot) * kv.pages_per_stream;
-  const int ldq = (H + 2 * kv.kv_heads) * HD;
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * chunks; u += gridDim.x * blockDim.x) {
-    const int i = u / chunks, c = u % chunks;
-    const int head = (c * 8) / HD, d = (c * 8) % HD;
-    const bf16* src = qkv + static_cast<size_t>(tok_base[b] + i) * ldq + H * HD;
+  const int ldq = heads_all * HD;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * heads_all * upr; u += gridDim.x * blockDim.x) {
+    const int i = u / (heads_all * upr);
+    const int hh = (u / upr) % heads_all;                // 0..H-1 q, H..H+Hkv-1 k, then v
+    const int d = (u % upr) * 8;
+    const int rowi = tok_base[b] + i;
+    bf16* src = qkv + static_cast<size_t>(rowi) * ldq + hh * HD;
+    uint4 lo = *reinterpret_cast<const uint4*>(src + d);
+    uint4 hi = *reinterpret_cast<const uint4*>(src + d + HALF);
     const int sl = kv_slot(base + i, sys_len, ring_start);
-    *reinterpret_cast<uint4*>(kv.pool + kv_offset(kv, table, sl, 0, head) + d) =
-        *reinterpret_cast<const uint4*>(src + c * 8);
-    *reinterpret_cast<uint4*>(kv.pool + kv_offset(kv, table, sl, 1, head) + d) =
-        *reinterpret_cast<const uint4*>(src + kv.kv_heads * HD + c * 8);
+    if (hh >= H + kv.kv_heads) {                         // V: plain copy
+      bf16* dst = kv.pool + kv_offset(kv, table, sl, 1, hh - H - kv.kv_heads);
+      *reinterpret_cast<uint4*>(dst + d) = lo;
+      *reinterpret_cast<uint4*>(dst + d + HALF) = hi;
+      continue;
+    }
+    const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
+    // keys of the pinned prefix keep absolute index == reference position (sys table); everything else
+    // (ring keys, ring-variant queries) sits at logical index + evicted (ring table)
+    const bool sys_key = hh >= H && base + i < sys_len;
+    const float2* cr = (sys_key ? tab_sys : tab_ring) + static_cast<size_t>(rowi) * HALF + d;
+    uint32_t ol[4], oh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16(wl[j]), bb = unpack_bf16(wh[j]);
+      const float2 c0 = cr[2 * j], c1 = cr[2 * j + 1];
+      ol[j] = pack_bf16(a.x * c0.x - bb.x * c0.y, a.y * c1.x - bb.y * c1.y);
+      oh[j] = pack_bf16(bb.x * c0.x + a.x * c0.y, bb.y * c1.x + a.y * c1.y);
+    }
+    if (hh < H) {                                        // q: in place (ring variant) + sys variant
+      *reinterpret_cast<uint4*>(src + d) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      *reinterpret_cast<uint4*>(src + d + HALF) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      const float2* cs = tab_sys + static_cast<size_t>(rowi) * HALF + d;
+      uint32_t sl_[4], sh_[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(wl[j]), bb = unpack_bf16(wh[j]);
+        const float2 c0 = cs[2 * j], c1 = cs[2 * j + 1];
+        sl_[j] = pack_bf16(a.x * c0.x - bb.x * c0.y, a.y * c1.x - bb.y * c1.y);
+        sh_[j] = pack_bf16(bb.x * c0.x + a.x * c0.y, bb.y * c1.x + a.y * c1.y);
+      }
+      bf16* qs = q_sys + static_cast<size_t>(rowi) * (H * HD) + hh * HD;
+      *reinterpret_cast<uint4*>(qs + d) = make_uint4(sl_[0], sl_[1], sl_[2], sl_[3]);
+      *reinterpret_cast<uint4*>(qs + d + HALF) = make_uint4(sh_[0], sh_[1], sh_[2], sh_[3]);
+    } else {                                             // k: rotated into the page
+      bf16* dst = kv.pool + kv_offset(kv, table, sl, 0, hh - H);
+      *reinterpret_cast<uint4*>(dst + d) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      *reinterpret_cast<uint4*>(dst + d + HALF) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    }
   }
 }
 
-// ----------------------------------------------------------------------------------------------
-// Decode attention (T = 1), split along the key axis.  One CTA = (split, kv_head, stream), 4 warps;
-// each warp owns whole keys: 16 lanes... layout: a key's 128 elements are covered by 16 lanes x
-// (4 + 4) elements (the half-split RoPE pair d / d+64 lives in the same lane), two keys per warp pass.
-// Partial (m, l, o[HD]) per (stream, q head, split) -> decode_combine_kernel.
-// Algorithmic bytes: 2 * L * Hkv * HD * 2 B per layer per stream.
-// ----------------------------------------------------------------------------------------------
-struct DecodeParams {
-  const bf16* qkv;        // [n, (H + 2 Hkv) * HD] : the single new token of each stream (already appended to KV)
-  PagedKV kv;             // kv_len = length BEFORE this token
-  const int* slots;
-  const bf162* rope;
-  float* part_o;          // [n][H][splits][HD]
-  float* part_ml;         // [n][H][splits][2]
-  int H;
-  int splits;
-  float scale_log2;
-};
-
-template <int HD, int GROUP>
-__global__ void __launch_bounds__(128)
-decode_attention_kernel(const DecodeParams p) {
-  static_assert(HD == 128, "decode kernel is specialised for head_dim 128");
-  const int split = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sub = lane >> 4;        // which of the two keys of this warp pass
-  const int l16 = lane & 15;        // owns elements [4*l16, 4*l16+4) and [64 + 4*l16, 64 + 4*l16 + 4)
-  const int slot = p.slots[b];
-  const int L = p.kv.kv_len[slot] + 1;
-  const int sys_len = p.kv.sys_len[slot], ring_start = p.kv.ring_start[slot];
-  const int* table = p.kv.page_table + static_cast<size_t>(slot) * p.kv.pages_per_stream;
-  const int per = (L + p.splits - 1) / p.splits;
-  const int j0 = split * per, j1 = min(L, j0 + per);
-
-  // rotated queries of the GROUP q heads sharing this kv head (position L-1), pre-multiplied by scale*log2e
-  float q[GROUP][8];
-  {
-    const int ldq = (p.H + 2 * p.kv.kv_heads) * HD;
-    const bf162* rp = p.rope + static_cast<size_t>(L - 1) * (HD / 2) + 4 * l16;
-#pragma unroll
-    for (int hq = 0; hq < GROUP; ++hq) {
-      const bf16* src = p.qkv + static_cast<size_t>(b) * ldq + (head * GROUP + hq) * HD;
-      uint2 lo = *reinterpret_cast<const uint2*>(src + 4 * l16);
-      uint2 hi = *reinterpret_cast<const uint2*>(src + 64 + 4 * l16);
-      const uint32_t wl[2] = {lo.x, lo.y}, wh[2] = {hi.x, hi.y};
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float2 a = unpack_bf16(wl[j]), bb = unpack_bf16(wh[j]);
-        float2 c0 = __bfloat1622float2(rp[2 * j]), c1 = __bfloat1622float2(rp[2 * j + 1]);
-        // HF rounds the rotated q to bf16 (apply_rotary_pos_emb in the model dtype)
-        q[hq][2 * j] = bf16_round(a.x * c0.x - bb.x * c0.y) * p.scale_log2;
-        q[hq][2 * j + 1] = bf16_round(a.y * c1.x - bb.y * c1.y) * p.scale_log2;
-        q[hq][4 + 2 * j] = bf16_round(bb.x * c0.x + a.x * c0.y) * p.scale_log2;
-        q[hq][4 + 2 * j + 1] = bf16_round(bb.y * c1.x + a.y * c1.y) * p.scale_log2;
-      }
-    }
-  }
-  float m[GROUP], l[GROUP], o[GROUP][8];
-#pragma unroll
-  for (int hq = 0; hq < GROUP; ++hq) {
-    m[hq] = -INFINITY; l[hq] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[hq][e] = 0.f;
-  }
-  // each warp pass handles 2 keys; 4 warps -> 8 keys per CTA iteration
-  for (int jb = j0 + warp * 2; jb < j1; jb += 8) {   // warp-uniform trip count (full-mask shuffles below)
-    const int j = jb + sub;
-    const bool valid = j < j1;
-    float kr[8], vv[8];
-    if (valid) {
-      const int sl = kv_slot(j, sys_len, ring_start);
-      const bf16* kp = p.kv.pool + kv_offset(p.kv, table, sl, 0, head);
-      const bf16* vp = p.kv.pool + kv_offset(p.kv, table, sl, 1, head);
-      uint2 klo = ld_nc_u2(kp + 4 * l16), khi = ld_nc_u2(kp + 64 + 4 * l16);
-      uint2 vlo = ld_nc_u2(vp + 4 * l16), vhi = ld_nc_u2(vp + 64 + 4 * l16);
-      const bf162* rp = p.rope + static_cast<size_t>(j) * (HD / 2) + 4 * l16;
-      const uint32_t wl[2] = {klo.x, klo.y}, wh[2] = {khi.x, khi.y};
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float2 a = unpack_bf16(wl[e]), bb = unpack_bf16(wh[e]);
-        float2 c0 = __bfloat1622float2(rp[2 * e]), c1 = __bfloat1622float2(rp[2 * e + 1]);
-        kr[2 * e] = a.x * c0.x - bb.x * c0.y;
-        kr[2 * e + 1] = a.y * c1.x - bb.y * c1.y;
-        kr[4 + 2 * e] = bb.x * c0.x + a.x * c0.y;
-        kr[4 + 2 * e + 1] = bb.y * c1.x + a.y * c1.y;
-      }
-      float2 f;
-      f = unpack_bf16(vlo.x); vv[0] = f.x; vv[1] = f.y;
-      f = unpack_bf16(vlo.y); vv[2] = f.x; vv[3] = f.y;
-      f = unpack_bf16(vhi.x); vv[4] = f.x; vv[5] = f.y;
-      f = unpack_bf16(vhi.y); vv[6] = f.x; vv[7] = f.y;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { kr[e] = 0.f; vv[e] = 0.f; }
-    }
-#pragma unroll
-    for (int hq = 0; hq < GROUP; ++hq) {
-      float s = 0.f;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s += q[hq][e] * kr[e];
-      // reduce over the 16 lanes of this key
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if (!valid) s = -INFINITY;
-      const float mn = fmaxf(m[hq], s);
-      const float ms = (mn == -INFINITY) ? 0.f : mn;
-      const float corr = (m[hq] == -INFINITY) ? 0.f : exp2f(m[hq] - ms);
-      const float pe = exp2f(s - ms);
-      m[hq] = mn;
-      l[hq] = l[hq] * corr + pe;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[hq][e] = o[hq][e] * corr + pe * vv[e];
-    }
-  }
-  // ---- merge the 8 (warp, sub) partial states of this CTA through shared memory ----
-  __shared__ float sm_m[GROUP][8], sm_l[GROUP][8];
-  __shared__ float sm_o[GROUP][8][HD];
-  const int ps = warp * 2 + sub;
-#pragma unroll
-  for (int hq = 0; hq < GROUP; ++hq) {
-    if (l16 == 0) { sm_m[hq][ps] = m[hq]; sm_l[hq][ps] = l[hq]; }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      sm_o[hq][ps][4 * l16 + e] = o[hq][e];
-      sm_o[hq][ps][64 + 4 * l16 + e] = o[hq][4 + e];
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < GROUP * HD; idx += 128) {
-    const int hq = idx / HD, d = idx % HD;
-    float mm = -INFINITY;
-#pragma unroll
-    for (int s8 = 0; s8 < 8; ++s8) mm = fmaxf(mm, sm_m[hq][s8]);
-    const float ms = (mm == -INFINITY) ? 0.f : mm;
-    float ll = 0.f, oo = 0.f;
-#pragma unroll
-    for (int s8 = 0; s8 < 8; ++s8) {
-      const float w = (sm_m[hq][s8] == -INFINITY) ? 0.f : exp2f(sm_m[hq][s8] - ms);
-      ll += w * sm_l[hq][s8];
-      oo += w * sm_o[hq][s8][d];
-    }
-    const size_t pidx = (static_cast<size_t>(b) * p.H + head * GROUP + hq) * p.splits + split;
-    p.part_o[pidx * HD + d] = oo;
-    if (d == 0) { p.part_ml[pidx * 2] = mm; p.part_ml[pidx * 2 + 1] = ll; }
-  }
-}
-
-// out[b, h, :] = sum_s w_s o_s / sum_s w_s l_s
+// out[b, h, :] = sum_s w_s o_s / sum_s w_s l_s  over the key splits of decode attention
 __global__ void decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                       bf16* __restrict__ out, int H, int HD, int splits) {
   const int bh = blockIdx.x;   // b * H + h

@@ -144,6 +144,7 @@ struct StreamHost {
   bool open = false;
   int enc_prefix = 0;               // W2V2RoPECache.n_steps
   int kv_len = 0, sys_len = 0, ring_start = 0;
+  long long evicted = 0;            // ring tokens dropped so far: absolute index of a ring token = logical index + evicted
   bool prefilled = false;
   std::vector<int> pages;           // page table entries (sys pages first, then ring pages)
 };
@@ -158,7 +159,6 @@ struct isst_ctx {
   int sm_count = 148;
   bool finalized = false;
   bool simple_gemm = false;
-  bool decode_v1 = false;   // ISST_DECODE=v1: CUDA-core validation kernel
   bool gemm_v1 = false;     // ISST_GEMM=v1: one-tile-per-CTA tcgen05 kernel (previous generation, kept for A/B runs)
   unsigned long long* gemm_dbg = nullptr;   // optional phase stamps of the last stream-K launch
   int64_t launches = 0;
@@ -181,11 +181,10 @@ struct isst_ctx {
   std::vector<EncLayerW> enc;
   std::vector<LlmLayerW> llm;
   bf16* embed = nullptr;
-  float *enc_rope_cos = nullptr, *enc_rope_sin = nullptr;
-  int enc_rope_npos = 0;
-  float *llm_rope_cos_f = nullptr, *llm_rope_sin_f = nullptr;
-  bf162* llm_rope = nullptr;
-  int llm_rope_npos = 0;
+  float *enc_inv_freq = nullptr, *llm_inv_freq = nullptr;          // RoPE frequencies (fp32, like the reference modules)
+  float2 *enc_rope_tab = nullptr, *llm_rope_ring = nullptr, *llm_rope_sys = nullptr;   // (cos, sin) of the new rows
+  bf16* lq_sys = nullptr;                                          // q rotated for the pinned prefix keys
+  int* d_evicted = nullptr;
   void* staging = nullptr;
   size_t staging_bytes = 0;
 
@@ -486,11 +485,6 @@ __global__ void cvt_conv0_kernel(const Src* __restrict__ src, float* __restrict_
     dst[kk * C + c] = bf16_round(static_cast<float>(src[i]));
   }
 }
-__global__ void build_llm_rope_kernel(const float* __restrict__ c, const float* __restrict__ s, bf162* out, long long n) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = __floats2bfloat162_rn(c[i], s[i]);
-}
 __global__ void fill_pattern_kernel(bf16* p, long long n, uint32_t seed) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -679,6 +673,13 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
   ISST_TRY(tap(ctx, st, "enc_post_proj", ctx->ex, static_cast<size_t>(M) * D * 2));
   // ---- 24 pre-LN layers (E4-E11) ----
   const int blocksize = c.block_size * multiplier;
+  {
+    // (cos, sin) of the absolute frame indices of this chunk: one table for all layers
+    ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (D / c.enc_heads / 2) * 8);
+    rope_table_kernel<true><<<dim3(ceil_div(frames * (D / c.enc_heads / 2), 256), n), 256, 0, st>>>(
+        ctx->enc_rope_tab, nullptr, nullptr, nullptr, d_prefix, nullptr, nullptr, ctx->enc_inv_freq, D / c.enc_heads / 2, frames);
+    LAUNCH_CHECK(ctx);
+  }
   for (int l = 0; l < c.enc_layers; ++l) {
     EncLayerW& w = ctx->enc[l];
     ISST_TRY(norm_rows(ctx, st, false, false, ctx->ex, ctx->eh, w.ln1_w, w.ln1_b, nullptr, M, D, 1e-5f));
@@ -692,13 +693,13 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(n) * frames * D * 2 * 4);
       dim3 grid(ceil_div(frames * D / 8, 256), n);
-      enc_kv_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, d_prefix, frames, H, HD, ctx->enc_cap);
+      enc_rope_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, d_prefix, ctx->enc_rope_tab, frames, H, HD, ctx->enc_cap);
       LAUNCH_CHECK(ctx);
     }
     {
       EncAttnParams ep{};
       ep.qkv = ctx->eqkv; ep.out = ctx->eattn; ep.k_ring = kr; ep.v_ring = vr; ep.slots = d_slots;
-      ep.prefix = d_prefix; ep.rope_cos = ctx->enc_rope_cos; ep.rope_sin = ctx->enc_rope_sin;
+      ep.prefix = d_prefix;
       ep.T = frames; ep.H = H; ep.cap = ctx->enc_cap; ep.max_cache = c.max_cache_size; ep.blocksize = blocksize;
       LlmAttnParams lp{};
       constexpr int NW = 4;
@@ -809,8 +810,8 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
     attr_set = true;
   }
   DecodeParams2 dp{};
-  dp.qkv = qkv; dp.kv = kv; dp.slots = d_slots; dp.rope_cos = ctx->llm_rope_cos_f; dp.rope_sin = ctx->llm_rope_sin_f;
-  dp.rope_tile = ctx->llm_rope; dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
+  dp.qkv = qkv; dp.q_sys = ctx->lq_sys; dp.kv = kv; dp.slots = d_slots;
+  dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
   dp.splits = splits; dp.scale_log2 = scale_log2;
   decode_attention_mma_kernel<4><<<dim3(splits, ctx->cfg.kv_heads, n), 128, kDecSmemBytes, st>>>(dp);
   LAUNCH_CHECK(ctx);
@@ -824,6 +825,14 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
   const int M = lb.M;
   const float scale_log2 = 1.4426950408889634f / std::sqrt(static_cast<float>(HD));
   ISST_CHECK(HD == 128 && H / Hkv == 4, "LLM attention kernels are built for head_dim 128 and 4:1 GQA");
+  {
+    // (cos, sin) of the new tokens' absolute / reference positions: one table pair for all layers
+    ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (HD / 2) * 16);
+    rope_table_kernel<false><<<dim3(ceil_div(lb.max_T * (HD / 2), 128), lb.n), 128, 0, st>>>(
+        ctx->llm_rope_ring, ctx->llm_rope_sys, lb.d_tok_base, lb.d_T, ctx->d_kv_len, ctx->d_evicted, lb.d_active,
+        ctx->llm_inv_freq, HD / 2, 0);
+    LAUNCH_CHECK(ctx);
+  }
   for (int l = 0; l < c.layers; ++l) {
     LlmLayerW& w = ctx->llm[l];
     ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms1, nullptr, nullptr, M, D, c.rms_eps));
@@ -833,15 +842,16 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
     }
     PagedKV kv = paged_kv(ctx, l);
     {
-      ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * Hkv * HD * 2 * 2 * 2);
-      dim3 grid(ceil_div(lb.max_T * Hkv * HD / 8, 128), lb.n);
-      llm_kv_append_kernel<<<grid, 128, 0, st>>>(ctx->lqkv, kv, lb.d_slots, lb.d_tok_base, lb.d_T, lb.d_active, H);
+      ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
+      dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
+      llm_rope_append_kernel<<<grid, 128, 0, st>>>(ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T, lb.d_active,
+                                                   ctx->llm_rope_ring, ctx->llm_rope_sys, H);
       LAUNCH_CHECK(ctx);
     }
     if (!lb.decode) {
       LlmAttnParams lp{};
-      lp.qkv = ctx->lqkv; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
-      lp.T = lb.d_T; lp.rope = ctx->llm_rope; lp.H = H; lp.scale_log2 = scale_log2;
+      lp.qkv = ctx->lqkv; lp.q_sys = ctx->lq_sys; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
+      lp.T = lb.d_T; lp.H = H; lp.scale_log2 = scale_log2;
       EncAttnParams ep{};
       constexpr int NW = 6;   // 96 query rows per CTA: the 4 x 22 rows of a steady-state turn in one CTA, 2 CTAs per SM
       ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
@@ -860,15 +870,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
       const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
-      if (ctx->decode_v1) {
-        DecodeParams dp{};
-        dp.qkv = ctx->lqkv; dp.kv = kv; dp.slots = lb.d_slots; dp.rope = ctx->llm_rope; dp.part_o = ctx->part_o;
-        dp.part_ml = ctx->part_ml; dp.H = H; dp.splits = splits; dp.scale_log2 = scale_log2;
-        decode_attention_kernel<128, 4><<<dim3(splits, Hkv, lb.n), 128, 0, st>>>(dp);
-        LAUNCH_CHECK(ctx);
-      } else {
-        ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2));
-      }
+      ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2));
       decode_combine_kernel<<<lb.n * H, 128, 0, st>>>(ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits);
       LAUNCH_CHECK(ctx);
     }
@@ -937,11 +939,15 @@ static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int
   int* h_len = h + static_cast<size_t>(ctx->cfg.max_batch) * pps;
   int* h_sys = h_len + ctx->cfg.max_batch;
   int* h_ring = h_sys + ctx->cfg.max_batch;
+  int* h_evi = h_ring + ctx->cfg.max_batch;
   for (int b = 0; b < n; ++b) {
     const StreamHost& s = ctx->streams[slots[b]];
     std::copy(s.pages.begin(), s.pages.end(), h + static_cast<size_t>(b) * pps);
     h_len[b] = s.kv_len; h_sys[b] = s.sys_len; h_ring[b] = s.ring_start;
+    ISST_CHECK(s.evicted + s.kv_len + 4096 < 2147483647LL, "stream exceeded 2^31 tokens");
+    h_evi[b] = static_cast<int>(s.evicted);
   }
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_evicted, h_evi, n * sizeof(int), cudaMemcpyHostToDevice, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->d_page_table, h, static_cast<size_t>(n) * pps * sizeof(int), cudaMemcpyHostToDevice, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->d_kv_len, h_len, n * sizeof(int), cudaMemcpyHostToDevice, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->d_sys_len, h_sys, n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -987,8 +993,6 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   const char* g = getenv("ISST_GEMM");
   ctx->simple_gemm = g && std::string(g) == "simple";
   ctx->gemm_v1 = g && std::string(g) == "v1";
-  const char* dv = getenv("ISST_DECODE");
-  ctx->decode_v1 = dv && std::string(dv) == "v1";
   const isst_config& c = ctx->cfg;
   ISST_CHECK(c.n_conv >= 2 && c.n_conv <= ISST_MAX_CONV && c.n_adapter >= 0 && c.n_adapter <= ISST_MAX_CONV, "bad conv config");
   ctx->C = c.conv_dim[0];
@@ -1044,13 +1048,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->final_norm, HID));
   ISST_TRY(alloc_w2d(ctx->lm_head, c.vocab, HID));
   ISST_TRY(dev_alloc(&ctx->embed, static_cast<size_t>(c.vocab) * HID));
-  ctx->enc_rope_npos = ctx->enc_cap;
-  ISST_TRY(dev_alloc(&ctx->enc_rope_cos, static_cast<size_t>(ctx->enc_rope_npos) * (D / c.enc_heads / 2)));
-  ISST_TRY(dev_alloc(&ctx->enc_rope_sin, static_cast<size_t>(ctx->enc_rope_npos) * (D / c.enc_heads / 2)));
-  ctx->llm_rope_npos = c.max_kv_len;
-  ISST_TRY(dev_alloc(&ctx->llm_rope_cos_f, static_cast<size_t>(c.max_kv_len) * (c.head_dim / 2)));
-  ISST_TRY(dev_alloc(&ctx->llm_rope_sin_f, static_cast<size_t>(c.max_kv_len) * (c.head_dim / 2)));
-  ISST_TRY(dev_alloc(&ctx->llm_rope, static_cast<size_t>(c.max_kv_len) * (c.head_dim / 2)));
+  ISST_TRY(dev_alloc(&ctx->enc_inv_freq, D / c.enc_heads / 2));
+  ISST_TRY(dev_alloc(&ctx->llm_inv_freq, c.head_dim / 2));
 
   // ---- stream state ----
   ctx->streams.resize(c.max_streams);
@@ -1062,6 +1061,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->d_page_table, static_cast<size_t>(c.max_streams) * ctx->pages_per_stream));
   ISST_TRY(dev_alloc(&ctx->d_kv_len, c.max_streams)); ISST_TRY(dev_alloc(&ctx->d_sys_len, c.max_streams));
   ISST_TRY(dev_alloc(&ctx->d_ring_start, c.max_streams));
+  ISST_TRY(dev_alloc(&ctx->d_evicted, c.max_streams));
+  ISST_CUDA(cudaMemset(ctx->d_evicted, 0, c.max_streams * sizeof(int)));
   ISST_CUDA(cudaMemset(ctx->d_page_table, 0, static_cast<size_t>(c.max_streams) * ctx->pages_per_stream * sizeof(int)));
   ISST_CUDA(cudaMemset(ctx->d_kv_len, 0, c.max_streams * sizeof(int)));
   ISST_CUDA(cudaMemset(ctx->d_sys_len, 0, c.max_streams * sizeof(int)));
@@ -1069,6 +1070,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_CUDA(cudaMemset(ctx->d_enc_prefix, 0, c.max_streams * sizeof(int)));
   ctx->kv_layer_elems = static_cast<size_t>(c.kv_pages) * 2 * c.kv_heads * kPageTokens * c.head_dim;
   ISST_TRY(dev_alloc(&ctx->kv_pool, ctx->kv_layer_elems * c.layers));
+  ISST_CUDA(cudaMemset(ctx->kv_pool, 0, ctx->kv_layer_elems * c.layers * sizeof(bf16)));   // masked rows must hold finite values
   for (int p = c.kv_pages - 1; p >= 0; --p) ctx->free_pages.push_back(p);
 
   // ---- workspaces ----
@@ -1090,6 +1092,10 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->lx, ML * HID)); ISST_TRY(dev_alloc(&ctx->lh, ML * HID)); ISST_TRY(dev_alloc(&ctx->lqkv, ML * QKV));
   ISST_TRY(dev_alloc(&ctx->lattn, ML * c.heads * c.head_dim)); ISST_TRY(dev_alloc(&ctx->lgu, ML * c.ffn));
   ISST_TRY(dev_alloc(&ctx->llast, static_cast<size_t>(nb) * HID));
+  ISST_TRY(dev_alloc(&ctx->lq_sys, ML * c.heads * c.head_dim));
+  ISST_TRY(dev_alloc(&ctx->llm_rope_ring, ML * (c.head_dim / 2)));
+  ISST_TRY(dev_alloc(&ctx->llm_rope_sys, ML * (c.head_dim / 2)));
+  ISST_TRY(dev_alloc(&ctx->enc_rope_tab, ME * (D / c.enc_heads / 2)));
   ISST_TRY(dev_alloc(&ctx->logits, static_cast<size_t>(nb) * c.vocab));
   ctx->decode_splits = 32;
   ISST_TRY(dev_alloc(&ctx->part_o, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * c.head_dim));
@@ -1103,7 +1109,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->d_meta, ctx->meta_ints));
   ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_meta), ctx->meta_ints * sizeof(int)));
   ISST_CUDA(cudaEventCreateWithFlags(&ctx->ev_active, cudaEventDisableTiming));
-  ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_tables), (static_cast<size_t>(nb) * (ctx->pages_per_stream + 3) + 16) * sizeof(int)));
+  ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_tables), (static_cast<size_t>(nb) * (ctx->pages_per_stream + 4) + 16) * sizeof(int)));
   ISST_CUDA(cudaDeviceSynchronize());
   *out = ctx;
   return 0;
@@ -1122,7 +1128,7 @@ void isst_destroy(isst_ctx* ctx) {
   for (auto& w : ctx->adapter) { cudaFree(w.w.ptr); cudaFree(w.ln_w); cudaFree(w.ln_b); }
   cudaFree(ctx->lm_head.ptr); cudaFree(ctx->post_proj.ptr); cudaFree(ctx->proj.ptr);
   void* misc[] = {ctx->feat_ln_w, ctx->feat_ln_b, ctx->post_b, ctx->enc_ln_w, ctx->enc_ln_b, ctx->proj_b, ctx->final_norm,
-                  ctx->enc_rope_cos, ctx->enc_rope_sin, ctx->llm_rope_cos_f, ctx->llm_rope_sin_f, ctx->llm_rope, ctx->staging,
+                  ctx->enc_inv_freq, ctx->llm_inv_freq, ctx->enc_rope_tab, ctx->llm_rope_ring, ctx->llm_rope_sys, ctx->lq_sys, ctx->d_evicted, ctx->staging,
                   ctx->tail, ctx->d_enc_prefix, ctx->d_page_table, ctx->d_kv_len, ctx->d_sys_len, ctx->d_ring_start,
                   ctx->d_pcm, ctx->conv_a, ctx->conv_b, ctx->ex, ctx->eh, ctx->eqkv, ctx->eattn, ctx->effn, ctx->ead0,
                   ctx->ead1, ctx->speech, ctx->lx, ctx->lh, ctx->lqkv, ctx->lattn, ctx->lgu, ctx->llast, ctx->logits,
@@ -1150,15 +1156,12 @@ int isst_load_weight(isst_ctx* ctx, const char* name_c, const void* data, const 
   auto done = [&]() { ctx->loaded[name] = true; return 0; };
 #define LM(dst, rows, cols) do { ISST_TRY(load_matrix(ctx, dst, rows, cols, data, shape, ndim, dtype)); return done(); } while (0)
 #define LV(dst, n) do { ISST_TRY(load_vector(ctx, dst, n, data, shape, ndim, dtype)); return done(); } while (0)
-  if (name == "rope.enc.cos" || name == "rope.enc.sin" || name == "rope.llm.cos" || name == "rope.llm.sin") {
+  if (name == "rope.enc.inv_freq" || name == "rope.llm.inv_freq") {
     const bool enc = name[5] == 'e';
     const int half = enc ? (D / c.enc_heads / 2) : HD / 2;
-    const int npos = enc ? ctx->enc_rope_npos : ctx->llm_rope_npos;
-    ISST_CHECK(ndim == 2 && shape[1] == half && shape[0] >= npos, "rope table must be [>= n_pos, head_dim/2]");
-    ISST_CHECK(dtype == ISST_DTYPE_F32, "rope tables are f32");
-    float* dst = enc ? (name[9] == 'c' ? ctx->enc_rope_cos : ctx->enc_rope_sin)
-                     : (name[9] == 'c' ? ctx->llm_rope_cos_f : ctx->llm_rope_sin_f);
-    ISST_CUDA(cudaMemcpy(dst, data, static_cast<size_t>(npos) * half * 4, cudaMemcpyDefault));
+    long long ne; numel(shape, ndim, &ne);
+    ISST_CHECK(ne == half && dtype == ISST_DTYPE_F32, "inv_freq must be f32 [head_dim / 2]");
+    ISST_CUDA(cudaMemcpy(enc ? ctx->enc_inv_freq : ctx->llm_inv_freq, data, half * sizeof(float), cudaMemcpyDefault));
     return done();
   }
   if (starts_with(name, ENC + "feature_extractor.conv_layers.")) {
@@ -1216,7 +1219,7 @@ int isst_load_weight(isst_ctx* ctx, const char* name_c, const void* data, const 
     if (leaf == "fc1.bias") LV(w.b1, F);
     if (leaf == "fc2.weight") LM(w.w2.ptr, D, F);
     if (leaf == "fc2.bias") LV(w.b2, D);
-    if (leaf == "self_attn.rotary_emb.freqs") return 0;   // consumed on the host to build rope.enc.*
+    if (leaf == "self_attn.rotary_emb.freqs") return 0;   // the host passes layer 0's copy as rope.enc.inv_freq
     return set_error("unknown encoder layer key: " + name);
   }
   if (starts_with(name, SPE + "length_shrink.conv_layers.")) {
@@ -1263,7 +1266,7 @@ int isst_finalize_weights(isst_ctx* ctx) {
   ISST_CUDA(cudaSetDevice(ctx->device));
   const isst_config& c = ctx->cfg;
   // every tensor of the hot path must have been loaded
-  std::vector<std::string> need = {"rope.enc.cos", "rope.enc.sin", "rope.llm.cos", "rope.llm.sin",
+  std::vector<std::string> need = {"rope.enc.inv_freq", "rope.llm.inv_freq",
                                    "model.embed_tokens.weight", "model.norm.weight", "lm_head.weight",
                                    "model.speech_encoder.proj.weight", "model.speech_encoder.proj.bias"};
   const std::string ENC = "model.speech_encoder.speech_encoder.";
@@ -1296,9 +1299,6 @@ int isst_finalize_weights(isst_ctx* ctx) {
   ISST_TRY(make_weight_map(ctx->post_proj)); ISST_TRY(make_weight_map(ctx->proj)); ISST_TRY(make_weight_map(ctx->lm_head));
   for (auto& w : ctx->enc) { ISST_TRY(make_weight_map(w.wqkv)); ISST_TRY(make_weight_map(w.wo)); ISST_TRY(make_weight_map(w.w1)); ISST_TRY(make_weight_map(w.w2)); }
   for (auto& w : ctx->llm) { ISST_TRY(make_weight_map(w.wqkv)); ISST_TRY(make_weight_map(w.wo)); ISST_TRY(make_weight_map(w.wgu)); ISST_TRY(make_weight_map(w.wd)); }
-  const long long nr = static_cast<long long>(ctx->llm_rope_npos) * (c.head_dim / 2);
-  build_llm_rope_kernel<<<256, 256>>>(ctx->llm_rope_cos_f, ctx->llm_rope_sin_f, ctx->llm_rope, nr);
-  ISST_CUDA(cudaGetLastError());
   ISST_CUDA(cudaDeviceSynchronize());
   if (ctx->staging) { cudaFree(ctx->staging); ctx->staging = nullptr; ctx->staging_bytes = 0; }
   ctx->finalized = true;
@@ -1597,6 +1597,7 @@ int isst_kv_evict(isst_ctx* ctx, int stream_id, int keep_prefix, int drop_upto) 
   if (n_drop == 0) return 0;
   s.ring_start += n_drop;
   s.kv_len -= n_drop;
+  s.evicted += n_drop;
   // release ring pages that fell completely behind ring_start
   const int sys_pages = ceil_div(s.sys_len, kPageTokens);
   int freeable = s.ring_start / kPageTokens - sys_pages;
@@ -1674,6 +1675,13 @@ int isst_profile_read(isst_ctx* ctx, int index, char* name, int name_cap, int64_
   return 0;
 }
 
+int isst_debug_shift_positions(isst_ctx* ctx, int stream_id, int64_t delta) {
+  ISST_CHECK(ctx && stream_id >= 0 && stream_id < ctx->cfg.max_streams && ctx->streams[stream_id].open, "bad stream id");
+  ISST_CHECK(delta >= 0 && ctx->streams[stream_id].evicted + delta < 2000000000LL, "delta out of range");
+  ctx->streams[stream_id].evicted += delta;
+  return 0;
+}
+
 int64_t isst_launch_count(isst_ctx* ctx) { return ctx ? ctx->launches : -1; }
 int isst_pages_free(isst_ctx* ctx) { return ctx ? static_cast<int>(ctx->free_pages.size()) : -1; }
 
@@ -1711,6 +1719,7 @@ int isst_op_decode_attention_bench(isst_ctx* ctx, int n, int L, int iters, float
   fill_pattern_kernel<<<1024, 256, 0, st>>>(ctx->kv_pool, static_cast<long long>(ctx->kv_layer_elems) * c.layers, 17u);
   const int QKV = (c.heads + 2 * c.kv_heads) * c.head_dim;
   fill_pattern_kernel<<<64, 256, 0, st>>>(ctx->lqkv, static_cast<long long>(n) * QKV, 3u);
+  fill_pattern_kernel<<<64, 256, 0, st>>>(ctx->lq_sys, static_cast<long long>(n) * c.heads * c.head_dim, 5u);
   MetaBuilder mb{ctx};
   const size_t o_slots = mb.alloc(n);
   for (int b = 0; b < n; ++b) mb.host(o_slots)[b] = b;

@@ -70,7 +70,6 @@ class Engine:
         self._c = c
         self.max_kv_len = max_kv_len
         self.max_multiplier = max_multiplier
-        self.enc_rope_npos = e.max_cache_size + e.block_size * max_multiplier
         h = C.c_void_p()
         _lib.check(self.lib.isst_create(C.byref(c), device, C.byref(h)))
         self.h = h
@@ -110,18 +109,14 @@ class Engine:
         for k, v in sd.items():
             self._load(k, v)
         e, l = self.cfg.enc, self.cfg.llm
-        freqs = sd[ENC + "encoder.layers.0.self_attn.rotary_emb.freqs"].detach().cpu()
-        n = self.enc_rope_npos
-        if e.rope_angle_dtype == "fp32":
-            ang = torch.arange(n, dtype=torch.float32)[:, None] * freqs.float()[None, :]
-        else:   # positions and frequencies in the model dtype (SURVEY App. A.2 dtype hazard)
-            ang = (torch.arange(n, dtype=torch.bfloat16)[:, None] * freqs.bfloat16()[None, :]).float()
-        # the rotation is applied in the model dtype: cos/sin are bf16 values
-        self._load("rope.enc.cos", ang.cos().bfloat16().float())
-        self._load("rope.enc.sin", ang.sin().bfloat16().float())
-        ang = torch.arange(self.max_kv_len, dtype=torch.float32)[:, None] * llama_inv_freq(l)[None, :]
-        self._load("rope.llm.cos", ang.cos())
-        self._load("rope.llm.sin", ang.sin())
+        if e.rope_angle_dtype != "fp32":
+            raise NotImplementedError("encoder RoPE angles are formed in fp32/fp64 (rope_angle_dtype='fp32'); the "
+                                      "bf16-position variant of some rotary_embedding_torch versions is not built")
+        # RoPE frequencies: rotary_embedding_torch's `freqs` parameter (one copy per layer, identical; layer 0 is
+        # used) and HF's llama3-scaled inv_freq.  The library forms the angles itself, at absolute positions.
+        freqs = sd[ENC + "encoder.layers.0.self_attn.rotary_emb.freqs"].detach().float().cpu().contiguous()
+        self._load("rope.enc.inv_freq", freqs)
+        self._load("rope.llm.inv_freq", llama_inv_freq(l).float().contiguous())
         _lib.check(self.lib.isst_finalize_weights(self.h))
 
     # ------------------------------------------------------------------ streams
@@ -145,6 +140,9 @@ class Engine:
 
     def kv_evict(self, sid: int, keep_prefix: int, drop_upto: int) -> None:
         _lib.check(self.lib.isst_kv_evict(self.h, sid, keep_prefix, drop_upto))
+
+    def debug_shift_positions(self, sid: int, delta: int) -> None:
+        _lib.check(self.lib.isst_debug_shift_positions(self.h, sid, delta))
 
     def pages_free(self) -> int:
         return self.lib.isst_pages_free(self.h)

@@ -186,6 +186,43 @@ def test_long_stream_no_drift():
     assert st["evictions"] >= 50 and st["worst_logit"] < LOGIT_TOL
 
 
+def test_absolute_position_invariance():
+    """Keys are rotated once at their absolute index (fp64 angles): a stream whose absolute positions start
+    2 000 000 tokens later (hours of speech) must produce the same logits and tokens as a fresh one,
+    through prefill, decode and sliding-window eviction with a pinned system prompt."""
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=2)
+    eng.debug(True)
+    n_chunks = 10
+    audio = make_audio(n_chunks * SEG / 16000.0)
+    from infinisst_b200.agent import S2TAgentStates, evict_plan
+    runs = []
+    for shift in (0, 2_000_000):
+        sid = eng.open_stream()
+        st = S2TAgentStates()
+        st.system_prompt_size = len(cfg.tpl.system_ids)
+        target, rec = [], []
+        for c in range(n_chunks):
+            eng.encode_chunk([sid], _chunk_pcm(audio, c), 1)
+            ids = O.build_prompt(cfg.tpl, c == 0)
+            if c == 0 and shift:
+                eng.debug_shift_positions(sid, shift)        # pinned prefix keys stay at 0..39, everything else moves
+            toks = eng.generate([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen,
+                                pin_prefix=len(cfg.tpl.system_ids))[0]
+            rec.append((toks, eng.read_tap("step_logits", torch.float32).clone()))
+            target.extend(toks[:-1])
+            plan = evict_plan(st, eng.kv_len(sid), cfg.gen.max_llm_cache_size, True)
+            if plan is not None:
+                eng.kv_evict(sid, plan[0], plan[1])
+        runs.append(rec)
+        eng.close_stream(sid)
+    for c, ((ta, la), (tb, lb)) in enumerate(zip(*runs)):
+        assert rel_l2(lb, la) < 1e-2, (c, rel_l2(lb, la))
+        assert ta == tb, (c, ta, tb)
+    eng.close()
+
+
 def test_golden_stream():
     """Committed golden vectors (tests/golden/make_golden.py): features, logits, tokens, KV log."""
     gold = np.load(GOLD)
