@@ -90,29 +90,42 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
   auto tile_j1 = [&](int t) { return t < n_sys_tiles ? min(sys_len, t * TILE + TILE) : min(L, sys_len + (t - n_sys_tiles + 1) * TILE); };
 
   // ---- tile loader: 64 keys x (K 256 B + V 256 B) = 2048 16-byte chunks, 16 per thread ----
+  // Thread (grp = tid / 16, chunk = tid % 16) copies chunk `chunk` of the 8 consecutive keys 8*grp .. 8*grp+7.
+  // The keys of a tile sit in one segment (pinned prefix or ring), so their slots are consecutive and touch at
+  // most two pages: two page-table lookups per thread and tile, issued one tile ahead of their use.
+  const int grp = tid >> 4, chunk = tid & 15;
+  const size_t page_elems = static_cast<size_t>(2) * p.kv.kv_heads * kPageTokens * HD;
+  const bf16* head_base = p.kv.pool + static_cast<size_t>(head) * kPageTokens * HD + chunk * 8;
+  const size_t v_off = static_cast<size_t>(p.kv.kv_heads) * kPageTokens * HD;     // V block of the same page
+  int nx_s0 = 0, nx_pa = 0, nx_pb = 0;                                             // lookups of the next tile to load
+  auto lookup = [&](int t) {
+    const int jg = min(tile_j0(t) + 8 * grp, L - 1);
+    nx_s0 = kv_slot(jg, sys_len, ring_start);
+    const int last = kv_slot(min(jg + 7, tile_j1(t) - 1 > jg ? tile_j1(t) - 1 : jg), sys_len, ring_start);
+    nx_pa = table[nx_s0 >> 4];
+    nx_pb = table[last >> 4];
+  };
   auto load_tile = [&](int t, int stage) {
-    bf16* sK = stage_base + stage * kDecStageElems;
+    bf16* sK = stage_base + stage * kDecStageElems + (8 * grp) * LDS + chunk * 8;
     bf16* sV = sK + TILE * LDS;
-    const int j0 = tile_j0(t), j1 = tile_j1(t);
-    const int chunk = tid & 15;
+    const int n_ok = tile_j1(t) - (tile_j0(t) + 8 * grp);          // keys of this group inside the tile
+    const int s0 = nx_s0;
+    const bf16* base_a = head_base + static_cast<size_t>(nx_pa) * page_elems;
+    const bf16* base_b = head_base + static_cast<size_t>(nx_pb) * page_elems;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int kl = (tid >> 4) + 8 * it;
-      const int j = j0 + kl;
-      const bool ok = j < j1;
-      const bf16* ksrc = p.kv.pool;
-      const bf16* vsrc = p.kv.pool;
-      if (ok) {
-        const int sl = kv_slot(j, sys_len, ring_start);
-        ksrc = p.kv.pool + kv_offset(p.kv, table, sl, 0, head) + chunk * 8;
-        vsrc = ksrc + static_cast<size_t>(p.kv.kv_heads) * kPageTokens * HD;      // V block of the same page
-      }
-      cp_async16(sK + kl * LDS + chunk * 8, ksrc, ok ? 16 : 0);                   // invalid keys: zero fill
-      cp_async16(sV + kl * LDS + chunk * 8, vsrc, ok ? 16 : 0);
+      const int sl = s0 + it;
+      const bf16* src = (((sl ^ s0) & ~15) == 0 ? base_a : base_b) + (sl & 15) * HD;
+      const bool ok = it < n_ok;
+      if (!ok) src = p.kv.pool;
+      cp_async16(sK + it * LDS, src, ok ? 16 : 0);                 // invalid keys: zero fill
+      cp_async16(sV + it * LDS, src + v_off, ok ? 16 : 0);
     }
+    if (t + 1 < t_hi) lookup(t + 1);
   };
 
   // prologue: first tiles in flight, then the two query variants -> qbuf[0] (ring), qbuf[1] (sys)
+  lookup(t_lo);
 #pragma unroll
   for (int s = 0; s < kDecStages - 1; ++s) {
     if (s < n_tiles) load_tile(t_lo + s, s);
@@ -126,6 +139,18 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
                              : p.q_sys + static_cast<size_t>(b) * (p.H * HD) + (head * GROUP + hq) * HD;
     *reinterpret_cast<uint4*>(qbuf + (v * GROUP + hq) * HD + c * 8) = *reinterpret_cast<const uint4*>(src + c * 8);
   }
+  __syncthreads();
+  // A fragments of the current query variant live in registers (rows >= GROUP are zero padding)
+  uint32_t qa0[8], qa2[8];
+  auto load_q = [&](bool sys_variant) {
+    const bf16* q = qbuf + (sys_variant ? GROUP * HD : 0) + (g & (GROUP - 1)) * HD + 2 * t4;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      qa0[kk] = g < GROUP ? *reinterpret_cast<const uint32_t*>(q + kk * 16) : 0u;
+      qa2[kk] = g < GROUP ? *reinterpret_cast<const uint32_t*>(q + kk * 16 + 8) : 0u;
+    }
+  };
+  load_q(t_lo < n_sys_tiles);
 
   float o[8][4];
 #pragma unroll
@@ -143,7 +168,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     }
     const bf16* sK = stage_base + (ti % kDecStages) * kDecStageElems;
     const bf16* sV = sK + TILE * LDS;
-    const bf16* q = qbuf + (t < n_sys_tiles ? GROUP * HD : 0);
+    if (t == n_sys_tiles && ti > 0) load_q(false);     // leaving the pinned prefix: switch to the ring variant
 
     // ---- S = Q K^T for this warp's 16 keys ----
     float s[2][4];
@@ -156,11 +181,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
       for (int kk = 0; kk < 8; ++kk) {
         uint32_t kf[4];
         ldmatrix_x4(kf, krow + kk * 16);
-        uint32_t qa[4] = {0u, 0u, 0u, 0u};
-        if (g < GROUP) {
-          qa[0] = *reinterpret_cast<const uint32_t*>(q + g * HD + kk * 16 + 2 * t4);
-          qa[2] = *reinterpret_cast<const uint32_t*>(q + g * HD + kk * 16 + 8 + 2 * t4);
-        }
+        const uint32_t qa[4] = {qa0[kk], 0u, qa2[kk], 0u};
         mma_bf16_16816(s[0], qa, kf[0], kf[1]);
         mma_bf16_16816(s[1], qa, kf[2], kf[3]);
       }
@@ -223,23 +244,33 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < GROUP * HD; idx += 128) {
-    const int hq = idx / HD, d = idx % HD;
+  float* sm_w = sm_l + 4 * GROUP;                              // [4 warps][GROUP] merge weights, then [GROUP] m, [GROUP] l
+  if (tid < GROUP) {
+    const int hq = tid;
     float mm = -INFINITY;
 #pragma unroll
     for (int w = 0; w < 4; ++w) mm = fmaxf(mm, sm_m[w * GROUP + hq]);
     const float ms = (mm == -INFINITY) ? 0.f : mm;
-    float ll = 0.f, oo = 0.f;
+    float ll = 0.f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float wm = sm_m[w * GROUP + hq];
       const float wgt = (wm == -INFINITY) ? 0.f : exp2f(wm - ms);
+      sm_w[w * GROUP + hq] = wgt;
       ll += wgt * sm_l[w * GROUP + hq];
-      oo += wgt * sm_o[(w * GROUP + hq) * HD + d];
     }
     const size_t pidx = pbase + static_cast<size_t>(hq) * p.splits;
-    p.part_o[pidx * HD + d] = oo;
-    if (d == 0) { p.part_ml[pidx * 2] = mm; p.part_ml[pidx * 2 + 1] = ll; }
+    p.part_ml[pidx * 2] = mm;
+    p.part_ml[pidx * 2 + 1] = ll;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int hq = 0; hq < GROUP; ++hq) {
+    const int d = tid;                                         // 128 threads == HD
+    float oo = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) oo += sm_w[w * GROUP + hq] * sm_o[(w * GROUP + hq) * HD + d];
+    p.part_o[(pbase + static_cast<size_t>(hq) * p.splits) * HD + d] = oo;
   }
 }
 

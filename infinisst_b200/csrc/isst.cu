@@ -797,7 +797,9 @@ static PagedKV paged_kv(isst_ctx* ctx, int layer) {
 // Decode attention launch: split count from the longest stream so that the grid is a few waves of
 // 2 CTAs per SM; every split is a whole number of 64-key tiles.
 static int decode_splits_for(isst_ctx* ctx, int n, int max_L) {
-  const int tiles_total = std::max(1, ceil_div(max_L, kDecTile));
+  static const char* force = getenv("ISST_DEC_SPLITS");          // tuning aid
+  if (force) return std::max(1, std::min(ctx->decode_splits, atoi(force)));
+  const int tiles_total = std::max(1, ceil_div(max_L, kDecTile) + 1);
   const int target = std::max(1, std::min(ctx->decode_splits, ceil_div(8 * ctx->sm_count, n * ctx->cfg.kv_heads)));
   const int tiles_per = ceil_div(tiles_total, target);
   return ceil_div(tiles_total, tiles_per);

