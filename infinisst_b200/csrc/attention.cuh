@@ -158,7 +158,7 @@ constexpr int chunk_attn_smem_bytes() {
 // LLM: the pinned system-prompt keys [0, sys_len) are visited first with the q_sys query variant, then the
 // query fragments are reloaded from the ring variant for the sliding part (see the header).
 template <int HD, bool ENC, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, HD == 128 ? 2 : 4)
 chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   constexpr int KT = 64;             // keys per tile
   constexpr int LDS = HD + 8;        // padded smem row (elements)
@@ -215,31 +215,59 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   auto tile_k1 = [&](int t) { return t < n_sys_tiles ? min(sys_end, t * KT + KT) : min(key_end, sys_end + (t - n_sys_tiles + 1) * KT); };
 
   // ---- tile loader (cp.async, zero fill beyond the tile's key range) ----
+  // LLM: threads 0-127 = 8 groups x 16 chunks; a group copies 8 consecutive keys, whose slots touch at most two
+  // pages -> two page-table lookups per thread and tile, issued one tile ahead (as in decode_attention.cuh).
+  const int grp = tid >> 4, chunk = tid & 15;
+  int nx_s0 = 0, nx_pa = 0, nx_pb = 0;
+  auto lookup = [&](int t) {
+    if (ENC || tid >= 128) return;
+    const int k1 = tile_k1(t);
+    const int jg = min(tile_k0(t) + 8 * grp, L - 1);
+    nx_s0 = kv_slot(jg, sys_len, ring_start);
+    const int last = kv_slot(min(jg + 7, k1 - 1 > jg ? k1 - 1 : jg), sys_len, ring_start);
+    nx_pa = table[nx_s0 >> 4];
+    nx_pb = table[last >> 4];
+  };
   auto load_tile = [&](int t, int stage) {
     constexpr int CH = HD / 8;
     bf16* dK = sRaw + stage * 2 * KT * LDS;
     bf16* dV = dK + KT * LDS;
     const int k0 = tile_k0(t), k1 = tile_k1(t);
-    for (int u = tid; u < KT * CH; u += NTHREADS) {
-      const int kl = u / CH, c = u % CH;
-      const int j = k0 + kl;
-      const bool ok = j < k1;
-      const bf16* ks;
-      const bf16* vs;
-      if (ENC) {
+    if (ENC) {
+      for (int u = tid; u < KT * CH; u += NTHREADS) {
+        const int kl = u / CH, c = u % CH;
+        const int j = k0 + kl;
+        const bool ok = j < k1;
         const int rs = ok ? (ring0 + j) % ep.cap : 0;
         const size_t off = ((static_cast<size_t>(slot) * ep.H + head) * ep.cap + rs) * HD + c * 8;
-        ks = ep.k_ring + off;
-        vs = ep.v_ring + off;
-      } else {
-        const int sl = ok ? kv_slot(j, sys_len, ring_start) : 0;
-        ks = lp.kv.pool + (ok ? kv_offset(lp.kv, table, sl, 0, head) : 0) + c * 8;
-        vs = ks + static_cast<size_t>(lp.kv.kv_heads) * kPageTokens * HD;
+        cpa16(dK + kl * LDS + c * 8, ep.k_ring + off, ok ? 16 : 0);
+        cpa16(dV + kl * LDS + c * 8, ep.v_ring + off, ok ? 16 : 0);
       }
-      cpa16(dK + kl * LDS + c * 8, ks, ok ? 16 : 0);
-      cpa16(dV + kl * LDS + c * 8, vs, ok ? 16 : 0);
+    } else {
+      if (tid < 128) {
+        const size_t page_elems = static_cast<size_t>(2) * lp.kv.kv_heads * kPageTokens * HD;
+        const bf16* head_base = lp.kv.pool + static_cast<size_t>(head) * kPageTokens * HD + chunk * 8;
+        const size_t v_off = static_cast<size_t>(lp.kv.kv_heads) * kPageTokens * HD;
+        const int n_ok = k1 - (k0 + 8 * grp);
+        const int s0 = nx_s0;
+        const bf16* base_a = head_base + static_cast<size_t>(nx_pa) * page_elems;
+        const bf16* base_b = head_base + static_cast<size_t>(nx_pb) * page_elems;
+        bf16* sk = dK + (8 * grp) * LDS + chunk * 8;
+        bf16* sv = dV + (8 * grp) * LDS + chunk * 8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int sl = s0 + it;
+          const bf16* src = (((sl ^ s0) & ~15) == 0 ? base_a : base_b) + (sl & 15) * HD;
+          const bool ok = it < n_ok;
+          if (!ok) src = lp.kv.pool;
+          cpa16(sk + it * LDS, src, ok ? 16 : 0);
+          cpa16(sv + it * LDS, src + v_off, ok ? 16 : 0);
+        }
+      }
+      if (t + 1 < n_tiles) lookup(t + 1);
     }
   };
+  if (n_tiles > 0) lookup(0);
   if (n_tiles > 0) load_tile(0, 0);
   cpa_commit();
 
