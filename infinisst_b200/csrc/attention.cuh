@@ -122,6 +122,8 @@ __global__ void rope_table_kernel(float2* __restrict__ tab_ring, float2* __restr
                                   const int* __restrict__ base_pos, const int* __restrict__ evicted,
                                   const int* __restrict__ active, const float* __restrict__ inv_freq, int n_freq,
                                   int T_fixed) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   if (active && !active[b]) return;
   const int T = ENC ? T_fixed : Tn[b];
@@ -160,6 +162,8 @@ constexpr int chunk_attn_smem_bytes() {
 template <int HD, bool ENC, int NW>
 __global__ void __launch_bounds__(NW * 32, HD == 128 ? 2 : 4)
 chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int KT = 64;             // keys per tile
   constexpr int LDS = HD + 8;        // padded smem row (elements)
   constexpr int NTHREADS = NW * 32;
@@ -466,6 +470,8 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
 __global__ void enc_rope_append_kernel(bf16* __restrict__ qkv, bf16* k_ring, bf16* v_ring,
                                        const int* __restrict__ slots, const int* __restrict__ prefix,
                                        const float2* __restrict__ tab, int T, int H, int HD, int cap) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int slot = slots[b];
   const int pre = prefix[b];   // per batch entry
@@ -504,6 +510,8 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict_
                                        const int* __restrict__ slots, const int* __restrict__ tok_base,
                                        const int* __restrict__ Tn, const int* __restrict__ active,
                                        const float2* __restrict__ tab_ring, const float2* __restrict__ tab_sys, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   if (active && !active[b]) return;
   const int slot = slots[b];
@@ -569,6 +577,8 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict_
 // out[b, h, :] = sum_s w_s o_s / sum_s w_s l_s  over the key splits of decode attention
 __global__ void decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                       bf16* __restrict__ out, int H, int HD, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int bh = blockIdx.x;   // b * H + h
   const int d = threadIdx.x;
   float mm = -INFINITY;

@@ -67,6 +67,13 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running; everything it does before pdl_wait() overlaps the
+// predecessor's tail (launch latency, barrier / TMEM setup, weight prefetch).  pdl_wait() returns once the
+// predecessor grid has completed and its writes are visible.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 16-byte streaming load (read-once data: weights / KV), bypassing L1 allocation.
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;

@@ -57,6 +57,8 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 template <int GROUP>
 __global__ void __launch_bounds__(128, 2)
 decode_attention_mma_kernel(const DecodeParams2 p) {
+  pdl_launch_dependents();
+  pdl_wait();
   static_assert(GROUP == 4, "4:1 GQA");
   constexpr int HD = 128, LDS = kDecLds, TILE = kDecTile;
   extern __shared__ __align__(16) uint8_t dec_smem[];

@@ -564,6 +564,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
   const int G = gridDim.x, cta = blockIdx.x;
   const int nkb = sk.num_kb;
   if (sk.dbg && threadIdx.x == 0) sk.dbg[cta * 8 + 0] = gtimer();
+  pdl_launch_dependents();      // the next kernel may start its own prologue / weight prefetch
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_act)) : "memory");
@@ -591,6 +592,9 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
 
   if (warp == 0) {
     // ================= TMA producer =================
+    // Weights do not depend on the previous kernel: the first ring-full of weight tiles is requested BEFORE
+    // pdl_wait(), so it streams from HBM while the predecessor is still finishing; the activation tiles of
+    // those stages follow once the dependency is resolved.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -598,18 +602,37 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
       long long tile;
       int kb_begin, kb_end;
       bool first = true;
+      int pre = 0;                                   // stages whose weights were requested ahead of the wait
+      int pre_row[C::kStages], pre_k0[C::kStages], pre_b[C::kStages];
+      bool waited = false;
       while (w.next(tile, kb_begin, kb_end)) {
         const SkTile t = sk_tile(tile, sk);
         const int act_row0 = t.tt * C::kActRows;
         const int w_row0 = t.tf * C::kWRows;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!waited && pre == C::kStages) {
+            // ring full of prefetched weights: resolve the dependency, then feed the activations
+            pdl_wait();
+            waited = true;
+            for (int s2 = 0; s2 < pre; ++s2) {
+              const int k0p = pre_k0[s2];
+              const int tapp = k0p / p.conv_c;
+              tma_load_4d(smem + s2 * C::kStageBytes, &tm_act, &full_bar[s2], k0p - tapp * p.conv_c, tapp % p.conv_s,
+                          pre_row[s2] + tapp / p.conv_s, pre_b[s2]);
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sw = sa + C::kActBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           const int k0 = kb * kBK;
           const int tap = k0 / p.conv_c;
-          tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, t.b);
+          if (waited) {
+            tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, t.b);
+          } else {
+            pre_row[pre] = act_row0; pre_k0[pre] = k0; pre_b[pre] = t.b;
+            ++pre;
+          }
 #pragma unroll
           for (int h = 0; h < C::kWRows / kBM; ++h)      // the weight map's box is 128 rows
             tma_load_2d(sw + h * (kBM * kBK * 2), &tm_w, &full_bar[stage], k0, w_row0 + h * kBM);
@@ -617,6 +640,15 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
           if (first && sk.dbg) sk.dbg[cta * 8 + 1] = gtimer();
           first = false;
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (!waited) {                                 // fewer units than stages
+        pdl_wait();
+        for (int s2 = 0; s2 < pre; ++s2) {
+          const int k0p = pre_k0[s2];
+          const int tapp = k0p / p.conv_c;
+          tma_load_4d(smem + s2 * C::kStageBytes, &tm_act, &full_bar[s2], k0p - tapp * p.conv_c, tapp % p.conv_s,
+                      pre_row[s2] + tapp / p.conv_s, pre_b[s2]);
         }
       }
     }
@@ -665,6 +697,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     }
   } else if (warp >= 4) {
     // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
+    pdl_wait();                                   // residual / workspace / output buffers belong to earlier kernels until now
     const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
     const int half = (warp - 4) >> 2;             // column half of the tile
     const int r = q * 32 + lane;                  // TMEM lane == row of the 128-row operand

@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "attention.cuh"
@@ -159,6 +160,7 @@ struct isst_ctx {
   int sm_count = 148;
   bool finalized = false;
   bool simple_gemm = false;
+  bool pdl = true;          // ISST_PDL=0 disables programmatic dependent launch
   bool gemm_v1 = false;     // ISST_GEMM=v1: one-tile-per-CTA tcgen05 kernel (previous generation, kept for A/B runs)
   unsigned long long* gemm_dbg = nullptr;   // optional phase stamps of the last stream-K launch
   int64_t launches = 0;
@@ -222,6 +224,22 @@ struct isst_ctx {
 };
 
 namespace isst {
+
+// Hot-path launcher: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL), so the next
+// kernel's prologue overlaps this kernel's tail; every kernel launched this way calls pdl_wait() before it
+// touches data of its predecessors.  ISST_PDL=0 falls back to plain stream order (A/B runs).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(isst_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (ctx->pdl && !ctx->prof.on) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 #define LAUNCH_CHECK(ctx)                                                                   \
   do {                                                                                      \
@@ -331,7 +349,7 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
              "gemm: stream-K workspace too small");
   CUtensorMap amap;
   ISST_TRY(get_act_map(ctx, &amap, v, C::kActRows));
-  kern<<<static_cast<unsigned>(G), tc::kSkThreads, C::kSmemBytes, st>>>(amap, w.map, p, sk);
+  ISST_CUDA(launch_k(ctx, kern, dim3(static_cast<unsigned>(G)), dim3(tc::kSkThreads), C::kSmemBytes, st, amap, w.map, p, sk));
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -615,9 +633,9 @@ static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const 
   ISST_CHECK(C % 8 == 0 && C <= 4096, "norm_rows: unsupported width");
   if (rows == 0) return 0;
   ProfScope ps(ctx, st, P_NORM, 0.0, static_cast<double>(rows) * C * 4);
-  if (rms) norm_rows_kernel<true, false><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
-  else if (gelu) norm_rows_kernel<false, true><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
-  else norm_rows_kernel<false, false><<<rows, 128, 0, st>>>(in, out, w, b, gather, C, eps);
+  if (rms) ISST_CUDA(launch_k(ctx, norm_rows_kernel<true, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps));
+  else if (gelu) ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, true>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps));
+  else ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps));
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -635,11 +653,11 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     ProfScope ps(ctx, st, P_CONV0, 2.0 * n * T * C * c.conv_k[0], static_cast<double>(n) * (window * 4 + static_cast<double>(T) * C * 2));
     dim3 grid(ceil_div(T, kConv0FramesPerCta), n);
     const size_t smem = (static_cast<size_t>(c.conv_k[0]) * C + kConv0FramesPerCta * c.conv_s[0] + c.conv_k[0]) * 4;
-    conv0_ln_gelu_kernel<<<grid, 256, smem, st>>>(ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail, ctx->conv[0].w0_t,
-                                                  ctx->conv[0].bias, ctx->conv[0].ln_w, ctx->conv[0].ln_b, ctx->conv_a,
-                                                  C, c.conv_k[0], c.conv_s[0], T);
+    ISST_CUDA(launch_k(ctx, conv0_ln_gelu_kernel, grid, dim3(256), smem, st, ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail,
+                       ctx->conv[0].w0_t, ctx->conv[0].bias, ctx->conv[0].ln_w, ctx->conv[0].ln_b, ctx->conv_a, C, c.conv_k[0],
+                       c.conv_s[0], T));
     LAUNCH_CHECK(ctx);
-    update_tail_kernel<<<n, 128, 0, st>>>(ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail);
+    ISST_CUDA(launch_k(ctx, update_tail_kernel, dim3(n), dim3(128), 0, st, ctx->d_pcm, ctx->tail, d_slots, n_new, ctx->n_tail));
     LAUNCH_CHECK(ctx);
   }
   bf16* cur = ctx->conv_a;
@@ -676,8 +694,9 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
   {
     // (cos, sin) of the absolute frame indices of this chunk: one table for all layers
     ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (D / c.enc_heads / 2) * 8);
-    rope_table_kernel<true><<<dim3(ceil_div(frames * (D / c.enc_heads / 2), 256), n), 256, 0, st>>>(
-        ctx->enc_rope_tab, nullptr, nullptr, nullptr, d_prefix, nullptr, nullptr, ctx->enc_inv_freq, D / c.enc_heads / 2, frames);
+    ISST_CUDA(launch_k(ctx, rope_table_kernel<true>, dim3(ceil_div(frames * (D / c.enc_heads / 2), 256), n), dim3(256), 0, st,
+                       ctx->enc_rope_tab, nullptr, nullptr, nullptr, d_prefix, nullptr, nullptr, ctx->enc_inv_freq,
+                       D / c.enc_heads / 2, frames));
     LAUNCH_CHECK(ctx);
   }
   for (int l = 0; l < c.enc_layers; ++l) {
@@ -693,7 +712,7 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(n) * frames * D * 2 * 4);
       dim3 grid(ceil_div(frames * D / 8, 256), n);
-      enc_rope_append_kernel<<<grid, 256, 0, st>>>(ctx->eqkv, kr, vr, d_slots, d_prefix, ctx->enc_rope_tab, frames, H, HD, ctx->enc_cap);
+      ISST_CUDA(launch_k(ctx, enc_rope_append_kernel, grid, dim3(256), 0, st, ctx->eqkv, kr, vr, d_slots, d_prefix, ctx->enc_rope_tab, frames, H, HD, ctx->enc_cap));
       LAUNCH_CHECK(ctx);
     }
     {
@@ -714,7 +733,7 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
         ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<64, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         enc_attr_set = true;
       }
-      chunk_attention_kernel<64, true, NW><<<grid, NW * 32, smem, st>>>(ep, lp);
+      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<64, true, NW>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
     }
     {
@@ -816,7 +835,7 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
   dp.qkv = qkv; dp.q_sys = ctx->lq_sys; dp.kv = kv; dp.slots = d_slots;
   dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
   dp.splits = splits; dp.scale_log2 = scale_log2;
-  decode_attention_mma_kernel<4><<<dim3(splits, ctx->cfg.kv_heads, n), 128, kDecSmemBytes, st>>>(dp);
+  ISST_CUDA(launch_k(ctx, decode_attention_mma_kernel<4>, dim3(splits, ctx->cfg.kv_heads, n), dim3(128), kDecSmemBytes, st, dp));
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -831,9 +850,9 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
   {
     // (cos, sin) of the new tokens' absolute / reference positions: one table pair for all layers
     ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (HD / 2) * 16);
-    rope_table_kernel<false><<<dim3(ceil_div(lb.max_T * (HD / 2), 128), lb.n), 128, 0, st>>>(
-        ctx->llm_rope_ring, ctx->llm_rope_sys, lb.d_tok_base, lb.d_T, ctx->d_kv_len, ctx->d_evicted, lb.d_active,
-        ctx->llm_inv_freq, HD / 2, 0);
+    ISST_CUDA(launch_k(ctx, rope_table_kernel<false>, dim3(ceil_div(lb.max_T * (HD / 2), 128), lb.n), dim3(128), 0, st,
+                       ctx->llm_rope_ring, ctx->llm_rope_sys, lb.d_tok_base, lb.d_T, ctx->d_kv_len, ctx->d_evicted, lb.d_active,
+                       ctx->llm_inv_freq, HD / 2, 0));
     LAUNCH_CHECK(ctx);
   }
   for (int l = 0; l < c.layers; ++l) {
@@ -847,8 +866,8 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
     {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
       dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
-      llm_rope_append_kernel<<<grid, 128, 0, st>>>(ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T, lb.d_active,
-                                                   ctx->llm_rope_ring, ctx->llm_rope_sys, H);
+      ISST_CUDA(launch_k(ctx, llm_rope_append_kernel, grid, dim3(128), 0, st, ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T,
+                         lb.d_active, ctx->llm_rope_ring, ctx->llm_rope_sys, H));
       LAUNCH_CHECK(ctx);
     }
     if (!lb.decode) {
@@ -867,14 +886,14 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
       }
-      chunk_attention_kernel<128, false, NW><<<grid, NW * 32, smem, st>>>(ep, lp);
+      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<128, false, NW>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
     } else {
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
       const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
       ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2));
-      decode_combine_kernel<<<lb.n * H, 128, 0, st>>>(ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits);
+      ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits));
       LAUNCH_CHECK(ctx);
     }
     {
@@ -896,7 +915,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
     if (tap_layers && ctx->debug)
       ISST_TRY(tap(ctx, st, "llm_layer_" + std::to_string(l), ctx->lx, static_cast<size_t>(M) * D * 2));
   }
-  advance_kv_len_kernel<<<ceil_div(lb.n, 128), 128, 0, st>>>(ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n);
+  ISST_CUDA(launch_k(ctx, advance_kv_len_kernel, dim3(ceil_div(lb.n, 128)), dim3(128), 0, st, ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n));
   LAUNCH_CHECK(ctx);
   // final norm + lm_head on the LAST position of each stream only (the reference computes and discards
   // the other T-1 rows, llm.py:236-237 / SURVEY §2.3 L9)
@@ -996,6 +1015,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   const char* g = getenv("ISST_GEMM");
   ctx->simple_gemm = g && std::string(g) == "simple";
   ctx->gemm_v1 = g && std::string(g) == "v1";
+  const char* pd = getenv("ISST_PDL");
+  ctx->pdl = !(pd && std::string(pd) == "0");
   const isst_config& c = ctx->cfg;
   ISST_CHECK(c.n_conv >= 2 && c.n_conv <= ISST_MAX_CONV && c.n_adapter >= 0 && c.n_adapter <= ISST_MAX_CONV, "bad conv config");
   ctx->C = c.conv_dim[0];
@@ -1442,7 +1463,7 @@ int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids
     ISST_CUDA(cudaMemcpyAsync(ctx->lx, embeds_override, static_cast<size_t>(lb.M) * ctx->cfg.hidden * 2, cudaMemcpyDefault, st));
   } else {
     ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(lb.M) * ctx->cfg.hidden * 4);
-    embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, ctx->cfg.hidden);
+    ISST_CUDA(launch_k(ctx, embed_splice_kernel, dim3(lb.M), dim3(128), 0, st, mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, ctx->cfg.hidden));
     LAUNCH_CHECK(ctx);
   }
   ISST_TRY(tap(ctx, st, "prompt_embeds", ctx->lx, static_cast<size_t>(lb.M) * ctx->cfg.hidden * 2));
@@ -1515,7 +1536,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   // ---- step 0: splice + chunk prefill ----
   {
     ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(lb.M) * c.hidden * 4);
-    embed_splice_kernel<<<lb.M, 128, 0, st>>>(mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, c.hidden);
+    ISST_CUDA(launch_k(ctx, embed_splice_kernel, dim3(lb.M), dim3(128), 0, st, mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, c.hidden));
     LAUNCH_CHECK(ctx);
   }
   ISST_TRY(tap(ctx, st, "prompt_embeds", ctx->lx, static_cast<size_t>(lb.M) * c.hidden * 2));
@@ -1525,7 +1546,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   g.step = 0;
   {
     ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(lbytes));
-    greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
+    ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(n), dim3(1024), 0, st, ctx->logits, c.vocab, g));
     LAUNCH_CHECK(ctx);
   }
   // ---- decode steps ----
@@ -1546,7 +1567,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     ISST_CUDA(cudaEventRecord(ctx->ev_active, st));
     {
       ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(n) * c.hidden * 4);
-      embed_splice_kernel<<<n, 128, 0, st>>>(mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden);
+      ISST_CUDA(launch_k(ctx, embed_splice_kernel, dim3(n), dim3(128), 0, st, mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden));
       LAUNCH_CHECK(ctx);
     }
     db.kv_tokens = 0;
@@ -1561,7 +1582,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     g.step = step;
     {
       ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(lbytes));
-      greedy_select_kernel<<<n, 1024, 0, st>>>(ctx->logits, c.vocab, g);
+      ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(n), dim3(1024), 0, st, ctx->logits, c.vocab, g));
       LAUNCH_CHECK(ctx);
     }
   }

@@ -25,6 +25,8 @@ conv0_ln_gelu_kernel(const float* __restrict__ pcm,      // [n][n_new] new sampl
                      const float* __restrict__ bias, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, bf16* __restrict__ out,   // [n][T0][C]
                      int C, int k, int stride, int T0) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float c0_smem[];
   float* s_w = c0_smem;                 // k*C
   float* s_x = s_w + k * C;             // window span of this CTA
@@ -81,6 +83,8 @@ conv0_ln_gelu_kernel(const float* __restrict__ pcm,      // [n][n_new] new sampl
 // tail <- last n_tail samples of [tail | new]
 __global__ void update_tail_kernel(const float* __restrict__ pcm, float* tail, const int* __restrict__ slots,
                                    int n_new, int n_tail) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int slot = slots[b];
   float* t = tail + static_cast<size_t>(slot) * n_tail;
@@ -99,6 +103,8 @@ template <bool kRms, bool kGelu>
 __global__ void __launch_bounds__(128)
 norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const float* __restrict__ bvec,
                  const int* __restrict__ gather, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const bf16* x = in + static_cast<size_t>(gather ? gather[row] : row) * C;
   bf16* o = out + static_cast<size_t>(row) * C;
@@ -184,6 +190,8 @@ norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const f
 __global__ void embed_splice_kernel(const int* __restrict__ ids, const int* __restrict__ speech_row,
                                     const bf16* __restrict__ embed, const bf16* __restrict__ speech,
                                     bf16* __restrict__ out, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const int sr = speech_row ? speech_row[r] : -1;
   const bf16* src = sr >= 0 ? speech + static_cast<size_t>(sr) * D : embed + static_cast<size_t>(ids[r]) * D;
@@ -216,6 +224,8 @@ struct GenState {
 
 __global__ void __launch_bounds__(1024)
 greedy_select_kernel(float* logits, int V, GenState g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   if (!g.active[b]) return;
   float* lg = logits + static_cast<size_t>(b) * V;
@@ -287,6 +297,8 @@ greedy_select_kernel(float* logits, int V, GenState g) {
 // kv_len[slot] += T[b] for active streams (after all layers appended their K/V)
 __global__ void advance_kv_len_kernel(int* kv_len, const int* __restrict__ slots, const int* __restrict__ Tn,
                                       const int* __restrict__ active, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < n && (!active || active[b])) kv_len[slots[b]] += Tn[b];
 }
