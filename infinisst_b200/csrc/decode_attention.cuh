@@ -24,6 +24,7 @@ struct DecodeParams2 {
   const bf16* q_sys;        // [n, H * HD]: q rotated at (absolute index - evicted), for the pinned prefix keys
   PagedKV kv;               // kv_len = length BEFORE this token (its K/V are already appended)
   const int* slots;         // [n]
+  bf16* out;                // [n][H * HD]: written directly when splits == 1 (no combine pass)
   float* part_o;            // [n][H][splits][HD]
   float* part_ml;           // [n][H][splits][2]
   int H;
@@ -264,6 +265,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     const size_t pidx = pbase + static_cast<size_t>(hq) * p.splits;
     p.part_ml[pidx * 2] = mm;
     p.part_ml[pidx * 2 + 1] = ll;
+    sm_w[4 * GROUP + hq] = ll > 0.f ? 1.f / ll : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -272,7 +274,8 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     float oo = 0.f;
 #pragma unroll
     for (int w = 0; w < 4; ++w) oo += sm_w[w * GROUP + hq] * sm_o[(w * GROUP + hq) * HD + d];
-    p.part_o[(pbase + static_cast<size_t>(hq) * p.splits) * HD + d] = oo;
+    if (p.splits == 1) p.out[(static_cast<size_t>(b) * p.H + head * GROUP + hq) * HD + d] = __float2bfloat16_rn(oo * sm_w[4 * GROUP + hq]);
+    else p.part_o[(pbase + static_cast<size_t>(hq) * p.splits) * HD + d] = oo;
   }
 }
 

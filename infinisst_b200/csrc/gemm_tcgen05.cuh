@@ -48,7 +48,9 @@ struct GemmParams {
   long long resid_batch_stride;
   int act;                      // 0 none, 1 gelu(erf)
   float* ws;                    // split-K workspace
-  int* counters;                // one per output tile, zero on entry, zero on exit
+  int* counters;                // split-reduction arrival counters: two halves used by alternate launches
+  int counter_half;             // ints per half
+  int counter_parity;           // which half this launch uses; the other half is re-armed for the next launch
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -456,13 +458,12 @@ struct SkParams {
   int tiles_tok, tiles_feat;   // tiles per batch entry
   int num_kb;                  // k-blocks per tile
   long long tiles;             // batch * tiles_tok * tiles_feat
-  long long tiles_dp;          // tiles handled data-parallel (multiple of the grid size)
+  long long tiles_dp;          // tiles handled data-parallel, dealt round-robin (tile i * G + cta)
   long long units_sk;          // (tiles - tiles_dp) * num_kb
   int g_sk;                    // CTAs taking part in the stream-K part (<= grid, <= units_sk)
   unsigned long long* dbg;     // optional [grid][8] globaltimer stamps (phase analysis), may be null
 };
 
-constexpr int kSkThreads = 384;      // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
 
 template <int kBN, bool kDual, bool kSwap>
 struct SkCfg {
@@ -478,7 +479,13 @@ struct SkCfg {
   static constexpr int kTmemColsRaw = 2 * kAccCols;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
-  static constexpr int kEpiHalves = kBN >= 32 ? 2 : 1;     // column halves handled by warps 4-7 / 8-11
+  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue: 8 warps (2 column halves) for the big
+  // tensor-bound tiles, 4 for the weight-streaming (swap) mode whose epilogue is tiny - the smaller CTA leaves
+  // registers for a co-resident neighbour kernel under programmatic dependent launch
+  static constexpr int kEpiWarps = kSwap ? 4 : 8;
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  static constexpr int kThreadsTotal = 128 + kEpiThreads;
+  static constexpr int kEpiHalves = (kEpiWarps == 8 && kBN >= 32) ? 2 : 1;     // column halves handled by warps 4-7 / 8-11
   static constexpr int kHalfCols = kBN / kEpiHalves;
   static constexpr int kNC = (kSwap && kHalfCols >= 32) ? 32 : 16;   // columns per epilogue step
   static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
@@ -523,7 +530,7 @@ struct SkWalker {
   long long u, u1;             // stream-K unit cursor / end (units are relative to tile tiles_dp)
   __device__ SkWalker(const SkParams& s, int G_, int cta_) : sk(s), G(G_), cta(cta_) {
     dp_i = 0;
-    dp_n = sk.tiles_dp / G;
+    dp_n = (sk.tiles_dp + G - 1 - cta) / G;      // tiles i * G + cta below tiles_dp
     if (cta < sk.g_sk) { u = sk.units_sk * cta / sk.g_sk; u1 = sk.units_sk * (cta + 1) / sk.g_sk; }
     else { u = 0; u1 = 0; }
   }
@@ -547,7 +554,7 @@ struct SkWalker {
 };
 
 template <int kBN, bool kDual, bool kSwap>
-__global__ void __launch_bounds__(kSkThreads, 1)
+__global__ void __launch_bounds__(kSwap ? 256 : 384) __maxnreg__(kSwap ? 184 : 168)
 gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const GemmParams p, const SkParams sk) {
   using C = SkCfg<kBN, kDual, kSwap>;
@@ -575,7 +582,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 256);
+      mbar_init(&tempty_bar[a], C::kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -701,8 +708,12 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
     const int half = (warp - 4) >> 2;             // column half of the tile
     const int r = q * 32 + lane;                  // TMEM lane == row of the 128-row operand
-    const int et = threadIdx.x - 128;             // 0..255
+    const int et = threadIdx.x - 128;             // 0..kEpiThreads-1
     const bool works = half < C::kEpiHalves;
+    const int* counters = p.counters + (p.counter_parity ? p.counter_half : 0);
+    // the other half of the counter array belongs to the next GEMM launch: re-arm this CTA's slot now
+    // (its previous user completed before pdl_wait() returned)
+    if (et == 0) p.counters[(p.counter_parity ? 0 : p.counter_half) + cta] = 0;
     const int hc0 = half * C::kHalfCols;          // first column of this warp's half
     constexpr int NC = C::kNC;
     constexpr size_t kSlot = static_cast<size_t>(C::kAccCols) * kBM;
@@ -759,8 +770,8 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         tcgen05_fence_before();
         mbar_arrive(&tempty_bar[acc]);            // the accumulator is free again: MMAs of the next segment go on
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) atomicAdd(&p.counters[c_first], 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+        if (et == 0) atomicAdd(const_cast<int*>(&counters[c_first]), 1);
         part_tile[n_part++] = tile;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -774,17 +785,16 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
       const int c_last = sk_cta_of(ut + nkb - 1, sk.units_sk, sk.g_sk);
       const int nc = c_last - c_first + 1;
       if (et == 0) {
-        while (ld_acquire(&p.counters[c_first]) < nc) __nanosleep(64);
+        while (ld_acquire(&counters[c_first]) < nc) __nanosleep(32);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
       const SkTile t = sk_tile(tl, sk);
       const int lane_idx = (kSwap ? t.tf : t.tt) * kBM + r;
       const int col_base = (kSwap ? t.tt : t.tf) * kBN;
       // chunk list: kBN / 16 chunks dealt to (contributor, half) pairs
       constexpr int kChunks = kBN / 16;
-      const int workers = nc * 2;
-      const int me = (cta - c_first) * 2 + half;
+      const int workers = nc * C::kEpiHalves;
+      const int me = (cta - c_first) * C::kEpiHalves + half;
       const int ch0 = kChunks * me / workers, ch1 = kChunks * (me + 1) / workers;
 #pragma unroll 1
       for (int ch = ch0; ch < ch1; ++ch) {
@@ -803,12 +813,6 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         }
         if (kSwap) epilogue_store_swap<kDual, 16>(p, t.b, lane_idx, col_base + c, v0, v1);
         else epilogue_store16<kDual, false>(p, t.b, lane_idx, col_base + c, v0, v1);
-      }
-      // second phase of the counter: the last contributor to finish re-arms it for the next launch
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et == 0) {
-        const int prev = atomicAdd(&p.counters[c_first], 1);
-        if (prev == 2 * nc - 1) p.counters[c_first] = 0;
       }
     }
     if (sk.dbg && et == 0) sk.dbg[cta * 8 + 5] = gtimer();

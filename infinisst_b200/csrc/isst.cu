@@ -214,6 +214,7 @@ struct isst_ctx {
   size_t gemm_ws_floats = 0;
   int* gemm_counters = nullptr;
   int n_counters = 0;
+  int gemm_parity = 0;          // alternates per stream-K launch (counter halves)
   // batch metadata (device) + pinned host staging
   int* d_meta = nullptr;
   int* h_meta = nullptr;
@@ -341,15 +342,28 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   sk.dbg = ctx->gemm_dbg;
   long long G = std::min<long long>(ctx->sm_count, sk.tiles * sk.num_kb);
   if (force_splits > 0) G = std::min<long long>(G, sk.tiles * force_splits);
-  sk.tiles_dp = (sk.tiles / G) * G;
+  // Remainder policy: the tiles beyond the last full round-robin wave are either dealt as one more (partly
+  // empty) data-parallel round, or cut stream-K style into equal unit ranges.  Stream-K pays a split reduction
+  // (~6 us: park partial, fence, wait, reduce) and wins only when it shortens the critical path by more than
+  // that, i.e. when a whole tile is long compared with the reduction: `gain` units saved vs `r_units`.
+  const long long rem = sk.tiles % G;
+  const long long r_units = (kSwap && !kDual) ? 16 : 24;
+  bool use_sk = rem > 0 && (sk.num_kb - ceil_div(static_cast<int>(rem * sk.num_kb), static_cast<int>(G))) > r_units;
+  if (force_splits > 1) use_sk = rem > 0;
+  sk.tiles_dp = use_sk ? sk.tiles - rem : sk.tiles;
+  if (!use_sk && sk.tiles < G) G = sk.tiles;
   sk.units_sk = (sk.tiles - sk.tiles_dp) * sk.num_kb;
   sk.g_sk = static_cast<int>(std::min<long long>(G, sk.units_sk));
+  tc::GemmParams pp = p;
+  pp.counter_half = ctx->n_counters / 2;
+  pp.counter_parity = ctx->gemm_parity;
+  ctx->gemm_parity ^= 1;
   const size_t slot = static_cast<size_t>(C::kAccCols) * tc::kBM;
-  ISST_CHECK(2 * static_cast<size_t>(G) * slot <= ctx->gemm_ws_floats && G <= ctx->n_counters,
+  ISST_CHECK(2 * static_cast<size_t>(G) * slot <= ctx->gemm_ws_floats && G <= ctx->n_counters / 2,
              "gemm: stream-K workspace too small");
   CUtensorMap amap;
   ISST_TRY(get_act_map(ctx, &amap, v, C::kActRows));
-  ISST_CUDA(launch_k(ctx, kern, dim3(static_cast<unsigned>(G)), dim3(tc::kSkThreads), C::kSmemBytes, st, amap, w.map, p, sk));
+  ISST_CUDA(launch_k(ctx, kern, dim3(static_cast<unsigned>(G)), dim3(C::kThreadsTotal), C::kSmemBytes, st, amap, w.map, pp, sk));
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -833,7 +847,7 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
   }
   DecodeParams2 dp{};
   dp.qkv = qkv; dp.q_sys = ctx->lq_sys; dp.kv = kv; dp.slots = d_slots;
-  dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
+  dp.out = ctx->lattn; dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
   dp.splits = splits; dp.scale_log2 = scale_log2;
   ISST_CUDA(launch_k(ctx, decode_attention_mma_kernel<4>, dim3(splits, ctx->cfg.kv_heads, n), dim3(128), kDecSmemBytes, st, dp));
   LAUNCH_CHECK(ctx);
@@ -893,8 +907,10 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
       const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
       ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2));
-      ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits));
-      LAUNCH_CHECK(ctx);
+      if (splits > 1) {
+        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits));
+        LAUNCH_CHECK(ctx);
+      }
     }
     {
       Epilogue e;
