@@ -711,9 +711,10 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     const int et = threadIdx.x - 128;             // 0..kEpiThreads-1
     const bool works = half < C::kEpiHalves;
     const int* counters = p.counters + (p.counter_parity ? p.counter_half : 0);
-    // the other half of the counter array belongs to the next GEMM launch: re-arm this CTA's slot now
+    // the other half of the counter array belongs to the next GEMM launch (whatever its grid size): re-arm it now
     // (its previous user completed before pdl_wait() returned)
-    if (et == 0) p.counters[(p.counter_parity ? 0 : p.counter_half) + cta] = 0;
+    for (int i = cta * C::kEpiThreads + et; i < p.counter_half; i += G * C::kEpiThreads)
+      p.counters[(p.counter_parity ? 0 : p.counter_half) + i] = 0;
     const int hc0 = half * C::kHalfCols;          // first column of this warp's half
     constexpr int NC = C::kNC;
     constexpr size_t kSlot = static_cast<size_t>(C::kAccCols) * kBM;
