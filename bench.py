@@ -224,7 +224,7 @@ def main_reference(args, env):
         "gpu_launches": 0,
         "latency": {"p50_ms": 1e3 * pct(times, 0.5), "p99_ms": 1e3 * pct(times, 0.99), "streams": 1},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -242,7 +242,7 @@ def main_native(args, env):
                          "(use --impl reference for the CPU path)")
     rank, world, dev = env["rank"], env["world"], env["local_rank"]
     torch.cuda.set_device(dev)
-    sp.init("nccl")
+    sp.init("nccl", device=dev)
     S = args.streams
     cfg = production_config()
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
@@ -401,6 +401,8 @@ def main_native(args, env):
     all_e2e = sp.gather_floats([1e3 * t for t in e2e_lat])
 
     if rank != 0:
+        eng.close()
+        sp.shutdown()
         return 0
     cpu = None
     if world == 1 and args.cpu_baseline_chunks > 0:
@@ -432,12 +434,32 @@ def main_native(args, env):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
+    sp.shutdown()
     return 0
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: keep a private handle on it and point fd 1 at stderr so that
+    library chatter (NCCL version banners, warnings) cannot get in front of the line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

@@ -26,11 +26,17 @@ def shard_streams(n_streams: int, world: int, rank: int) -> List[int]:
     return list(range(rank, n_streams, world))
 
 
-def init(backend: str) -> None:
+def init(backend: str, device: int = -1) -> None:
     """Join the job described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun)."""
     if env_world()["world"] > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend)
+        kw = {"device_id": torch.device(f"cuda:{device}")} if (backend == "nccl" and device >= 0) else {}
+        dist.init_process_group(backend=backend, **kw)
+
+
+def shutdown() -> None:
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def barrier() -> None:
