@@ -506,10 +506,13 @@ __global__ void enc_rope_append_kernel(bf16* __restrict__ qkv, bf16* k_ring, bf1
 // patch_llm.py:294-299).  active[b] == 0 -> stream finished (EOS): nothing is appended.
 // One unit = 8 elements d..d+7 of the first half of a head together with d+64..d+71.
 // ----------------------------------------------------------------------------------------------
+// `part` (optional): fp32 split-K partial sums [n_part][rows][ldq] of the QKV projection; the row is then
+// bf16(sum_s part[s]) instead of the contents of `qkv` (deferred split reduction, see rowops.cuh).
 __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ q_sys, PagedKV kv,
                                        const int* __restrict__ slots, const int* __restrict__ tok_base,
                                        const int* __restrict__ Tn, const int* __restrict__ active,
-                                       const float2* __restrict__ tab_ring, const float2* __restrict__ tab_sys, int H) {
+                                       const float2* __restrict__ tab_ring, const float2* __restrict__ tab_sys, int H,
+                                       const float* __restrict__ part, int n_part, long long part_stride) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y;
@@ -529,8 +532,24 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict_
     const int d = (u % upr) * 8;
     const int rowi = tok_base[b] + i;
     bf16* src = qkv + static_cast<size_t>(rowi) * ldq + hh * HD;
-    uint4 lo = *reinterpret_cast<const uint4*>(src + d);
-    uint4 hi = *reinterpret_cast<const uint4*>(src + d + HALF);
+    uint4 lo, hi;
+    if (part) {
+      float al[8], ah[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { al[j] = 0.f; ah[j] = 0.f; }
+      for (int sp = 0; sp < n_part; ++sp) {
+        const float4* pl = reinterpret_cast<const float4*>(part + sp * part_stride + static_cast<size_t>(rowi) * ldq + hh * HD + d);
+        const float4* ph = reinterpret_cast<const float4*>(part + sp * part_stride + static_cast<size_t>(rowi) * ldq + hh * HD + d + HALF);
+        const float4 a0 = __ldcg(pl), a1 = __ldcg(pl + 1), b0 = __ldcg(ph), b1 = __ldcg(ph + 1);
+        al[0] += a0.x; al[1] += a0.y; al[2] += a0.z; al[3] += a0.w; al[4] += a1.x; al[5] += a1.y; al[6] += a1.z; al[7] += a1.w;
+        ah[0] += b0.x; ah[1] += b0.y; ah[2] += b0.z; ah[3] += b0.w; ah[4] += b1.x; ah[5] += b1.y; ah[6] += b1.z; ah[7] += b1.w;
+      }
+      lo = make_uint4(pack_bf16(al[0], al[1]), pack_bf16(al[2], al[3]), pack_bf16(al[4], al[5]), pack_bf16(al[6], al[7]));
+      hi = make_uint4(pack_bf16(ah[0], ah[1]), pack_bf16(ah[2], ah[3]), pack_bf16(ah[4], ah[5]), pack_bf16(ah[6], ah[7]));
+    } else {
+      lo = *reinterpret_cast<const uint4*>(src + d);
+      hi = *reinterpret_cast<const uint4*>(src + d + HALF);
+    }
     const int sl = kv_slot(base + i, sys_len, ring_start);
     if (hh >= H + kv.kv_heads) {                         // V: plain copy
       bf16* dst = kv.pool + kv_offset(kv, table, sl, 1, hh - H - kv.kv_heads);

@@ -47,6 +47,8 @@ struct GemmParams {
   long long ldr;
   long long resid_batch_stride;
   int act;                      // 0 none, 1 gelu(erf)
+  float* part_out;              // deferred split reduction: fp32 partials [split][M_tok][N_out] (consumer kernel sums), or null
+  int part_splits;              // k-ranges per tile in that mode
   float* ws;                    // split-K workspace
   int* counters;                // split-reduction arrival counters: two halves used by alternate launches
   int counter_half;             // ints per half
@@ -753,6 +755,26 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         tcgen05_fence_before();
         mbar_arrive(&tempty_bar[acc]);
       } else {
+        if (kSwap && p.part_out) {
+          // ---- deferred split reduction: this CTA's fp32 partial goes to part_out[split][tok][feature]; the
+          //      consumer row kernel (norm / RoPE-append) sums the splits - no fence, counter or wait here ----
+          const int split = cta % p.part_splits;
+          float* dst = p.part_out + (static_cast<size_t>(split) * p.M_tok) * p.N_out + lane_idx;
+          if (lane_idx < p.N_out) {
+#pragma unroll 1
+            for (int c = 0; c < kBN; c += 16) {
+              float v[16];
+              tmem_ld16(taddr + c, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col_base + c + i < p.M_tok) dst[static_cast<size_t>(col_base + c + i) * p.N_out] = v[i];
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         // ---- partial tile: park the fp32 partial and announce it; the reduction happens after the walk ----
         const long long ut = (tile - sk.tiles_dp) * nkb;
         const int c_first = sk_cta_of(ut, sk.units_sk, sk.g_sk);

@@ -215,6 +215,9 @@ struct isst_ctx {
   int* gemm_counters = nullptr;
   int n_counters = 0;
   int gemm_parity = 0;          // alternates per stream-K launch (counter halves)
+  float* defer_ws = nullptr;    // fp32 split partials of a deferred-reduction GEMM [splits][tokens][features]
+  size_t defer_ws_floats = 0;
+  int last_defer_splits = 0;    // splits the last gemm() call left in defer_ws (0: output complete)
   // batch metadata (device) + pinned host staging
   int* d_meta = nullptr;
   int* h_meta = nullptr;
@@ -291,6 +294,7 @@ struct Epilogue {
   long long resid_batch_stride = 0;
   int out_f32 = 0;
   int dual = 0;   // 1: weights hold [gate; up] stacked, rows N_out and dual_off + N_out
+  bool defer = false;   // weight-streaming mode only: leave fp32 split partials in ctx->defer_ws for the consumer row kernel
   int dual_off = 0;
 };
 
@@ -355,6 +359,23 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   sk.units_sk = (sk.tiles - sk.tiles_dp) * sk.num_kb;
   sk.g_sk = static_cast<int>(std::min<long long>(G, sk.units_sk));
   tc::GemmParams pp = p;
+  ctx->last_defer_splits = 0;
+  if (p.part_out) {
+    // Deferred split reduction: every tile is cut into S equal k-ranges (one CTA each, tiles * S <= #SMs) and the
+    // partials are summed by the consumer row kernel; falls back to the in-kernel schemes when S would be 1.
+    pp.part_out = nullptr;
+    const long long S = std::min<long long>(std::min<long long>(ctx->sm_count / std::max<long long>(sk.tiles, 1), 8), sk.num_kb / 8);
+    if (kSwap && p.batch == 1 && S >= 2 && force_splits == 0 &&
+        static_cast<size_t>(S) * p.M_tok * p.N_out <= ctx->defer_ws_floats) {
+      G = sk.tiles * S;
+      sk.tiles_dp = 0;
+      sk.units_sk = sk.tiles * sk.num_kb;
+      sk.g_sk = static_cast<int>(G);
+      pp.part_out = ctx->defer_ws;
+      pp.part_splits = static_cast<int>(S);
+      ctx->last_defer_splits = static_cast<int>(S);
+    }
+  }
   pp.counter_half = ctx->n_counters / 2;
   pp.counter_parity = ctx->gemm_parity;
   ctx->gemm_parity ^= 1;
@@ -391,6 +412,9 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
   p.act = e.act;
   p.ws = ctx->gemm_ws;
   p.counters = ctx->gemm_counters;
+  p.part_out = e.defer ? ctx->defer_ws : nullptr;   // request; launch_sk decides (ctx->last_defer_splits)
+  p.part_splits = 0;
+  ctx->last_defer_splits = 0;
   ISST_CHECK(v.K == w.K, "gemm: K mismatch");
   const bool simple = force_simple >= 0 ? (force_simple != 0) : ctx->simple_gemm;
   // algorithmic work: every operand touched once (weights dominate when few tokens stream them)
@@ -643,13 +667,13 @@ struct MetaBuilder {
 // encoder
 // ------------------------------------------------------------------------------------------------
 static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const bf16* in, bf16* out, const float* w,
-                     const float* b, const int* gather, int rows, int C, float eps) {
+                     const float* b, const int* gather, int rows, int C, float eps, DeferredSum ds = DeferredSum{nullptr, 0, 0, nullptr}) {
   ISST_CHECK(C % 8 == 0 && C <= 4096, "norm_rows: unsupported width");
   if (rows == 0) return 0;
   ProfScope ps(ctx, st, P_NORM, 0.0, static_cast<double>(rows) * C * 4);
-  if (rms) ISST_CUDA(launch_k(ctx, norm_rows_kernel<true, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps));
-  else if (gelu) ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, true>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps));
-  else ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps));
+  if (rms) ISST_CUDA(launch_k(ctx, norm_rows_kernel<true, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps, ds));
+  else if (gelu) ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, true>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps, ds));
+  else ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps, ds));
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -869,19 +893,29 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
                        ctx->llm_inv_freq, HD / 2, 0));
     LAUNCH_CHECK(ctx);
   }
+  // Weight-streaming regime (few tokens): the QKV / o_proj / down_proj GEMMs leave fp32 split partials and the
+  // following row kernel (RoPE-append, RMSNorm) sums them while it reads the row anyway, adds the residual and
+  // writes the residual stream back - the GEMMs lose their whole cross-CTA reduction phase.
+  const bool defer = M <= 128;
+  DeferredSum pending{nullptr, 0, 0, nullptr};     // down_proj partials of the previous layer
   for (int l = 0; l < c.layers; ++l) {
     LlmLayerW& w = ctx->llm[l];
-    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms1, nullptr, nullptr, M, D, c.rms_eps));
+    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms1, nullptr, nullptr, M, D, c.rms_eps, pending));
+    pending = DeferredSum{nullptr, 0, 0, nullptr};
+    int qkv_splits = 0;
     {
       Epilogue e;
+      e.defer = defer;
       ISST_TRY(gemm(ctx, st, plain_view(ctx->lh, M, D), w.wqkv, QKV, ctx->lqkv, QKV, 0, e));
+      qkv_splits = ctx->last_defer_splits;
     }
     PagedKV kv = paged_kv(ctx, l);
     {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
       dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
       ISST_CUDA(launch_k(ctx, llm_rope_append_kernel, grid, dim3(128), 0, st, ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T,
-                         lb.d_active, ctx->llm_rope_ring, ctx->llm_rope_sys, H));
+                         lb.d_active, ctx->llm_rope_ring, ctx->llm_rope_sys, H, qkv_splits ? ctx->defer_ws : nullptr, qkv_splits,
+                         static_cast<long long>(M) * QKV));
       LAUNCH_CHECK(ctx);
     }
     if (!lb.decode) {
@@ -912,12 +946,15 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
         LAUNCH_CHECK(ctx);
       }
     }
+    DeferredSum o_sum{nullptr, 0, 0, nullptr};
     {
       Epilogue e;
+      e.defer = defer;
       e.resid = ctx->lx; e.ldr = D;
       ISST_TRY(gemm(ctx, st, plain_view(ctx->lattn, M, H * HD), w.wo, D, ctx->lx, D, 0, e));
+      if (ctx->last_defer_splits) o_sum = DeferredSum{ctx->defer_ws, ctx->last_defer_splits, static_cast<long long>(M) * D, ctx->lx};
     }
-    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms2, nullptr, nullptr, M, D, c.rms_eps));
+    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms2, nullptr, nullptr, M, D, c.rms_eps, o_sum));
     {
       Epilogue e;
       e.dual = 1; e.dual_off = F;
@@ -925,17 +962,25 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
     }
     {
       Epilogue e;
+      e.defer = defer;
       e.resid = ctx->lx; e.ldr = D;
       ISST_TRY(gemm(ctx, st, plain_view(ctx->lgu, M, F), w.wd, D, ctx->lx, D, 0, e));
+      if (ctx->last_defer_splits) pending = DeferredSum{ctx->defer_ws, ctx->last_defer_splits, static_cast<long long>(M) * D, ctx->lx};
     }
-    if (tap_layers && ctx->debug)
+    if (tap_layers && ctx->debug) {
+      if (pending.part) {   // materialise the layer output for the tap (debug only)
+        ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms1, nullptr, nullptr, M, D, c.rms_eps, pending));
+        pending = DeferredSum{nullptr, 0, 0, nullptr};
+      }
       ISST_TRY(tap(ctx, st, "llm_layer_" + std::to_string(l), ctx->lx, static_cast<size_t>(M) * D * 2));
+    }
   }
   ISST_CUDA(launch_k(ctx, advance_kv_len_kernel, dim3(ceil_div(lb.n, 128)), dim3(128), 0, st, ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n));
   LAUNCH_CHECK(ctx);
   // final norm + lm_head on the LAST position of each stream only (the reference computes and discards
   // the other T-1 rows, llm.py:236-237 / SURVEY §2.3 L9)
-  ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->llast, ctx->final_norm, nullptr, lb.d_last_row, lb.n, D, c.rms_eps));
+  pending.x_out = nullptr;   // only the gathered last rows are completed; the residual stream is not needed any more
+  ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->llast, ctx->final_norm, nullptr, lb.d_last_row, lb.n, D, c.rms_eps, pending));
   {
     Epilogue e;
     e.out_f32 = 1;
@@ -1142,6 +1187,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->part_ml, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * 2));
   ctx->gemm_ws_floats = static_cast<size_t>(16) << 20;   // 64 MB
   ISST_TRY(dev_alloc(&ctx->gemm_ws, ctx->gemm_ws_floats));
+  ctx->defer_ws_floats = static_cast<size_t>(8) * 128 * std::max(QKV, HID);   // <= 8 splits x <= 128 tokens x widest deferred output
+  ISST_TRY(dev_alloc(&ctx->defer_ws, ctx->defer_ws_floats));
   ctx->n_counters = 4096;
   ISST_TRY(dev_alloc(&ctx->gemm_counters, ctx->n_counters));
   ISST_CUDA(cudaMemset(ctx->gemm_counters, 0, ctx->n_counters * sizeof(int)));
@@ -1172,7 +1219,7 @@ void isst_destroy(isst_ctx* ctx) {
                   ctx->tail, ctx->d_enc_prefix, ctx->d_page_table, ctx->d_kv_len, ctx->d_sys_len, ctx->d_ring_start,
                   ctx->d_pcm, ctx->conv_a, ctx->conv_b, ctx->ex, ctx->eh, ctx->eqkv, ctx->eattn, ctx->effn, ctx->ead0,
                   ctx->ead1, ctx->speech, ctx->lx, ctx->lh, ctx->lqkv, ctx->lattn, ctx->lgu, ctx->llast, ctx->logits,
-                  ctx->part_o, ctx->part_ml, ctx->gemm_ws, ctx->gemm_counters, ctx->d_meta};
+                  ctx->part_o, ctx->part_ml, ctx->gemm_ws, ctx->defer_ws, ctx->gemm_counters, ctx->d_meta};
   for (void* p : misc) cudaFree(p);
   for (auto& t : ctx->taps) cudaFree(t.second.first);
   cudaFreeHost(ctx->h_meta);

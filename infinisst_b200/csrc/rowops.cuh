@@ -99,14 +99,26 @@ __global__ void update_tail_kernel(const float* __restrict__ pcm, float* tail, c
 //   kGelu: GELU(erf) after the norm (conv feature extractor / length adapter blocks)
 //   gather: optional row indices into `in` (last-token gather before the final norm + lm_head)
 // ----------------------------------------------------------------------------------------------
+// Deferred split-K reduction (weight-streaming GEMMs): when `part` is given, the row is first completed as
+//   x = bf16( in + sum_s part[s][row] )        (fp32 partial sums of the preceding GEMM, in split order)
+// and written back to `x_out` (the residual stream) before it is normalised - the GEMM then needs no
+// cross-CTA reduction phase of its own.
+struct DeferredSum {
+  const float* part;        // [n_part][rows][C] fp32, or null
+  int n_part;
+  long long stride;         // rows * C
+  bf16* x_out;              // completed rows (may alias `in`), or null
+};
+
 template <bool kRms, bool kGelu>
 __global__ void __launch_bounds__(128)
 norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const float* __restrict__ bvec,
-                 const int* __restrict__ gather, int C, float eps) {
+                 const int* __restrict__ gather, int C, float eps, DeferredSum ds) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x;
-  const bf16* x = in + static_cast<size_t>(gather ? gather[row] : row) * C;
+  const size_t src_row = gather ? gather[row] : row;
+  const bf16* x = in + src_row * C;
   bf16* o = out + static_cast<size_t>(row) * C;
   const int tid = threadIdx.x;
   float v[4][8];
@@ -116,6 +128,26 @@ norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const f
     const int c0 = (it * 128 + tid) * 8;
     if (c0 < C) {
       uint4 raw = *reinterpret_cast<const uint4*>(x + c0);
+      if (ds.part) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int sp = 0; sp < ds.n_part; ++sp) {
+          const float4* pp = reinterpret_cast<const float4*>(ds.part + sp * ds.stride + src_row * C + c0);
+          const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        const uint32_t ru[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t nu[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(ru[j]);
+          nu[j] = pack_bf16(acc[2 * j] + f.x, acc[2 * j + 1] + f.y);
+        }
+        raw = make_uint4(nu[0], nu[1], nu[2], nu[3]);
+        if (ds.x_out) *reinterpret_cast<uint4*>(ds.x_out + src_row * C + c0) = raw;
+      }
       const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
