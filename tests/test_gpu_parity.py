@@ -104,9 +104,11 @@ def test_gemm_vs_torch_fp32(op_engine, impl):
 # ----------------------------------------------------------------------------------------------
 # the per-chunk step, tiny config (production head sizes -> production kernels)
 # ----------------------------------------------------------------------------------------------
-def _run_stream(cfg, n_chunks, check_taps=True, yardstick=False):
+def _run_stream(cfg, n_chunks, check_taps=True, yardstick=False, m=1):
+    SEG = 15360 * m                                   # samples per policy call at latency multiplier m
+    cfg.gen.latency_multiplier, cfg.gen.max_new_tokens = m, 10 * m
     sd = bf16_weights(make_state_dict(cfg, seed=0))
-    eng = _engine(cfg, sd, max_streams=2)
+    eng = _engine(cfg, sd, max_streams=2, max_multiplier=m, max_prompt=64 + 12 * m)
     eng.debug(True)
     audio = make_audio(n_chunks * SEG / 16000.0)
     orc = OracleStream(cfg, sd)
@@ -116,11 +118,14 @@ def _run_stream(cfg, n_chunks, check_taps=True, yardstick=False):
     stats = {"near_ties": 0, "steps": 0, "evictions": 0, "worst_logit": 0.0}
     for c in range(n_chunks):
         out_o, rec, taps = orc.chunk(audio[: (c + 1) * SEG].tolist())
-        ids = O.build_prompt(cfg.tpl, c == 0)
+        ids = O.build_prompt(cfg.tpl, c == 0, m)
         forced = rec.sequences[0][len(ids):]
         if yardstick:
             _, rec16, taps16 = orc16.chunk(audio[: (c + 1) * SEG].tolist(), forced=forced)
-        feats = eng.encode_chunk([sid], _chunk_pcm(audio, c), 1, return_feats=True)
+        pcm = audio[c * SEG:(c + 1) * SEG][None].clone()
+        if c == 0:
+            pcm = torch.cat([torch.zeros(1, 399), pcm], 1)
+        feats = eng.encode_chunk([sid], pcm, m, return_feats=True)
         torch.cuda.synchronize()
         if check_taps:
             for name, okey in [("enc_conv", "conv"), ("enc_post_proj", "post_proj"), ("enc_layer_0", "enc_layer_0"),
@@ -178,6 +183,15 @@ def test_stream_with_both_windows_sliding():
     st = _run_stream(tiny_config(max_cache_size=96, max_llm_cache_size=150), 12, check_taps=True)
     assert st["evictions"] >= 6
     assert st["near_ties"] <= 0.01 * st["steps"] + 1
+
+
+@pytest.mark.parametrize("m", [2, 4])
+def test_latency_multipliers(m):
+    """48*m-frame chunks (block size scales with m, speech_encoder.py:143-145), 12*m speech
+    tokens per turn and max_new_tokens = 10*m (agents/infinisst.py:125-128,245)."""
+    st = _run_stream(tiny_config(max_cache_size=192, max_llm_cache_size=300), 6, check_taps=True, m=m)
+    assert st["evictions"] >= 1
+    assert st["near_ties"] <= 0.02 * st["steps"] + 1
 
 
 def test_long_stream_no_drift():
