@@ -295,6 +295,25 @@ def main_native(args, env):
         log(f"[bench] ncu step done, launches so far {eng.launch_count()}")
         eng.close()
         return 0
+    if args.timeline:
+        # profiling aid (never a bench value): CUPTI kernel timeline of one steady-state step, with the real
+        # overlaps of programmatic dependent launch (ncu serialises kernels and cannot show them)
+        from torch.profiler import ProfilerActivity, profile
+        x = next_pcm()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run.step_device(x)
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                     key=lambda e: e.time_range.start)
+        t0 = evs[0].time_range.start
+        with open(args.timeline, "w") as f:
+            f.write("# start_us dur_us name   (one steady-state step, 64 streams; CUPTI activity records)\n")
+            for e in evs:
+                f.write(f"{e.time_range.start - t0:.2f} {e.time_range.end - e.time_range.start:.2f} {e.name[:60]}\n")
+        log(f"[bench] timeline of {len(evs)} kernels written to {args.timeline}")
+        eng.close()
+        return 0
     inputs = [next_pcm() for _ in range(args.steps)]
     clocks = ClockSampler(dev)
     torch.cuda.synchronize()
@@ -468,6 +487,7 @@ def main():
     ap.add_argument("--streams", type=int, default=64, help="concurrent streams per GPU")
     ap.add_argument("--prime", type=int, default=34, help="untimed chunks run first so both sliding windows are full")
     ap.add_argument("--latency-chunks", type=int, default=20, help="single-stream latency sample (0 = skip)")
+    ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline of one step to this file and exit")
     ap.add_argument("--ncu-step", action="store_true", help="run ONE profiled step after priming and exit (for ncu)")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=3, help="oracle chunks timed on the host at N=1 (0 = skip)")
     args = ap.parse_args()

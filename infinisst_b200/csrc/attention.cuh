@@ -537,12 +537,26 @@ __global__ void llm_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict_
       float al[8], ah[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { al[j] = 0.f; ah[j] = 0.f; }
-      for (int sp = 0; sp < n_part; ++sp) {
-        const float4* pl = reinterpret_cast<const float4*>(part + sp * part_stride + static_cast<size_t>(rowi) * ldq + hh * HD + d);
-        const float4* ph = reinterpret_cast<const float4*>(part + sp * part_stride + static_cast<size_t>(rowi) * ldq + hh * HD + d + HALF);
-        const float4 a0 = __ldcg(pl), a1 = __ldcg(pl + 1), b0 = __ldcg(ph), b1 = __ldcg(ph + 1);
-        al[0] += a0.x; al[1] += a0.y; al[2] += a0.z; al[3] += a0.w; al[4] += a1.x; al[5] += a1.y; al[6] += a1.z; al[7] += a1.w;
-        ah[0] += b0.x; ah[1] += b0.y; ah[2] += b0.z; ah[3] += b0.w; ah[4] += b1.x; ah[5] += b1.y; ah[6] += b1.z; ah[7] += b1.w;
+      const float* p0 = part + static_cast<size_t>(rowi) * ldq + hh * HD + d;
+      for (int sp0 = 0; sp0 < n_part; sp0 += 4) {          // four partials' loads in flight at once
+        float4 a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (sp0 + q < n_part) {
+            const float4* pl = reinterpret_cast<const float4*>(p0 + (sp0 + q) * part_stride);
+            const float4* ph = reinterpret_cast<const float4*>(p0 + (sp0 + q) * part_stride + HALF);
+            a0[q] = __ldcg(pl); a1[q] = __ldcg(pl + 1); b0[q] = __ldcg(ph); b1[q] = __ldcg(ph + 1);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (sp0 + q < n_part) {
+            al[0] += a0[q].x; al[1] += a0[q].y; al[2] += a0[q].z; al[3] += a0[q].w;
+            al[4] += a1[q].x; al[5] += a1[q].y; al[6] += a1[q].z; al[7] += a1[q].w;
+            ah[0] += b0[q].x; ah[1] += b0[q].y; ah[2] += b0[q].z; ah[3] += b0[q].w;
+            ah[4] += b1[q].x; ah[5] += b1[q].y; ah[6] += b1[q].z; ah[7] += b1[q].w;
+          }
+        }
       }
       lo = make_uint4(pack_bf16(al[0], al[1]), pack_bf16(al[2], al[3]), pack_bf16(al[4], al[5]), pack_bf16(al[6], al[7]));
       hi = make_uint4(pack_bf16(ah[0], ah[1]), pack_bf16(ah[2], ah[3]), pack_bf16(ah[4], ah[5]), pack_bf16(ah[6], ah[7]));

@@ -164,28 +164,31 @@ template <bool kDual, int NC>
 __device__ __forceinline__ void epilogue_store_swap(const GemmParams& p, int b, int f, int col0,
                                                     const float* v0, const float* v1) {
   if (f >= p.N_out) return;
-  const long long obase = static_cast<long long>(b) * p.out_batch_stride;
-  const long long rbase = static_cast<long long>(b) * p.resid_batch_stride;
   const float bias = p.bias ? p.bias[f] : 0.f;
+  const int n = min(NC, p.M_tok - col0);          // valid token columns of this chunk
   // Residual values are read up front: `resid` may alias `out` (x += ...), so a load issued after a store
   // is serialised behind it (one dependent L2 round trip per token otherwise).
   float rv[NC];
+  if (p.resid) {
+    const bf16* r = p.resid + static_cast<long long>(b) * p.resid_batch_stride + static_cast<long long>(col0) * p.ldr + f;
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int tok = col0 + i;
-    rv[i] = (p.resid && tok < p.M_tok) ? __bfloat162float(p.resid[rbase + static_cast<long long>(tok) * p.ldr + f]) : 0.f;
+    for (int i = 0; i < NC; ++i) rv[i] = i < n ? __bfloat162float(r[static_cast<long long>(i) * p.ldr]) : 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) rv[i] = 0.f;
   }
+  const long long o0 = static_cast<long long>(b) * p.out_batch_stride + static_cast<long long>(col0) * p.ldo + f;
+  float* of = reinterpret_cast<float*>(p.out) + o0;
+  bf16* ob = reinterpret_cast<bf16*>(p.out) + o0;
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    const int tok = col0 + i;
-    if (tok < p.M_tok) {
-      float x = v0[i] + bias;
-      if (kDual) x = silu(x) * v1[i];
-      if (p.act == 1) x = gelu_erf(x);
-      x += rv[i];
-      const long long oi = obase + static_cast<long long>(tok) * p.ldo + f;
-      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = x;
-      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(x);
+    float x = v0[i] + bias;
+    if (kDual) x = __fdividef(x, 1.0f + __expf(-x)) * v1[i];      // SiLU(gate) * up; the result is rounded to bf16
+    if (p.act == 1) x = gelu_erf(x);
+    x += rv[i];
+    if (i < n) {
+      if (p.out_f32) of[static_cast<long long>(i) * p.ldo] = x;
+      else ob[static_cast<long long>(i) * p.ldo] = __float2bfloat16_rn(x);
     }
   }
 }
@@ -484,12 +487,12 @@ struct SkCfg {
   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue: 8 warps (2 column halves) for the big
   // tensor-bound tiles, 4 for the weight-streaming (swap) mode whose epilogue is tiny - the smaller CTA leaves
   // registers for a co-resident neighbour kernel under programmatic dependent launch
-  static constexpr int kEpiWarps = kSwap ? 4 : 8;
+  static constexpr int kEpiWarps = 8;
   static constexpr int kEpiThreads = kEpiWarps * 32;
   static constexpr int kThreadsTotal = 128 + kEpiThreads;
   static constexpr int kEpiHalves = (kEpiWarps == 8 && kBN >= 32) ? 2 : 1;     // column halves handled by warps 4-7 / 8-11
   static constexpr int kHalfCols = kBN / kEpiHalves;
-  static constexpr int kNC = (kSwap && kHalfCols >= 32) ? 32 : 16;   // columns per epilogue step
+  static constexpr int kNC = (kSwap && !kDual && kHalfCols >= 32) ? 32 : 16;   // columns per epilogue step
   static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
   static_assert(kTmemColsRaw <= 512, "two accumulators must fit TMEM");
   static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
@@ -556,7 +559,7 @@ struct SkWalker {
 };
 
 template <int kBN, bool kDual, bool kSwap>
-__global__ void __launch_bounds__(kSwap ? 256 : 384) __maxnreg__(kSwap ? 184 : 168)
+__global__ void __launch_bounds__(384) __maxnreg__(kSwap ? 128 : 168)
 gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const GemmParams p, const SkParams sk) {
   using C = SkCfg<kBN, kDual, kSwap>;
@@ -759,15 +762,16 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
           // ---- deferred split reduction: this CTA's fp32 partial goes to part_out[split][tok][feature]; the
           //      consumer row kernel (norm / RoPE-append) sums the splits - no fence, counter or wait here ----
           const int split = cta % p.part_splits;
-          float* dst = p.part_out + (static_cast<size_t>(split) * p.M_tok) * p.N_out + lane_idx;
-          if (lane_idx < p.N_out) {
+          if (works && lane_idx < p.N_out) {
+            float* dst = p.part_out + (static_cast<size_t>(split) * p.M_tok + col_base + hc0) * p.N_out + lane_idx;
+            const int n_tok = p.M_tok - col_base - hc0;          // valid token columns from hc0 on
 #pragma unroll 1
-            for (int c = 0; c < kBN; c += 16) {
+            for (int c = 0; c < C::kHalfCols; c += 16) {
               float v[16];
-              tmem_ld16(taddr + c, v);
+              tmem_ld16(taddr + hc0 + c, v);
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (col_base + c + i < p.M_tok) dst[static_cast<size_t>(col_base + c + i) * p.N_out] = v[i];
+                if (c + i < n_tok) dst[static_cast<size_t>(c + i) * p.N_out] = v[i];
             }
           }
           tcgen05_fence_before();

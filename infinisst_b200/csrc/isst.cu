@@ -208,6 +208,7 @@ struct isst_ctx {
   int speech_rows_per_stream = 0;
   bf16 *lx = nullptr, *lh = nullptr, *lqkv = nullptr, *lattn = nullptr, *lgu = nullptr, *llast = nullptr;
   float* logits = nullptr;
+  SelectWs sel_ws{nullptr, nullptr, nullptr};
   float *part_o = nullptr, *part_ml = nullptr;
   int decode_splits = 1;
   float* gemm_ws = nullptr;
@@ -351,7 +352,8 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   // (~6 us: park partial, fence, wait, reduce) and wins only when it shortens the critical path by more than
   // that, i.e. when a whole tile is long compared with the reduction: `gain` units saved vs `r_units`.
   const long long rem = sk.tiles % G;
-  const long long r_units = (kSwap && !kDual) ? 16 : 24;
+  static const char* ru_env = getenv("ISST_SK_RUNITS");     // tuning aid
+  const long long r_units = ru_env ? atoi(ru_env) : ((kSwap && !kDual) ? 16 : 24);
   bool use_sk = rem > 0 && (sk.num_kb - ceil_div(static_cast<int>(rem * sk.num_kb), static_cast<int>(G))) > r_units;
   if (force_splits > 1) use_sk = rem > 0;
   sk.tiles_dp = use_sk ? sk.tiles - rem : sk.tiles;
@@ -671,9 +673,18 @@ static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const 
   ISST_CHECK(C % 8 == 0 && C <= 4096, "norm_rows: unsupported width");
   if (rows == 0) return 0;
   ProfScope ps(ctx, st, P_NORM, 0.0, static_cast<double>(rows) * C * 4);
-  if (rms) ISST_CUDA(launch_k(ctx, norm_rows_kernel<true, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps, ds));
-  else if (gelu) ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, true>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps, ds));
-  else ISST_CUDA(launch_k(ctx, norm_rows_kernel<false, false>, dim3(rows), dim3(128), 0, st, in, out, w, b, gather, C, eps, ds));
+  // few rows (decode: one row per stream): one 16-byte column group per thread, every load in flight at once
+  const bool wide = rows <= 512 && C >= 1024;
+  const int threads = wide ? ((C / 8 + 31) / 32) * 32 : 128;
+#define ISST_NORM(RMS, GELU) \
+  do { \
+    if (wide) ISST_CUDA(launch_k(ctx, norm_rows_kernel<RMS, GELU, 1>, dim3(rows), dim3(threads), 0, st, in, out, w, b, gather, C, eps, ds)); \
+    else ISST_CUDA(launch_k(ctx, norm_rows_kernel<RMS, GELU, 4>, dim3(rows), dim3(threads), 0, st, in, out, w, b, gather, C, eps, ds)); \
+  } while (0)
+  if (rms) ISST_NORM(true, false);
+  else if (gelu) ISST_NORM(false, true);
+  else ISST_NORM(false, false);
+#undef ISST_NORM
   LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1182,6 +1193,10 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->llm_rope_sys, ML * (c.head_dim / 2)));
   ISST_TRY(dev_alloc(&ctx->enc_rope_tab, ME * (D / c.enc_heads / 2)));
   ISST_TRY(dev_alloc(&ctx->logits, static_cast<size_t>(nb) * c.vocab));
+  ISST_TRY(dev_alloc(&ctx->sel_ws.best, static_cast<size_t>(nb) * kSelParts));
+  ISST_TRY(dev_alloc(&ctx->sel_ws.idx, static_cast<size_t>(nb) * kSelParts));
+  ISST_TRY(dev_alloc(&ctx->sel_ws.count, static_cast<size_t>(nb)));
+  ISST_CUDA(cudaMemset(ctx->sel_ws.count, 0, static_cast<size_t>(nb) * sizeof(int)));
   ctx->decode_splits = 32;
   ISST_TRY(dev_alloc(&ctx->part_o, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * c.head_dim));
   ISST_TRY(dev_alloc(&ctx->part_ml, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * 2));
@@ -1219,7 +1234,8 @@ void isst_destroy(isst_ctx* ctx) {
                   ctx->tail, ctx->d_enc_prefix, ctx->d_page_table, ctx->d_kv_len, ctx->d_sys_len, ctx->d_ring_start,
                   ctx->d_pcm, ctx->conv_a, ctx->conv_b, ctx->ex, ctx->eh, ctx->eqkv, ctx->eattn, ctx->effn, ctx->ead0,
                   ctx->ead1, ctx->speech, ctx->lx, ctx->lh, ctx->lqkv, ctx->lattn, ctx->lgu, ctx->llast, ctx->logits,
-                  ctx->part_o, ctx->part_ml, ctx->gemm_ws, ctx->defer_ws, ctx->gemm_counters, ctx->d_meta};
+                  ctx->part_o, ctx->part_ml, ctx->gemm_ws, ctx->defer_ws, ctx->gemm_counters, ctx->d_meta,
+                  ctx->sel_ws.best, ctx->sel_ws.idx, ctx->sel_ws.count};
   for (void* p : misc) cudaFree(p);
   for (auto& t : ctx->taps) cudaFree(t.second.first);
   cudaFreeHost(ctx->h_meta);
@@ -1609,7 +1625,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   g.step = 0;
   {
     ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(lbytes));
-    ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(n), dim3(1024), 0, st, ctx->logits, c.vocab, g));
+    ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(kSelParts, n), dim3(kSelThreads), 0, st, ctx->logits, c.vocab, g, ctx->sel_ws));
     LAUNCH_CHECK(ctx);
   }
   // ---- decode steps ----
@@ -1645,7 +1661,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     g.step = step;
     {
       ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(lbytes));
-      ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(n), dim3(1024), 0, st, ctx->logits, c.vocab, g));
+      ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(kSelParts, n), dim3(kSelThreads), 0, st, ctx->logits, c.vocab, g, ctx->sel_ws));
       LAUNCH_CHECK(ctx);
     }
   }

@@ -110,33 +110,72 @@ struct DeferredSum {
   bf16* x_out;              // completed rows (may alias `in`), or null
 };
 
-template <bool kRms, bool kGelu>
-__global__ void __launch_bounds__(128)
+// kIts = 16-byte column groups per thread: 4 with 128 threads when there are many rows (bandwidth), 1 with up
+// to 512 threads when there are few (the decode step's 64 rows are latency-bound: every load of a thread is
+// issued up front, including all split partials).
+template <bool kRms, bool kGelu, int kIts>
+__global__ void __launch_bounds__(kIts == 1 ? 512 : 128)
 norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const float* __restrict__ bvec,
                  const int* __restrict__ gather, int C, float eps, DeferredSum ds) {
   pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  // weights do not depend on the predecessor kernel: fetch them ahead of the dependency wait
+  float wv[kIts][8], bv[kIts][8];
+#pragma unroll
+  for (int it = 0; it < kIts; ++it) {
+    const int c0 = (it * nthr + tid) * 8;
+    if (c0 < C) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w + c0), w1 = *reinterpret_cast<const float4*>(w + c0 + 4);
+      wv[it][0] = w0.x; wv[it][1] = w0.y; wv[it][2] = w0.z; wv[it][3] = w0.w;
+      wv[it][4] = w1.x; wv[it][5] = w1.y; wv[it][6] = w1.z; wv[it][7] = w1.w;
+      if (!kRms) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bvec + c0), b1 = *reinterpret_cast<const float4*>(bvec + c0 + 4);
+        bv[it][0] = b0.x; bv[it][1] = b0.y; bv[it][2] = b0.z; bv[it][3] = b0.w;
+        bv[it][4] = b1.x; bv[it][5] = b1.y; bv[it][6] = b1.z; bv[it][7] = b1.w;
+      }
+    }
+  }
   pdl_wait();
   const int row = blockIdx.x;
   const size_t src_row = gather ? gather[row] : row;
   const bf16* x = in + src_row * C;
   bf16* o = out + static_cast<size_t>(row) * C;
-  const int tid = threadIdx.x;
-  float v[4][8];
+  float v[kIts][8];
   float sum = 0.f, sq = 0.f;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c0 = (it * 128 + tid) * 8;
+  for (int it = 0; it < kIts; ++it) {
+    const int c0 = (it * nthr + tid) * 8;
     if (c0 < C) {
       uint4 raw = *reinterpret_cast<const uint4*>(x + c0);
       if (ds.part) {
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int sp = 0; sp < ds.n_part; ++sp) {
-          const float4* pp = reinterpret_cast<const float4*>(ds.part + sp * ds.stride + src_row * C + c0);
-          const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
-          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        const float* p0 = ds.part + src_row * C + c0;
+        if (kIts == 1 && ds.n_part <= 8) {
+          float4 pa[8], pb[8];
+#pragma unroll
+          for (int sp = 0; sp < 8; ++sp) {
+            if (sp < ds.n_part) {
+              const float4* pp = reinterpret_cast<const float4*>(p0 + sp * ds.stride);
+              pa[sp] = __ldcg(pp); pb[sp] = __ldcg(pp + 1);
+            }
+          }
+#pragma unroll
+          for (int sp = 0; sp < 8; ++sp) {
+            if (sp < ds.n_part) {
+              acc[0] += pa[sp].x; acc[1] += pa[sp].y; acc[2] += pa[sp].z; acc[3] += pa[sp].w;
+              acc[4] += pb[sp].x; acc[5] += pb[sp].y; acc[6] += pb[sp].z; acc[7] += pb[sp].w;
+            }
+          }
+        } else {
+          for (int sp = 0; sp < ds.n_part; ++sp) {
+            const float4* pp = reinterpret_cast<const float4*>(p0 + sp * ds.stride);
+            const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          }
         }
         const uint32_t ru[4] = {raw.x, raw.y, raw.z, raw.w};
         uint32_t nu[4];
@@ -158,28 +197,25 @@ norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const f
       }
     }
   }
-  __shared__ float red[2][4];
+  __shared__ float red[2][16];
   __shared__ float stat[2];
+  const int nwarp = nthr >> 5;
   sum = warp_sum(sum); sq = warp_sum(sq);
   if ((tid & 31) == 0) { red[0][tid >> 5] = sum; red[1][tid >> 5] = sq; }
   __syncthreads();
   if (tid == 0) {
-    const float s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-    const float q = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < nwarp; ++i) { s += red[0][i]; q += red[1][i]; }
     if (kRms) { stat[0] = 0.f; stat[1] = rsqrtf(q / C + eps); }
-    else {
-      const float mean = s / C;
-      stat[0] = mean;
-      stat[1] = -1.f;   // second pass below
-    }
+    else { stat[0] = s / C; stat[1] = -1.f; }   // variance in a second pass below
   }
   __syncthreads();
   float mean = stat[0], rstd = stat[1];
   if (!kRms) {
     float var = 0.f;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int c0 = (it * 128 + tid) * 8;
+    for (int it = 0; it < kIts; ++it) {
+      const int c0 = (it * nthr + tid) * 8;
       if (c0 < C) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mean; var += d * d; }
@@ -189,11 +225,13 @@ norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const f
     __syncthreads();
     if ((tid & 31) == 0) red[0][tid >> 5] = var;
     __syncthreads();
-    rstd = rsqrtf((red[0][0] + red[0][1] + red[0][2] + red[0][3]) / C + eps);
+    float tv = 0.f;
+    for (int i = 0; i < nwarp; ++i) tv += red[0][i];
+    rstd = rsqrtf(tv / C + eps);
   }
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c0 = (it * 128 + tid) * 8;
+  for (int it = 0; it < kIts; ++it) {
+    const int c0 = (it * nthr + tid) * 8;
     if (c0 < C) {
       uint32_t pk[4];
 #pragma unroll
@@ -201,10 +239,10 @@ norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const f
         float y[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int c = c0 + 2 * j + e;
+          const int k = 2 * j + e;
           float t;
-          if (kRms) t = w[c] * bf16_round(v[it][2 * j + e] * rstd);
-          else t = (v[it][2 * j + e] - mean) * rstd * w[c] + bvec[c];
+          if (kRms) t = wv[it][k] * bf16_round(v[it][k] * rstd);
+          else t = (v[it][k] - mean) * rstd * wv[it][k] + bv[it][k];
           if (kGelu) t = gelu_erf(bf16_round(t));
           y[e] = t;
         }
@@ -234,7 +272,7 @@ __global__ void embed_splice_kernel(const int* __restrict__ ids, const int* __re
 // ----------------------------------------------------------------------------------------------
 // Device-side greedy step: HF processor order RepetitionPenalty ->
 // NoRepeatNGram -> EncoderNoRepeatNGram -> SuppressTokens, then arg-max (lowest index wins ties),
-// EOS / max-length bookkeeping.  One CTA per stream; the host only ever sees token ids.
+// EOS / max-length bookkeeping.  kSelParts CTAs per stream; the host only ever sees token ids.
 // ----------------------------------------------------------------------------------------------
 struct GenState {
   int* ctx_ids;        // [n][ctx_cap]  prompt of this call + generated tokens
@@ -254,21 +292,42 @@ struct GenState {
   int step;
 };
 
-__global__ void __launch_bounds__(1024)
-greedy_select_kernel(float* logits, int V, GenState g) {
+constexpr int kSelParts = 16;       // CTAs per stream: each scans a contiguous 1/16 of the vocabulary
+constexpr int kSelThreads = 256;
+constexpr int kSelCtxSmem = 1024;   // prompt + generated ids staged in shared memory
+
+struct SelectWs {
+  float* best;   // [n][kSelParts]
+  int* idx;      // [n][kSelParts]
+  int* count;    // [n] arrival counters (left at 0 by the last CTA of every stream)
+};
+
+// grid (kSelParts, n).  A CTA applies the processors to the ids that fall into its slice of the vocabulary
+// (in place: nobody else touches that slice), takes the slice arg-max, and the last CTA of a stream to arrive
+// merges the kSelParts candidates and does the token bookkeeping.
+__global__ void __launch_bounds__(kSelThreads)
+greedy_select_kernel(float* logits, int V, GenState g, SelectWs ws) {
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int part = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   if (!g.active[b]) return;
   float* lg = logits + static_cast<size_t>(b) * V;
-  const int* ctx = g.ctx_ids + static_cast<size_t>(b) * g.ctx_cap;
+  const int per = (V + kSelParts - 1) / kSelParts;
+  const int lo = part * per, hi = min(V, lo + per);
   const int n_ctx = g.ctx_len[b];
   const int* enc = g.enc_ids + static_cast<size_t>(b) * g.enc_cap;
   const int n_enc = g.enc_len[b];
+  __shared__ int ctx_s[kSelCtxSmem];
+  const int* ctx_g = g.ctx_ids + static_cast<size_t>(b) * g.ctx_cap;
+  const bool staged = n_ctx <= kSelCtxSmem;
+  if (staged) for (int i = tid; i < n_ctx; i += kSelThreads) ctx_s[i] = ctx_g[i];
+  __syncthreads();
+  const int* ctx = staged ? ctx_s : ctx_g;
   // (1) repetition penalty, once per distinct id
   if (g.penalty != 1.0f) {
-    for (int i = tid; i < n_ctx; i += blockDim.x) {
+    for (int i = tid; i < n_ctx; i += kSelThreads) {
       const int id = ctx[i];
+      if (id < lo || id >= hi) continue;
       bool first = true;
       for (int j = 0; j < i; ++j) if (ctx[j] == id) { first = false; break; }
       if (first) { const float s = lg[id]; lg[id] = s < 0.f ? s * g.penalty : s / g.penalty; }
@@ -279,29 +338,45 @@ greedy_select_kernel(float* logits, int V, GenState g) {
   if (g.ngram > 0 && n_ctx + 1 >= g.ngram) {
     const int m = g.ngram - 1;
     const int* tail = ctx + n_ctx - m;
-    for (int t = tid; t + g.ngram <= n_ctx; t += blockDim.x) {
+    for (int t = tid; t + g.ngram <= n_ctx; t += kSelThreads) {
+      const int id = ctx[t + m];
+      if (id < lo || id >= hi) continue;
       bool eq = true;
       for (int j = 0; j < m; ++j) if (ctx[t + j] != tail[j]) { eq = false; break; }
-      if (eq) lg[ctx[t + m]] = -INFINITY;
+      if (eq) lg[id] = -INFINITY;
     }
-    for (int t = tid; t + g.ngram <= n_enc; t += blockDim.x) {
+    for (int t = tid; t + g.ngram <= n_enc; t += kSelThreads) {
+      const int id = enc[t + m];
+      if (id < lo || id >= hi) continue;
       bool eq = true;
       for (int j = 0; j < m; ++j) if (enc[t + j] != tail[j]) { eq = false; break; }
-      if (eq) lg[enc[t + m]] = -INFINITY;
+      if (eq) lg[id] = -INFINITY;
     }
   }
   // (4) suppress tokens
-  for (int i = tid; i < g.n_suppress; i += blockDim.x) lg[g.suppress[i]] = -INFINITY;
+  for (int i = tid; i < g.n_suppress; i += kSelThreads) {
+    const int id = g.suppress[i];
+    if (id >= lo && id < hi) lg[id] = -INFINITY;
+  }
   __syncthreads();
-  // (5) arg-max
+  // (5) slice arg-max (lowest index wins ties); four independent loads in flight per thread
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = tid; i < V; i += blockDim.x) {
-    const float s = lg[i];
-    if (s > best || (s == best && i < bi)) { best = s; bi = i; }
+  int i = lo + tid;
+  for (; i + 3 * kSelThreads < hi; i += 4 * kSelThreads) {
+    const float s0 = lg[i], s1 = lg[i + kSelThreads], s2 = lg[i + 2 * kSelThreads], s3 = lg[i + 3 * kSelThreads];
+    if (s0 > best) { best = s0; bi = i; }
+    if (s1 > best) { best = s1; bi = i + kSelThreads; }
+    if (s2 > best) { best = s2; bi = i + 2 * kSelThreads; }
+    if (s3 > best) { best = s3; bi = i + 3 * kSelThreads; }
   }
-  __shared__ float sb[32];
-  __shared__ int si[32];
+  for (; i < hi; i += kSelThreads) {
+    const float s = lg[i];
+    if (s > best) { best = s; bi = i; }
+  }
+  __shared__ float sb[kSelThreads / 32];
+  __shared__ int si[kSelThreads / 32];
+  __shared__ int last_flag;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -311,19 +386,33 @@ greedy_select_kernel(float* logits, int V, GenState g) {
   if ((tid & 31) == 0) { sb[tid >> 5] = best; si[tid >> 5] = bi; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < (blockDim.x >> 5); ++w)
+    for (int w = 1; w < kSelThreads / 32; ++w)
       if (sb[w] > best || (sb[w] == best && si[w] < bi)) { best = sb[w]; bi = si[w]; }
-    int tok = (bi == 0x7fffffff) ? 0 : bi;
-    if (g.forced) tok = g.forced[static_cast<size_t>(b) * g.max_new + g.step];
-    g.out_tokens[static_cast<size_t>(b) * g.max_new + g.step] = tok;
-    g.out_count[b] = g.step + 1;
-    g.next_token[b] = tok;
-    if (n_ctx < g.ctx_cap) g.ctx_ids[static_cast<size_t>(b) * g.ctx_cap + n_ctx] = tok;
-    g.ctx_len[b] = n_ctx + 1;
-    bool stop = false;
-    for (int e = 0; e < g.n_eos; ++e) if (tok == g.eos[e]) stop = true;
-    if (stop) g.active[b] = 0;
+    ws.best[b * kSelParts + part] = best;
+    ws.idx[b * kSelParts + part] = bi;
+    __threadfence();
+    last_flag = atomicAdd(&ws.count[b], 1) == kSelParts - 1;
   }
+  __syncthreads();
+  if (!last_flag || tid != 0) return;
+  __threadfence();
+  best = -INFINITY; bi = 0x7fffffff;
+  for (int p = 0; p < kSelParts; ++p) {
+    const float pb = __ldcg(ws.best + b * kSelParts + p);
+    const int pi = __ldcg(ws.idx + b * kSelParts + p);
+    if (pb > best || (pb == best && pi < bi)) { best = pb; bi = pi; }
+  }
+  ws.count[b] = 0;
+  int tok = (bi == 0x7fffffff) ? 0 : bi;
+  if (g.forced) tok = g.forced[static_cast<size_t>(b) * g.max_new + g.step];
+  g.out_tokens[static_cast<size_t>(b) * g.max_new + g.step] = tok;
+  g.out_count[b] = g.step + 1;
+  g.next_token[b] = tok;
+  if (n_ctx < g.ctx_cap) g.ctx_ids[static_cast<size_t>(b) * g.ctx_cap + n_ctx] = tok;
+  g.ctx_len[b] = n_ctx + 1;
+  bool stop = false;
+  for (int e = 0; e < g.n_eos; ++e) if (tok == g.eos[e]) stop = true;
+  if (stop) g.active[b] = 0;
 }
 
 // kv_len[slot] += T[b] for active streams (after all layers appended their K/V)
