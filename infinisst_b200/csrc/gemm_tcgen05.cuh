@@ -478,7 +478,7 @@ struct SkCfg {
   static constexpr int kActBytes = kActRows * kBK * 2;
   static constexpr int kWBytes = kWRows * kBK * 2;
   static constexpr int kStageBytes = kActBytes + kNW * kWBytes;
-  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+  static constexpr int kStagesRaw = (224 * 1024) / kStageBytes;     // 227 KB per CTA minus barriers / alignment slack
   static constexpr int kStages = kStagesRaw > 10 ? 10 : kStagesRaw;
   static constexpr int kAccCols = kBN * kNW;
   static constexpr int kTmemColsRaw = 2 * kAccCols;
@@ -578,29 +578,38 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
   if (sk.dbg && threadIdx.x == 0) sk.dbg[cta * 8 + 0] = gtimer();
   pdl_launch_dependents();      // the next kernel may start its own prologue / weight prefetch
 
-  if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_act)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
-    for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+  // Start-up: the producer warp initialises the barriers, ARRIVES at named barrier 2 and starts requesting weight
+  // tiles at once; everybody else waits there for the barriers and for the TMEM allocation (the producer needs
+  // neither the TMEM address nor the other warps).
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_act)) : "memory");
+      for (int s = 0; s < C::kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull_bar[a], 1);
+        mbar_init(&tempty_bar[a], C::kEpiThreads);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], C::kEpiThreads);
+    __syncwarp();
+    asm volatile("bar.arrive 2, %0;" ::"n"(C::kThreadsTotal) : "memory");
+  } else {
+    if (warp == 2) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(static_cast<uint32_t>(C::kTmemCols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tcgen05_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(C::kThreadsTotal) : "memory");
+    tcgen05_fence_after();
+    tmem_base = *tmem_ptr_smem;
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(static_cast<uint32_t>(C::kTmemCols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ================= TMA producer =================

@@ -43,7 +43,7 @@ from infinisst_b200.synthetic import make_audio, make_state_dict      # noqa: E4
 from parity_utils import bf16_weights                                  # noqa: E402
 from oracle import infinisst_oracle as O                               # noqa: E402  (prompt ids for the fake tokenizer only)
 
-N_CHUNKS = 8
+N_CHUNKS = int(os.environ.get("REF_PINS_CHUNKS", "8"))
 MAX_CACHE, MAX_LLM = 96, 150
 SEG_MS = 960
 
@@ -174,6 +174,7 @@ def build_reference_agent(cfg, sd):
 
     def generate(**kw):
         out = RS.greedy_generate(agent.model, eos_token_ids=g.eos_token_ids, **kw)
+        out.past_key_values_pre = [out.past_key_values.key_cache[-1].clone()]   # last layer: rows depend on the context, so they are unique
         taps["gen"] = out
         return out
     agent.model.generate = generate
@@ -195,6 +196,10 @@ def main():
         states.source = audio[: (c + 1) * seg].tolist()
         kv_before = 0 if states.past_key_values is None else states.past_key_values[0][0].size(2)
         agent.policy(states)
+        k_pre = taps["gen"].past_key_values_pre[0][0, 0]       # last-layer K right after generate (un-rotated rows)
+        k_post = states.past_key_values[len(states.past_key_values) - 1][0][0, 0]
+        kept_idx = [int((k_pre == row).all(dim=1).nonzero()[0]) for row in k_post]
+        out[f"c{c}_kept_idx"] = np.array(kept_idx, dtype=np.int32)
         gen = taps["gen"]
         out[f"c{c}_speech_feats"] = taps["speech_feats"][0].numpy().astype(np.float32)
         out[f"c{c}_step_logits"] = torch.stack([x[0] for x in gen.step_logits]).numpy().astype(np.float32)
@@ -207,6 +212,86 @@ def main():
         out[f"c{c}_enc_steps"] = np.int32(states.speech_cache.n_steps)
         out[f"c{c}_target_len"] = np.int32(len(states.target_ids))
         print(f"chunk {c}: kv {kv_before} -> {cur} -> {after}, emitted {out[f'c{c}_output_ids'].tolist()}")
+    # ---- latency multiplier 2: 1920 ms policy calls, 96-frame blocks, 24 speech tokens per
+    #      turn, max_new_tokens 20 (agents/infinisst.py:125-128,245; speech_encoder.py:143-145) ----
+    if N_CHUNKS >= 8:
+        m = 2
+        agent.update_multiplier(m)
+        agent.max_llm_cache_size, agent.cache_checkpoints = 200, []
+        st_m = agent.build_states()
+        st_m.reset()
+        st_m.source_sample_rate = 16000
+        n_m = 4
+        out["m2_n_chunks"], out["m2_max_llm"] = np.int32(n_m), np.int32(200)
+        for c in range(n_m):
+            st_m.source = audio[: (c + 1) * seg * m].tolist()
+            kv_before = 0 if st_m.past_key_values is None else st_m.past_key_values[0][0].size(2)
+            agent.policy(st_m)
+            gen = taps["gen"]
+            out[f"m2_c{c}_speech_feats"] = taps["speech_feats"][0].numpy().astype(np.float32)
+            out[f"m2_c{c}_step_logits"] = torch.stack([x[0] for x in gen.step_logits]).numpy().astype(np.float32)
+            out[f"m2_c{c}_sequence"] = gen.sequences[0].numpy().astype(np.int32)
+            out[f"m2_c{c}_kv"] = np.array([kv_before + gen.sequences.size(1) - 1, st_m.past_key_values[0][0].size(2)], dtype=np.int32)
+            print(f"m=2 chunk {c}: kv {kv_before} -> {out[f'm2_c{c}_kv'].tolist()}")
+        agent.update_multiplier(1)
+    # ---- eviction timelines: the agent's own eviction code (agents/infinisst.py:334-361) on a cache whose
+    #      entries are token serial numbers, so the kept index set can be read off directly.  `generate` is a
+    #      stub that only grows the cache by prompt + n_generated - 1 entries (drop-last rule). ----
+    scenarios = [  # (name, max_llm_cache_size, always_cache_system_prompt, n_chunks, gen-length pattern)
+        ("prod", 1000, True, 80, [10]),                                  # no EOS, 9 forwarded tokens
+        ("prod_ragged", 1000, True, 120, [10, 3, 7, 1, 10, 5, 2, 9]),     # early EOS: variable turn lengths
+        ("nosys", 300, False, 40, [10, 4, 8]),                           # --always-cache-system-prompt off
+        ("tight", 64, True, 12, [10]),                                   # window barely larger than a turn
+        ("overflow", 20, True, 6, [10]),                                 # a single turn exceeds the window (quirk: -0 slice)
+    ]
+    for name, max_llm, keep_sys, n_chunks, pattern in scenarios:
+        agent.max_llm_cache_size, agent.always_cache_system_prompt = max_llm, keep_sys
+        agent.cache_checkpoints = []
+        st2 = agent.build_states()
+        st2.reset()
+        st2.source_sample_rate = 16000
+        serial = [0]
+        step = [0]
+
+        def fake_generate(input_ids=None, past_key_values=None, max_new_tokens=10, **kw):
+            n_gen = min(pattern[step[0] % len(pattern)], max_new_tokens)
+            step[0] += 1
+            n_add = input_ids.size(1) + n_gen - 1
+            tags = torch.arange(serial[0], serial[0] + n_add, dtype=torch.float32).view(1, 1, n_add, 1)
+            serial[0] += n_add
+            cache = past_key_values if past_key_values is not None else RS.DynamicCache447()
+            cache.update(tags, tags.clone(), 0)
+            st2.speech_cache = object()                                   # "not the first chunk any more"
+            seq = torch.cat([input_ids, torch.full((1, n_gen), 7, dtype=torch.long)], dim=1)
+            return types.SimpleNamespace(sequences=seq, past_key_values=cache)
+        agent.model.generate = fake_generate
+        rows = []
+        alive = []                                                        # serial numbers currently in the cache
+        for c in range(n_chunks):
+            st2.source = [0.0] * ((c + 1) * seg)
+            serial_before = serial[0]
+            agent.policy(st2)
+            kept = st2.past_key_values[0][0][0, 0, :, 0].to(torch.int64).tolist()
+            pre = alive + list(range(serial_before, serial[0]))          # cache contents right after generate
+            idx = [pre.index(t) for t in kept]                            # logical indices kept (first match for duplicates)
+            rows.append((len(pre), len(kept), idx))
+            alive = kept
+        out[f"evict_{name}_cfg"] = np.array([max_llm, int(keep_sys), n_chunks, agent.system_prompt_size], dtype=np.int32)
+        out[f"evict_{name}_gen"] = np.array([pattern[i % len(pattern)] for i in range(n_chunks)], dtype=np.int32)
+        out[f"evict_{name}_cur_after"] = np.array([(r[0], r[1]) for r in rows], dtype=np.int32)
+        # kept logical indices as (start, stop) runs
+        runs = []
+        for ci, (_, _, idx) in enumerate(rows):
+            a = 0
+            while a < len(idx):
+                b = a
+                while b + 1 < len(idx) and idx[b + 1] == idx[b] + 1:
+                    b += 1
+                runs.append((ci, idx[a], idx[b] + 1))
+                a = b + 1
+        out[f"evict_{name}_runs"] = np.array(runs, dtype=np.int32)
+        n_ev = sum(1 for r in rows if r[1] != r[0])
+        print(f"eviction scenario {name}: {n_chunks} chunks, {n_ev} evictions, final kv {rows[-1][1]}")
     # the reference's masks (patch_speech_encoder.py:30-77) on a grid of shapes
     import model.patches.patch_speech_encoder as ref_pse
     grid = []
@@ -222,7 +307,7 @@ def main():
              else ref_pse.get_attn_mask_training(seq, cache, bs, "cpu"))
         out[f"mask_{i}"] = np.packbits((m == 0).numpy())
         out[f"mask_{i}_shape"] = np.array(m.shape, dtype=np.int32)
-    path = os.path.join(HERE, "ref_tiny_stream.npz")
+    path = os.environ.get("REF_PINS_OUT") or os.path.join(HERE, "ref_tiny_stream.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
