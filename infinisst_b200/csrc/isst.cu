@@ -673,6 +673,22 @@ static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const 
   ISST_CHECK(C % 8 == 0 && C <= 4096, "norm_rows: unsupported width");
   if (rows == 0) return 0;
   ProfScope ps(ctx, st, P_NORM, 0.0, static_cast<double>(rows) * C * 4);
+  // many narrow rows (conv stack, encoder LayerNorms): one warp per row
+  if (rows > 512 && !gather && !ds.part && (C == 256 || C == 512 || C == 1024)) {
+    const dim3 grid(ceil_div(rows, 8));
+#define ISST_NORMW(RMS, GELU) \
+  do { \
+    if (C == 256) ISST_CUDA(launch_k(ctx, norm_rows_warp_kernel<RMS, GELU, 1>, grid, dim3(256), 0, st, in, out, w, b, rows, eps)); \
+    else if (C == 512) ISST_CUDA(launch_k(ctx, norm_rows_warp_kernel<RMS, GELU, 2>, grid, dim3(256), 0, st, in, out, w, b, rows, eps)); \
+    else ISST_CUDA(launch_k(ctx, norm_rows_warp_kernel<RMS, GELU, 4>, grid, dim3(256), 0, st, in, out, w, b, rows, eps)); \
+  } while (0)
+    if (rms) ISST_NORMW(true, false);
+    else if (gelu) ISST_NORMW(false, true);
+    else ISST_NORMW(false, false);
+#undef ISST_NORMW
+    LAUNCH_CHECK(ctx);
+    return 0;
+  }
   // few rows (decode: one row per stream): one 16-byte column group per thread, every load in flight at once
   const bool wide = rows <= 512 && C >= 1024;
   const int threads = wide ? ((C / 8 + 31) / 32) * 32 : 128;

@@ -253,6 +253,80 @@ norm_rows_kernel(const bf16* in, bf16* out, const float* __restrict__ w, const f
   }
 }
 
+// Many rows, narrow rows (conv stack C = 512, encoder C = 1024): one WARP per row, kG 16-byte groups per lane,
+// shuffles only - no shared memory, no block barrier, 8 rows per CTA and all of a row's loads in flight at once.
+template <bool kRms, bool kGelu, int kG>
+__global__ void __launch_bounds__(256)
+norm_rows_warp_kernel(const bf16* in, bf16* out, const float* __restrict__ w,   // `in` may alias `out`
+                      const float* __restrict__ bvec, int rows, float eps) {
+  pdl_launch_dependents();
+  constexpr int C = kG * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  float wv[kG][8], bv[kG][8];
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const int c0 = (g * 32 + lane) * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(w + c0), w1 = *reinterpret_cast<const float4*>(w + c0 + 4);
+    wv[g][0] = w0.x; wv[g][1] = w0.y; wv[g][2] = w0.z; wv[g][3] = w0.w; wv[g][4] = w1.x; wv[g][5] = w1.y; wv[g][6] = w1.z; wv[g][7] = w1.w;
+    if (!kRms) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bvec + c0), b1 = *reinterpret_cast<const float4*>(bvec + c0 + 4);
+      bv[g][0] = b0.x; bv[g][1] = b0.y; bv[g][2] = b0.z; bv[g][3] = b0.w; bv[g][4] = b1.x; bv[g][5] = b1.y; bv[g][6] = b1.z; bv[g][7] = b1.w;
+    }
+  }
+  pdl_wait();
+  if (row >= rows) return;
+  const bf16* x = in + static_cast<size_t>(row) * C;
+  uint4 raw[kG];
+#pragma unroll
+  for (int g = 0; g < kG; ++g) raw[g] = *reinterpret_cast<const uint4*>(x + (g * 32 + lane) * 8);
+  float v[kG][8];
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const uint32_t u[4] = {raw[g].x, raw[g].y, raw[g].z, raw[g].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16(u[j]);
+      v[g][2 * j] = f.x; v[g][2 * j + 1] = f.y;
+      sum += f.x + f.y;
+      sq += f.x * f.x + f.y * f.y;
+    }
+  }
+  float mean = 0.f, rstd;
+  if (kRms) {
+    rstd = rsqrtf(warp_sum(sq) / C + eps);
+  } else {
+    mean = warp_sum(sum) / C;
+    float var = 0.f;
+#pragma unroll
+    for (int g = 0; g < kG; ++g)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[g][j] - mean; var += d * d; }
+    rstd = rsqrtf(warp_sum(var) / C + eps);
+  }
+  bf16* o = out + static_cast<size_t>(row) * C;
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 2 * j + e;
+        float t;
+        if (kRms) t = wv[g][k] * bf16_round(v[g][k] * rstd);
+        else t = (v[g][k] - mean) * rstd * wv[g][k] + bv[g][k];
+        if (kGelu) t = gelu_erf(bf16_round(t));
+        y[e] = t;
+      }
+      pk[j] = pack_bf16(y[0], y[1]);
+    }
+    *reinterpret_cast<uint4*>(o + (g * 32 + lane) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Embedding gather + speech splice (SpeechLlamaModel.forward, llm.py:86-115): row r takes
 // speech[speech_row[r]] when speech_row[r] >= 0 (the <sp_patch> slots), else embed[ids[r]].

@@ -58,7 +58,7 @@ def stamps(eng, M, N, K, kw):
     resid = torch.randn(M, N, device=dev).bfloat16() if kw.get("resid") else None
     eng.debug(2)
     for _ in range(2):
-        eng.op_gemm(a, w, resid=resid, dual=dual, out_f32=kw.get("out_f32", False))
+        eng.op_gemm(a, w, bias=(torch.randn(N, device=dev) if kw.get("bias") else None), gelu=kw.get("gelu", False), resid=resid, dual=dual, out_f32=kw.get("out_f32", False))
     torch.cuda.synchronize()
     t = eng.read_tap("gemm_stamps", torch.int64).view(4096, 8)[:148].double()
     eng.debug(0)
@@ -79,7 +79,7 @@ def main():
         for (name, M, N, K, kw) in SHAPES:
             us, tf, gbs = bench(eng, name, M, N, K, kw)
             line = f"[{mode}] {name:12s} M={M:5d} N={N:6d} K={K:5d}  {us:8.1f} us  {tf:7.1f} TFLOP/s  {gbs:7.1f} GB/s"
-            if mode == "sk" and M <= 64:
+            if mode == "sk":
                 line += "  stamps(start, first_tma, first_acc, walk_done, reduce_done, exit) mean/max us: " + " ".join(stamps(eng, M, N, K, kw))
             print(line, flush=True)
         eng.close()
