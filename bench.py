@@ -382,7 +382,21 @@ def main_native(args, env):
                          "share": v["ms"] / tot_ms}
     dom = max(classes, key=lambda k: classes[k]["ms_per_step"])
     roof = {k: classes[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-    roof.update({"kernel": dom, "traffic": None, "peaks": pk["source"],
+    # measured DRAM traffic per launch of the dominant class, from the committed `ncu --set full` capture
+    # (profiles/traffic.json, written by tools/make_profiles.py; ncu cannot run inside a bench)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if dom in tj:
+            traffic, traffic_src = tj[dom]["dram_bytes_per_launch"], tj[dom]["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    v_dom = prof[dom]
+    roof.update({"kernel": dom, "traffic": traffic, "traffic_unit": "bytes per launch (mean over the captured launches)",
+                 "traffic_source": traffic_src,
+                 "algorithmic_per_launch": (v_dom["flops"] if roof["bound"] == "tensor" else v_dom["bytes"]) / max(v_dom["launches"], 1),
+                 "peaks": pk["source"],
                  "note": "algorithmic bytes/flops per launch (DESIGN.md §4) / CUDA-event time of the launches of this "
                          "class inside the step; sustained bf16 peak for tensor-bound classes (timed inside a long step)"})
 
