@@ -128,6 +128,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// tcgen05.ld of 16 columns WITHOUT the completion wait: the registers may only be read after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -190,6 +199,69 @@ __device__ __forceinline__ void epilogue_store_swap(const GemmParams& p, int b, 
       if (p.out_f32) of[static_cast<long long>(i) * p.ldo] = x;
       else ob[static_cast<long long>(i) * p.ldo] = __float2bfloat16_rn(x);
     }
+  }
+}
+
+// Non-swap (row = token) epilogue of 16 feature columns, split in two so that the caller can put the TMEM load
+// between them: `epi_row_prefetch` issues every global load the chunk needs (bias as 4 x float4, residual as
+// 2 x uint4 - they do not depend on the accumulator), `epi_row_finish` does the branch-free arithmetic and the two
+// 16-byte stores.  Only for full, aligned chunks (`epi_row_fast`); everything else takes epilogue_store16.
+struct EpiRowPre {
+  float4 b[4];
+  uint4 r0, r1;
+};
+__device__ __forceinline__ bool epi_row_fast(const GemmParams& p, int col0) {
+  return col0 + 16 <= p.N_out && (p.ldo & 7) == 0 && (!p.resid || (p.ldr & 7) == 0) && !p.out_f32;
+}
+__device__ __forceinline__ void epi_row_prefetch(const GemmParams& p, int b, int tok, int col0, EpiRowPre& e) {
+  if (p.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e.b[i] = __ldg(bp + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  e.r0 = make_uint4(0u, 0u, 0u, 0u);
+  e.r1 = e.r0;
+  if (p.resid && tok < p.M_tok) {
+    const bf16* r = p.resid + static_cast<long long>(b) * p.resid_batch_stride + static_cast<long long>(tok) * p.ldr + col0;
+    e.r0 = *reinterpret_cast<const uint4*>(r);
+    e.r1 = *reinterpret_cast<const uint4*>(r + 8);
+  }
+}
+template <bool kDual>
+__device__ __forceinline__ void epi_row_finish(const GemmParams& p, int b, int tok, int col0, const float* v0,
+                                               const float* v1, const EpiRowPre& e) {
+  float y[16];
+  const float bz[16] = {e.b[0].x, e.b[0].y, e.b[0].z, e.b[0].w, e.b[1].x, e.b[1].y, e.b[1].z, e.b[1].w,
+                        e.b[2].x, e.b[2].y, e.b[2].z, e.b[2].w, e.b[3].x, e.b[3].y, e.b[3].z, e.b[3].w};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x = v0[i] + bz[i];
+    if (kDual) x = __fdividef(x, 1.0f + __expf(-x)) * v1[i];
+    y[i] = x;
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = gelu_erf(y[i]);
+  }
+  const uint32_t rr[8] = {e.r0.x, e.r0.y, e.r0.z, e.r0.w, e.r1.x, e.r1.y, e.r1.z, e.r1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {            // zeros when there is no residual
+    const float2 f2 = unpack_bf16(rr[i]);
+    y[2 * i] += f2.x;
+    y[2 * i + 1] += f2.y;
+  }
+  if (tok < p.M_tok) {
+    bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(b) * p.out_batch_stride + static_cast<long long>(tok) * p.ldo + col0;
+    uint4 s0, s1;
+    s0.x = pack_bf16(y[0], y[1]);   s0.y = pack_bf16(y[2], y[3]);
+    s0.z = pack_bf16(y[4], y[5]);   s0.w = pack_bf16(y[6], y[7]);
+    s1.x = pack_bf16(y[8], y[9]);   s1.y = pack_bf16(y[10], y[11]);
+    s1.z = pack_bf16(y[12], y[13]); s1.w = pack_bf16(y[14], y[15]);
+    *reinterpret_cast<uint4*>(o) = s0;
+    *reinterpret_cast<uint4*>(o + 8) = s1;
   }
 }
 
@@ -753,15 +825,48 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         // ---- the whole k-range of this tile was accumulated here: final epilogue straight from TMEM ----
         if (works) {
 #pragma unroll 1
-          for (int c = hc0; c < hc0 + C::kHalfCols; c += NC) {
-            float v0[NC], v1[NC];
+          for (int c = hc0; c < hc0 + C::kHalfCols; c += (kSwap ? NC : 32)) {
+            if (!kSwap) {
+              // two 16-column chunks per step: their global loads and both TMEM loads are in flight together
+              constexpr int W = (C::kHalfCols % 32 == 0) ? 2 : 1;
+              const bool fast = epi_row_fast(p, col_base + c + (W - 1) * 16);      // warp-uniform
+              if (fast) {
+                EpiRowPre pre[W];
+                uint32_t r0[W][16], r1[W][16];
 #pragma unroll
-            for (int j = 0; j < NC; j += 16) {
-              tmem_ld16(taddr + c + j, v0 + j);
-              if (kDual) tmem_ld16(taddr + kBN + c + j, v1 + j);
+                for (int h = 0; h < W; ++h) epi_row_prefetch(p, t.b, lane_idx, col_base + c + 16 * h, pre[h]);
+#pragma unroll
+                for (int h = 0; h < W; ++h) {
+                  tmem_ld16_issue(taddr + c + 16 * h, r0[h]);
+                  if (kDual) tmem_ld16_issue(taddr + kBN + c + 16 * h, r1[h]);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < W; ++h) {
+                  float v0[16], v1[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r0[h][i]); v1[i] = kDual ? __uint_as_float(r1[h][i]) : 0.f; }
+                  epi_row_finish<kDual>(p, t.b, lane_idx, col_base + c + 16 * h, v0, v1, pre[h]);
+                }
+              } else {
+#pragma unroll 1
+                for (int h = 0; h < W; ++h) {
+                  float v0[16], v1[16];
+                  tmem_ld16(taddr + c + 16 * h, v0);
+                  if (kDual) tmem_ld16(taddr + kBN + c + 16 * h, v1);
+                  epilogue_store16<kDual, false>(p, t.b, lane_idx, col_base + c + 16 * h, v0, v1);
+                }
+              }
+              if (W == 1) c -= 16;          // (kHalfCols is a multiple of 32 for every non-swap tile shape in use)
+            } else {
+              float v0[NC], v1[NC];
+#pragma unroll
+              for (int j = 0; j < NC; j += 16) {
+                tmem_ld16(taddr + c + j, v0 + j);
+                if (kDual) tmem_ld16(taddr + kBN + c + j, v1 + j);
+              }
+              epilogue_store_swap<kDual, NC>(p, t.b, lane_idx, col_base + c, v0, v1);
             }
-            if (kSwap) epilogue_store_swap<kDual, NC>(p, t.b, lane_idx, col_base + c, v0, v1);
-            else epilogue_store16<kDual, false>(p, t.b, lane_idx, col_base + c, v0, v1);
           }
         }
         tcgen05_fence_before();
