@@ -30,13 +30,24 @@ struct DecodeParams2 {
   int H;
   int splits;
   float scale_log2;
+  // ---- fused RoPE + KV append (decode step inside llm_forward): the kernel itself completes the QKV row of its
+  // (stream, kv head) from the GEMM's fp32 split partials, rotates q (both variants) and k, writes K / V of the
+  // new token to the page and attends to it from shared memory; kv.kv_len then EXCLUDES the new token and
+  // llm_rope_append_kernel is not launched.  fuse == 0: q / q_sys / cache were prepared by llm_rope_append_kernel.
+  int fuse;
+  const float* part;        // [n_part][n][ldq] fp32 split-K partials of the QKV GEMM, or null (then `qkv` holds bf16 rows)
+  int n_part;
+  long long part_stride;    // n * ldq
+  const float2* tab_ring;   // [n][HD/2] (cos, sin) at the absolute index of the new token
+  const float2* tab_sys;    // [n][HD/2] (cos, sin) at (absolute index - evicted): query variant for the pinned prefix
+  const int* active;        // [n] or null: finished streams append nothing
 };
 
 constexpr int kDecTile = 64;              // keys per tile
 constexpr int kDecStages = 3;
 constexpr int kDecLds = 128 + 8;          // padded row (elements): conflict-free ldmatrix
 constexpr int kDecStageElems = 2 * kDecTile * kDecLds;                  // K tile + V tile
-constexpr int kDecSmemBytes = kDecStages * kDecStageElems * 2 + 2 * 4 * 128 * 2;   // + the two query variants
+constexpr int kDecSmemBytes = kDecStages * kDecStageElems * 2 + 2 * 4 * 128 * 2 + 2 * 128 * 2;   // + the two query variants + K/V of the new token
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -65,12 +76,14 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
   extern __shared__ __align__(16) uint8_t dec_smem[];
   bf16* stage_base = reinterpret_cast<bf16*>(dec_smem);
   bf16* qbuf = stage_base + kDecStages * kDecStageElems;       // [2][GROUP][HD] rotated queries
+  bf16* newkv = qbuf + 2 * GROUP * HD;                         // [2][HD] rotated K and plain V of the new token (fused mode)
 
   const int split = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int slot = p.slots[b];
-  const int L = p.kv.kv_len[slot] + 1;
+  const int L_old = p.kv.kv_len[slot];
+  const int L = p.fuse ? L_old : L_old + 1;      // keys read from the cache (fused: the new token comes from shared memory)
   const int sys_len = min(p.kv.sys_len[slot], L), ring_start = p.kv.ring_start[slot];
   const int* table = p.kv.page_table + static_cast<size_t>(slot) * p.kv.pages_per_stream;
   // tile list: [0, sys_len) in 64-key tiles (q_sys variant), then [sys_len, L) (ring variant); a split is a
@@ -134,7 +147,58 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     if (s < n_tiles) load_tile(t_lo + s, s);
     cp_async_commit();
   }
-  {
+  const bool owns_new = p.fuse && t_hi == tiles_total;          // the split that holds the last tile also takes the new token
+  if (p.fuse) {
+    // ---- fused llm_rope_append: complete this (stream, kv head)'s slice of the QKV row, rotate, append ----
+    // items: 256 q pairs (4 heads x 64), 64 k pairs, 64 v pairs; a pair is (d, d + 64) of one head (half-split RoPE)
+    const int ldq = (p.H + 2 * p.kv.kv_heads) * HD;
+    const bool writer = owns_new && (!p.active || p.active[b]);
+    const int sl_new = kv_slot(L_old, p.kv.sys_len[slot], ring_start);
+    const size_t koff = kv_offset(p.kv, table, sl_new, 0, head), voff = kv_offset(p.kv, table, sl_new, 1, head);
+    for (int item = tid; item < 384; item += 128) {
+      int col, d, hq = 0;
+      if (item < 256) { hq = item >> 6; d = item & 63; col = (head * GROUP + hq) * HD; }
+      else if (item < 320) { d = item - 256; col = (p.H + head) * HD; }
+      else { d = item - 320; col = (p.H + p.kv.kv_heads + head) * HD; }
+      float a, bb;
+      if (p.part) {
+        const float* p0 = p.part + static_cast<size_t>(b) * ldq + col + d;
+        float sa = 0.f, sb = 0.f;
+        for (int sp0 = 0; sp0 < p.n_part; sp0 += 4) {
+          float va[4], vb[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (sp0 + q < p.n_part) { va[q] = __ldcg(p0 + (sp0 + q) * p.part_stride); vb[q] = __ldcg(p0 + (sp0 + q) * p.part_stride + 64); }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (sp0 + q < p.n_part) { sa += va[q]; sb += vb[q]; }
+        }
+        a = bf16_round(sa); bb = bf16_round(sb);                 // the projection output is a bf16 tensor in the reference
+      } else {
+        const bf16* src = p.qkv + static_cast<size_t>(b) * ldq + col + d;
+        a = __bfloat162float(src[0]); bb = __bfloat162float(src[64]);
+      }
+      if (item >= 320) {                                         // V: plain
+        const bf16 v0 = __float2bfloat16_rn(a), v1 = __float2bfloat16_rn(bb);
+        newkv[HD + d] = v0; newkv[HD + d + 64] = v1;
+        if (writer) { p.kv.pool[voff + d] = v0; p.kv.pool[voff + d + 64] = v1; }
+        continue;
+      }
+      // a new token that still falls inside the pinned prefix keeps the prefix convention (sys table) for its key
+      const bool sys_key = item >= 256 && L_old < p.kv.sys_len[slot];
+      const float2 cr = (sys_key ? p.tab_sys : p.tab_ring)[static_cast<size_t>(b) * 64 + d];
+      const bf16 lo = __float2bfloat16_rn(a * cr.x - bb * cr.y), hi = __float2bfloat16_rn(bb * cr.x + a * cr.y);
+      if (item < 256) {
+        qbuf[hq * HD + d] = lo; qbuf[hq * HD + d + 64] = hi;
+        const float2 cs = p.tab_sys[static_cast<size_t>(b) * 64 + d];
+        qbuf[(GROUP + hq) * HD + d] = __float2bfloat16_rn(a * cs.x - bb * cs.y);
+        qbuf[(GROUP + hq) * HD + d + 64] = __float2bfloat16_rn(bb * cs.x + a * cs.y);
+      } else {
+        newkv[d] = lo; newkv[d + 64] = hi;
+        if (writer) { p.kv.pool[koff + d] = lo; p.kv.pool[koff + d + 64] = hi; }
+      }
+    }
+  } else {
     const int ldq = (p.H + 2 * p.kv.kv_heads) * HD;
     // 2 variants x 4 heads x 128 dims = 128 16-byte chunks, one per thread
     const int v = tid >> 6, hq = (tid >> 4) & 3, c = tid & 15;
@@ -153,26 +217,41 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
       qa2[kk] = g < GROUP ? *reinterpret_cast<const uint32_t*>(q + kk * 16 + 8) : 0u;
     }
   };
-  load_q(t_lo < n_sys_tiles);
+  bool q_is_sys = t_lo < n_sys_tiles;
+  load_q(q_is_sys);
 
   float o[8][4];
 #pragma unroll
   for (int mt = 0; mt < 8; ++mt) { o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f; }
   float m_run = -INFINITY, l_run = 0.f;      // row g of S (query head g; rows >= GROUP are padding)
 
-  for (int ti = 0; ti < n_tiles; ++ti) {
+  for (int ti = 0; ti < n_tiles + (owns_new ? 1 : 0); ++ti) {
     const int t = t_lo + ti;
-    cp_async_wait<kDecStages - 2>();
-    __syncthreads();                         // tile landed for everyone; everyone is done with the previous tile
-    {
-      const int nt = ti + kDecStages - 1;
-      if (nt < n_tiles) load_tile(t_lo + nt, nt % kDecStages);
-      cp_async_commit();
+    const bool fresh = ti == n_tiles;        // fused mode, last iteration: the new token itself, from shared memory
+    const bf16* sK;
+    if (!fresh) {
+      cp_async_wait<kDecStages - 2>();
+      __syncthreads();                       // tile landed for everyone; everyone is done with the previous tile
+      {
+        const int nt = ti + kDecStages - 1;
+        if (nt < n_tiles) load_tile(t_lo + nt, nt % kDecStages);
+        cp_async_commit();
+      }
+      sK = stage_base + (ti % kDecStages) * kDecStageElems;
+      if (t == n_sys_tiles && ti > 0 && q_is_sys) { load_q(false); q_is_sys = false; }   // leaving the pinned prefix: ring variant
+    } else {
+      // stage 0 held tile t_lo: 64 finite K / V rows.  Row 0 becomes the new token; the other 63 rows are masked.
+      cp_async_wait<0>();
+      __syncthreads();
+      bf16* s0 = stage_base;
+      if (tid < 32) *reinterpret_cast<uint2*>(s0 + tid * 4) = *reinterpret_cast<const uint2*>(newkv + tid * 4);
+      else if (tid < 64) *reinterpret_cast<uint2*>(s0 + TILE * LDS + (tid - 32) * 4) = *reinterpret_cast<const uint2*>(newkv + HD + (tid - 32) * 4);
+      __syncthreads();
+      sK = s0;
+      const bool new_is_sys = L_old < p.kv.sys_len[slot];
+      if (q_is_sys != new_is_sys) { load_q(new_is_sys); q_is_sys = new_is_sys; }
     }
-    const bf16* sK = stage_base + (ti % kDecStages) * kDecStageElems;
     const bf16* sV = sK + TILE * LDS;
-    if (t == n_sys_tiles && ti > 0) load_q(false);     // leaving the pinned prefix: switch to the ring variant
-
     // ---- S = Q K^T for this warp's 16 keys ----
     float s[2][4];
 #pragma unroll
@@ -190,8 +269,8 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
       }
     }
     // ---- online softmax on row g (rows >= GROUP are zero padding; harmless) ----
-    const int jw = tile_j0(t) + 16 * warp;
-    const int j1 = tile_j1(t);
+    const int jw = (fresh ? L_old : tile_j0(t)) + 16 * warp;
+    const int j1 = fresh ? L_old + 1 : tile_j1(t);
     float mx = m_run;
 #pragma unroll
     for (int n = 0; n < 2; ++n)

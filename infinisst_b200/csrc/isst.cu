@@ -889,8 +889,15 @@ static int decode_splits_for(isst_ctx* ctx, int n, int max_L) {
   const int tiles_per = ceil_div(tiles_total, target);
   return ceil_div(tiles_total, tiles_per);
 }
+struct DecodeFuse {          // fused RoPE + KV append inside the decode attention kernel (see DecodeParams2)
+  const float* part = nullptr;
+  int n_part = 0;
+  long long part_stride = 0;
+  const int* active = nullptr;
+  bool on = false;
+};
 static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* qkv, const PagedKV& kv, const int* d_slots,
-                                   int n, int splits, float scale_log2) {
+                                   int n, int splits, float scale_log2, const DecodeFuse& fz = DecodeFuse{}) {
   static bool attr_set = false;
   if (!attr_set) {
     ISST_CUDA(cudaFuncSetAttribute(decode_attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes));
@@ -900,6 +907,8 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
   dp.qkv = qkv; dp.q_sys = ctx->lq_sys; dp.kv = kv; dp.slots = d_slots;
   dp.out = ctx->lattn; dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
   dp.splits = splits; dp.scale_log2 = scale_log2;
+  dp.fuse = fz.on ? 1 : 0; dp.part = fz.part; dp.n_part = fz.n_part; dp.part_stride = fz.part_stride;
+  dp.tab_ring = ctx->llm_rope_ring; dp.tab_sys = ctx->llm_rope_sys; dp.active = fz.active;
   ISST_CUDA(launch_k(ctx, decode_attention_mma_kernel<4>, dim3(splits, ctx->cfg.kv_heads, n), dim3(128), kDecSmemBytes, st, dp));
   LAUNCH_CHECK(ctx);
   return 0;
@@ -937,7 +946,9 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       qkv_splits = ctx->last_defer_splits;
     }
     PagedKV kv = paged_kv(ctx, l);
-    {
+    static const bool fuse_env = !(getenv("ISST_DEC_FUSE") && atoi(getenv("ISST_DEC_FUSE")) == 0);   // A/B aid
+    const bool fuse_append = lb.decode && fuse_env;    // decode: the attention kernel rotates and appends by itself
+    if (!fuse_append) {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
       dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
       ISST_CUDA(launch_k(ctx, llm_rope_append_kernel, grid, dim3(128), 0, st, ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T,
@@ -967,7 +978,12 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
       const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
-      ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2));
+      DecodeFuse fz;
+      if (fuse_append) {
+        fz.on = true; fz.active = lb.d_active;
+        if (qkv_splits) { fz.part = ctx->defer_ws; fz.n_part = qkv_splits; fz.part_stride = static_cast<long long>(M) * QKV; }
+      }
+      ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2, fz));
       if (splits > 1) {
         ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits));
         LAUNCH_CHECK(ctx);

@@ -124,6 +124,51 @@ __global__ void __launch_bounds__(128) gemm_like_kernel(const __grid_constant__ 
   }
 }
 
+// Decode-attention-like ring: a producer WARP fills stages of 64 K rows + 64 V rows (256 B each, padded to 272 B in
+// shared memory) with 128 row-sized bulk copies per stage (4 per lane); one consumer thread releases the stages.
+// Tests whether 256-byte bulk copies sustain HBM bandwidth (2 CTAs per SM, 3 stages).
+__global__ void __launch_bounds__(160, 2) rows_ring_kernel(const uint8_t* base, long long n_rows_total, int tiles_per_cta, int stages,
+                                                           unsigned long long* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int kStage = 2 * 64 * 272;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * kStage);
+  uint64_t* empty = full + stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = static_cast<long long>(blockIdx.x) * tiles_per_cta * 128;
+  if (warp == 4) {
+    int stage = 0, phase = 0;
+    for (int t = 0; t < tiles_per_cta; ++t) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (lane == 0) mbar_expect_tx(&full[stage], 128 * 256);
+      __syncwarp();
+      uint8_t* s = smem + stage * kStage;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = q * 32 + lane;                         // 0..127: 64 K rows then 64 V rows
+        const long long gr = (row0 + static_cast<long long>(t) * 128 + r) % n_rows_total;
+        bulk_load_1d(s + r * 272, base + gr * 256, 256, &full[stage]);
+      }
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (threadIdx.x == 0) {
+    int stage = 0, phase = 0;
+    unsigned long long acc = 0;
+    for (int t = 0; t < tiles_per_cta; ++t) {
+      mbar_wait(&full[stage], phase);
+      acc += *reinterpret_cast<volatile uint32_t*>(smem + stage * kStage + 64);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+  }
+}
+
 __global__ void __launch_bounds__(512) ldg_kernel(const uint4* __restrict__ p, long long n_vec, unsigned long long* sink) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -262,6 +307,25 @@ int main() {
         const double us = ms * 1e3 / iters;
         printf("%s stages=%d: %7.1f us per launch  %6.2f TB/s (weights only)\n", names[act_mode], stages, us, bytes / 8 / us / 1e6);
       }
+  }
+  // (d) decode-attention-like: 512 CTAs (64 streams x 8 kv heads), 16 tiles of 64 keys each, rows of 256 B
+  {
+    CK(cudaFuncSetAttribute(rows_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    printf("# decode-attention-like: 512 CTAs x 16 tiles x (64 K + 64 V rows of 256 B) = 268 MB per launch, 2 CTAs per SM\n");
+    const long long n_rows = static_cast<long long>(bytes / 256);
+    for (int stages : {2, 3}) {
+      const size_t smem = static_cast<size_t>(stages) * 2 * 64 * 272 + 256 + 128;
+      const int iters = 8;
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      for (int it = 0; it < iters; ++it)
+        rows_ring_kernel<<<512, 160, smem>>>(w + static_cast<size_t>(it % 7) * 268435456ull, 1048576ll, 16, stages, sink);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double us = ms * 1e3 / iters;
+      printf("rows 256B bulk, stages=%d: %7.1f us per launch  %6.2f TB/s\n", stages, us, 512.0 * 16 * 128 * 256 / us / 1e6);
+    }
   }
   CK(cudaGetLastError());
   return 0;
