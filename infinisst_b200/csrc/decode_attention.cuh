@@ -155,44 +155,60 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     const bool writer = owns_new && (!p.active || p.active[b]);
     const int sl_new = kv_slot(L_old, p.kv.sys_len[slot], ring_start);
     const size_t koff = kv_offset(p.kv, table, sl_new, 0, head), voff = kv_offset(p.kv, table, sl_new, 1, head);
-    for (int item = tid; item < 384; item += 128) {
-      int col, d, hq = 0;
-      if (item < 256) { hq = item >> 6; d = item & 63; col = (head * GROUP + hq) * HD; }
-      else if (item < 320) { d = item - 256; col = (p.H + head) * HD; }
-      else { d = item - 320; col = (p.H + p.kv.kv_heads + head) * HD; }
-      float a, bb;
-      if (p.part) {
-        const float* p0 = p.part + static_cast<size_t>(b) * ldq + col + d;
-        float sa = 0.f, sb = 0.f;
-        for (int sp0 = 0; sp0 < p.n_part; sp0 += 4) {
-          float va[4], vb[4];
+    // every thread owns three items (tid, tid + 128, tid + 256): all of their loads are issued before any use
+    int col[3], dd[3];
+    float a[3], bb[3];
+    float2 cr[3], cs[3];
+    const bool sys_new = L_old < p.kv.sys_len[slot];   // new token still inside the pinned prefix: prefix convention for its key
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (sp0 + q < p.n_part) { va[q] = __ldcg(p0 + (sp0 + q) * p.part_stride); vb[q] = __ldcg(p0 + (sp0 + q) * p.part_stride + 64); }
+    for (int k = 0; k < 3; ++k) {
+      const int item = tid + 128 * k;
+      if (item < 256) { dd[k] = item & 63; col[k] = (head * GROUP + (item >> 6)) * HD; }
+      else if (item < 320) { dd[k] = item - 256; col[k] = (p.H + head) * HD; }
+      else { dd[k] = item - 320; col[k] = (p.H + p.kv.kv_heads + head) * HD; }
+      cr[k] = ((item >= 256 && sys_new) ? p.tab_sys : p.tab_ring)[static_cast<size_t>(b) * 64 + dd[k]];
+      cs[k] = p.tab_sys[static_cast<size_t>(b) * 64 + dd[k]];
+    }
+    if (p.part) {
+      float va[3][4], vb[3][4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (sp0 + q < p.n_part) { sa += va[q]; sb += vb[q]; }
+      for (int k = 0; k < 3; ++k) {
+        const float* p0 = p.part + static_cast<size_t>(b) * ldq + col[k] + dd[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          va[k][q] = 0.f; vb[k][q] = 0.f;
+          if (q < p.n_part) { va[k][q] = __ldcg(p0 + q * p.part_stride); vb[k][q] = __ldcg(p0 + q * p.part_stride + 64); }
         }
-        a = bf16_round(sa); bb = bf16_round(sb);                 // the projection output is a bf16 tensor in the reference
-      } else {
-        const bf16* src = p.qkv + static_cast<size_t>(b) * ldq + col + d;
-        a = __bfloat162float(src[0]); bb = __bfloat162float(src[64]);
       }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float sa = ((va[k][0] + va[k][1]) + va[k][2]) + va[k][3], sb = ((vb[k][0] + vb[k][1]) + vb[k][2]) + vb[k][3];
+        const float* p0 = p.part + static_cast<size_t>(b) * ldq + col[k] + dd[k];
+        for (int q = 4; q < p.n_part; ++q) { sa += __ldcg(p0 + q * p.part_stride); sb += __ldcg(p0 + q * p.part_stride + 64); }
+        a[k] = bf16_round(sa); bb[k] = bf16_round(sb);             // the projection output is a bf16 tensor in the reference
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const bf16* src = p.qkv + static_cast<size_t>(b) * ldq + col[k] + dd[k];
+        a[k] = __bfloat162float(src[0]); bb[k] = __bfloat162float(src[64]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int item = tid + 128 * k, d = dd[k];
       if (item >= 320) {                                         // V: plain
-        const bf16 v0 = __float2bfloat16_rn(a), v1 = __float2bfloat16_rn(bb);
+        const bf16 v0 = __float2bfloat16_rn(a[k]), v1 = __float2bfloat16_rn(bb[k]);
         newkv[HD + d] = v0; newkv[HD + d + 64] = v1;
         if (writer) { p.kv.pool[voff + d] = v0; p.kv.pool[voff + d + 64] = v1; }
         continue;
       }
-      // a new token that still falls inside the pinned prefix keeps the prefix convention (sys table) for its key
-      const bool sys_key = item >= 256 && L_old < p.kv.sys_len[slot];
-      const float2 cr = (sys_key ? p.tab_sys : p.tab_ring)[static_cast<size_t>(b) * 64 + d];
-      const bf16 lo = __float2bfloat16_rn(a * cr.x - bb * cr.y), hi = __float2bfloat16_rn(bb * cr.x + a * cr.y);
+      const bf16 lo = __float2bfloat16_rn(a[k] * cr[k].x - bb[k] * cr[k].y), hi = __float2bfloat16_rn(bb[k] * cr[k].x + a[k] * cr[k].y);
       if (item < 256) {
+        const int hq = item >> 6;
         qbuf[hq * HD + d] = lo; qbuf[hq * HD + d + 64] = hi;
-        const float2 cs = p.tab_sys[static_cast<size_t>(b) * 64 + d];
-        qbuf[(GROUP + hq) * HD + d] = __float2bfloat16_rn(a * cs.x - bb * cs.y);
-        qbuf[(GROUP + hq) * HD + d + 64] = __float2bfloat16_rn(bb * cs.x + a * cs.y);
+        qbuf[(GROUP + hq) * HD + d] = __float2bfloat16_rn(a[k] * cs[k].x - bb[k] * cs[k].y);
+        qbuf[(GROUP + hq) * HD + d + 64] = __float2bfloat16_rn(bb[k] * cs[k].x + a[k] * cs[k].y);
       } else {
         newkv[d] = lo; newkv[d + 64] = hi;
         if (writer) { p.kv.pool[koff + d] = lo; p.kv.pool[koff + d + 64] = hi; }
