@@ -148,18 +148,20 @@ __global__ void rope_table_kernel(float2* __restrict__ tab_ring, float2* __restr
   }
 }
 
-// Shared-memory bytes of chunk_attention_kernel<HD, *, NW>: Q staging + 2 (K, V) stages.
-template <int HD, int NW>
+// Shared-memory bytes of chunk_attention_kernel<HD, *, NW, NS>: NS (K, V) stages of 64 keys; the query staging area
+// aliases the last stage (the query fragments live in registers while the tiles stream).
+template <int HD, int NW, int NS>
 constexpr int chunk_attn_smem_bytes() {
-  return (NW * 16 + 4 * 64) * (HD + 8) * 2;
+  static_assert(NW * 16 <= 2 * 64, "query staging must fit one stage");
+  return NS * 2 * 64 * (HD + 8) * 2;
 }
 
 // One CTA = NW warps x 16 query rows, walking the keys in 64-key tiles.  K (already rotated) and V tiles
-// stream global -> shared memory with cp.async through two stages, so the next tile is in flight while
-// the current one is consumed by the tensor cores; 2+ CTAs per SM keep further pipelines running.
+// stream global -> shared memory with cp.async through an NS-stage ring (NS - 1 tiles in flight while the current
+// one is consumed by the tensor cores); 2+ CTAs per SM keep further pipelines running.
 // LLM: the pinned system-prompt keys [0, sys_len) are visited first with the q_sys query variant, then the
 // query fragments are reloaded from the ring variant for the sliding part (see the header).
-template <int HD, bool ENC, int NW>
+template <int HD, bool ENC, int NW, int NS>
 __global__ void __launch_bounds__(NW * 32, HD == 128 ? 2 : 4)
 chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   pdl_launch_dependents();
@@ -168,8 +170,8 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   constexpr int LDS = HD + 8;        // padded smem row (elements)
   constexpr int NTHREADS = NW * 32;
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(attn_smem);            // [NW*16][LDS] queries of the current variant
-  bf16* sRaw = sQ + NW * 16 * LDS;                          // [2 stages][K | V][KT][LDS]
+  bf16* sRaw = reinterpret_cast<bf16*>(attn_smem);          // [NS stages][K | V][KT][LDS]
+  bf16* sQ = sRaw + (NS - 1) * 2 * KT * LDS;                // [NW*16][LDS] query staging: aliases a stage that is free at that time
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -272,11 +274,14 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     }
   };
   if (n_tiles > 0) lookup(0);
-  if (n_tiles > 0) load_tile(0, 0);
-  cpa_commit();
+#pragma unroll
+  for (int s0 = 0; s0 < NS - 1; ++s0) {
+    if (s0 < n_tiles) load_tile(s0, s0);
+    cpa_commit();
+  }
 
   // ---- query staging: rows r = hq * T + i ----
-  auto stage_q = [&](bool sys_variant) {
+  auto stage_q = [&](bool sys_variant, bf16* sQ) {
     constexpr int CH = HD / 8;
     for (int u = tid; u < NW * 16 * CH; u += NTHREADS) {
       const int rl = u / CH, c = u % CH;
@@ -296,7 +301,7 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     }
   };
   uint32_t qf[HD / 16][4];
-  auto load_qf = [&]() {
+  auto load_qf = [&](const bf16* sQ) {
     const bf16* q0 = sQ + (warp * 16 + g) * LDS;
     const bf16* q1 = q0 + 8 * LDS;
 #pragma unroll
@@ -307,9 +312,9 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
       qf[kk][3] = *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + 2 * t4);
     }
   };
-  stage_q(n_sys_tiles > 0);
+  stage_q(n_sys_tiles > 0, sQ);
   __syncthreads();
-  load_qf();
+  load_qf(sQ);
 
   float o_acc[HD / 8][4];
 #pragma unroll
@@ -338,21 +343,32 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
   const float sl2 = ENC ? 1.4426950408889634f : lp.scale_log2;
   const bool warp_live = row0 + warp * 16 < n_rows;
 
+  // rows of this warp see every key of a tile when the tile lies inside [wlo, whi): such tiles skip the mask
+  int wlo = max(qlo[0], qlo[1]), whi = min(qhi[0], qhi[1]);
+  // (a dead row has qhi == 0, which keeps its warp on the masked path)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wlo = max(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+    whi = min(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+  }
+
   for (int t = 0; t < n_tiles; ++t) {
     const int k0 = tile_k0(t);
+    cpa_wait<NS - 2>();
+    __syncthreads();   // tile t landed; every warp is done with tile t-1, whose stage is free now
     if (!ENC && t == n_sys_tiles && n_sys_tiles > 0) {
-      // switch from the system-prompt segment to the sliding segment: reload the ring query variant
+      // switch from the system-prompt segment to the sliding segment: the ring query variant is staged through the
+      // stage that was just released (the next prefetch goes there afterwards)
+      bf16* sQ2 = sRaw + ((t + NS - 1) % NS) * 2 * KT * LDS;
+      stage_q(false, sQ2);
       __syncthreads();
-      stage_q(false);
+      load_qf(sQ2);
       __syncthreads();
-      load_qf();
     }
-    cpa_wait<0>();
-    __syncthreads();   // tile t landed; every warp is done with tile t-1
-    if (t + 1 < n_tiles) load_tile(t + 1, (t + 1) & 1);
+    if (t + NS - 1 < n_tiles) load_tile(t + NS - 1, (t + NS - 1) % NS);
     cpa_commit();
     if (!warp_live) continue;   // warp has no valid rows (still takes part in loading)
-    const bf16* sK = sRaw + (t & 1) * 2 * KT * LDS;
+    const bf16* sK = sRaw + (t % NS) * 2 * KT * LDS;
     const bf16* sV = sK + KT * LDS;
 
     // ---- S = Q K^T ----
@@ -376,15 +392,26 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     // ---- mask + online softmax (rows g, g+8; cols n*8 + 2*t4 + {0,1}) ----
     const int k1 = tile_k1(t);
     float mx[2] = {m_run[0], m_run[1]};
+    if (k0 >= wlo && k0 + KT <= whi && k0 + KT <= k1) {      // interior tile: every key visible to every row of the warp
 #pragma unroll
-    for (int n = 0; n < KT / 8; ++n) {
+      for (int n = 0; n < KT / 8; ++n) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int h = e >> 1;
-        const int j = k0 + n * 8 + 2 * t4 + (e & 1);
-        const bool ok = (j >= qlo[h]) && (j < qhi[h]) && (j < k1);
-        s[n][e] = ok ? s[n][e] * sl2 : -INFINITY;
-        mx[h] = fmaxf(mx[h], s[n][e]);
+        for (int e = 0; e < 4; ++e) {
+          s[n][e] *= sl2;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[n][e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < KT / 8; ++n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = e >> 1;
+          const int j = k0 + n * 8 + 2 * t4 + (e & 1);
+          const bool ok = (j >= qlo[h]) && (j < qhi[h]) && (j < k1);
+          s[n][e] = ok ? s[n][e] * sl2 : -INFINITY;
+          mx[h] = fmaxf(mx[h], s[n][e]);
+        }
       }
     }
 #pragma unroll

@@ -690,7 +690,7 @@ static int norm_rows(isst_ctx* ctx, cudaStream_t st, bool rms, bool gelu, const 
     return 0;
   }
   // few rows (decode: one row per stream): one 16-byte column group per thread, every load in flight at once
-  const bool wide = rows <= 512 && C >= 1024;
+  const bool wide = (rows <= 512 && C >= 1024) || C > 1024;     // 4096-wide LLM rows always take one 16-byte group per thread
   const int threads = wide ? ((C / 8 + 31) / 32) * 32 : 128;
 #define ISST_NORM(RMS, GELU) \
   do { \
@@ -791,14 +791,15 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
       for (int b = 0; b < n; ++b) keys += std::min(ctx->streams[slots_h[b]].enc_prefix, c.max_cache_size) + frames;
       ProfScope ps(ctx, st, P_ATTN_ENC, 4.0 * frames * keys * D, keys * D * 2 * 2 + static_cast<double>(M) * D * 2 * 2);
       dim3 grid(ceil_div(frames, NW * 16), H, n);
-      constexpr int smem = chunk_attn_smem_bytes<64, NW>();
+      constexpr int NS = 3;
+      constexpr int smem = chunk_attn_smem_bytes<64, NW, NS>();
       ISST_CHECK(HD == 64, "encoder attention kernel is built for head_dim 64");
       static bool enc_attr_set = false;
       if (!enc_attr_set) {
-        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<64, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<64, true, NW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         enc_attr_set = true;
       }
-      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<64, true, NW>, grid, dim3(NW * 32), smem, st, ep, lp));
+      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<64, true, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
     }
     {
@@ -965,14 +966,15 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
                    lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
       dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
-      constexpr int smem = chunk_attn_smem_bytes<128, NW>();
+      constexpr int NS = 3;
+      constexpr int smem = chunk_attn_smem_bytes<128, NW, NS>();
       static bool attr_set = false;
       if (!attr_set) {
-        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<128, false, NW>,
+        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<128, false, NW, NS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
       }
-      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<128, false, NW>, grid, dim3(NW * 32), smem, st, ep, lp));
+      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<128, false, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
     } else {
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
