@@ -47,13 +47,34 @@ constexpr int kDecTile = 64;              // keys per tile
 constexpr int kDecStages = 3;
 constexpr int kDecLds = 128 + 8;          // padded row (elements): conflict-free ldmatrix
 constexpr int kDecStageElems = 2 * kDecTile * kDecLds;                  // K tile + V tile
-constexpr int kDecSmemBytes = kDecStages * kDecStageElems * 2 + 2 * 4 * 128 * 2 + 2 * 128 * 2;   // + the two query variants + K/V of the new token
+constexpr int kDecSmemBytes = kDecStages * kDecStageElems * 2 + 2 * 4 * 128 * 2 + 2 * 128 * 2 + 2 * kDecStages * 8;   // + the two query variants + K/V of the new token + full / empty barriers
+constexpr int kDecLoaders = 2;            // loader warps
+constexpr int kDecThreads = 128 + 32 * kDecLoaders;   // 4 compute warps + the loader warps
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// the mbarrier receives one arrival from this thread once all of its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void dec_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void dec_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void dec_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nDEC_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DEC_DONE;\nbra DEC_WAIT;\nDEC_DONE:\n}\n" ::"r"(
+          static_cast<uint32_t>(__cvta_generic_to_shared(bar))),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void dec_bar_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 compute warps
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
@@ -67,7 +88,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 template <int GROUP>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kDecThreads, 2)
 decode_attention_mma_kernel(const DecodeParams2 p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -77,6 +98,8 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
   bf16* stage_base = reinterpret_cast<bf16*>(dec_smem);
   bf16* qbuf = stage_base + kDecStages * kDecStageElems;       // [2][GROUP][HD] rotated queries
   bf16* newkv = qbuf + 2 * GROUP * HD;                         // [2][HD] rotated K and plain V of the new token (fused mode)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(newkv + 2 * HD);   // [kDecStages] tile landed (32 loader lanes arrive)
+  uint64_t* empty_bar = full_bar + kDecStages;                  // [kDecStages] tile consumed (4 compute warps arrive)
 
   const int split = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -94,7 +117,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
   const int t_lo = split * tiles_per, t_hi = min(tiles_total, t_lo + tiles_per);
   const size_t pbase = (static_cast<size_t>(b) * p.H + head * GROUP) * p.splits + split;   // + hq * splits
   if (t_lo >= t_hi) {   // empty split: neutral partial
-    for (int idx = tid; idx < GROUP * HD; idx += 128) {
+    for (int idx = tid; idx < GROUP * HD; idx += kDecThreads) {
       const int hq = idx / HD, d = idx % HD;
       p.part_o[(pbase + static_cast<size_t>(hq) * p.splits) * HD + d] = 0.f;
       if (d == 0) { p.part_ml[(pbase + static_cast<size_t>(hq) * p.splits) * 2] = -INFINITY; p.part_ml[(pbase + static_cast<size_t>(hq) * p.splits) * 2 + 1] = 0.f; }
@@ -105,48 +128,65 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
   auto tile_j0 = [&](int t) { return t < n_sys_tiles ? t * TILE : sys_len + (t - n_sys_tiles) * TILE; };
   auto tile_j1 = [&](int t) { return t < n_sys_tiles ? min(sys_len, t * TILE + TILE) : min(L, sys_len + (t - n_sys_tiles + 1) * TILE); };
 
-  // ---- tile loader: 64 keys x (K 256 B + V 256 B) = 2048 16-byte chunks, 16 per thread ----
-  // Thread (grp = tid / 16, chunk = tid % 16) copies chunk `chunk` of the 8 consecutive keys 8*grp .. 8*grp+7.
-  // The keys of a tile sit in one segment (pinned prefix or ring), so their slots are consecutive and touch at
-  // most two pages: two page-table lookups per thread and tile, issued one tile ahead of their use.
-  const int grp = tid >> 4, chunk = tid & 15;
-  const size_t page_elems = static_cast<size_t>(2) * p.kv.kv_heads * kPageTokens * HD;
-  const bf16* head_base = p.kv.pool + static_cast<size_t>(head) * kPageTokens * HD + chunk * 8;
-  const size_t v_off = static_cast<size_t>(p.kv.kv_heads) * kPageTokens * HD;     // V block of the same page
-  int nx_s0 = 0, nx_pa = 0, nx_pb = 0;                                             // lookups of the next tile to load
-  auto lookup = [&](int t) {
-    const int jg = min(tile_j0(t) + 8 * grp, L - 1);
-    nx_s0 = kv_slot(jg, sys_len, ring_start);
-    const int last = kv_slot(min(jg + 7, tile_j1(t) - 1 > jg ? tile_j1(t) - 1 : jg), sys_len, ring_start);
-    nx_pa = table[nx_s0 >> 4];
-    nx_pb = table[last >> 4];
-  };
-  auto load_tile = [&](int t, int stage) {
-    bf16* sK = stage_base + stage * kDecStageElems + (8 * grp) * LDS + chunk * 8;
-    bf16* sV = sK + TILE * LDS;
-    const int n_ok = tile_j1(t) - (tile_j0(t) + 8 * grp);          // keys of this group inside the tile
-    const int s0 = nx_s0;
-    const bf16* base_a = head_base + static_cast<size_t>(nx_pa) * page_elems;
-    const bf16* base_b = head_base + static_cast<size_t>(nx_pb) * page_elems;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int sl = s0 + it;
-      const bf16* src = (((sl ^ s0) & ~15) == 0 ? base_a : base_b) + (sl & 15) * HD;
-      const bool ok = it < n_ok;
-      if (!ok) src = p.kv.pool;
-      cp_async16(sK + it * LDS, src, ok ? 16 : 0);                 // invalid keys: zero fill
-      cp_async16(sV + it * LDS, src + v_off, ok ? 16 : 0);
-    }
-    if (t + 1 < t_hi) lookup(t + 1);
-  };
-
-  // prologue: first tiles in flight, then the two query variants -> qbuf[0] (ring), qbuf[1] (sys)
-  lookup(t_lo);
-#pragma unroll
-  for (int s = 0; s < kDecStages - 1; ++s) {
-    if (s < n_tiles) load_tile(t_lo + s, s);
-    cp_async_commit();
+  // ---- warp specialisation: warps 4.. only stream K / V tiles into the ring, warps 0-3 only compute ----
+  if (tid == 0) {
+    for (int s0 = 0; s0 < kDecStages; ++s0) { dec_mbar_init(&full_bar[s0], 32 * kDecLoaders); dec_mbar_init(&empty_bar[s0], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  if (warp >= 4) {
+    constexpr int kPass = 4 / kDecLoaders;           // 16-key passes per loader warp and tile
+    const int pass0 = (warp - 4) * kPass;
+    // Tile loader: 64 keys x (K 256 B + V 256 B) = 2048 16-byte chunks.  Lane (g2 = lane / 16, chunk = lane % 16)
+    // copies chunk `chunk` of the keys 8*grp .. 8*grp+7 for grp = 2*pass + g2; the 4 passes are split over the loader warps.
+    // The keys of a tile sit in one segment (pinned prefix or ring), so the 8 slots of a group are consecutive and
+    // touch at most two pages: two page-table lookups per group, fetched one tile ahead of their use.
+    const int g2 = lane >> 4, chunk = lane & 15;
+    const size_t page_elems = static_cast<size_t>(2) * p.kv.kv_heads * kPageTokens * HD;
+    const bf16* head_base = p.kv.pool + static_cast<size_t>(head) * kPageTokens * HD + chunk * 8;
+    const size_t v_off = static_cast<size_t>(p.kv.kv_heads) * kPageTokens * HD;     // V block of the same page
+    int nx_s0[kPass], nx_pa[kPass], nx_pb[kPass];
+    auto lookup = [&](int t) {
+#pragma unroll
+      for (int ps = 0; ps < kPass; ++ps) {
+        const int grp = 2 * (pass0 + ps) + g2;
+        const int jg = min(tile_j0(t) + 8 * grp, L - 1);
+        nx_s0[ps] = kv_slot(jg, sys_len, ring_start);
+        const int last = kv_slot(min(jg + 7, tile_j1(t) - 1 > jg ? tile_j1(t) - 1 : jg), sys_len, ring_start);
+        nx_pa[ps] = table[nx_s0[ps] >> 4];
+        nx_pb[ps] = table[last >> 4];
+      }
+    };
+    lookup(t_lo);
+    for (int ti = 0; ti < n_tiles; ++ti) {
+      const int t = t_lo + ti, stage = ti % kDecStages;
+      if (ti >= kDecStages) dec_mbar_wait(&empty_bar[stage], ((ti / kDecStages) - 1) & 1);
+#pragma unroll
+      for (int ps = 0; ps < kPass; ++ps) {
+        const int grp = 2 * (pass0 + ps) + g2;
+        bf16* sK = stage_base + stage * kDecStageElems + (8 * grp) * LDS + chunk * 8;
+        bf16* sV = sK + TILE * LDS;
+        const int n_ok = tile_j1(t) - (tile_j0(t) + 8 * grp);          // keys of this group inside the tile
+        const int s0 = nx_s0[ps];
+        const bf16* base_a = head_base + static_cast<size_t>(nx_pa[ps]) * page_elems;
+        const bf16* base_b = head_base + static_cast<size_t>(nx_pb[ps]) * page_elems;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int sl = s0 + it;
+          const bf16* src = (((sl ^ s0) & ~15) == 0 ? base_a : base_b) + (sl & 15) * HD;
+          const bool ok = it < n_ok;
+          if (!ok) src = p.kv.pool;
+          cp_async16(sK + it * LDS, src, ok ? 16 : 0);                 // invalid keys: zero fill
+          cp_async16(sV + it * LDS, src + v_off, ok ? 16 : 0);
+        }
+      }
+      cp_async_arrive_noinc(&full_bar[stage]);
+      if (t + 1 < t_hi) lookup(t + 1);
+    }
+    cp_async_wait_all();
+    return;
+  }
+
   const bool owns_new = p.fuse && t_hi == tiles_total;          // the split that holds the last tile also takes the new token
   if (p.fuse) {
     // ---- fused llm_rope_append: complete this (stream, kv head)'s slice of the QKV row, rotate, append ----
@@ -222,7 +262,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
                              : p.q_sys + static_cast<size_t>(b) * (p.H * HD) + (head * GROUP + hq) * HD;
     *reinterpret_cast<uint4*>(qbuf + (v * GROUP + hq) * HD + c * 8) = *reinterpret_cast<const uint4*>(src + c * 8);
   }
-  __syncthreads();
+  dec_bar_compute();
   // A fragments of the current query variant live in registers (rows >= GROUP are zero padding)
   uint32_t qa0[8], qa2[8];
   auto load_q = [&](bool sys_variant) {
@@ -246,23 +286,17 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     const bool fresh = ti == n_tiles;        // fused mode, last iteration: the new token itself, from shared memory
     const bf16* sK;
     if (!fresh) {
-      cp_async_wait<kDecStages - 2>();
-      __syncthreads();                       // tile landed for everyone; everyone is done with the previous tile
-      {
-        const int nt = ti + kDecStages - 1;
-        if (nt < n_tiles) load_tile(t_lo + nt, nt % kDecStages);
-        cp_async_commit();
-      }
+      dec_mbar_wait(&full_bar[ti % kDecStages], (ti / kDecStages) & 1);   // tile landed
       sK = stage_base + (ti % kDecStages) * kDecStageElems;
       if (t == n_sys_tiles && ti > 0 && q_is_sys) { load_q(false); q_is_sys = false; }   // leaving the pinned prefix: ring variant
     } else {
-      // stage 0 held tile t_lo: 64 finite K / V rows.  Row 0 becomes the new token; the other 63 rows are masked.
-      cp_async_wait<0>();
-      __syncthreads();
+      // every tile has landed and been consumed.  Stage 0 held real tiles: 64 finite K / V rows.  Row 0 becomes the
+      // new token; the other 63 rows are masked.
+      dec_bar_compute();
       bf16* s0 = stage_base;
       if (tid < 32) *reinterpret_cast<uint2*>(s0 + tid * 4) = *reinterpret_cast<const uint2*>(newkv + tid * 4);
       else if (tid < 64) *reinterpret_cast<uint2*>(s0 + TILE * LDS + (tid - 32) * 4) = *reinterpret_cast<const uint2*>(newkv + HD + (tid - 32) * 4);
-      __syncthreads();
+      dec_bar_compute();
       sK = s0;
       const bool new_is_sys = L_old < p.kv.sys_len[slot];
       if (q_is_sys != new_is_sys) { load_q(new_is_sys); q_is_sys = new_is_sys; }
@@ -321,9 +355,12 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
       if (rescale) { o[mt][0] *= c_lo; o[mt][1] *= c_hi; o[mt][2] *= c_lo; o[mt][3] *= c_hi; }
       mma_bf16_16816(o[mt], va, pb0, pb1);
     }
+    if (!fresh) {                            // this warp is done with the stage: hand it back to the loader
+      __syncwarp();
+      if (lane == 0) dec_mbar_arrive(&empty_bar[ti % kDecStages]);
+    }
   }
-  cp_async_wait<0>();
-  __syncthreads();                           // all warps done with the stage buffers: reuse them for the merge
+  dec_bar_compute();                         // all compute warps done with the stage buffers (every tile has landed): reuse them for the merge
 
   // ---- merge the 4 warps (each saw a quarter of every tile) ----
   float* sm_o = reinterpret_cast<float*>(dec_smem);            // [4 warps][GROUP][HD]
@@ -341,7 +378,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
       sm_o[(warp * GROUP + 2 * t4 + 1) * HD + mt * 16 + 8 + g] = o[mt][3];
     }
   }
-  __syncthreads();
+  dec_bar_compute();
   float* sm_w = sm_l + 4 * GROUP;                              // [4 warps][GROUP] merge weights, then [GROUP] m, [GROUP] l
   if (tid < GROUP) {
     const int hq = tid;
@@ -362,7 +399,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     p.part_ml[pidx * 2 + 1] = ll;
     sm_w[4 * GROUP + hq] = ll > 0.f ? 1.f / ll : 0.f;
   }
-  __syncthreads();
+  dec_bar_compute();
 #pragma unroll
   for (int hq = 0; hq < GROUP; ++hq) {
     const int d = tid;                                         // 128 threads == HD

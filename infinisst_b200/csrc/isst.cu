@@ -910,7 +910,7 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
   dp.splits = splits; dp.scale_log2 = scale_log2;
   dp.fuse = fz.on ? 1 : 0; dp.part = fz.part; dp.n_part = fz.n_part; dp.part_stride = fz.part_stride;
   dp.tab_ring = ctx->llm_rope_ring; dp.tab_sys = ctx->llm_rope_sys; dp.active = fz.active;
-  ISST_CUDA(launch_k(ctx, decode_attention_mma_kernel<4>, dim3(splits, ctx->cfg.kv_heads, n), dim3(128), kDecSmemBytes, st, dp));
+  ISST_CUDA(launch_k(ctx, decode_attention_mma_kernel<4>, dim3(splits, ctx->cfg.kv_heads, n), dim3(kDecThreads), kDecSmemBytes, st, dp));
   LAUNCH_CHECK(ctx);
   return 0;
 }
