@@ -48,7 +48,7 @@ constexpr int kDecStages = 3;
 constexpr int kDecLds = 128 + 8;          // padded row (elements): conflict-free ldmatrix
 constexpr int kDecStageElems = 2 * kDecTile * kDecLds;                  // K tile + V tile
 constexpr int kDecSmemBytes = kDecStages * kDecStageElems * 2 + 2 * 4 * 128 * 2 + 2 * 128 * 2 + 2 * kDecStages * 8;   // + the two query variants + K/V of the new token + full / empty barriers
-constexpr int kDecLoaders = 2;            // loader warps
+constexpr int kDecLoaders = 4;            // loader warps
 constexpr int kDecThreads = 128 + 32 * kDecLoaders;   // 4 compute warps + the loader warps
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
