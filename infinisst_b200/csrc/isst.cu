@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "decode_attention.cuh"
 #include "gemm_tcgen05.cuh"
+#include "prefill_attention_tc.cuh"
 #include "rowops.cuh"
 
 namespace isst {
@@ -965,6 +966,17 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       constexpr int NW = 6;   // 96 query rows per CTA: the 4 x 22 rows of a steady-state turn in one CTA, 2 CTAs per SM
       ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
                    lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
+      static const bool pa_tc = getenv("ISST_PREFILL_TC") && atoi(getenv("ISST_PREFILL_TC")) != 0;   // tcgen05 prefill attention
+      if (pa_tc) {
+        static bool pa_attr = false;
+        if (!pa_attr) {
+          ISST_CUDA(cudaFuncSetAttribute(prefill_attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
+          pa_attr = true;
+        }
+        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4>, dim3(ceil_div(4 * lb.max_T, 128), Hkv, lb.n), dim3(kPaThreads),
+                           kPaSmemBytes, st, lp));
+        LAUNCH_CHECK(ctx);
+      } else {
       dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
       constexpr int NS = 3;
       constexpr int smem = chunk_attn_smem_bytes<128, NW, NS>();
@@ -976,6 +988,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       }
       ISST_CUDA(launch_k(ctx, chunk_attention_kernel<128, false, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
+      }
     } else {
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
