@@ -966,7 +966,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       constexpr int NW = 6;   // 96 query rows per CTA: the 4 x 22 rows of a steady-state turn in one CTA, 2 CTAs per SM
       ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
                    lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
-      static const bool pa_tc = getenv("ISST_PREFILL_TC") && atoi(getenv("ISST_PREFILL_TC")) != 0;   // tcgen05 prefill attention
+      static const bool pa_tc = !(getenv("ISST_PREFILL_TC") && atoi(getenv("ISST_PREFILL_TC")) == 0);   // tcgen05 prefill attention (ISST_PREFILL_TC=0: the mma.sync kernel, for A/B runs)
       if (pa_tc) {
         static bool pa_attr = false;
         if (!pa_attr) {

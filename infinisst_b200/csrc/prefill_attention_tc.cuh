@@ -6,12 +6,15 @@
 // of the kv head are streamed exactly once.  Per 64-key tile:
 //     S[128 x 64]  = Q[128 x 128] K^T      tcgen05.mma, both operands K-major in shared memory, S in TMEM (double-buffered)
 //     P = exp2(S * scale - m)                4 softmax warps: thread = query row = TMEM lane; P (bf16) -> shared memory
-//     Ot[128 x 128] = P[128 x 64] V          tcgen05.mma, A = P (K-major), B = V ([key][dim] = MN-major), Ot in TMEM
-//     O = O * corr + Ot                      the running output lives in the softmax threads' registers
+//     O[128 x 128] += P[128 x 64] V          tcgen05.mma, A = P (K-major), B = V ([key][dim] = MN-major), O stays in TMEM
+// The running maximum is only raised when it grows by more than 2^8 (then O in TMEM is rescaled in place), so P may
+// reach 256 instead of 1 - exact in the same relative precision - and almost every tile skips the correction.
 // Roles: warps 0-3 softmax / output, warp 4 MMA issuer (+ TMEM allocation), warps 5-6 K/V loaders (cp.async into the
-// 128-byte-swizzled layout the UMMA descriptors expect, 3-stage ring with full / empty mbarriers).
+// 128-byte-swizzled layout the UMMA descriptors expect, 2-stage ring with full / empty mbarriers).  112 KB of shared
+// memory, 256 TMEM columns and < 128 registers per thread: two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
 // Keys are stored rotated at their absolute index (attention.cuh header): tiles of the pinned system prompt use the
-// q_sys query variant, tiles of the sliding part the ring variant; both variants sit in shared memory.
+// q_sys query variant, tiles of the sliding part the ring variant; the softmax warps swap the variant in shared memory
+// at the boundary.
 #pragma once
 #include "attention.cuh"
 #include "gemm_tcgen05.cuh"
@@ -19,13 +22,14 @@
 namespace isst {
 
 constexpr int kPaKT = 64;                 // keys per tile
-constexpr int kPaStages = 3;
+constexpr int kPaStages = 2;
 constexpr int kPaThreads = 224;           // 4 softmax warps + MMA warp + 2 loader warps
 constexpr int kPaQBytes = 128 * 256;      // one query variant: 2 halves x [128 rows][128 B]
 constexpr int kPaStageBytes = 4 * 64 * 128;   // K half 0, K half 1, V half 0, V half 1: each [64 keys][128 B]
 constexpr int kPaPBytes = 128 * 128;      // P tile [128 rows][64 keys] bf16
-constexpr int kPaSmemBytes = 2 * kPaQBytes + kPaStages * kPaStageBytes + kPaPBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kPaTmemCols = 256;          // S0 [0,64) S1 [64,128) Ot [128,256)
+constexpr int kPaSmemBytes = kPaQBytes + kPaStages * kPaStageBytes + kPaPBytes + 256 /*barriers*/;
+constexpr int kPaTmemCols = 256;          // S0 [0,64) S1 [64,128) O [128,256)
+constexpr float kPaRescaleThreshold = 8.0f;   // log2 units
 
 // MN-major, SWIZZLE_128B shared-memory matrix descriptor for the V tile ([key][dim], dim contiguous): canonical layout
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute::UMMA::make_umma_desc<Major::MN>): 64 dims = one 128-byte
@@ -43,26 +47,34 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int umma_m, int umma_n) {
   return tc::make_idesc(umma_m, umma_n) | (1u << 16);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int GROUP>
-__global__ void __launch_bounds__(kPaThreads, 1)
+__global__ void __launch_bounds__(kPaThreads, 2)
 prefill_attention_tc_kernel(const LlmAttnParams lp) {
   using namespace tc;
   pdl_launch_dependents();
   pdl_wait();
   constexpr int HD = 128, KT = kPaKT, NS = kPaStages;
-  extern __shared__ uint8_t pa_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pa_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [variant 0 ring | 1 sys][half][128 rows][128 B]
-  uint8_t* sStage = smem + 2 * kPaQBytes;               // [NS][K h0 | K h1 | V h0 | V h1][64][128 B]
+  extern __shared__ __align__(1024) uint8_t pa_smem_raw[];
+  uint8_t* smem = pa_smem_raw;                          // 1024-byte aligned (SWIZZLE_128B atoms)
+  uint8_t* sQ = smem;                                   // [half][128 rows][128 B]: the query variant in use
+  uint8_t* sStage = smem + kPaQBytes;                   // [NS][K h0 | K h1 | V h0 | V h1][64][128 B]
   uint8_t* sP = sStage + NS * kPaStageBytes;            // [128 rows][128 B]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sP + kPaPBytes);   // [NS] tile landed (64 loader lanes arrive)
   uint64_t* empty_bar = full_bar + NS;                  // [NS] tile consumed (tcgen05.commit after P V)
   uint64_t* s_bar = empty_bar + NS;                     // [2]  S buffer ready (tcgen05.commit after Q K^T)
   uint64_t* p_bar = s_bar + 2;                          // P written (128 softmax threads arrive)
-  uint64_t* pv_bar = p_bar + 1;                         // Ot ready (tcgen05.commit after P V)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_bar + 1);
+  uint64_t* pv_bar = p_bar + 1;                         // P V of a tile done (tcgen05.commit): P and O may be touched
+  uint64_t* q_bar = pv_bar + 1;                         // ring query variant staged (128 softmax threads arrive)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, head = blockIdx.y, row0 = blockIdx.x * 128;
@@ -90,6 +102,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
     mbar_init(p_bar, 128);
     mbar_init(pv_bar, 1);
+    mbar_init(q_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -98,25 +111,26 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {
-    // 2 variants x 128 rows x 16 chunks of 16 B; rows beyond n_rows are zero
+  // one query variant: 128 rows x 16 chunks of 16 B into the swizzled K-major layout; rows beyond n_rows are zero
+  auto stage_q = [&](bool sys_variant, int t0, int nthr) {
     const int ldq = (lp.H + 2 * lp.kv.kv_heads) * HD;
-    for (int u = tid; u < 2 * 128 * 16; u += kPaThreads) {
-      const int v = u >> 11, rl = (u >> 4) & 127, ch = u & 15;
+    for (int u = t0; u < 128 * 16; u += nthr) {
+      const int rl = u >> 4, ch = u & 15;
       const int r = row0 + rl;
       uint4 val = make_uint4(0u, 0u, 0u, 0u);
       if (r < n_rows) {
         const int hq = r / T, i = r % T;
         const int qh = head * GROUP + hq;
-        const bf16* src = v == 0 ? lp.qkv + static_cast<size_t>(tok0 + i) * ldq + qh * HD
-                                 : lp.q_sys + static_cast<size_t>(tok0 + i) * (lp.H * HD) + qh * HD;
+        const bf16* src = sys_variant ? lp.q_sys + static_cast<size_t>(tok0 + i) * (lp.H * HD) + qh * HD
+                                      : lp.qkv + static_cast<size_t>(tok0 + i) * ldq + qh * HD;
         val = *reinterpret_cast<const uint4*>(src + ch * 8);
       }
       const int h = ch >> 3, c = ch & 7;
-      *reinterpret_cast<uint4*>(sQ + v * kPaQBytes + h * (128 * 128) + rl * 128 + ((c ^ (rl & 7)) << 4)) = val;
+      *reinterpret_cast<uint4*>(sQ + h * (128 * 128) + rl * 128 + ((c ^ (rl & 7)) << 4)) = val;
     }
     fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
-  }
+  };
+  stage_q(n_sys_tiles > 0, tid, kPaThreads);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -161,21 +175,24 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     };
     // classic multi-stage cp.async pipeline inside the loader: tile t is published (proxy fence + arrive) once its
     // group has landed, while the next NS-1 tiles are already in flight
+    // Tile t+NS-1 is requested as soon as its slot is free (P V of tile t-1 done), then tile t is published once
+    // this thread's copies of it have landed: NS-1 tiles stay in flight.  (The MMA warp finishes tile t-1 without
+    // needing tile t, so waiting for the slot before publishing cannot deadlock.)
     for (int t = 0; t < NS - 1; ++t) {
       if (t < n_tiles) issue(t);
       else cpa_commit();                                 // keep the group count uniform
     }
     for (int t = 0; t < n_tiles; ++t) {
-      cpa_wait<NS - 2>();                                // tile t landed (this thread's copies); NS-2 younger groups may fly
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[t % NS]);                    // publish BEFORE blocking on a free slot (the MMA warp needs tile
-      const int nt = t + NS - 1;                         // t+1 to get past tile t, whose completion frees the slot)
+      const int nt = t + NS - 1;
       if (nt < n_tiles) {
         if (nt >= NS) mbar_wait(&empty_bar[nt % NS], ((nt / NS) - 1) & 1);
         issue(nt);
       } else {
-        cpa_commit();                                    // keep the group count uniform
+        cpa_commit();
       }
+      cpa_wait<NS - 1>();                                // tile t landed (this thread's copies)
+      fence_proxy_async_smem();
+      mbar_arrive(&full_bar[t % NS]);
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -184,9 +201,10 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     auto mma_s = [&](int t) {
       const int stage = t % NS;
       mbar_wait(&full_bar[stage], (t / NS) & 1);
+      if (t == n_sys_tiles && n_sys_tiles > 0) mbar_wait(q_bar, 0);   // the softmax warps swapped in the ring variant
       tcgen05_fence_after();
       if (lane == 0) {
-        const uint32_t q = smem_u32(sQ + (t < n_sys_tiles ? kPaQBytes : 0));
+        const uint32_t q = smem_u32(sQ);
         const uint32_t k = smem_u32(sStage + stage * kPaStageBytes);
         const uint32_t tS = tmem_base + (t & 1) * KT;
 #pragma unroll
@@ -199,9 +217,8 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
       }
       __syncwarp();
     };
-    if (n_tiles > 0) mma_s(0);
     for (int t = 0; t < n_tiles; ++t) {
-      if (t + 1 < n_tiles) mma_s(t + 1);                       // S of the next tile while the softmax warps work on this one
+      mma_s(t);                                                // (the other CTA on this SM fills the tensor pipe meanwhile)
       mbar_wait(p_bar, t & 1);
       tcgen05_fence_after();
       if (lane == 0) {
@@ -212,7 +229,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
 #pragma unroll
         for (int kk = 0; kk < KT / 16; ++kk)                   // 4 k-steps of 16 keys
           umma_bf16(tO, make_smem_desc(pa + kk * 32), make_smem_desc_mn(v + kk * (16 * 128), 64 * 128, 1024), idesc_o,
-                    kk > 0 ? 1u : 0u);
+                    (t > 0 || kk > 0) ? 1u : 0u);                // O accumulates in TMEM over all tiles
         umma_commit(pv_bar);
         umma_commit(&empty_bar[stage]);
       }
@@ -226,9 +243,6 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     const int hq = live ? r / T : 0, i = live ? r % T : 0;
     const int qhi = live ? L - T + i + 1 : 0;                  // causal, bottom-right aligned
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
       const int k0 = tile_k0(t), k1 = min(tile_k1(t), qhi);
@@ -238,19 +252,53 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) tmem_ld16_issue(tmem_base + lane_addr + (t & 1) * KT + q4 * 16, sr[q4]);
       tmem_ld_wait();
-      float mx = m_run;
+      float mx = -INFINITY;
+      if (k0 + KT <= k1) {                                     // interior tile for this row: no mask
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)
+        for (int q4 = 0; q4 < 4; ++q4)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int j = k0 + q4 * 16 + e;
-          const float sv = (j < k1) ? __uint_as_float(sr[q4][e]) * lp.scale_log2 : -INFINITY;
-          sr[q4][e] = __float_as_uint(sv);
-          mx = fmaxf(mx, sv);
+          for (int e = 0; e < 16; ++e) {
+            const float sv = __uint_as_float(sr[q4][e]) * lp.scale_log2;
+            sr[q4][e] = __float_as_uint(sv);
+            mx = fmaxf(mx, sv);
+          }
+      } else {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int j = k0 + q4 * 16 + e;
+            const float sv = (j < k1) ? __uint_as_float(sr[q4][e]) * lp.scale_log2 : -INFINITY;
+            sr[q4][e] = __float_as_uint(sv);
+            mx = fmaxf(mx, sv);
+          }
+      }
+      // lazy running maximum: raise it only when the tile exceeds it by more than the threshold
+      float corr = 1.f;
+      const bool raise = mx > m_run + kPaRescaleThreshold || (m_run == -INFINITY && mx != -INFINITY);
+      if (raise) {
+        corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - mx);
+        m_run = mx;
+        l_run *= corr;
+      }
+      const float msafe = (m_run == -INFINITY) ? 0.f : m_run;
+      // P V of the previous tile must be complete before P is overwritten / O is rescaled
+      if (t > 0) { mbar_wait(pv_bar, (t - 1) & 1); tcgen05_fence_after(); }
+      if (t > 0 && __any_sync(0xffffffffu, raise)) {
+        // ---- rare: rescale this warp's 32 rows of O in TMEM (rows that did not raise use corr = 1) ----
+#pragma unroll 1
+        for (int c8 = 0; c8 < HD / 32; ++c8) {
+          uint32_t orr[2][16];
+          tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32, orr[0]);
+          tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32 + 16, orr[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) orr[e >> 4][e & 15] = __float_as_uint(__uint_as_float(orr[e >> 4][e & 15]) * corr);
+          tmem_st16(tmem_base + lane_addr + 2 * KT + c8 * 32, orr[0]);
+          tmem_st16(tmem_base + lane_addr + 2 * KT + c8 * 32 + 16, orr[1]);
         }
-      const float msafe = (mx == -INFINITY) ? 0.f : mx;
-      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - msafe);
-      m_run = mx;
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
       float ls = 0.f;
       // P row (64 bf16 = 128 B = 8 chunks) into the swizzled K-major layout
 #pragma unroll
@@ -266,35 +314,37 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
         }
         *reinterpret_cast<uint4*>(sP + rl * 128 + ((c ^ (rl & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      l_run = l_run * corr + ls;
+      l_run += ls;
       fence_proxy_async_smem();                                // P stores -> visible to the tensor core
-      tcgen05_fence_before();                                  // the S loads above are complete (tmem_ld_wait)
+      tcgen05_fence_before();                                  // S loads / O stores above are complete
       mbar_arrive(p_bar);
-      // ---- O = O * corr + Ot ----
-      mbar_wait(pv_bar, t & 1);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int c8 = 0; c8 < HD / 32; ++c8) {
-        uint32_t orr[2][16];
-        tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32, orr[0]);
-        tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32 + 16, orr[1]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c8 * 32 + e] = o[c8 * 32 + e] * corr + __uint_as_float(orr[e >> 4][e & 15]);
+      if (t + 1 == n_sys_tiles && t + 1 < n_tiles) {
+        // leaving the pinned prefix: Q K^T of every prefix tile is complete (s_bar), swap in the ring variant
+        stage_q(false, tid, 128);
+        mbar_arrive(q_bar);
       }
-      tcgen05_fence_before();
     }
-    if (live) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      bf16* dst = lp.out + static_cast<size_t>(tok0 + i) * (lp.H * HD) + (head * GROUP + hq) * HD;
+    // ---- O = O / l ----
+    mbar_wait(pv_bar, (n_tiles - 1) & 1);
+    tcgen05_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* dst = lp.out + static_cast<size_t>(tok0 + i) * (lp.H * HD) + (head * GROUP + hq) * HD;
+#pragma unroll 1
+    for (int c8 = 0; c8 < HD / 32; ++c8) {
+      uint32_t orr[2][16];
+      tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32, orr[0]);
+      tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32 + 16, orr[1]);
+      tmem_ld_wait();
+      if (live) {
 #pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        uint4 v;
-        v.x = pack_bf16(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
-        v.y = pack_bf16(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
-        v.z = pack_bf16(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
-        v.w = pack_bf16(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + c * 8) = v;
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(orr[c >> 1][(c & 1) * 8 + 0]) * inv, __uint_as_float(orr[c >> 1][(c & 1) * 8 + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(orr[c >> 1][(c & 1) * 8 + 2]) * inv, __uint_as_float(orr[c >> 1][(c & 1) * 8 + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(orr[c >> 1][(c & 1) * 8 + 4]) * inv, __uint_as_float(orr[c >> 1][(c & 1) * 8 + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(orr[c >> 1][(c & 1) * 8 + 6]) * inv, __uint_as_float(orr[c >> 1][(c & 1) * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c8 * 32 + c * 8) = v;
+        }
       }
     }
   }
