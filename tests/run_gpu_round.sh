@@ -14,8 +14,13 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
       --log-file $O/launches.csv python bench.py --ncu-step --warmup 1 > $O/ncu_launches.log 2>&1; echo "ncu launches exit=$?"
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:gemm_sk -s 300 -c 8 -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit=$?"
+      -k regex:gemm_sk -s 300 -c 8 -f -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit=$?"
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:decode_attention -s 32 -c 2 -o $O/prof_decode_attn python bench.py --ncu-step --warmup 1 > $O/ncu_attn.log 2>&1; echo "ncu attn exit=$?"
+      -k regex:decode_attention -s 32 -c 2 -f -o $O/prof_decode_attn python bench.py --ncu-step --warmup 1 > $O/ncu_attn.log 2>&1; echo "ncu attn exit=$?"
 fi
 ls -la $O
+if [ "${NCU:-1}" = "1" ]; then
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:prefill_attention_tc -s 2 -c 2 -f -o $O/prof_prefill_attn python bench.py --ncu-step --warmup 1 > $O/ncu_pattn.log 2>&1; echo "ncu prefill attn exit=$?"
+  timeout 600 python bench.py --timeline $O/timeline.txt --warmup 2 > $O/timeline.log 2>&1; echo "timeline exit=$?"
+fi

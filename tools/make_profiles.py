@@ -51,6 +51,10 @@ def full_summary(rep, title):
 def main(tag):
     os.makedirs(PROF, exist_ok=True)
     bench = os.path.join(OUT, "bench.json")
+    tl = os.path.join(OUT, "timeline.txt")
+    if os.path.exists(tl):
+        with open(tl) as f, open(os.path.join(PROF, f"{tag}_timeline_step64.txt"), "w") as g:
+            g.write(f.read())
     if os.path.exists(bench):
         with open(bench) as f, open(os.path.join(PROF, f"{tag}_bench.json"), "w") as g:
             g.write(f.read())
@@ -63,7 +67,8 @@ def main(tag):
         open(os.path.join(PROF, f"{tag}_launch_list.txt"), "w").write(txt)
     traffic = {}
     for rep, name, title, cls in [("prof_gemm_decode.ncu-rep", "gemm_decode", "weight-streaming GEMMs of two decode layers (o_proj, gate/up, down, qkv; 64 tokens)", "gemm_stream"),
-                                  ("prof_decode_attn.ncu-rep", "decode_attention", "decode attention, 64 streams x kv_len ~1001, layers 0-1 of one decode forward", "attn_decode")]:
+                                  ("prof_decode_attn.ncu-rep", "decode_attention", "decode attention, 64 streams x kv_len ~1001, layers 0-1 of one decode forward", "attn_decode"),
+                                  ("prof_prefill_attn.ncu-rep", "prefill_attention", "tcgen05 chunk-prefill attention, 64 streams x 22 tokens over kv_len ~1023", "attn_prefill")]:
         p = os.path.join(OUT, rep)
         if not os.path.exists(p):
             continue
