@@ -384,17 +384,18 @@ def main_native(args, env):
     roof = {k: classes[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
     # measured DRAM traffic per launch of the dominant class, from the committed `ncu --set full` capture
     # (profiles/traffic.json, written by tools/make_profiles.py; ncu cannot run inside a bench)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_alg = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         if dom in tj:
             traffic, traffic_src = tj[dom]["dram_bytes_per_launch"], tj[dom]["source"]
+            traffic_alg = tj[dom].get("algorithmic_bytes_per_launch_same_launches")
     except (OSError, ValueError, KeyError):
         pass
     v_dom = prof[dom]
     roof.update({"kernel": dom, "traffic": traffic, "traffic_unit": "bytes per launch (mean over the captured launches)",
-                 "traffic_source": traffic_src,
+                 "traffic_source": traffic_src, "traffic_algorithmic_same_launches": traffic_alg,
                  "algorithmic_per_launch": (v_dom["flops"] if roof["bound"] == "tensor" else v_dom["bytes"]) / max(v_dom["launches"], 1),
                  "peaks": pk["source"],
                  "note": "algorithmic bytes/flops per launch (DESIGN.md §4) / CUDA-event time of the launches of this "

@@ -77,7 +77,14 @@ def main(tag):
         tot = [to_bytes(*r["dram__bytes_read.sum"]) + to_bytes(*r["dram__bytes_write.sum"]) for r in recs
                if "dram__bytes_read.sum" in r and "dram__bytes_write.sum" in r]
         if tot:
+            # algorithmic bytes of the SAME captured launches (production dims), so that traffic can be compared like with like
+            alg = None
+            if cls == "gemm_stream":      # o_proj, gate/up, down, qkv weights of a decode layer (bf16) - activations are < 2 %
+                alg = (4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336 + 6144 * 4096) * 2 / 4.0
+            elif cls in ("attn_decode", "attn_prefill"):   # K and V of 64 streams x ~1001-1023 tokens x 8 kv heads x 128 x bf16
+                alg = 64 * (1001 if cls == "attn_decode" else 1023) * 8 * 128 * 2 * 2
             traffic[cls] = {"dram_bytes_per_launch": sum(tot) / len(tot), "launches_captured": len(tot),
+                            "algorithmic_bytes_per_launch_same_launches": alg,
                             "per_launch": [round(t) for t in tot],
                             "source": f"profiles/{tag}_ncu_full_{name}.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"}
     if traffic:
