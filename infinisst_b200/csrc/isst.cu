@@ -330,6 +330,48 @@ static int get_act_map(isst_ctx* ctx, CUtensorMap* map, const ActView& v, int bo
   return 0;
 }
 
+// Work split of one persistent stream-K launch (see tc::SkParams): grid size G, data-parallel / stream-K tile
+// counts, and S > 0 when the deferred split reduction is used (every tile cut into S k-ranges, one CTA each).
+static void sk_plan(isst_ctx* ctx, int M_tok, int N_out, int K, int batch, int act_rows, int w_rows, bool swap, bool dual,
+                    bool want_defer, int force_splits, tc::SkParams* out, long long* G_out, int* S_out) {
+  tc::SkParams sk{};
+  sk.tiles_tok = ceil_div(M_tok, act_rows);
+  sk.tiles_feat = ceil_div(N_out, w_rows);
+  sk.num_kb = ceil_div(K, tc::kBK);
+  sk.tiles = static_cast<long long>(sk.tiles_tok) * sk.tiles_feat * batch;
+  long long G = std::min<long long>(ctx->sm_count, sk.tiles * sk.num_kb);
+  if (force_splits > 0) G = std::min<long long>(G, sk.tiles * force_splits);
+  // Remainder policy: the tiles beyond the last full round-robin wave are either dealt as one more (partly
+  // empty) data-parallel round, or cut stream-K style into equal unit ranges.  Stream-K pays a split reduction
+  // (~6 us: park partial, fence, wait, reduce) and wins only when it shortens the critical path by more than
+  // that, i.e. when a whole tile is long compared with the reduction: `gain` units saved vs `r_units`.
+  const long long rem = sk.tiles % G;
+  static const char* ru_env = getenv("ISST_SK_RUNITS");     // tuning aid
+  const long long r_units = ru_env ? atoi(ru_env) : ((swap && !dual) ? 16 : 24);
+  bool use_sk = rem > 0 && (sk.num_kb - ceil_div(static_cast<int>(rem * sk.num_kb), static_cast<int>(G))) > r_units;
+  if (force_splits > 1) use_sk = rem > 0;
+  sk.tiles_dp = use_sk ? sk.tiles - rem : sk.tiles;
+  if (!use_sk && sk.tiles < G) G = sk.tiles;
+  sk.units_sk = (sk.tiles - sk.tiles_dp) * sk.num_kb;
+  sk.g_sk = static_cast<int>(std::min<long long>(G, sk.units_sk));
+  *S_out = 0;
+  if (want_defer) {
+    // Deferred split reduction: every tile is cut into S equal k-ranges (one CTA each, tiles * S <= #SMs) and the
+    // partials are summed by the consumer row kernel; falls back to the in-kernel schemes when S would be 1.
+    const long long S = std::min<long long>(std::min<long long>(ctx->sm_count / std::max<long long>(sk.tiles, 1), 8), sk.num_kb / 8);
+    if (swap && batch == 1 && S >= 2 && force_splits == 0 &&
+        static_cast<size_t>(S) * M_tok * N_out <= ctx->defer_ws_floats) {
+      G = sk.tiles * S;
+      sk.tiles_dp = 0;
+      sk.units_sk = sk.tiles * sk.num_kb;
+      sk.g_sk = static_cast<int>(G);
+      *S_out = static_cast<int>(S);
+    }
+  }
+  *out = sk;
+  *G_out = G;
+}
+
 template <int kBN, bool kDual, bool kSwap>
 static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
                      int force_splits) {
@@ -341,44 +383,14 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
     attr_set = true;
   }
   tc::SkParams sk{};
-  sk.tiles_tok = ceil_div(p.M_tok, C::kActRows);
-  sk.tiles_feat = ceil_div(p.N_out, C::kWRows);
-  sk.num_kb = ceil_div(p.K, tc::kBK);
-  sk.tiles = static_cast<long long>(sk.tiles_tok) * sk.tiles_feat * p.batch;
+  long long G = 0;
+  int S = 0;
+  sk_plan(ctx, p.M_tok, p.N_out, p.K, p.batch, C::kActRows, C::kWRows, kSwap, kDual, p.part_out != nullptr, force_splits, &sk, &G, &S);
   sk.dbg = ctx->gemm_dbg;
-  long long G = std::min<long long>(ctx->sm_count, sk.tiles * sk.num_kb);
-  if (force_splits > 0) G = std::min<long long>(G, sk.tiles * force_splits);
-  // Remainder policy: the tiles beyond the last full round-robin wave are either dealt as one more (partly
-  // empty) data-parallel round, or cut stream-K style into equal unit ranges.  Stream-K pays a split reduction
-  // (~6 us: park partial, fence, wait, reduce) and wins only when it shortens the critical path by more than
-  // that, i.e. when a whole tile is long compared with the reduction: `gain` units saved vs `r_units`.
-  const long long rem = sk.tiles % G;
-  static const char* ru_env = getenv("ISST_SK_RUNITS");     // tuning aid
-  const long long r_units = ru_env ? atoi(ru_env) : ((kSwap && !kDual) ? 16 : 24);
-  bool use_sk = rem > 0 && (sk.num_kb - ceil_div(static_cast<int>(rem * sk.num_kb), static_cast<int>(G))) > r_units;
-  if (force_splits > 1) use_sk = rem > 0;
-  sk.tiles_dp = use_sk ? sk.tiles - rem : sk.tiles;
-  if (!use_sk && sk.tiles < G) G = sk.tiles;
-  sk.units_sk = (sk.tiles - sk.tiles_dp) * sk.num_kb;
-  sk.g_sk = static_cast<int>(std::min<long long>(G, sk.units_sk));
   tc::GemmParams pp = p;
-  ctx->last_defer_splits = 0;
-  if (p.part_out) {
-    // Deferred split reduction: every tile is cut into S equal k-ranges (one CTA each, tiles * S <= #SMs) and the
-    // partials are summed by the consumer row kernel; falls back to the in-kernel schemes when S would be 1.
-    pp.part_out = nullptr;
-    const long long S = std::min<long long>(std::min<long long>(ctx->sm_count / std::max<long long>(sk.tiles, 1), 8), sk.num_kb / 8);
-    if (kSwap && p.batch == 1 && S >= 2 && force_splits == 0 &&
-        static_cast<size_t>(S) * p.M_tok * p.N_out <= ctx->defer_ws_floats) {
-      G = sk.tiles * S;
-      sk.tiles_dp = 0;
-      sk.units_sk = sk.tiles * sk.num_kb;
-      sk.g_sk = static_cast<int>(G);
-      pp.part_out = ctx->defer_ws;
-      pp.part_splits = static_cast<int>(S);
-      ctx->last_defer_splits = static_cast<int>(S);
-    }
-  }
+  pp.part_out = S ? ctx->defer_ws : nullptr;
+  pp.part_splits = S;
+  ctx->last_defer_splits = S;
   pp.counter_half = ctx->n_counters / 2;
   pp.counter_parity = ctx->gemm_parity;
   ctx->gemm_parity ^= 1;
