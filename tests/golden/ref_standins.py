@@ -423,6 +423,176 @@ def greedy_generate(model, input_ids, num_beams=1, max_new_tokens=10, encoder_in
 
 
 # ------------------------------------------------------------------------------------------------
+# beam search: the reference's own loop + scorer (model/patches/patch_hf.py:43-302, 687-967) under stand-ins
+# for the transformers 4.47 classes it extends (transformers.generation.beam_search is gone in 5.x)
+# ------------------------------------------------------------------------------------------------
+class BeamHypotheses447:
+    """transformers 4.47 BeamHypotheses minus `add` (the reference installs its own, patch_hf.py:278-302)."""
+
+    def __init__(self, num_beams, length_penalty, early_stopping, max_length=None):
+        self.length_penalty, self.early_stopping, self.max_length = length_penalty, early_stopping, max_length
+        self.num_beams = num_beams
+        self.beams = []
+        self.worst_score = 1e9
+
+    def __len__(self):
+        return len(self.beams)
+
+    def is_done(self, best_sum_logprobs, cur_len, decoder_prompt_len=0):
+        if len(self) < self.num_beams:
+            return False
+        if self.early_stopping is True:
+            return True
+        if self.early_stopping is False:
+            highest_attainable_score = best_sum_logprobs / (cur_len - decoder_prompt_len) ** self.length_penalty
+            return self.worst_score >= highest_attainable_score
+        raise NotImplementedError("early_stopping='never' is not used by the reference")
+
+
+class BeamScorer447:
+    pass
+
+
+class BeamSearchScorer447(BeamScorer447):
+    """transformers 4.47 BeamSearchScorer constructor / `is_done`; `process` and `finalize` are the reference's
+    (patch_hf.py:43-275), attached by load_ref_patch_hf() the way patch_hf() does (:968-972)."""
+
+    def __init__(self, batch_size, num_beams, device, length_penalty=1.0, do_early_stopping=False,
+                 num_beam_hyps_to_keep=1, num_beam_groups=1, max_length=None):
+        self.num_beams, self.device, self.length_penalty = num_beams, device, length_penalty
+        self.do_early_stopping, self.num_beam_hyps_to_keep = do_early_stopping, num_beam_hyps_to_keep
+        self.num_beam_groups = num_beam_groups
+        self.group_size = num_beams // num_beam_groups
+        self._beam_hyps = [BeamHypotheses447(self.group_size, length_penalty, do_early_stopping, max_length)
+                           for _ in range(batch_size * num_beam_groups)]
+        self._done = torch.tensor([False] * (batch_size * num_beam_groups), dtype=torch.bool, device=device)
+
+    @property
+    def is_done(self):
+        return self._done.all()
+
+
+class SizedDynamicCache447(DynamicCache447):
+    """`DynamicCache(num_hidden_layers)` as the reference's scorer constructs it (patch_hf.py:114, 192)."""
+
+    def __init__(self, num_hidden_layers=None):
+        super().__init__()
+
+
+def load_ref_patch_hf():
+    """Executes /root/reference/model/patches/patch_hf.py itself (not the no-op placeholder install() registers
+    for the agent's import) with the 4.47-only names it imports supplied by the stand-ins above."""
+    if getattr(load_ref_patch_hf, "mod", None) is not None:
+        return load_ref_patch_hf.mod
+    import importlib.util
+    import transformers.generation.utils as gu
+    bs = types.ModuleType("transformers.generation.beam_search")
+    bs.BeamSearchScorer, bs.BeamScorer, bs.BeamHypotheses = BeamSearchScorer447, BeamScorer447, BeamHypotheses447
+    sys.modules["transformers.generation.beam_search"] = bs
+    for name in ("_split_model_inputs", "stack_model_outputs"):      # only used with low_memory=True
+        if not hasattr(gu, name):
+            setattr(gu, name, None)
+    spec = importlib.util.spec_from_file_location("ref_patch_hf", REFERENCE + "/model/patches/patch_hf.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.DynamicCache = SizedDynamicCache447
+    BeamSearchScorer447.process = mod.beam_search_process           # patch_hf.py:968-972
+    BeamSearchScorer447.finalize = mod.beam_search_finalize
+    BeamHypotheses447.add = mod.beam_hypotheses_add
+    load_ref_patch_hf.mod = mod
+    return mod
+
+
+class _BeamSelf:
+    """The GenerationMixin surface `generation_mixin_beam_search` (patch_hf.py:687-967) touches: HF 4.47 helper
+    methods restated minimally; forward / prepare_inputs_for_generation are the reference model's own."""
+
+    def __init__(self, model):
+        self.model, self.config = model, model.config
+
+    def __call__(self, **kw):
+        return self.model(**kw)
+
+    def prepare_inputs_for_generation(self, input_ids, **kw):
+        return self.model.prepare_inputs_for_generation(input_ids, **kw)
+
+    def _get_initial_cache_position(self, input_ids, model_kwargs):
+        return model_kwargs
+
+    def _has_unfinished_sequences(self, this_peer_finished, synced_gpus, device=None, **kw):
+        return not this_peer_finished
+
+    def _update_model_kwargs_for_generation(self, outputs, model_kwargs, is_encoder_decoder=False, **kw):
+        if getattr(outputs, "past_key_values", None) is not None:
+            model_kwargs["past_key_values"] = outputs.past_key_values
+        return model_kwargs
+
+    def _temporary_reorder_cache(self, past_key_values, beam_idx):
+        # 4.47: DynamicCache.reorder_cache = index_select of every layer on the batch dim
+        for i in range(len(past_key_values.key_cache)):
+            past_key_values.key_cache[i] = past_key_values.key_cache[i].index_select(0, beam_idx)
+            past_key_values.value_cache[i] = past_key_values.value_cache[i].index_select(0, beam_idx)
+        return past_key_values
+
+
+def beam_generate(model, input_ids, num_beams=4, max_new_tokens=10, encoder_input_ids=None,
+                  encoder_no_repeat_ngram_size=0, no_repeat_ngram_size=0, repetition_penalty=1.0,
+                  suppress_tokens=None, past_key_values=None, eos_token_ids=(), pad_token_id=None, record=None,
+                  **model_kwargs):
+    """The beam branch of the reference's `generate` (patch_hf.py:626-655): HF's set-up steps restated (real
+    transformers processors / stopping criteria, 4.47-style scorer), then the REFERENCE's
+    `_expand_inputs_for_generation` (:305-342), `_beam_search` (:687-967), `process` / `finalize` / `add`."""
+    from transformers.generation.logits_process import (EncoderNoRepeatNGramLogitsProcessor, LogitsProcessorList,
+                                                        NoRepeatNGramLogitsProcessor,
+                                                        RepetitionPenaltyLogitsProcessor,
+                                                        SuppressTokensLogitsProcessor)
+    from transformers.generation.stopping_criteria import EosTokenCriteria, MaxLengthCriteria, StoppingCriteriaList
+    mod = load_ref_patch_hf()
+    procs = LogitsProcessorList()
+    if repetition_penalty is not None and repetition_penalty != 1.0:
+        procs.append(RepetitionPenaltyLogitsProcessor(penalty=repetition_penalty))
+    if no_repeat_ngram_size:
+        procs.append(NoRepeatNGramLogitsProcessor(no_repeat_ngram_size))
+    if encoder_no_repeat_ngram_size and encoder_input_ids is not None and encoder_input_ids.numel() > 0:
+        procs.append(EncoderNoRepeatNGramLogitsProcessor(encoder_no_repeat_ngram_size, encoder_input_ids))
+    if suppress_tokens:
+        procs.append(SuppressTokensLogitsProcessor(suppress_tokens, device=input_ids.device))
+    for k in ("attention_mask", "do_sample", "top_p", "top_k", "epsilon_cutoff", "temperature",
+              "num_return_sequences", "return_dict_in_generate", "return_legacy_cache", "use_cache"):
+        model_kwargs.pop(k, None)
+    if past_key_values is None:
+        past_key_values = DynamicCache447()              # HF generate step 7 creates the cache when none is passed
+    max_length = input_ids.shape[1] + max_new_tokens
+    eos = torch.tensor([int(e) for e in eos_token_ids], dtype=torch.long)
+    stop = StoppingCriteriaList([MaxLengthCriteria(max_length=max_length), EosTokenCriteria(eos_token_id=eos)])
+    gen_cfg = types.SimpleNamespace(_pad_token_tensor=torch.tensor(pad_token_id), _eos_token_tensor=eos,
+                                    output_attentions=False, output_hidden_states=False, output_scores=False,
+                                    output_logits=False, return_dict_in_generate=True, low_memory=False,
+                                    do_sample=False)
+    scorer = BeamSearchScorer447(batch_size=input_ids.shape[0], num_beams=num_beams, device=input_ids.device,
+                                 length_penalty=1.0, do_early_stopping=False, num_beam_hyps_to_keep=1,
+                                 max_length=max_length)
+    if record is not None:                                # per-step candidates as the reference's scorer receives them
+        inner = scorer.process
+
+        def process(input_ids_, next_scores, next_tokens, next_indices, **kw):
+            out = inner(input_ids_, next_scores, next_tokens, next_indices, **kw)
+            record.append({"scores": next_scores[0].clone(), "tokens": next_tokens[0].clone(),
+                           "beams": next_indices[0].clone(), "next_scores": out["next_beam_scores"].clone(),
+                           "next_tokens": out["next_beam_tokens"].clone(),
+                           "next_beams": out["next_beam_indices"].clone(),
+                           "n_hyps": len(scorer._beam_hyps[0]), "done": bool(scorer._done[0])})
+            return out
+        scorer.process = process
+    ids_k, kw_k = mod.generation_mixin_expand_inputs_for_generation(
+        expand_size=num_beams, is_encoder_decoder=False, input_ids=input_ids, past_key_values=past_key_values,
+        **model_kwargs)
+    return mod.generation_mixin_beam_search(_BeamSelf(model), ids_k, scorer, logits_processor=procs,
+                                            stopping_criteria=stop, generation_config=gen_cfg, synced_gpus=False,
+                                            **kw_k)
+
+
+# ------------------------------------------------------------------------------------------------
 def install() -> None:
     """Put the stand-ins into sys.modules, auto-stub the rest, and make /root/reference importable."""
     if getattr(install, "done", False):
