@@ -105,6 +105,36 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
                   const isst_gen_params* gen, const int32_t* forced, int32_t* out_tokens, int* out_counts,
                   void* cuda_stream);
 
+/* Beam search with KV hand-back: the reference's shipped decoding (scripts/infer/infinisst.sh:48 `--beam 4`).
+ * Replaces model.generate(num_beams=k, ...) as agents/infinisst.py:307-336 calls it: patch_hf.py:626-655 (dispatch),
+ * :305-342 (k-fold input expansion - here the prompt is prefilled ONCE per stream and the beams share its KV pages),
+ * :687-967 (loop: log-softmax, logits processors on the log-probs, top max(2, 1 + n_eos) * k candidates, KV reorder),
+ * :43-157 / :278-302 (scorer: EOS candidates close hypotheses, `is_done` bound), :159-275 (finalize: best hypothesis
+ * and ITS KV cache).  out_tokens [n][max_new_tokens + 1]: generated part of `sequences` (the closing EOS is appended
+ * when it fits, as :262-264 does), -1 padded; out_counts [n]; out_scores [n] (may be null) = sequence score.
+ * After the call each stream's KV holds its prompt and the forwarded tokens of the winning hypothesis.
+ * n * num_beams must not exceed max_batch; the page pool needs 3 * num_beams spare tail page sets
+ * per stream of the call.  `follow` (may be null) teacher-forces the discrete choices for tolerance-aware parity
+ * tests; `trace` (may be null) returns every step's candidates and choices.  All pointers are HOST pointers. */
+typedef struct isst_beam_follow {
+  const int32_t* closed;   /* [n][max_new][k][2] (parent beam, eos token) closed at each step, -1 terminated per step */
+  const int32_t* next;     /* [n][max_new][k][2] (parent beam, token) continued at each step */
+  const int32_t* steps;    /* [n] selection steps to run */
+  const int32_t* done;     /* [n] 1: the scorer declared the sentence done at the last of those steps */
+} isst_beam_follow;
+typedef struct isst_beam_trace {
+  float* cand_scores;      /* [n][max_new][n_keep] best first */
+  int32_t* cand_index;     /* [n][max_new][n_keep] parent beam * vocab + token */
+  int32_t* next;           /* [n][max_new][k][2] (parent beam, token) */
+  float* next_scores;      /* [n][max_new][k] */
+  int32_t* steps;          /* [n] selection steps run */
+} isst_beam_trace;
+int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                       const int32_t* speech_slot, const int32_t* enc_ids, const int* enc_lens,
+                       const isst_gen_params* gen, int num_beams, float length_penalty,
+                       const isst_beam_follow* follow, int32_t* out_tokens, int* out_counts, float* out_scores,
+                       isst_beam_trace* trace, void* cuda_stream);
+
 /* model.forward (model/llm.py:192-270) on the stream caches: append T_b tokens per stream and return
  * the logits of every stream's last position ([n][vocab] f32, device or host pointer).  embeds_override
  * (optional device pointer, bf16 [sum(lens)][hidden]) replaces the embedding/splice step. */

@@ -37,6 +37,16 @@ class IsstGenParams(C.Structure):
     ]
 
 
+class IsstBeamFollow(C.Structure):
+    _fields_ = [("closed", C.POINTER(C.c_int32)), ("next", C.POINTER(C.c_int32)), ("steps", C.POINTER(C.c_int32)),
+                ("done", C.POINTER(C.c_int32))]
+
+
+class IsstBeamTrace(C.Structure):
+    _fields_ = [("cand_scores", C.POINTER(C.c_float)), ("cand_index", C.POINTER(C.c_int32)),
+                ("next", C.POINTER(C.c_int32)), ("next_scores", C.POINTER(C.c_float)), ("steps", C.POINTER(C.c_int32))]
+
+
 # every symbol include/infinisst_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _I = C.c_int
@@ -53,6 +63,9 @@ SYMBOLS = {
     "isst_encode_chunk": (_I, [_P, _I, _IP, _P, _I, _I, _P, _P]),
     "isst_generate": (_I, [_P, _I, _IP, _I32P, _IP, _I32P, _I32P, _IP, C.POINTER(IsstGenParams), _I32P, _I32P,
                            _IP, _P]),
+    "isst_generate_beam": (_I, [_P, _I, _IP, _I32P, _IP, _I32P, _I32P, _IP, C.POINTER(IsstGenParams), _I, C.c_float,
+                                C.POINTER(IsstBeamFollow), _I32P, _IP, C.POINTER(C.c_float), C.POINTER(IsstBeamTrace),
+                                _P]),
     "isst_forward": (_I, [_P, _I, _IP, _I32P, _IP, _I32P, _P, _I, _P, _P]),
     "isst_kv_len": (_I, [_P, _I, _IP]),
     "isst_kv_evict": (_I, [_P, _I, _I, _I]),

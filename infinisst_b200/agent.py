@@ -158,8 +158,8 @@ class InfiniSST(SpeechToTextAgent):
         self.source_lang = args.source_lang
         self.target_lang = args.target_lang
         self.beam = args.beam
-        if self.beam != 1:
-            raise NotImplementedError("infinisst_b200 runs the greedy path (--beam 1); beam search is §8f next")
+        if self.beam < 1:
+            raise ValueError("--beam must be >= 1")
         self.no_repeat_ngram_lookback = args.no_repeat_ngram_lookback
         self.no_repeat_ngram_size = args.no_repeat_ngram_size
         self.repetition_penalty = args.repetition_penalty

@@ -24,6 +24,7 @@
 #include "decode_attention.cuh"
 #include "gemm_tcgen05.cuh"
 #include "prefill_attention_tc.cuh"
+#include "beam.cuh"
 #include "rowops.cuh"
 
 namespace isst {
@@ -227,6 +228,8 @@ struct isst_ctx {
   int* h_tables = nullptr;   // pinned staging of the per-batch page tables / lengths
   size_t meta_ints = 0;
   int* d_step_logits_dummy = nullptr;
+  float* beam_ws = nullptr;     // beam search selection workspace (BeamSel partials / candidates / results)
+  int* beam_count = nullptr;    // [max_batch] arrival counters
 };
 
 namespace isst {
@@ -1084,9 +1087,13 @@ static int ensure_capacity(isst_ctx* ctx, int slot, int extra_tokens, int pin_pr
   return 0;
 }
 
-// The LLM kernels index the per-stream tables by BATCH entry (their `slots` argument is the identity), so one
-// call's tables are four contiguous uploads from pinned memory instead of four small copies per stream.
-static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int* slots) {
+struct KvView {                 // one batch entry's KV addressing: a stream, or a beam (shared prefix pages + private tail)
+  const int* pages0; int n0;    // leading page-table entries
+  const int* pages1; int n1;    // entries that follow them (may be empty)
+  int kv_len, sys_len, ring_start;
+  long long evicted;
+};
+static int upload_kv_views(isst_ctx* ctx, cudaStream_t st, int n, const KvView* v) {
   const int pps = ctx->pages_per_stream;
   int* h = ctx->h_tables;
   int* h_len = h + static_cast<size_t>(ctx->cfg.max_batch) * pps;
@@ -1094,11 +1101,12 @@ static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int
   int* h_ring = h_sys + ctx->cfg.max_batch;
   int* h_evi = h_ring + ctx->cfg.max_batch;
   for (int b = 0; b < n; ++b) {
-    const StreamHost& s = ctx->streams[slots[b]];
-    std::copy(s.pages.begin(), s.pages.end(), h + static_cast<size_t>(b) * pps);
-    h_len[b] = s.kv_len; h_sys[b] = s.sys_len; h_ring[b] = s.ring_start;
-    ISST_CHECK(s.evicted + s.kv_len + 4096 < 2147483647LL, "stream exceeded 2^31 tokens");
-    h_evi[b] = static_cast<int>(s.evicted);
+    ISST_CHECK(v[b].n0 + v[b].n1 <= pps, "batch entry needs more pages than pages_per_stream");
+    std::copy(v[b].pages0, v[b].pages0 + v[b].n0, h + static_cast<size_t>(b) * pps);
+    std::copy(v[b].pages1, v[b].pages1 + v[b].n1, h + static_cast<size_t>(b) * pps + v[b].n0);
+    h_len[b] = v[b].kv_len; h_sys[b] = v[b].sys_len; h_ring[b] = v[b].ring_start;
+    ISST_CHECK(v[b].evicted + v[b].kv_len + 4096 < 2147483647LL, "stream exceeded 2^31 tokens");
+    h_evi[b] = static_cast<int>(v[b].evicted);
   }
   ISST_CUDA(cudaMemcpyAsync(ctx->d_evicted, h_evi, n * sizeof(int), cudaMemcpyHostToDevice, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->d_page_table, h, static_cast<size_t>(n) * pps * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1106,6 +1114,17 @@ static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int
   ISST_CUDA(cudaMemcpyAsync(ctx->d_sys_len, h_sys, n * sizeof(int), cudaMemcpyHostToDevice, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->d_ring_start, h_ring, n * sizeof(int), cudaMemcpyHostToDevice, st));
   return 0;
+}
+
+// The LLM kernels index the per-stream tables by BATCH entry (their `slots` argument is the identity), so one
+// call's tables are four contiguous uploads from pinned memory instead of four small copies per stream.
+static int upload_stream_tables(isst_ctx* ctx, cudaStream_t st, int n, const int* slots) {
+  std::vector<KvView> v(n);
+  for (int b = 0; b < n; ++b) {
+    const StreamHost& s = ctx->streams[slots[b]];
+    v[b] = KvView{s.pages.data(), static_cast<int>(s.pages.size()), nullptr, 0, s.kv_len, s.sys_len, s.ring_start, s.evicted};
+  }
+  return upload_kv_views(ctx, st, n, v.data());
 }
 
 static int check_batch(isst_ctx* ctx, int n, const int* ids) {
@@ -1213,15 +1232,17 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->enc_k, ctx->enc_layer_elems * c.enc_layers));
   ISST_TRY(dev_alloc(&ctx->enc_v, ctx->enc_layer_elems * c.enc_layers));
   ISST_TRY(dev_alloc(&ctx->d_enc_prefix, c.max_streams));
-  ISST_TRY(dev_alloc(&ctx->d_page_table, static_cast<size_t>(c.max_streams) * ctx->pages_per_stream));
-  ISST_TRY(dev_alloc(&ctx->d_kv_len, c.max_streams)); ISST_TRY(dev_alloc(&ctx->d_sys_len, c.max_streams));
-  ISST_TRY(dev_alloc(&ctx->d_ring_start, c.max_streams));
-  ISST_TRY(dev_alloc(&ctx->d_evicted, c.max_streams));
-  ISST_CUDA(cudaMemset(ctx->d_evicted, 0, c.max_streams * sizeof(int)));
-  ISST_CUDA(cudaMemset(ctx->d_page_table, 0, static_cast<size_t>(c.max_streams) * ctx->pages_per_stream * sizeof(int)));
-  ISST_CUDA(cudaMemset(ctx->d_kv_len, 0, c.max_streams * sizeof(int)));
-  ISST_CUDA(cudaMemset(ctx->d_sys_len, 0, c.max_streams * sizeof(int)));
-  ISST_CUDA(cudaMemset(ctx->d_ring_start, 0, c.max_streams * sizeof(int)));
+  // per-batch-entry KV tables (uploaded before every forward): a beam-search batch has streams x beams entries
+  const size_t nt = static_cast<size_t>(std::max(c.max_streams, c.max_batch));
+  ISST_TRY(dev_alloc(&ctx->d_page_table, nt * ctx->pages_per_stream));
+  ISST_TRY(dev_alloc(&ctx->d_kv_len, nt)); ISST_TRY(dev_alloc(&ctx->d_sys_len, nt));
+  ISST_TRY(dev_alloc(&ctx->d_ring_start, nt));
+  ISST_TRY(dev_alloc(&ctx->d_evicted, nt));
+  ISST_CUDA(cudaMemset(ctx->d_evicted, 0, nt * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_page_table, 0, nt * ctx->pages_per_stream * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_kv_len, 0, nt * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_sys_len, 0, nt * sizeof(int)));
+  ISST_CUDA(cudaMemset(ctx->d_ring_start, 0, nt * sizeof(int)));
   ISST_CUDA(cudaMemset(ctx->d_enc_prefix, 0, c.max_streams * sizeof(int)));
   ctx->kv_layer_elems = static_cast<size_t>(c.kv_pages) * 2 * c.kv_heads * kPageTokens * c.head_dim;
   ISST_TRY(dev_alloc(&ctx->kv_pool, ctx->kv_layer_elems * c.layers));
@@ -1256,6 +1277,9 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->sel_ws.idx, static_cast<size_t>(nb) * kSelParts));
   ISST_TRY(dev_alloc(&ctx->sel_ws.count, static_cast<size_t>(nb)));
   ISST_CUDA(cudaMemset(ctx->sel_ws.count, 0, static_cast<size_t>(nb) * sizeof(int)));
+  ISST_TRY(dev_alloc(&ctx->beam_ws, static_cast<size_t>(nb) * (kSelParts * (2 + 2 * kBeamMaxKeep) + 2 * kBeamMaxKeep)));
+  ISST_TRY(dev_alloc(&ctx->beam_count, static_cast<size_t>(nb)));
+  ISST_CUDA(cudaMemset(ctx->beam_count, 0, static_cast<size_t>(nb) * sizeof(int)));
   ctx->decode_splits = 32;
   ISST_TRY(dev_alloc(&ctx->part_o, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * c.head_dim));
   ISST_TRY(dev_alloc(&ctx->part_ml, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * 2));
@@ -1281,6 +1305,7 @@ void isst_destroy(isst_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   // the context owns every device allocation it made; release the big pools explicitly
+  cudaFree(ctx->beam_ws); cudaFree(ctx->beam_count);
   cudaFree(ctx->kv_pool); cudaFree(ctx->enc_k); cudaFree(ctx->enc_v); cudaFree(ctx->embed);
   for (auto& w : ctx->llm) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.wgu.ptr); cudaFree(w.wd.ptr); cudaFree(w.rms1); cudaFree(w.rms2); }
   for (auto& w : ctx->enc) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.w1.ptr); cudaFree(w.w2.ptr);
@@ -1734,6 +1759,405 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     for (int s = 0; s < max_new; ++s) out_tokens[static_cast<size_t>(b) * max_new + s] = ctx->h_meta[o_out + static_cast<size_t>(b) * max_new + s];
     // KV holds the prompt and every chosen token except the last (drop-last rule)
     ctx->streams[stream_ids[b]].kv_len += lens[b] + std::max(0, cnt - 1);
+  }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// beam search (the reference's shipped decoding: scripts/infer/infinisst.sh:48, patch_hf.py:43-302, 687-967)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct BeamHypH {               // a finished hypothesis (BeamHypotheses.beams entry, patch_hf.py:296)
+  float score;                  // sum_logprobs / generated_len ** length_penalty
+  std::vector<int> tokens;      // generated tokens (without the EOS that closed it)
+  std::vector<int> pages;       // snapshot of the private tail pages (the KV hand-back, :113-128)
+  int kv_extra;                 // generated tokens whose KV the hypothesis holds
+  int order;
+};
+struct BeamRowH {
+  std::vector<int> gen;         // tokens generated on this beam
+  float score = 0.f;
+  std::vector<int> priv[2];     // two sets of private tail pages (ping-pong across reorders)
+  int cur = 0;
+};
+struct BeamGroupH {
+  int slot = 0, P = 0, L1 = 0;  // stream slot, prompt length, KV length after the prompt
+  int ids_off = 0;              // offset of the prompt in the packed `ids`
+  int tail0 = 0;                // index in the stream's page list where the private tail starts
+  int n_priv = 0;               // private pages per beam
+  bool partial = false;         // the page at tail0 already holds prompt tokens (copied into every beam)
+  std::vector<BeamRowH> rows;
+  std::vector<BeamHypH> hyps;
+  float worst = 1e9f;
+  int n_added = 0;
+  bool done = false;
+  int steps = 0;
+};
+}  // namespace
+
+static void beam_free_pages(isst_ctx* ctx, std::vector<int>& pages) {
+  for (int p : pages) ctx->free_pages.push_back(p);
+  pages.clear();
+}
+static int beam_alloc_pages(isst_ctx* ctx, std::vector<int>& pages, int n) {
+  ISST_CHECK(static_cast<int>(ctx->free_pages.size()) >= n, "KV page pool exhausted (beam search tails)");
+  for (int i = 0; i < n; ++i) { pages.push_back(ctx->free_pages.back()); ctx->free_pages.pop_back(); }
+  return 0;
+}
+// BeamHypotheses.add as the reference patches it (patch_hf.py:278-302); returns pages of a dropped hypothesis
+static void beam_hyp_add(isst_ctx* ctx, BeamGroupH& g, int num_beams, float length_penalty, BeamHypH&& h, float sum_logprobs,
+                         int generated_len) {
+  const float score = sum_logprobs / std::pow(static_cast<float>(generated_len), length_penalty);
+  h.score = score;
+  if (static_cast<int>(g.hyps.size()) < num_beams || score > g.worst) {
+    h.order = g.n_added++;
+    g.hyps.push_back(std::move(h));
+    if (static_cast<int>(g.hyps.size()) > num_beams) {
+      int lo = 0;
+      for (int i = 1; i < static_cast<int>(g.hyps.size()); ++i)
+        if (g.hyps[i].score < g.hyps[lo].score) lo = i;       // sorted()[0]: lowest score, earliest on ties
+      beam_free_pages(ctx, g.hyps[lo].pages);
+      g.hyps.erase(g.hyps.begin() + lo);
+      float w = g.hyps[0].score;
+      for (const BeamHypH& x : g.hyps) w = std::min(w, x.score);
+      g.worst = w;
+    } else {
+      g.worst = std::min(score, g.worst);
+    }
+  } else {
+    beam_free_pages(ctx, h.pages);
+  }
+}
+
+int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                       const int32_t* speech_slot, const int32_t* enc_ids, const int* enc_lens,
+                       const isst_gen_params* gen, int num_beams, float length_penalty, const isst_beam_follow* follow,
+                       int32_t* out_tokens, int* out_counts, float* out_scores, isst_beam_trace* trace,
+                       void* cuda_stream) {
+  ISST_TRY(check_batch(ctx, n, stream_ids));
+  ISST_CHECK(ids && lens && gen && out_tokens && out_counts, "null argument");
+  ISST_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const isst_config& c = ctx->cfg;
+  const int k = num_beams, V = c.vocab;
+  const int max_new = gen->max_new_tokens;
+  const int R = n * k;
+  ISST_CHECK(k >= 2, "beam search needs num_beams >= 2 (isst_generate is the greedy path)");
+  ISST_CHECK(R <= c.max_batch, "streams x beams exceeds max_batch");
+  ISST_CHECK(max_new >= 1 && max_new <= c.max_new_tokens, "max_new_tokens out of range");
+  ISST_CHECK(gen->n_eos >= 0 && gen->n_eos <= 8, "too many eos ids");
+  const int n_keep = std::max(2, 1 + gen->n_eos) * k;                       // patch_hf.py:869-870
+  ISST_CHECK(n_keep <= kBeamMaxKeep && n_keep <= V, "too many beam candidates per sentence");
+  auto is_eos = [&](int t) { for (int e = 0; e < gen->n_eos; ++e) if (gen->eos_token_ids[e] == t) return true; return false; };
+
+  // ---- prompt prefill on one row per stream (the reference runs it on k identical rows, :305-342) ----
+  MetaBuilder mb{ctx, kEncMetaInts};
+  LlmBatch lb;
+  size_t o_ids, o_srow;
+  ISST_TRY(setup_llm_batch(ctx, st, mb, n, stream_ids, lens, ids, speech_slot, 0, gen->pin_prefix, &lb, &o_ids, &o_srow));
+  const int ctx_cap = c.max_prompt + max_new;
+  const int enc_cap = 128;
+  const size_t o_ctx = mb.alloc(static_cast<size_t>(R) * ctx_cap), o_ctxlen = mb.alloc(R);
+  const size_t o_enc = mb.alloc(static_cast<size_t>(n) * enc_cap), o_enclen = mb.alloc(n);
+  const size_t o_active = mb.alloc(R), o_next = mb.alloc(R), o_score = mb.alloc(R);
+  const size_t o_sup = mb.alloc(gen->n_suppress), o_ones = mb.alloc(R), o_iota = mb.alloc(R);
+  const size_t o_pairs = mb.alloc(static_cast<size_t>(R) * 2 * 8 * 2);       // page copy pairs of one step
+  const size_t o_res_s = mb.alloc(static_cast<size_t>(n) * n_keep), o_res_i = mb.alloc(static_cast<size_t>(n) * n_keep);
+  const size_t meta_end = mb.used;
+  ISST_CHECK(meta_end <= ctx->meta_ints, "metadata buffer too small");
+  std::vector<BeamGroupH> groups(n);
+  int row = 0, eoff = 0;
+  for (int b = 0; b < n; ++b) {
+    BeamGroupH& g = groups[b];
+    g.slot = stream_ids[b]; g.P = lens[b]; g.ids_off = row;
+    for (int t = 0; t < lens[b]; ++t) mb.host(o_ctx)[static_cast<size_t>(b) * ctx_cap + t] = ids[row + t];
+    mb.host(o_ctxlen)[b] = lens[b];
+    const int el = enc_lens ? enc_lens[b] : 0;
+    ISST_CHECK(el >= 0 && el <= enc_cap, "encoder id history longer than 128");
+    for (int t = 0; t < el; ++t) mb.host(o_enc)[static_cast<size_t>(b) * enc_cap + t] = enc_ids[eoff + t];
+    mb.host(o_enclen)[b] = el;
+    row += lens[b];
+    eoff += el;
+  }
+  for (int r = 0; r < R; ++r) { mb.host(o_ones)[r] = 1; mb.host(o_iota)[r] = r; mb.host(o_active)[r] = 1; }
+  for (int b = 0; b < n; ++b) reinterpret_cast<float*>(mb.host(o_score))[b] = 0.f;
+  for (int i = 0; i < gen->n_suppress; ++i) mb.host(o_sup)[i] = gen->suppress_tokens[i];
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_meta + kEncMetaInts, ctx->h_meta + kEncMetaInts, (meta_end - kEncMetaInts) * sizeof(int),
+                            cudaMemcpyHostToDevice, st));
+  {
+    ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(lb.M) * c.hidden * 4);
+    ISST_CUDA(launch_k(ctx, embed_splice_kernel, dim3(lb.M), dim3(128), 0, st, mb.dev(o_ids), mb.dev(o_srow), ctx->embed, ctx->speech, ctx->lx, c.hidden));
+    LAUNCH_CHECK(ctx);
+  }
+  ISST_TRY(llm_forward(ctx, st, lb, false));
+  for (int b = 0; b < n; ++b) {
+    StreamHost& s = ctx->streams[stream_ids[b]];
+    s.kv_len += lens[b];
+    groups[b].L1 = s.kv_len;
+  }
+
+  BeamSel sel{};
+  sel.ctx_ids = mb.dev(o_ctx); sel.ctx_len = mb.dev(o_ctxlen); sel.enc_ids = mb.dev(o_enc); sel.enc_len = mb.dev(o_enclen);
+  sel.beam_score = reinterpret_cast<const float*>(mb.dev(o_score)); sel.suppress = mb.dev(o_sup);
+  sel.n_suppress = gen->n_suppress; sel.ctx_cap = ctx_cap; sel.enc_cap = enc_cap; sel.ngram = gen->no_repeat_ngram_size;
+  sel.penalty = gen->repetition_penalty; sel.n_keep = n_keep;
+  {
+    float* w = ctx->beam_ws;
+    const size_t nb = c.max_batch;
+    sel.part_max = w; w += nb * kSelParts;
+    sel.part_sum = w; w += nb * kSelParts;
+    sel.cand_s = w; w += nb * kSelParts * kBeamMaxKeep;
+    sel.cand_i = reinterpret_cast<int*>(w); w += nb * kSelParts * kBeamMaxKeep;
+    sel.out_s = w; w += nb * kBeamMaxKeep;
+    sel.out_i = reinterpret_cast<int*>(w);
+    sel.count = ctx->beam_count;
+  }
+  float* h_res_s = reinterpret_cast<float*>(ctx->h_meta + o_res_s);
+  int* h_res_i = ctx->h_meta + o_res_i;
+  const size_t page_elems = static_cast<size_t>(2) * c.kv_heads * kPageTokens * c.head_dim;
+  std::vector<int> pairs;                               // (src page, dst page) copies queued for this step
+  auto flush_pairs = [&]() -> int {
+    const size_t cap = static_cast<size_t>(R) * 8 * 2;  // pairs per launch (o_pairs holds 2 ints each)
+    for (size_t off = 0; off < pairs.size() / 2; off += cap) {
+      const size_t cnt = std::min(cap, pairs.size() / 2 - off);
+      // the pinned staging is reused: wait for the previous copy of it to be consumed
+      ISST_CUDA(cudaStreamSynchronize(st));
+      std::copy(pairs.begin() + 2 * off, pairs.begin() + 2 * (off + cnt), mb.host(o_pairs));
+      ISST_CUDA(cudaMemcpyAsync(mb.dev(o_pairs), mb.host(o_pairs), cnt * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+      ISST_CUDA(launch_k(ctx, kv_page_copy_kernel, dim3(static_cast<unsigned>(cnt), c.layers), dim3(256), 0, st, ctx->kv_pool,
+                         ctx->kv_layer_elems, static_cast<int>(page_elems), mb.dev(o_pairs)));
+      LAUNCH_CHECK(ctx);
+    }
+    pairs.clear();
+    return 0;
+  };
+  // Runs the selection kernels on `rows` logits rows (rows_per_group live beams per sentence), reads the 2k
+  // candidates per sentence back and applies `beam_search_process` (patch_hf.py:43-157) on the host.
+  std::vector<std::vector<std::pair<int, int>>> nxt(n);           // per sentence: (parent beam, token) of the next beams
+  std::vector<std::vector<float>> nxt_score(n);
+  auto select = [&](int step, int rows_per_group) -> int {
+    sel.rows_per_group = rows_per_group;
+    const int rows = n * rows_per_group;
+    ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(rows) * V * 4 * 3);
+    ISST_CUDA(launch_k(ctx, beam_lse_kernel, dim3(kSelParts, rows), dim3(kSelThreads), 0, st, static_cast<const float*>(ctx->logits), V, sel));
+    LAUNCH_CHECK(ctx);
+    ISST_CUDA(launch_k(ctx, beam_topk_kernel, dim3(kSelParts, rows), dim3(kSelThreads), 0, st, ctx->logits, V, sel));
+    LAUNCH_CHECK(ctx);
+    ISST_CUDA(cudaMemcpyAsync(h_res_s, sel.out_s, static_cast<size_t>(n) * n_keep * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ISST_CUDA(cudaMemcpyAsync(h_res_i, sel.out_i, static_cast<size_t>(n) * n_keep * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ISST_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < n; ++b) {
+      BeamGroupH& g = groups[b];
+      nxt[b].clear(); nxt_score[b].clear();
+      if (g.done) continue;
+      const float* cs = h_res_s + static_cast<size_t>(b) * n_keep;
+      const int* ci = h_res_i + static_cast<size_t>(b) * n_keep;
+      if (trace && trace->cand_scores) {
+        for (int j = 0; j < n_keep; ++j) {
+          trace->cand_scores[(static_cast<size_t>(b) * max_new + step) * n_keep + j] = cs[j];
+          trace->cand_index[(static_cast<size_t>(b) * max_new + step) * n_keep + j] = ci[j];
+        }
+      }
+      const int gen_len = step + 1;                                // cur_len - decoder_prompt_len (:57, :121)
+      auto close = [&](int par, float score) -> int {              // EOS candidate: the parent beam becomes a hypothesis
+        BeamHypH h;
+        if (step > 0) {
+          const BeamRowH& pr = g.rows[par];
+          h.tokens = pr.gen;
+          ISST_TRY(beam_alloc_pages(ctx, h.pages, g.n_priv));
+          for (int i = 0; i < g.n_priv; ++i) { pairs.push_back(pr.priv[pr.cur][i]); pairs.push_back(h.pages[i]); }
+        }
+        h.kv_extra = step;
+        beam_hyp_add(ctx, g, k, length_penalty, std::move(h), score, gen_len);
+        return 0;
+      };
+      if (follow) {
+        // teacher forcing (parity tests): the caller dictates which beams are closed / continued; their scores are
+        // this run's own processed scores, read from the score matrix the selection kernel left in `logits`
+        const int32_t* fc = follow->closed + ((static_cast<size_t>(b) * max_new + step) * k) * 2;
+        const int32_t* fn = follow->next + ((static_cast<size_t>(b) * max_new + step) * k) * 2;
+        auto score_of = [&](int par, int tok, float* out) -> int {
+          float lp = 0.f;
+          ISST_CUDA(cudaMemcpy(&lp, ctx->logits + (static_cast<size_t>(b) * rows_per_group + par) * V + tok, sizeof(float), cudaMemcpyDeviceToHost));
+          *out = lp + (step > 0 ? g.rows[par].score : 0.f);
+          return 0;
+        };
+        for (int j = 0; j < k && fc[2 * j] >= 0; ++j) {
+          float sc;
+          ISST_TRY(score_of(fc[2 * j], fc[2 * j + 1], &sc));
+          ISST_TRY(close(fc[2 * j], sc));
+        }
+        for (int j = 0; j < k; ++j) {
+          float sc;
+          ISST_TRY(score_of(fn[2 * j], fn[2 * j + 1], &sc));
+          nxt[b].push_back({fn[2 * j], fn[2 * j + 1]});
+          nxt_score[b].push_back(sc);
+        }
+        g.done = step + 1 >= follow->steps[b] && follow->done[b];
+      } else {
+        for (int rank = 0; rank < n_keep && static_cast<int>(nxt[b].size()) < k; ++rank) {
+          ISST_CHECK(ci[rank] >= 0, "beam search ran out of finite candidates");
+          const int par = ci[rank] / V, tok = ci[rank] % V;
+          if (is_eos(tok)) {
+            if (rank >= k) continue;                               // :100-103
+            ISST_TRY(close(par, cs[rank]));
+          } else {
+            nxt[b].push_back({par, tok});
+            nxt_score[b].push_back(cs[rank]);
+          }
+        }
+        ISST_CHECK(static_cast<int>(nxt[b].size()) == k, "beam search: fewer than num_beams non-EOS candidates");
+        // BeamHypotheses.is_done with early_stopping=False (transformers 4.47): the kept hypotheses cannot be beaten
+        if (!g.done && static_cast<int>(g.hyps.size()) >= k) {
+          const float highest = cs[0] / std::pow(static_cast<float>(gen_len), length_penalty);
+          g.done = g.worst >= highest;
+        }
+      }
+      g.steps = step + 1;
+      if (trace && trace->next) {
+        for (int j = 0; j < k; ++j) {
+          trace->next[((static_cast<size_t>(b) * max_new + step) * k + j) * 2] = nxt[b][j].first;
+          trace->next[((static_cast<size_t>(b) * max_new + step) * k + j) * 2 + 1] = nxt[b][j].second;
+          if (trace->next_scores) trace->next_scores[(static_cast<size_t>(b) * max_new + step) * k + j] = nxt_score[b][j];
+        }
+      }
+    }
+    return 0;
+  };
+
+  // ---- step 0: candidates of the single live beam ----
+  ISST_TRY(select(0, 1));
+  // fork: every beam gets private tail pages; the partially filled last prompt page is copied into each
+  for (int b = 0; b < n; ++b) {
+    BeamGroupH& g = groups[b];
+    StreamHost& s = ctx->streams[g.slot];
+    const int slot1 = g.L1 < s.sys_len ? g.L1 : g.L1 - s.sys_len + s.ring_start;
+    g.tail0 = slot1 / kPageTokens;
+    g.partial = slot1 % kPageTokens != 0;
+    g.n_priv = max_new > 1 ? ceil_div(slot1 % kPageTokens + max_new - 1, kPageTokens) : 0;
+    ISST_CHECK(g.tail0 + g.n_priv <= ctx->pages_per_stream, "stream needs more pages than pages_per_stream");
+    ISST_CHECK(g.L1 + max_new - 1 <= c.max_kv_len, "stream KV length would exceed max_kv_len");
+    g.rows.resize(k);
+    for (int j = 0; j < k; ++j) {
+      BeamRowH& r = g.rows[j];
+      if (!g.done && max_new > 1) {
+        ISST_TRY(beam_alloc_pages(ctx, r.priv[0], g.n_priv));
+        ISST_TRY(beam_alloc_pages(ctx, r.priv[1], g.n_priv));
+        if (g.partial) { pairs.push_back(s.pages[g.tail0]); pairs.push_back(r.priv[0][0]); }
+      }
+      r.gen.assign(1, nxt[b].empty() ? 0 : nxt[b][j].second);
+      r.score = nxt[b].empty() ? 0.f : nxt_score[b][j];
+    }
+  }
+  ISST_TRY(flush_pairs());
+
+  // ---- decode steps on n * k rows ----
+  LlmBatch db;
+  db.n = R; db.M = R; db.max_T = 1; db.d_slots = mb.dev(o_iota); db.d_tok_base = mb.dev(o_iota); db.d_T = mb.dev(o_ones);
+  db.d_last_row = mb.dev(o_iota); db.d_active = mb.dev(o_active); db.decode = true;
+  std::vector<KvView> views(R);
+  for (int step = 1; step < max_new; ++step) {
+    bool any = false;
+    for (const BeamGroupH& g : groups) any = any || !g.done;
+    if (!any) break;
+    db.kv_tokens = 0; db.max_L = 1;
+    for (int b = 0; b < n; ++b) {
+      BeamGroupH& g = groups[b];
+      const StreamHost& s = ctx->streams[g.slot];
+      for (int j = 0; j < k; ++j) {
+        const int r = b * k + j;
+        BeamRowH& br = g.rows[j];
+        // a finished sentence rides along inactive: it attends to its shared prefix only and appends nothing
+        views[r] = g.done ? KvView{s.pages.data(), std::min(static_cast<int>(s.pages.size()), g.tail0 + 1), nullptr, 0, g.L1 - 1, s.sys_len, s.ring_start, s.evicted}
+                          : KvView{s.pages.data(), g.tail0, br.priv[br.cur].data(), static_cast<int>(br.priv[br.cur].size()),
+                                   g.L1 + step - 1, s.sys_len, s.ring_start, s.evicted};
+        mb.host(o_active)[r] = g.done ? 0 : 1;
+        mb.host(o_next)[r] = br.gen.back();
+        reinterpret_cast<float*>(mb.host(o_score))[r] = br.score;
+        // context ids of the row: prompt + the beam's own tokens (rebuilt every step: beams were reordered)
+        int* cx = mb.host(o_ctx) + static_cast<size_t>(r) * ctx_cap;
+        for (int t = 0; t < g.P; ++t) cx[t] = ids[g.ids_off + t];
+        for (size_t t = 0; t < br.gen.size(); ++t) cx[g.P + t] = br.gen[t];
+        mb.host(o_ctxlen)[r] = g.P + static_cast<int>(br.gen.size());
+        if (!g.done) { db.kv_tokens += g.L1 + step; db.max_L = std::max(db.max_L, g.L1 + step); }
+      }
+    }
+    ISST_TRY(upload_kv_views(ctx, st, R, views.data()));
+    ISST_CUDA(cudaMemcpyAsync(ctx->d_meta + o_ctx, ctx->h_meta + o_ctx, (o_sup - o_ctx) * sizeof(int), cudaMemcpyHostToDevice, st));
+    {
+      ProfScope ps(ctx, st, P_EMBED, 0.0, static_cast<double>(R) * c.hidden * 4);
+      ISST_CUDA(launch_k(ctx, embed_splice_kernel, dim3(R), dim3(128), 0, st, mb.dev(o_next), nullptr, ctx->embed, ctx->speech, ctx->lx, c.hidden));
+      LAUNCH_CHECK(ctx);
+    }
+    ISST_TRY(llm_forward(ctx, st, db, false));
+    ISST_TRY(select(step, k));
+    // reorder (`_temporary_reorder_cache`, patch_hf.py:910-913): a beam that continues another beam copies that
+    // beam's private tail into its own spare page set; beams that continue themselves keep their pages
+    for (int b = 0; b < n; ++b) {
+      BeamGroupH& g = groups[b];
+      if (nxt[b].empty()) continue;
+      std::vector<BeamRowH> old = g.rows;
+      for (int j = 0; j < k; ++j) {
+        const int par = nxt[b][j].first;
+        BeamRowH& r = g.rows[j];                      // the page sets stay with the row index
+        r.gen = old[par].gen;
+        r.gen.push_back(nxt[b][j].second);
+        r.score = nxt_score[b][j];
+        if (par != j && !g.done) {                    // (after the last step finalize still hands back the parent's KV)
+          for (int i = 0; i < g.n_priv; ++i) { pairs.push_back(old[par].priv[old[par].cur][i]); pairs.push_back(r.priv[1 - r.cur][i]); }
+          r.cur = 1 - r.cur;
+        }
+      }
+    }
+    ISST_TRY(flush_pairs());
+  }
+  ISST_TRY(flush_pairs());
+
+  // ---- finalize (patch_hf.py:159-275): open beams become hypotheses WITHOUT the KV of their last token ----
+  ISST_CUDA(cudaStreamSynchronize(st));
+  prof_flush(ctx);
+  for (int b = 0; b < n; ++b) {
+    BeamGroupH& g = groups[b];
+    StreamHost& s = ctx->streams[g.slot];
+    if (!g.done) {
+      for (int j = 0; j < k; ++j) {
+        BeamRowH& r = g.rows[j];
+        BeamHypH h;
+        h.tokens = r.gen;
+        h.kv_extra = static_cast<int>(r.gen.size()) - 1;
+        h.pages = r.priv[r.cur];
+        r.priv[r.cur].clear();
+        beam_hyp_add(ctx, g, k, length_penalty, std::move(h), r.score, static_cast<int>(r.gen.size()));
+      }
+    }
+    for (BeamRowH& r : g.rows) { beam_free_pages(ctx, r.priv[0]); beam_free_pages(ctx, r.priv[1]); }
+    int best = 0;
+    for (int i = 1; i < static_cast<int>(g.hyps.size()); ++i)               // sorted(...).pop(): highest score, latest on ties
+      if (g.hyps[i].score >= g.hyps[best].score) best = i;
+    BeamHypH& w = g.hyps[best];
+    int cnt = static_cast<int>(w.tokens.size());
+    for (int t = 0; t < cnt; ++t) out_tokens[static_cast<size_t>(b) * (max_new + 1) + t] = w.tokens[t];
+    if (cnt < max_new) out_tokens[static_cast<size_t>(b) * (max_new + 1) + cnt++] = gen->eos_token_ids[0];   // :262-264
+    for (int t = cnt; t < max_new + 1; ++t) out_tokens[static_cast<size_t>(b) * (max_new + 1) + t] = -1;
+    out_counts[b] = cnt;
+    if (out_scores) out_scores[b] = w.score;
+    if (trace && trace->steps) trace->steps[b] = g.steps;
+    // KV hand-back (agents/infinisst.py:334-336): the stream continues from the best hypothesis' cache
+    if (w.kv_extra > 0) {
+      const int new_len = g.L1 + w.kv_extra;
+      const int last_slot = new_len <= s.sys_len ? new_len - 1 : new_len - 1 - s.sys_len + s.ring_start;
+      const int need = last_slot / kPageTokens + 1 - g.tail0;               // private pages that hold tokens
+      for (size_t i = g.tail0; i < s.pages.size(); ++i) ctx->free_pages.push_back(s.pages[i]);   // replaced by the hypothesis' copy
+      s.pages.resize(g.tail0);
+      for (int i = 0; i < static_cast<int>(w.pages.size()); ++i) {
+        if (i < need) s.pages.push_back(w.pages[i]);
+        else ctx->free_pages.push_back(w.pages[i]);
+      }
+      w.pages.clear();
+      s.kv_len = new_len;
+    }
+    for (BeamHypH& h : g.hyps) beam_free_pages(ctx, h.pages);
   }
   return 0;
 }

@@ -40,20 +40,22 @@ def _ints(vals: Sequence[int], ctype=C.c_int):
 class Engine:
     def __init__(self, cfg: InfiniSSTConfig, device: int = 0, max_streams: int = 8, max_batch: Optional[int] = None,
                  max_multiplier: int = 1, kv_pages: Optional[int] = None, max_kv_len: Optional[int] = None,
-                 max_prompt: int = 64, max_new_tokens: Optional[int] = None):
+                 max_prompt: int = 64, max_new_tokens: Optional[int] = None, max_beams: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("infinisst_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device
         e, l, g = cfg.enc, cfg.llm, cfg.gen
-        max_batch = max_batch or max_streams
+        max_batch = max_batch or max_streams * max_beams        # beam search advances streams x beams rows per step
         max_new = max_new_tokens or max(g.max_new_tokens, 10 * max_multiplier)
         if max_kv_len is None:
             # window + pinned system prompt + one full turn of slack (the cache is trimmed after the turn)
             max_kv_len = g.max_llm_cache_size + len(cfg.tpl.system_ids) + 2 * (max_prompt + max_new) + 64
         if kv_pages is None:
             kv_pages = max_streams * (max_kv_len // 16 + 3)
+            if max_beams > 1:       # private tail page sets: 2 per beam + the kept hypotheses' snapshots (+1 in flight)
+                kv_pages += max_streams * (3 * max_beams + 1) * ((15 + max_new) // 16 + 1)
         c = _lib.IsstConfig()
         c.n_conv = len(e.conv_layers)
         for j, (d, k, s) in enumerate(e.conv_layers):
@@ -210,6 +212,70 @@ class Engine:
                                           _ints([len(r) for r in enc_ids]), C.byref(gp), fptr, out, cnt,
                                           self._stream_ptr()))
         return [[out[b * mn + s] for s in range(cnt[b])] for b in range(n)]
+
+    def generate_beam(self, sids: Sequence[int], ids: Sequence[Sequence[int]], speech_slots: Sequence[Sequence[int]],
+                      enc_ids: Sequence[Sequence[int]], gen, num_beams: int, pin_prefix: int = 0,
+                      max_new: Optional[int] = None, length_penalty: float = 1.0, follow: Optional[Sequence[dict]] = None,
+                      want_trace: bool = False):
+        """Prefill each stream's turn prompt once and beam-search `num_beams` continuations (patch_hf.py:687-967);
+        the stream's KV continues from the best hypothesis (agents/infinisst.py:334-336).  Returns per stream the
+        generated part of `sequences` (closing EOS appended when it fits) and the sequence scores; with
+        `want_trace` also every step's candidates / chosen beams.  `follow`: per stream {"steps": [{"closed":
+        [(parent, tok)], "next": [(parent, tok)]}], "done": bool} teacher-forces the discrete choices."""
+        n, k = len(sids), num_beams
+        gp = self._gen_params(gen, max_new, pin_prefix)
+        mn = gp.max_new_tokens
+        n_keep = max(2, 1 + len(gen.eos_token_ids)) * k
+        flat = [t for row in ids for t in row]
+        slots = [t for row in speech_slots for t in row]
+        eflat = [t for row in enc_ids for t in row]
+        out = (C.c_int32 * (n * (mn + 1)))()
+        cnt = (C.c_int * n)()
+        scores = (C.c_float * n)()
+        fptr = None
+        if follow is not None:
+            closed = [-1] * (n * mn * k * 2)
+            nxt = [0] * (n * mn * k * 2)
+            for b, f in enumerate(follow):
+                for s_, st in enumerate(f["steps"]):
+                    base = ((b * mn + s_) * k) * 2
+                    for j, (par, tok) in enumerate(st["closed"]):
+                        closed[base + 2 * j], closed[base + 2 * j + 1] = par, tok
+                    for j, (par, tok) in enumerate(st["next"]):
+                        nxt[base + 2 * j], nxt[base + 2 * j + 1] = par, tok
+            keep = (_ints(closed, C.c_int32), _ints(nxt, C.c_int32), _ints([len(f["steps"]) for f in follow], C.c_int32),
+                    _ints([int(f["done"]) for f in follow], C.c_int32))
+            fs = _lib.IsstBeamFollow(*[C.cast(x, C.POINTER(C.c_int32)) for x in keep])
+            fptr = C.byref(fs)
+        tptr, tr = None, None
+        if want_trace:
+            tr = ((C.c_float * (n * mn * n_keep))(), (C.c_int32 * (n * mn * n_keep))(), (C.c_int32 * (n * mn * k * 2))(),
+                  (C.c_float * (n * mn * k))(), (C.c_int32 * n)())
+            ts = _lib.IsstBeamTrace(C.cast(tr[0], C.POINTER(C.c_float)), C.cast(tr[1], C.POINTER(C.c_int32)),
+                                    C.cast(tr[2], C.POINTER(C.c_int32)), C.cast(tr[3], C.POINTER(C.c_float)),
+                                    C.cast(tr[4], C.POINTER(C.c_int32)))
+            tptr = C.byref(ts)
+        _lib.check(self.lib.isst_generate_beam(self.h, n, _ints(sids), _ints(flat, C.c_int32),
+                                               _ints([len(r) for r in ids]), _ints(slots, C.c_int32),
+                                               _ints(eflat, C.c_int32), _ints([len(r) for r in enc_ids]), C.byref(gp),
+                                               k, length_penalty, fptr, out, cnt, scores, tptr, self._stream_ptr()))
+        toks = [[out[b * (mn + 1) + s_] for s_ in range(cnt[b])] for b in range(n)]
+        sc = [scores[b] for b in range(n)]
+        if not want_trace:
+            return toks, sc
+        V = self.cfg.llm.vocab
+        trace = []
+        for b in range(n):
+            steps = []
+            for s_ in range(tr[4][b]):
+                o = (b * mn + s_) * n_keep
+                cand = [(tr[0][o + j], tr[1][o + j] // V, tr[1][o + j] % V) for j in range(n_keep)]
+                o2 = (b * mn + s_) * k
+                steps.append({"cand": cand,
+                              "next": [(tr[2][(o2 + j) * 2], tr[2][(o2 + j) * 2 + 1]) for j in range(k)],
+                              "scores": [tr[3][o2 + j] for j in range(k)]})
+            trace.append(steps)
+        return toks, sc, trace
 
     def forward(self, sids: Sequence[int], ids: Optional[Sequence[Sequence[int]]], speech_slots=None,
                 embeds: Optional[torch.Tensor] = None, lens: Optional[Sequence[int]] = None,

@@ -70,6 +70,8 @@ class GenerateOutput:
     sequences: torch.Tensor            # int64 [B, prompt + generated], right-padded with pad_token_id
     past_key_values: object            # StreamHandle (B == 1) or list of StreamHandle
     generated: Optional[List[List[int]]] = None   # extension: chosen tokens per row without padding
+    sequences_scores: Optional[torch.Tensor] = None     # beam search: score of the returned hypothesis per row
+    beam_trace: Optional[list] = None                   # beam search, beam_trace=True: candidates / choices per step
 
 
 @dataclass
@@ -176,10 +178,13 @@ class SpeechLlamaForCausalLM:
                  encoder_input_ids=None, encoder_no_repeat_ngram_size=0, no_repeat_ngram_size=0,
                  repetition_penalty=1.0, pad_token_id=None, return_dict_in_generate=True, return_legacy_cache=False,
                  use_cache=True, past_key_values=None, suppress_tokens=None, states=None, multiplier=1,
-                 forced_tokens=None, pin_prefix=0, **_unused) -> GenerateOutput:
-        if num_beams != 1 or do_sample:
-            raise NotImplementedError("infinisst_b200 implements the greedy path (num_beams=1, do_sample=False); "
-                                      "beam search is the next §8f item")
+                 forced_tokens=None, pin_prefix=0, length_penalty=1.0, beam_follow=None, beam_trace=False,
+                 **_unused) -> GenerateOutput:
+        if do_sample:
+            raise NotImplementedError("infinisst_b200 implements greedy and beam search (do_sample=False), the "
+                                      "modes the shipped scripts use")
+        if num_beams > 1 and forced_tokens is not None:
+            raise ValueError("forced_tokens is the greedy teacher forcing; beam search takes beam_follow")
         if encoder_no_repeat_ngram_size not in (0, no_repeat_ngram_size):
             raise NotImplementedError("encoder_no_repeat_ngram_size must equal no_repeat_ngram_size "
                                       "(agents/infinisst.py:319-320 passes the same value)")
@@ -202,8 +207,18 @@ class SpeechLlamaForCausalLM:
         g.repetition_penalty = float(repetition_penalty)
         g.eos_token_ids = list(self.cfg.gen.eos_token_ids)
         g.suppress_tokens = list(suppress_tokens or [])
-        toks = self.engine.generate([h.sid for h in handles], ids, [self._slot_map(r) for r in ids], enc, g,
-                                    pin_prefix=pin_prefix, forced=forced_tokens)
+        extra = {}
+        if num_beams > 1:
+            # beam search with KV hand-back (patch_hf.py:626-655, 687-967; agents/infinisst.py:334-336): `sequences`
+            # is the best hypothesis (closing EOS appended when it fits), the handle continues from ITS cache
+            res = self.engine.generate_beam([h.sid for h in handles], ids, [self._slot_map(r) for r in ids], enc, g,
+                                            num_beams, pin_prefix=pin_prefix, length_penalty=float(length_penalty),
+                                            follow=beam_follow, want_trace=beam_trace)
+            toks = res[0]
+            extra = {"sequences_scores": torch.tensor(res[1]), "beam_trace": res[2] if beam_trace else None}
+        else:
+            toks = self.engine.generate([h.sid for h in handles], ids, [self._slot_map(r) for r in ids], enc, g,
+                                        pin_prefix=pin_prefix, forced=forced_tokens)
         pad = self.cfg.gen.pad_token_id if pad_token_id is None else pad_token_id
         width = max(len(r) + len(t) for r, t in zip(ids, toks))
         seqs = torch.full((B, width), pad, dtype=torch.long)
@@ -211,7 +226,7 @@ class SpeechLlamaForCausalLM:
             row = ids[b] + toks[b]
             seqs[b, :len(row)] = torch.tensor(row, dtype=torch.long)
         pkv = handles[0] if B == 1 else handles
-        return GenerateOutput(sequences=seqs, past_key_values=pkv, generated=toks)
+        return GenerateOutput(sequences=seqs, past_key_values=pkv, generated=toks, **extra)
 
     @torch.inference_mode()
     def forward(self, input_ids=None, text_input_ids=None, attention_mask=None, text_attention_mask=None,
