@@ -248,14 +248,15 @@ def main_native(args, env):
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
     t0 = time.perf_counter()
-    eng = Engine(cfg, device=dev, max_streams=2 * S + 2, max_batch=S, max_prompt=64)   # + scratch streams of the stand-alone kernel bench and the latency stream
+    K = args.beam
+    eng = Engine(cfg, device=dev, max_streams=2 * S + 2, max_batch=S * K, max_prompt=64, max_beams=K)   # + scratch streams of the stand-alone kernel bench and the latency stream
     sd = make_state_dict(cfg, seed=0, device=f"cuda:{dev}", dtype=torch.bfloat16)
     eng.load_state_dict(sd)
     del sd
     torch.cuda.empty_cache()
     log(f"[bench] model ready in {time.perf_counter() - t0:.1f}s")
 
-    run = LockstepRunner(eng, cfg, S)
+    run = LockstepRunner(eng, cfg, S, beam=K)
     n_prime = args.prime
     n_total = n_prime + args.warmup + args.steps + 1 + args.steps + 2 + 2
     gen = torch.Generator(device=f"cuda:{dev}").manual_seed(998244353 + rank)
@@ -413,7 +414,7 @@ def main_native(args, env):
     # ---- single-stream per-chunk latency (BASELINE.json configs[1]) through the same API ----
     lat = {}
     if args.latency_chunks > 0:
-        one = LockstepRunner(eng, cfg, 1)
+        one = LockstepRunner(eng, cfg, 1, beam=K)
         g1 = torch.Generator().manual_seed(7)
         buf = torch.empty(1, CHUNK, dtype=torch.float32).pin_memory()
         first = torch.cat([torch.zeros(1, 399), 0.1 * torch.randn(1, CHUNK, generator=g1)], 1).pin_memory()
@@ -449,7 +450,8 @@ def main_native(args, env):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"BASELINE.json configs[2] per GPU ({S} concurrent streams, batched chunk-prefill + decode; "
                                f"x{world} GPUs = configs[4] partition): wav2vec2-large + Llama-3.1-8B bf16 random-init, "
-                               "960 ms chunks, 22-token turn prompt, greedy <= 10 tokens, max_llm_cache_size 1000 + "
+                               "960 ms chunks, 22-token turn prompt, " + (f"beam search ({K} beams, KV hand-back)" if K > 1 else "greedy") +
+                               " <= 10 tokens, max_llm_cache_size 1000 + "
                                "pinned 40-token system prompt, steady state",
                    "streams_per_gpu": S, "streams_total": S * world, "parallelism": f"stream-parallel replicas x{world}, "
                    "no collective on the data path", "kv_len_at_start": kv0, "prime_chunks": n_prime,
@@ -500,6 +502,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="concurrent streams per GPU")
+    ap.add_argument("--beam", type=int, default=1, help="1 = greedy (the north-star workload); k > 1 = the reference's beam search")
     ap.add_argument("--prime", type=int, default=34, help="untimed chunks run first so both sliding windows are full")
     ap.add_argument("--latency-chunks", type=int, default=20, help="single-stream latency sample (0 = skip)")
     ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline of one step to this file and exit")

@@ -2,7 +2,8 @@
 
 Same class / method / flag names (agents/infinisst.py:69-72,115-128,185-198,270-394;
 agents/options.py:1-125).  Differences, each deliberate:
-  * greedy decoding (`--beam 1`) instead of the reference's asserted beam > 1: beam search is §8f "next";
+  * `--beam 1` (greedy) is accepted besides the reference's asserted beam > 1; `--beam k` runs the
+    reference's beam search with KV hand-back (patch_hf.py:43-302, 687-967) on the CUDA path;
   * `cache_checkpoints` and `system_prompt_size` live on the per-stream states (quirk Q3) so several
     streams can share one agent/engine;
   * `policy_batch` advances many independent streams in lock-step (the reference can only tile one
@@ -198,7 +199,7 @@ class InfiniSST(SpeechToTextAgent):
         self.bad_words_ids = list(getattr(args, "bad_words_ids", []) or [])
         self.model = SpeechLlamaForCausalLM(
             cfg, engine=getattr(args, "engine", None), max_streams=getattr(args, "max_streams", 8),
-            max_multiplier=self.max_latency_multiplier)
+            max_multiplier=self.max_latency_multiplier, max_beams=self.beam)
         sd = getattr(args, "state_dict", None)
         if sd is None and getattr(args, "state_dict_path", None):
             sd = torch.load(args.state_dict_path, map_location="cpu", weights_only=True)

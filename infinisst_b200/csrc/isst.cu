@@ -452,6 +452,8 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
     return 0;
   }
   ISST_CHECK(v.conv_c % tc::kBK == 0, "gemm: conv_c must be a multiple of 64");
+  // weights on the 128-lane operand up to 64 token rows; measured at 128 / 256 rows (tests/gemm_bench_rows.py):
+  // tokens on the 128-lane operand is as fast or faster (133 vs 137 us, 197 vs 210 us per decode layer)
   bool swap = (v.rows <= 64 && v.batch == 1);
   if (force_swap >= 0) swap = force_swap != 0;
   ISST_CHECK(!(swap && v.batch != 1), "gemm: swap mode needs batch == 1");
@@ -1925,6 +1927,7 @@ int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_
       ISST_CUDA(cudaStreamSynchronize(st));
       std::copy(pairs.begin() + 2 * off, pairs.begin() + 2 * (off + cnt), mb.host(o_pairs));
       ISST_CUDA(cudaMemcpyAsync(mb.dev(o_pairs), mb.host(o_pairs), cnt * 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+      ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(cnt) * page_elems * 2 * c.layers * 2);
       ISST_CUDA(launch_k(ctx, kv_page_copy_kernel, dim3(static_cast<unsigned>(cnt), c.layers), dim3(256), 0, st, ctx->kv_pool,
                          ctx->kv_layer_elems, static_cast<int>(page_elems), mb.dev(o_pairs)));
       LAUNCH_CHECK(ctx);

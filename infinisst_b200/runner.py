@@ -15,8 +15,8 @@ from .model import SpeechLlamaForCausalLM, StreamHandle
 
 
 class LockstepRunner:
-    def __init__(self, engine: Engine, cfg: InfiniSSTConfig, n_streams: int):
-        self.engine, self.cfg = engine, cfg
+    def __init__(self, engine: Engine, cfg: InfiniSSTConfig, n_streams: int, beam: int = 1):
+        self.engine, self.cfg, self.beam = engine, cfg, beam
         self.model = SpeechLlamaForCausalLM(cfg, engine=engine)
         self.tok = TemplateTokenizer(cfg)
         self.states: List[S2TAgentStates] = []
@@ -72,7 +72,10 @@ class LockstepRunner:
         self.engine.encode_chunk(self.sids, pcm, g.latency_multiplier)
         enc = [st.target_ids[-g.no_repeat_ngram_lookback:] for st in self.states]
         pin = self.states[0].system_prompt_size if g.always_cache_system_prompt else 0
-        toks = self.engine.generate(self.sids, [ids] * self.n, [slots] * self.n, enc, g, pin_prefix=pin, forced=forced)
+        if self.beam > 1:      # the reference's shipped decoding: beam search, KV of the best hypothesis handed back
+            toks, _ = self.engine.generate_beam(self.sids, [ids] * self.n, [slots] * self.n, enc, g, self.beam, pin_prefix=pin)
+        else:
+            toks = self.engine.generate(self.sids, [ids] * self.n, [slots] * self.n, enc, g, pin_prefix=pin, forced=forced)
         self.last_tokens = toks
         return self._after_generate(toks)
 
@@ -84,7 +87,7 @@ class LockstepRunner:
         enc_t = [st.target_ids[-g.no_repeat_ngram_lookback:] for st in self.states]
         pin = self.states[0].system_prompt_size if g.always_cache_system_prompt else 0
         out = self.model.generate(
-            attention_mask=None, input_ids=ids, speech_batch=pcm_host, do_sample=False, num_beams=1,
+            attention_mask=None, input_ids=ids, speech_batch=pcm_host, do_sample=False, num_beams=self.beam,
             max_new_tokens=g.max_new_tokens, num_return_sequences=1, encoder_input_ids=enc_t,
             encoder_no_repeat_ngram_size=g.no_repeat_ngram_size, no_repeat_ngram_size=g.no_repeat_ngram_size,
             repetition_penalty=g.repetition_penalty, pad_token_id=g.pad_token_id, return_dict_in_generate=True,

@@ -214,3 +214,40 @@ def test_beam_batched_streams(pins):
     print(f"batched beams: {agree}/6 (stream, chunk) results identical to the single-stream runs")
     assert agree >= 5          # different GEMM shapes (8 rows vs 4) may flip a near-tie
     eng.close()
+
+
+def test_agent_drop_in_api_with_beam(pins):
+    """The SimulEval-facing agent with the reference's shipped `--beam 4`: same flags / methods as
+    agents/infinisst.py; emitted ids and KV lengths equal the reference agent's up to the first near-tie."""
+    import argparse
+    from infinisst_b200.agent import InfiniSST
+    name = "plain"
+    n, k = int(pins[f"{name}_n_chunks"]), int(pins["beam"])
+    cfg = tiny_config(max_cache_size=int(pins["max_cache"]), max_llm_cache_size=int(pins["max_llm"]))
+    sd = beam_weights(cfg, 1.0)
+    ap = argparse.ArgumentParser()
+    InfiniSST.add_args(ap)
+    args = ap.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", str(int(pins["max_cache"])),
+                          "--xpos", "0", "--latency-multiplier", "1", "--max-latency-multiplier", "1",
+                          "--max-new-tokens", "10", "--no-repeat-ngram-size", "5", "--max-llm-cache-size",
+                          str(int(pins["max_llm"])), "--always-cache-system-prompt", "--beam", str(k)])
+    args.model_config, args.state_dict = cfg, sd
+    agent = InfiniSST(args)
+    states = agent.build_states()
+    states.source_sample_rate = 16000
+    audio = make_audio(n * SEG / 16000.0)
+    same = 0
+    for c in range(n):
+        p = f"{name}_c{c}_"
+        states.source = audio[: (c + 1) * SEG].tolist()
+        states.source_finished = c == n - 1
+        n_before = len(states.target_ids)
+        act = agent.policy(states)
+        assert not act.is_read()
+        if states.target_ids[n_before:] != pins[p + "output_ids"].tolist():
+            break
+        assert states.past_key_values[0][0].size(2) == int(pins[p + "kv"][2])      # after hand-back + eviction
+        same += 1
+    print(f"agent --beam {k}: {same}/{n} chunks identical to the reference agent before the first divergence")
+    assert same >= 2
+    agent.model.engine.close()
