@@ -251,3 +251,46 @@ def test_agent_drop_in_api_with_beam(pins):
     print(f"agent --beam {k}: {same}/{n} chunks identical to the reference agent before the first divergence")
     assert same >= 2
     agent.model.engine.close()
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_beam_many_rows_and_multipliers(pins, m):
+    """18 streams x 4 beams = 72 rows per decode step (the > 64-row GEMM / attention paths), latency multipliers 1
+    and 2 (20 new tokens: three private tail pages per beam): identical streams must stay identical to each other,
+    agree with the single-stream run, hand back prompt + forwarded tokens, and leak no page."""
+    from infinisst_b200.engine import Engine
+    k, B = int(pins["beam"]), 18
+    cfg = tiny_config(max_cache_size=int(pins["max_cache"]), max_llm_cache_size=int(pins["max_llm"]))
+    cfg.gen.latency_multiplier, cfg.gen.max_new_tokens = m, 10 * m
+    sd = beam_weights(cfg, 1.0)
+    eng = Engine(cfg, device=0, max_streams=B + 1, max_beams=k, max_multiplier=m, max_prompt=128)
+    eng.load_state_dict(sd)
+    free0 = eng.pages_free()
+    audio = make_audio(3 * m * SEG / 16000.0)
+
+    def pcm(c):
+        x = audio[c * m * SEG:(c + 1) * m * SEG][None].clone()
+        return torch.cat([torch.zeros(1, 399), x], 1) if c == 0 else x
+    solo_sid = eng.open_stream()
+    sids = [eng.open_stream() for _ in range(B)]
+    agree = 0
+    for c in range(3):
+        ids = O.build_prompt(cfg.tpl, c == 0, m)
+        eng.encode_chunk([solo_sid], pcm(c), m)
+        solo, _ = eng.generate_beam([solo_sid], [ids], [slot_map(cfg, ids)], [[]], cfg.gen, k,
+                                    pin_prefix=len(cfg.tpl.system_ids))
+        kv0 = eng.kv_len(sids[0])
+        eng.encode_chunk(sids, pcm(c).repeat(B, 1), m)
+        toks, _ = eng.generate_beam(sids, [ids] * B, [slot_map(cfg, ids)] * B, [[]] * B, cfg.gen, k,
+                                    pin_prefix=len(cfg.tpl.system_ids))
+        assert all(t == toks[0] for t in toks), (c, toks)                       # same input, same row arithmetic
+        assert all(eng.kv_len(s) == eng.kv_len(sids[0]) for s in sids)
+        fwd = len(toks[0]) - 1                                                  # closing EOS / last token: no KV
+        assert eng.kv_len(sids[0]) == kv0 + len(ids) + fwd
+        agree += toks[0] == solo[0]
+    print(f"m={m}: {B} x {k} rows, {agree}/3 chunks identical to the single-stream run")
+    assert agree >= 2
+    for s in sids + [solo_sid]:
+        eng.close_stream(s)
+    assert eng.pages_free() == free0
+    eng.close()
