@@ -72,3 +72,23 @@ def test_oracle_reproduces_reference_beam_search(pins, name):
     assert evictions >= 2
     if name == "eos":
         assert closed_by_eos >= 10 and early_done >= 2                       # the EOS paths were exercised
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_beam_pins_regenerate_from_reference(pins, tmp_path):
+    """In the build container: re-run the reference's beam search and require the committed fixture to be what it
+    produces."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(PINS), "make_ref_beam_pins.py")
+    env = dict(os.environ, REF_PINS_OUT=str(tmp_path / "beam.npz"))
+    r = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    fresh = np.load(tmp_path / "beam.npz")
+    for name in ("plain", "eos"):
+        for c in range(int(pins[f"{name}_n_chunks"])):
+            p = f"{name}_c{c}_"
+            assert fresh[p + "sequence"].tolist() == pins[p + "sequence"].tolist()
+            assert fresh[p + "cand_tokens"].tolist() == pins[p + "cand_tokens"].tolist()
+            np.testing.assert_allclose(fresh[p + "cand_scores"], pins[p + "cand_scores"], atol=1e-4)
+            assert fresh[p + "kv"].tolist() == pins[p + "kv"].tolist()
