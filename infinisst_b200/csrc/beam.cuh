@@ -15,6 +15,7 @@
 namespace isst {
 
 constexpr int kBeamMaxKeep = 32;     // candidates kept per sentence: max(2, 1 + n_eos) * num_beams
+constexpr int kBeamCandCap = 512;    // slice elements that pass the threshold pre-filter (overflow: slow exact path)
 
 struct BeamSel {
   const int* ctx_ids;        // [R][ctx_cap]  prompt of this call + tokens generated on this beam
@@ -181,9 +182,40 @@ beam_topk_kernel(float* logits, int V, BeamSel s) {
   const float bs = s.beam_score[r];
   float* cs = s.cand_s + (static_cast<size_t>(r) * kSelParts + part) * s.n_keep;
   int* ci = s.cand_i + (static_cast<size_t>(r) * kSelParts + part) * s.n_keep;
-  block_top_n(hi - lo, s.n_keep,
-              [&](int i, float* v, long long* k) { *v = lg[lo + i] + bs; *k = lo + i; },
-              [&](int t, float v, long long k) { cs[t] = v; ci[t] = static_cast<int>(k); });
+  // Slice top-n in two levels: the n-th largest of the 256 per-thread maxima is a lower bound T of the slice's n-th
+  // largest score, so only elements >= T (a few dozen) enter the exact selection; ties that overflow the candidate
+  // list fall back to selecting over the whole slice.
+  __shared__ float tmax_s[kSelThreads];
+  __shared__ float cand_v[kBeamCandCap];
+  __shared__ int cand_k[kBeamCandCap];
+  __shared__ float thr_s;
+  __shared__ int cand_n;
+  float tmax = -INFINITY;
+  for (int i = lo + tid; i < hi; i += kSelThreads) tmax = fmaxf(tmax, lg[i] + bs);
+  tmax_s[tid] = tmax;
+  if (tid == 0) { thr_s = -INFINITY; cand_n = 0; }
+  __syncthreads();
+  block_top_n(kSelThreads, s.n_keep,
+              [&](int i, float* v, long long* k) { *v = tmax_s[i]; *k = tmax_s[i] > -INFINITY ? i : -1; },
+              [&](int t, float v, long long k) { if (t == s.n_keep - 1) thr_s = k >= 0 ? v : -INFINITY; });
+  const float thr = thr_s;
+  for (int i = lo + tid; i < hi; i += kSelThreads) {
+    const float v = lg[i] + bs;
+    if (v >= thr && v > -INFINITY) {
+      const int pos = atomicAdd(&cand_n, 1);
+      if (pos < kBeamCandCap) { cand_v[pos] = v; cand_k[pos] = i; }
+    }
+  }
+  __syncthreads();
+  if (cand_n <= kBeamCandCap) {
+    block_top_n(cand_n, s.n_keep,
+                [&](int i, float* v, long long* k) { *v = cand_v[i]; *k = cand_k[i]; },
+                [&](int t, float v, long long k) { cs[t] = v; ci[t] = static_cast<int>(k); });
+  } else {
+    block_top_n(hi - lo, s.n_keep,
+                [&](int i, float* v, long long* k) { *v = lg[lo + i] + bs; *k = lo + i; },
+                [&](int t, float v, long long k) { cs[t] = v; ci[t] = static_cast<int>(k); });
+  }
   __shared__ int last_flag;
   if (tid == 0) {
     __threadfence();

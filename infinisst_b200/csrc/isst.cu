@@ -22,6 +22,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "decode_attention.cuh"
+#include "decode_attention_group.cuh"
 #include "gemm_tcgen05.cuh"
 #include "prefill_attention_tc.cuh"
 #include "beam.cuh"
@@ -882,6 +883,14 @@ struct LlmBatch {
   double kv_tokens = 0;            // sum over streams of the KV length attended to (profiling only)
   double qk_pairs = 0;             // sum over streams of T_b * L_b (profiling only)
   int max_L = 0;                   // longest KV length attended to in this batch (grid sizing)
+  // beam search decode: rows come in groups of `group` beams that share their sentence's prompt pages; the shared
+  // prefix [0, key_hi[g]) is attended to once per group and the private tails per beam, in one launch
+  // (decode_attention_group_kernel)
+  int group = 1;
+  const int* d_key_hi = nullptr;   // [n / group]
+  const int* d_tail_page = nullptr;   // [n / group] page-table index of the first private page
+  int max_prefix = 0;
+  double prefix_tokens = 0;        // sum over groups of the shared prefix length (profiling only)
 };
 
 static PagedKV paged_kv(isst_ctx* ctx, int layer) {
@@ -966,7 +975,9 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
     }
     PagedKV kv = paged_kv(ctx, l);
     static const bool fuse_env = !(getenv("ISST_DEC_FUSE") && atoi(getenv("ISST_DEC_FUSE")) == 0);   // A/B aid
-    const bool fuse_append = lb.decode && fuse_env;    // decode: the attention kernel rotates and appends by itself
+    static const bool group_env = !(getenv("ISST_BEAM_GROUP") && atoi(getenv("ISST_BEAM_GROUP")) == 0);   // A/B aid
+    const bool grouped = lb.decode && lb.group == 4 && lb.d_key_hi && group_env;   // beam search: shared-prefix attention
+    const bool fuse_append = lb.decode && fuse_env && !grouped;    // decode: the attention kernel rotates and appends by itself
     if (!fuse_append) {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
       dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
@@ -1005,6 +1016,27 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       }
       ISST_CUDA(launch_k(ctx, chunk_attention_kernel<128, false, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
+      }
+    } else if (grouped) {
+      // algorithmic bytes: the shared prefix once per sentence + every beam's private tail
+      const double tok = lb.prefix_tokens + (lb.kv_tokens - lb.prefix_tokens * lb.group);
+      ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, tok * Hkv * HD * 2 * 2);
+      static bool grp_attr = false;
+      if (!grp_attr) {
+        ISST_CUDA(cudaFuncSetAttribute(decode_attention_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpSmemBytes));
+        grp_attr = true;
+      }
+      const int n_groups = lb.n / lb.group;
+      const int splits_p = decode_splits_for(ctx, n_groups, std::max(lb.max_prefix, 1));
+      DecodeGroupParams gp{};
+      gp.qkv = ctx->lqkv; gp.q_sys = ctx->lq_sys; gp.kv = kv; gp.slots = lb.d_slots; gp.key_hi = lb.d_key_hi;
+      gp.tail_page = lb.d_tail_page; gp.out = ctx->lattn;
+      gp.part_o = ctx->part_o; gp.part_ml = ctx->part_ml; gp.H = H; gp.splits = splits_p; gp.scale_log2 = scale_log2;
+      ISST_CUDA(launch_k(ctx, decode_attention_group_kernel, dim3(splits_p, Hkv, n_groups), dim3(kDecThreads), kGrpSmemBytes, st, gp));
+      LAUNCH_CHECK(ctx);
+      if (splits_p > 1) {
+        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits_p));
+        LAUNCH_CHECK(ctx);
       }
     } else {
       // algorithmic bytes: K and V of every attended token once (4096 * L per layer per stream)
@@ -1864,6 +1896,7 @@ int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_
   const size_t o_enc = mb.alloc(static_cast<size_t>(n) * enc_cap), o_enclen = mb.alloc(n);
   const size_t o_active = mb.alloc(R), o_next = mb.alloc(R), o_score = mb.alloc(R);
   const size_t o_sup = mb.alloc(gen->n_suppress), o_ones = mb.alloc(R), o_iota = mb.alloc(R);
+  const size_t o_khi = mb.alloc(n), o_tpg = mb.alloc(n);                      // shared-prefix length per sentence, first private page
   const size_t o_pairs = mb.alloc(static_cast<size_t>(R) * 2 * 8 * 2);       // page copy pairs of one step
   const size_t o_res_s = mb.alloc(static_cast<size_t>(n) * n_keep), o_res_i = mb.alloc(static_cast<size_t>(n) * n_keep);
   const size_t meta_end = mb.used;
@@ -2029,6 +2062,8 @@ int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_
     return 0;
   };
 
+  int db_max_prefix = 0;
+  double db_prefix_tokens = 0;
   // ---- step 0: candidates of the single live beam ----
   ISST_TRY(select(0, 1));
   // fork: every beam gets private tail pages; the partially filled last prompt page is copied into each
@@ -2040,6 +2075,15 @@ int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_
     g.partial = slot1 % kPageTokens != 0;
     g.n_priv = max_new > 1 ? ceil_div(slot1 % kPageTokens + max_new - 1, kPageTokens) : 0;
     ISST_CHECK(g.tail0 + g.n_priv <= ctx->pages_per_stream, "stream needs more pages than pages_per_stream");
+    {
+      // logical index of the first key that lives in a private page: the shared prefix is [0, lb)
+      const int sb = g.tail0 * kPageTokens;
+      const int lbnd = sb < s.sys_len ? sb : (sb < s.ring_start ? s.sys_len : sb - s.ring_start + s.sys_len);
+      mb.host(o_khi)[b] = lbnd;
+      mb.host(o_tpg)[b] = g.tail0;
+      db_max_prefix = std::max(db_max_prefix, lbnd);
+      db_prefix_tokens += lbnd;
+    }
     ISST_CHECK(g.L1 + max_new - 1 <= c.max_kv_len, "stream KV length would exceed max_kv_len");
     g.rows.resize(k);
     for (int j = 0; j < k; ++j) {
@@ -2059,6 +2103,9 @@ int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_
   LlmBatch db;
   db.n = R; db.M = R; db.max_T = 1; db.d_slots = mb.dev(o_iota); db.d_tok_base = mb.dev(o_iota); db.d_T = mb.dev(o_ones);
   db.d_last_row = mb.dev(o_iota); db.d_active = mb.dev(o_active); db.decode = true;
+  db.group = k; db.d_key_hi = mb.dev(o_khi); db.d_tail_page = mb.dev(o_tpg); db.max_prefix = db_max_prefix;
+  db.prefix_tokens = db_prefix_tokens;
+  ISST_CUDA(cudaMemcpyAsync(ctx->d_meta + o_khi, ctx->h_meta + o_khi, (o_pairs - o_khi) * sizeof(int), cudaMemcpyHostToDevice, st));
   std::vector<KvView> views(R);
   for (int step = 1; step < max_new; ++step) {
     bool any = false;
