@@ -124,8 +124,22 @@ class TemplateTokenizer:
         return [t.start_header_id, t.user_token_id, t.end_header_id, t.nl_id] + [t.sp_patch_id] * n_speech + \
                [t.eot_id, t.start_header_id, t.assist_token_id, t.end_header_id, t.nl_id]
 
-    def decode(self, ids: Sequence[int], skip_special_tokens: bool = True) -> str:
+    def decode(self, ids, skip_special_tokens: bool = True) -> str:
+        if isinstance(ids, int):
+            ids = [ids]
         return " ".join(f"t{i}" for i in ids)
+
+
+def non_language_token_ids(tokenizer, n_vocab: int) -> List[int]:
+    """`--suppress-non-language` (agents/infinisst.py:142-148): ids of every token whose decoded text contains an
+    opening parenthesis (ASCII or full-width); they are passed to generate as `suppress_tokens` (:329)."""
+    bad_words = ["(", "\uff08"]
+    out = []
+    for idx in range(n_vocab):
+        decoded = tokenizer.decode(idx, skip_special_tokens=True)
+        if any(b in decoded for b in bad_words):
+            out.append(idx)
+    return out
 
 
 def evict_plan(states: S2TAgentStates, cur: int, max_llm_cache_size: int, always_cache_system_prompt: bool):
@@ -197,6 +211,9 @@ class InfiniSST(SpeechToTextAgent):
         self.cfg = cfg
         self.tokenizer = getattr(args, "tokenizer", None) or TemplateTokenizer(cfg)
         self.bad_words_ids = list(getattr(args, "bad_words_ids", []) or [])
+        if self.suppress_non_language and not self.bad_words_ids:
+            n_vocab = len(self.tokenizer) if hasattr(self.tokenizer, "__len__") else cfg.llm.vocab
+            self.bad_words_ids = non_language_token_ids(self.tokenizer, n_vocab)
         self.model = SpeechLlamaForCausalLM(
             cfg, engine=getattr(args, "engine", None), max_streams=getattr(args, "max_streams", 8),
             max_multiplier=self.max_latency_multiplier, max_beams=self.beam)

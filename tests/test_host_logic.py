@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from infinisst_b200 import production_config, tiny_config
 from infinisst_b200 import stream_parallel as sp
-from infinisst_b200.agent import InfiniSST, S2TAgentStates, TemplateTokenizer, evict_plan
+from infinisst_b200.agent import InfiniSST, S2TAgentStates, TemplateTokenizer, evict_plan, non_language_token_ids
 from infinisst_b200.engine import llama_inv_freq
 from infinisst_b200.model import SpeechLlamaForCausalLM
 from oracle import infinisst_oracle as O
@@ -142,3 +142,14 @@ def test_stream_parallel_world2_gloo():
         assert red["ms"] == 200.0 and abs(red["units"] - 9 * 0.96) < 1e-9 and red["world"] == 2
         assert lat == [0.0, 0.5, 1.0, 1.5]
     assert res[0][3] == [0, 2, 4, 6, 8] and res[1][3] == [1, 3, 5, 7]
+
+
+def test_suppress_non_language_token_ids():
+    """agents/infinisst.py:142-148: tokens whose text contains '(' or the full-width '\uff08' are suppressed."""
+    class Tok:
+        words = ["hello", " (", "a(b", "\uff08", "\uff09", ")", "x"]
+
+        def decode(self, idx, skip_special_tokens=True):
+            return self.words[idx]
+    assert non_language_token_ids(Tok(), 7) == [1, 2, 3]
+    assert non_language_token_ids(TemplateTokenizer(tiny_config()), 16) == []
