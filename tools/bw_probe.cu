@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) ring_kernel(const __grid_constant__ CUten
 // about the same time) or private per CTA.  act_mode: 0 none, 1 shared, 2 private.
 __global__ void __launch_bounds__(128) gemm_like_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_act,
                                                         int num_kb, int tiles, int up_off_rows, int stages, int act_mode,
-                                                        unsigned long long* sink) {
+                                                        unsigned long long* sink, int blocked = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 2 * kTileBytes + 8192;
@@ -106,8 +106,14 @@ __global__ void __launch_bounds__(128) gemm_like_kernel(const __grid_constant__ 
         mbar_expect_tx(&full[stage], 2 * kTileBytes + (act_mode ? 8192 : 0));
         uint8_t* s = smem + stage * stage_bytes;
         if (act_mode) tma_load_2d(s, &tm_act, &full[stage], kb * 64, act_mode == 2 ? blockIdx.x * 64 : 0);
-        tma_load_2d(s + 8192, &tm, &full[stage], kb * 64, tile * 128);
-        tma_load_2d(s + 8192 + kTileBytes, &tm, &full[stage], kb * 64, tile * 128 + up_off_rows);
+        if (!blocked) {
+          tma_load_2d(s + 8192, &tm, &full[stage], kb * 64, tile * 128);
+          tma_load_2d(s + 8192 + kTileBytes, &tm, &full[stage], kb * 64, tile * 128 + up_off_rows);
+        } else {
+          // pre-tiled weights [row tile][k-block][128 rows][64]: every box is one contiguous 16 KB block
+          tma_load_2d(s + 8192, &tm, &full[stage], 0, (tile * num_kb + kb) * 128);
+          tma_load_2d(s + 8192 + kTileBytes, &tm, &full[stage], 0, ((tile + up_off_rows / 128) * num_kb + kb) * 128);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
   } else if (threadIdx.x == 32) {
@@ -307,6 +313,40 @@ int main() {
         const double us = ms * 1e3 / iters;
         printf("%s stages=%d: %7.1f us per launch  %6.2f TB/s (weights only)\n", names[act_mode], stages, us, bytes / 8 / us / 1e6);
       }
+  }
+  // (c2) the same GEMM-like stream over PRE-TILED weights (each 128 x 64 box contiguous in memory)
+  {
+    uint8_t* act;
+    CK(cudaMalloc(&act, static_cast<size_t>(148) * 64 * K * 2));
+    CK(cudaMemset(act, 1, static_cast<size_t>(148) * 64 * K * 2));
+    CUtensorMap tma;
+    cuuint64_t da[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(148 * 64)};
+    cuuint32_t boxa[2] = {64, 64};
+    r = encode(&tma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, act, da, strides, boxa, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("encode act failed %d\n", (int)r); return 1; }
+    printf("# GEMM-like over pre-tiled weights ([row tile][k-block][128][64], contiguous 16 KB boxes), act shared\n");
+    cuuint64_t strides_b[1] = {128};
+    for (int stages : {4, 5}) {
+      const size_t smem = static_cast<size_t>(stages) * (2 * kTileBytes + 8192) + 1024 + 256;
+      const int iters = 16;
+      std::vector<CUtensorMap> maps(8);
+      for (int i = 0; i < 8; ++i) {
+        cuuint64_t d2[2] = {64, static_cast<cuuint64_t>(rows / 8) * (K / 64)};
+        r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w + static_cast<size_t>(i) * (bytes / 8), d2, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode blocked failed %d\n", (int)r); return 1; }
+      }
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      for (int it = 0; it < iters; ++it)
+        gemm_like_kernel<<<112, 128, smem>>>(maps[it % 8], tma, num_kb, 112, 14336, stages, 1, sink, 1);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double us = ms * 1e3 / iters;
+      printf("pre-tiled  stages=%d: %7.1f us per launch  %6.2f TB/s (weights only)\n", stages, us, bytes / 8 / us / 1e6);
+    }
   }
   // (d) decode-attention-like: 512 CTAs (64 streams x 8 kv heads), 16 tiles of 64 keys each, rows of 256 B
   {
