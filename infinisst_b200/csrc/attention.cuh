@@ -90,6 +90,12 @@ struct LlmAttnParams {
   const int* T;           // [n] new tokens of this stream
   int H;                  // q heads
   float scale_log2;       // HD^-0.5 * log2(e)
+  // key splits (prefill_attention_tc_kernel, few streams: one CTA per (stream, kv head) would leave the SMs idle):
+  // split s of every row tile takes a contiguous range of key tiles and leaves an un-normalised fp32 partial
+  // [(row * H + q head) * key_splits + s]; decode_combine_kernel merges.  1 (or 0): the kernel writes `out` itself.
+  int key_splits;
+  float* part_o;
+  float* part_ml;
 };
 
 __device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, int src_bytes) {

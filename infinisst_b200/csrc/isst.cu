@@ -998,12 +998,37 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       if (pa_tc) {
         static bool pa_attr = false;
         if (!pa_attr) {
-          ISST_CUDA(cudaFuncSetAttribute(prefill_attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
+          ISST_CUDA(cudaFuncSetAttribute(prefill_attention_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
           pa_attr = true;
         }
-        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4>, dim3(ceil_div(4 * lb.max_T, 128), Hkv, lb.n), dim3(kPaThreads),
-                           kPaSmemBytes, st, lp));
+        // few streams: one CTA per (row tile, kv head, stream) leaves most SMs idle and walks the whole KV serially -
+        // cut the key range into splits (fp32 partials merged by decode_combine_kernel)
+        const int row_tiles = ceil_div(4 * lb.max_T, 128);
+        const int ctas = row_tiles * Hkv * lb.n;
+        const int key_tiles = ceil_div(lb.max_L, kPaKT) + 1;
+        int ks = 1;
+        static const bool ks_env = !(getenv("ISST_PREFILL_SPLITS") && atoi(getenv("ISST_PREFILL_SPLITS")) == 0);   // A/B aid
+        if (ks_env && 2 * ctas <= ctx->sm_count) ks = std::max(1, std::min({ctx->sm_count / ctas, key_tiles / 2, 8}));
+        const size_t part_cap = static_cast<size_t>(c.max_batch) * H * ctx->decode_splits;     // (row, head, split) slots of part_o
+        while (ks > 1 && static_cast<size_t>(M) * H * ks > part_cap) --ks;
+        lp.key_splits = ks; lp.part_o = ctx->part_o; lp.part_ml = ctx->part_ml;
+        if (ks > 1) {
+          static bool pas_attr = false;
+          if (!pas_attr) {
+            ISST_CUDA(cudaFuncSetAttribute(prefill_attention_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
+            pas_attr = true;
+          }
+          ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, true>, dim3(row_tiles * ks, Hkv, lb.n), dim3(kPaThreads),
+                             kPaSmemBytes, st, lp));
+        } else {
+          ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, false>, dim3(row_tiles, Hkv, lb.n), dim3(kPaThreads),
+                             kPaSmemBytes, st, lp));
+        }
         LAUNCH_CHECK(ctx);
+        if (ks > 1) {
+          ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(M * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, ks));
+          LAUNCH_CHECK(ctx);
+        }
       } else {
       dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
       constexpr int NS = 3;

@@ -56,7 +56,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int GROUP>
+template <int GROUP, bool kSplit = false>
 __global__ void __launch_bounds__(kPaThreads, 2)
 prefill_attention_tc_kernel(const LlmAttnParams lp) {
   using namespace tc;
@@ -77,7 +77,9 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, head = blockIdx.y, row0 = blockIdx.x * 128;
+  const int KS = kSplit ? lp.key_splits : 1;                 // key splits (few streams), see LlmAttnParams
+  const int split = kSplit ? blockIdx.x % KS : 0;
+  const int b = blockIdx.z, head = blockIdx.y, row0 = (kSplit ? blockIdx.x / KS : blockIdx.x) * 128;
   const int slot = lp.slots[b];
   const int T = lp.T[b];
   const int tok0 = lp.tok_base[b];
@@ -92,7 +94,21 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
   const int key_end = L - T + i_hi + 1;
   const int sys_end = min(sys_len, key_end);
   const int n_sys_tiles = (sys_end + KT - 1) / KT;
-  const int n_tiles = n_sys_tiles + (key_end - sys_end + KT - 1) / KT;
+  const int n_tiles_all = n_sys_tiles + (key_end - sys_end + KT - 1) / KT;
+  // this CTA's key tiles: [t_lo, t_lo + n_tiles); u = t - t_lo indexes ring stages / barrier phases
+  const int tiles_per = (n_tiles_all + KS - 1) / KS;
+  const int t_lo = kSplit ? min(n_tiles_all, split * tiles_per) : 0;
+  const int n_tiles = kSplit ? min(n_tiles_all, t_lo + tiles_per) - t_lo : n_tiles_all;
+  if (kSplit && n_tiles <= 0) {                                     // empty split (KS > 1 only): neutral partials
+    for (int idx = tid; idx < 128 * HD; idx += kPaThreads) {
+      const int r = row0 + idx / HD, d = idx % HD;
+      if (r >= n_rows) break;
+      const size_t pi = (static_cast<size_t>(tok0 + r % T) * lp.H + head * GROUP + r / T) * KS + split;
+      lp.part_o[pi * HD + d] = 0.f;
+      if (d == 0) { lp.part_ml[pi * 2] = -INFINITY; lp.part_ml[pi * 2 + 1] = 0.f; }
+    }
+    return;
+  }
   auto tile_k0 = [&](int t) { return t < n_sys_tiles ? t * KT : sys_end + (t - n_sys_tiles) * KT; };
   auto tile_k1 = [&](int t) { return t < n_sys_tiles ? min(sys_end, t * KT + KT) : min(key_end, sys_end + (t - n_sys_tiles + 1) * KT); };
 
@@ -130,7 +146,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     }
     fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
   };
-  stage_q(n_sys_tiles > 0, tid, kPaThreads);
+  stage_q(t_lo < n_sys_tiles, tid, kPaThreads);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -145,8 +161,9 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     const size_t page_elems = static_cast<size_t>(2) * lp.kv.kv_heads * kPageTokens * HD;
     const bf16* head_base = lp.kv.pool + static_cast<size_t>(head) * kPageTokens * HD + chunk * 8;
     const size_t v_off = static_cast<size_t>(lp.kv.kv_heads) * kPageTokens * HD;
-    auto issue = [&](int t) {
-      const int stage = t % NS;
+    auto issue = [&](int u) {
+      const int stage = u % NS;
+      const int t = t_lo + u;
       uint8_t* dK = sStage + stage * kPaStageBytes + hh * (64 * 128);
       uint8_t* dV = dK + 2 * (64 * 128);
       const int k0 = tile_k0(t), k1 = tile_k1(t);
@@ -198,10 +215,10 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc_s = make_idesc(128, KT);          // S = Q K^T : N = 64 keys
     constexpr uint32_t idesc_o = make_idesc_bmn(128, HD);      // Ot = P V  : N = 128 dims, B MN-major
-    auto mma_s = [&](int t) {
+    auto mma_s = [&](int t) {                                  // t: local tile index
       const int stage = t % NS;
       mbar_wait(&full_bar[stage], (t / NS) & 1);
-      if (t == n_sys_tiles && n_sys_tiles > 0) mbar_wait(q_bar, 0);   // the softmax warps swapped in the ring variant
+      if (t_lo + t == n_sys_tiles && t > 0) mbar_wait(q_bar, 0);   // the softmax warps swapped in the ring variant
       tcgen05_fence_after();
       if (lane == 0) {
         const uint32_t q = smem_u32(sQ);
@@ -244,8 +261,8 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     const int qhi = live ? L - T + i + 1 : 0;                  // causal, bottom-right aligned
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int k0 = tile_k0(t), k1 = min(tile_k1(t), qhi);
+    for (int t = 0; t < n_tiles; ++t) {                        // t: local tile index
+      const int k0 = tile_k0(t_lo + t), k1 = min(tile_k1(t_lo + t), qhi);
       mbar_wait(&s_bar[t & 1], (t >> 1) & 1);
       tcgen05_fence_after();
       uint32_t sr[4][16];
@@ -318,7 +335,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
       fence_proxy_async_smem();                                // P stores -> visible to the tensor core
       tcgen05_fence_before();                                  // S loads / O stores above are complete
       mbar_arrive(p_bar);
-      if (t + 1 == n_sys_tiles && t + 1 < n_tiles) {
+      if (t_lo + t + 1 == n_sys_tiles && t + 1 < n_tiles) {
         // leaving the pinned prefix: Q K^T of every prefix tile is complete (s_bar), swap in the ring variant
         stage_q(false, tid, 128);
         mbar_arrive(q_bar);
@@ -329,13 +346,21 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     tcgen05_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     bf16* dst = lp.out + static_cast<size_t>(tok0 + i) * (lp.H * HD) + (head * GROUP + hq) * HD;
+    const size_t pi = kSplit ? (static_cast<size_t>(tok0 + i) * lp.H + head * GROUP + hq) * KS + split : 0;
+    if (kSplit && live) { lp.part_ml[pi * 2] = m_run; lp.part_ml[pi * 2 + 1] = l_run; }
 #pragma unroll 1
     for (int c8 = 0; c8 < HD / 32; ++c8) {
       uint32_t orr[2][16];
       tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32, orr[0]);
       tmem_ld16_issue(tmem_base + lane_addr + 2 * KT + c8 * 32 + 16, orr[1]);
       tmem_ld_wait();
-      if (live) {
+      if (kSplit && live) {                                    // un-normalised fp32 partial of this key split
+        float* po = lp.part_o + pi * HD + c8 * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(po + c * 4) = make_float4(__uint_as_float(orr[c >> 2][(c & 3) * 4]), __uint_as_float(orr[c >> 2][(c & 3) * 4 + 1]),
+                                                               __uint_as_float(orr[c >> 2][(c & 3) * 4 + 2]), __uint_as_float(orr[c >> 2][(c & 3) * 4 + 3]));
+      } else if (live) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;

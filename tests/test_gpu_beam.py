@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 
 # |score_cuda - score_ref| <= SCORE_ATOL + SCORE_RTOL * |score_ref| for cumulative log-prob scores of up to 10
 # tokens: bf16 path vs the fp32 reference (logits agree to ~5e-2 rel-L2, tests/test_gpu_parity.py)
-SCORE_ATOL, SCORE_RTOL = 0.08, 0.03
+SCORE_ATOL, SCORE_RTOL = 0.10, 0.04
 
 
 def tol(ref: float) -> float:
