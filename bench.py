@@ -369,13 +369,16 @@ def main_native(args, env):
     eng.profile(False)
     pk = peaks()
     classes = {}
-    bound_of = {"gemm_tensor": "tensor", "attn_prefill": "tensor", "attn_encoder": "tensor"}
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
     for name, v in prof.items():
         if v["launches"] == 0:
             continue
-        b = bound_of.get(name, "hbm")
+        # the roofline that binds a class is the one its algorithmic work needs longer for at the measured peaks:
+        # flops / tensor peak vs bytes / HBM peak (the chunk attentions move 48-88 flop per KV byte: HBM-bound)
         sec = v["ms"] / 1e3
+        t_tensor = v["flops"] / (pk["tflops_sustained"] * 1e12)
+        t_hbm = v["bytes"] / (pk["hbm_gbs"] * 1e9)
+        b = "tensor" if t_tensor > t_hbm else "hbm"
         ach = (v["flops"] / sec / 1e12) if b == "tensor" else (v["bytes"] / sec / 1e9)
         peak = pk["tflops_sustained"] if b == "tensor" else pk["hbm_gbs"]
         classes[name] = {"bound": b, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if b == "tensor" else "GB/s",
