@@ -14,7 +14,7 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
       --log-file $O/launches.csv python bench.py --ncu-step --warmup 1 > $O/ncu_launches.log 2>&1; echo "ncu launches exit=$?"
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:gemm_sk -s 300 -c 8 -f -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit=$?"
+      -k regex:gemm_sk -s 300 -c 4 -f -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit=$?"
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:decode_attention -s 32 -c 2 -f -o $O/prof_decode_attn python bench.py --ncu-step --warmup 1 > $O/ncu_attn.log 2>&1; echo "ncu attn exit=$?"
 fi
@@ -23,4 +23,8 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:prefill_attention_tc -s 2 -c 2 -f -o $O/prof_prefill_attn python bench.py --ncu-step --warmup 1 > $O/ncu_pattn.log 2>&1; echo "ncu prefill attn exit=$?"
   timeout 600 python bench.py --timeline $O/timeline.txt --warmup 2 > $O/timeline.log 2>&1; echo "timeline exit=$?"
+  # beam search (the reference's shipped decoding): bench line + full capture of the shared-prefix group attention
+  timeout 600 python bench.py --beam 4 --steps 4 --warmup 3 --latency-chunks 10 --cpu-baseline-chunks 0 > $O/bench_beam4.json 2> $O/bench_beam4.err; echo "bench beam4 exit=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:decode_attention_group -s 32 -c 1 -f -o $O/prof_group_attn python bench.py --beam 4 --ncu-step --warmup 1 > $O/ncu_gattn.log 2>&1; echo "ncu group attn exit=$?"
 fi

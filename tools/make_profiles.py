@@ -58,6 +58,10 @@ def main(tag):
     if os.path.exists(bench):
         with open(bench) as f, open(os.path.join(PROF, f"{tag}_bench.json"), "w") as g:
             g.write(f.read())
+    beam = os.path.join(OUT, "bench_beam4.json")
+    if os.path.exists(beam):
+        with open(beam) as f, open(os.path.join(PROF, f"{tag}_bench_beam4_64streams.json"), "w") as g:
+            g.write(f.read())
     ll = os.path.join(OUT, "launches.csv")
     if os.path.exists(ll):
         hdr = ("# ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python bench.py --ncu-step --warmup 1\n"
@@ -68,7 +72,8 @@ def main(tag):
     traffic = {}
     for rep, name, title, cls in [("prof_gemm_decode.ncu-rep", "gemm_decode", "weight-streaming GEMMs of two decode layers (o_proj, gate/up, down, qkv; 64 tokens)", "gemm_stream"),
                                   ("prof_decode_attn.ncu-rep", "decode_attention", "decode attention, 64 streams x kv_len ~1001, layers 0-1 of one decode forward", "attn_decode"),
-                                  ("prof_prefill_attn.ncu-rep", "prefill_attention", "tcgen05 chunk-prefill attention, 64 streams x 22 tokens over kv_len ~1023", "attn_prefill")]:
+                                  ("prof_prefill_attn.ncu-rep", "prefill_attention", "tcgen05 chunk-prefill attention, 64 streams x 22 tokens over kv_len ~1023", "attn_prefill"),
+                                  ("prof_group_attn.ncu-rep", "beam_group_attention", "beam search shared-prefix decode attention, 64 sentences x 4 beams, prefix ~1010 keys + 4 private tails", "attn_decode_beam4")]:
         p = os.path.join(OUT, rep)
         if not os.path.exists(p):
             continue
@@ -81,6 +86,8 @@ def main(tag):
             alg = None
             if cls == "gemm_stream":      # o_proj, gate/up, down, qkv weights of a decode layer (bf16) - activations are < 2 %
                 alg = (4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336 + 6144 * 4096) * 2 / 4.0
+            elif cls == "attn_decode_beam4":  # shared prefix once per sentence + one private page pair per beam (<= 32 keys)
+                alg = 64 * (1008 + 4 * 20) * 8 * 128 * 2 * 2
             elif cls in ("attn_decode", "attn_prefill"):   # K and V of 64 streams x ~1001-1023 tokens x 8 kv heads x 128 x bf16
                 alg = 64 * (1001 if cls == "attn_decode" else 1023) * 8 * 128 * 2 * 2
             traffic[cls] = {"dram_bytes_per_launch": sum(tot) / len(tot), "launches_captured": len(tot),
