@@ -196,20 +196,44 @@ class InfiniSST(SpeechToTextAgent):
         self.max_new_tokens = 10 * multiplier
 
     def load_model(self, args):
-        """agents/infinisst.py:130-183.  `args.model_config` is an InfiniSSTConfig (or 'tiny' /
-        'production'); `args.state_dict` a reference-layout state dict (or `args.state_dict_path`)."""
-        cfg = getattr(args, "model_config", None) or "production"
+        """agents/infinisst.py:130-183.  Architecture: `args.model_config` (an InfiniSSTConfig, 'tiny' or
+        'production') when given, otherwise read off the checkpoint itself (`--state-dict-path` shapes +
+        `--model-name` config.json / generation_config.json + `--w2v2-path` arguments + `--length-shrink-cfg`,
+        checkpoint.py).  Weights: `args.state_dict` or `--state-dict-path`, strict like `load_state_dict` (:180).
+        Tokenizer: `args.tokenizer`, else `AutoTokenizer.from_pretrained(--model-name, padding_side="right",
+        use_fast=False)` when that is a local directory (:135-140) followed by the reference's `preprocess`
+        (:177), else the template stand-in."""
+        from . import checkpoint as ck
+        cfg = getattr(args, "model_config", None)
+        sd = getattr(args, "state_dict", None)
+        path = getattr(args, "state_dict_path", None)
+        if sd is None and path:
+            sd = ck.load_reference_state_dict(path)
+        if cfg is None and sd is not None and path:
+            hf, gen = ck.read_hf_config(getattr(args, "model_name", None))
+            w2v2 = getattr(args, "w2v2_path", None)
+            import os
+            wa = ck.read_w2v2_args(w2v2) if w2v2 and os.path.isfile(w2v2) else None
+            cfg = ck.infer_config(sd, block_size=args.block_size, max_cache_size=args.max_cache_size,
+                                  length_shrink_cfg=getattr(args, "length_shrink_cfg", None), xpos=bool(args.xpos),
+                                  rope=bool(args.rope), hf_config=hf, w2v2_args=wa, generation_config=gen)
+            cfg.tpl.system_ids = production_config().tpl.system_ids if cfg.llm.vocab >= 128256 else []
+        cfg = cfg or "production"
         if isinstance(cfg, str):
             cfg = tiny_config() if cfg == "tiny" else production_config()
         cfg.enc.block_size = args.block_size
         cfg.enc.max_cache_size = args.max_cache_size
         cfg.enc.rope, cfg.enc.xpos = bool(args.rope), bool(args.xpos)
-        if cfg.enc.xpos or not cfg.enc.rope:
-            raise NotImplementedError("--xpos 1 / --rope 0 encoder variants are §8f next")
         if args.w2v2_type != "w2v2":
             raise ValueError(f"Unsupported type: {args.w2v2_type}")            # agents/infinisst.py:171
         self.cfg = cfg
-        self.tokenizer = getattr(args, "tokenizer", None) or TemplateTokenizer(cfg)
+        self.tokenizer = getattr(args, "tokenizer", None)
+        if self.tokenizer is None:
+            self.tokenizer = self._hf_tokenizer(getattr(args, "model_name", None))
+        if self.tokenizer is None:
+            self.tokenizer = TemplateTokenizer(cfg)
+        elif not isinstance(self.tokenizer, TemplateTokenizer) and hasattr(self.tokenizer, "add_tokens"):
+            ck.preprocess_tokenizer(self.tokenizer, cfg, self.max_latency_multiplier)       # :177
         self.bad_words_ids = list(getattr(args, "bad_words_ids", []) or [])
         if self.suppress_non_language and not self.bad_words_ids:
             n_vocab = len(self.tokenizer) if hasattr(self.tokenizer, "__len__") else cfg.llm.vocab
@@ -217,12 +241,22 @@ class InfiniSST(SpeechToTextAgent):
         self.model = SpeechLlamaForCausalLM(
             cfg, engine=getattr(args, "engine", None), max_streams=getattr(args, "max_streams", 8),
             max_multiplier=self.max_latency_multiplier, max_beams=self.beam)
-        sd = getattr(args, "state_dict", None)
-        if sd is None and getattr(args, "state_dict_path", None):
-            sd = torch.load(args.state_dict_path, map_location="cpu", weights_only=True)
         if sd is not None:
+            ck.check_state_dict(sd, cfg)
             self.model.load_state_dict(sd)
         self.model.model.inference = True
+        self.llama31 = "3.1" in str(getattr(args, "model_name", ""))         # :183
+
+    @staticmethod
+    def _hf_tokenizer(model_name):
+        """agents/infinisst.py:135-140 for a local model directory (this build never reaches for the hub)."""
+        import os
+        if not model_name or not os.path.isdir(model_name):
+            return None
+        import transformers
+        tok = transformers.AutoTokenizer.from_pretrained(model_name, padding_side="right", use_fast=False)
+        tok.pad_token = "<|finetune_right_pad_id|>"
+        return tok
 
     @staticmethod
     def add_args(parser):

@@ -87,7 +87,7 @@ class FakeTokenizer:
         return " ".join(str(i) for i in ids)
 
 
-def build_reference_agent(cfg, sd):
+def build_reference_agent(cfg, sd, xpos=0, rope=1):
     RS.install()
     import transformers
     from transformers import LlamaConfig
@@ -146,7 +146,7 @@ def build_reference_agent(cfg, sd):
         max_llm_cache_size=g.max_llm_cache_size, always_cache_system_prompt=g.always_cache_system_prompt,
         dpo_sampling=False, model_name="synthetic-llama-3.1", w2v2_path="synthetic", ctc_finetuned=True,
         w2v2_type="w2v2", length_shrink_cfg=adapter, block_size=e.block_size, max_cache_size=e.max_cache_size,
-        xpos=0, rope=1, state_dict_path=sd_path)
+        xpos=xpos, rope=rope, state_dict_path=sd_path)
     # torch.cuda device placement: the agent moves tensors to model.device, which is the CPU here
     agent = ref_agent.InfiniSST(args)          # runs the reference's __init__ and load_model
     os.unlink(sd_path)

@@ -21,7 +21,7 @@ reference code - the same third-party semantics the oracle has to restate anyway
                              MultiheadAttention *constructors and containers only* (their forward methods are
                              replaced by the reference's patch_w2v2), ConvFeatureExtractionModel (layer_norm
                              mode), Fp32LayerNorm, TransposeLast, gelu, utils.softmax, pad_to_multiple, ...
-  rotary_embedding_torch     RotaryEmbedding(dim, use_xpos=False).rotate_queries_with_cached_keys
+  rotary_embedding_torch     RotaryEmbedding(dim, use_xpos).rotate_queries_with_cached_keys (+ xPos get_scale)
   simuleval                  SpeechToTextAgent / AgentStates / ReadAction / WriteAction / entrypoint
   lightning                  LightningModule = nn.Module
   transformers 4.47 names    LlamaSdpaAttention / LlamaFlashAttention2 (placeholders so patch_llm imports),
@@ -267,13 +267,18 @@ class HubertModel(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
-# rotary_embedding_torch stand-in: interleaved pairs, fp32 angles, no xpos
+# rotary_embedding_torch stand-in: interleaved pairs, fp32 angles; xPos as in the
+# library's 0.8 line: scale_d = (2d + 0.4 dim) / (1.4 dim), power = (t - len(t) // 2) / 512 where `t` is the
+# position slice handed to get_scale (so queries are centred on q_len // 2 and keys on k_len // 2),
+# scale repeated per interleaved pair, keys take scale ** -1
 # ------------------------------------------------------------------------------------------------
 class RotaryEmbedding(nn.Module):
-    def __init__(self, dim, use_xpos=False, theta=10000):
+    def __init__(self, dim, use_xpos=False, theta=10000, xpos_scale_base=512):
         super().__init__()
-        assert not use_xpos, "production runs --xpos 0"
+        self.use_xpos = bool(use_xpos)
+        self.scale_base = xpos_scale_base
         self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)))
+        self.register_buffer("scale", (torch.arange(0, dim, 2) + 0.4 * dim) / (1.4 * dim), persistent=False)
 
     @staticmethod
     def _rotate_half(x):
@@ -281,18 +286,29 @@ class RotaryEmbedding(nn.Module):
         x1, x2 = x.unbind(dim=-1)
         return torch.stack((-x2, x1), dim=-1).reshape(*x.shape[:-2], -1)
 
-    def _rotate(self, t, offset):
+    def get_scale(self, t):
+        power = (t - len(t) // 2) / self.scale_base
+        scale = self.scale.float() ** power[:, None]
+        return scale.repeat_interleave(2, dim=-1)
+
+    def _rotate(self, t, offset, scale=1.0):
         n = t.shape[-2]
         pos = torch.arange(n, device=t.device, dtype=torch.float32) + offset
         freqs = torch.einsum("i,j->ij", pos, self.freqs.float())
         freqs = freqs.repeat_interleave(2, dim=-1)
-        out = t.float() * freqs.cos() + self._rotate_half(t.float()) * freqs.sin()
+        out = t.float() * freqs.cos() * scale + self._rotate_half(t.float()) * freqs.sin() * scale
         return out.type_as(t)
 
     def rotate_queries_with_cached_keys(self, q, k, seq_dim=-2):
         q_len, k_len = q.shape[-2], k.shape[-2]
         assert q_len <= k_len
-        return self._rotate(q, k_len - q_len), self._rotate(k, 0)
+        q_scale = k_scale = 1.0
+        if self.use_xpos:
+            seq = torch.arange(k_len, device=q.device, dtype=torch.float32)
+            q_scale = self.get_scale(seq[-q_len:]).type(q.dtype)
+            k_scale = self.get_scale(seq).type(q.dtype)
+            k_scale = k_scale ** -1
+        return self._rotate(q, k_len - q_len, q_scale), self._rotate(k, 0, k_scale)
 
 
 # ------------------------------------------------------------------------------------------------

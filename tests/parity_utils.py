@@ -46,3 +46,21 @@ def tie_aware_match(scores: torch.Tensor, token: int, eps: float) -> bool:
     """Accept `token` if the oracle's processed score for it is within eps of the oracle's max
     (SURVEY §7 hard part 2: near-ties under random weights)."""
     return bool(scores[token] >= scores.max() - eps)
+
+
+ENC_VARIANTS = {"xpos": (True, True, 3.0), "norope": (False, False, 1.0)}     # name -> (xpos, rope, q/k sharpening)
+
+
+def variant_state_dict(cfg, name: str, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Weights of the encoder-variant pins (tests/golden/make_ref_variant_pins.py).  Under the plain synthetic
+    init the encoder's attention is nearly uniform, and xPos - a per-distance rescaling of the scores - moves the
+    features by less than the bf16 tolerance; the xpos variant therefore multiplies the encoder's q / k
+    projections by 3 so that the flag changes the features by ~0.14 rel-L2 (3x the bf16-eager noise)."""
+    from infinisst_b200.synthetic import make_state_dict
+    sd = make_state_dict(cfg, seed=seed)
+    f = ENC_VARIANTS[name][2]
+    if f != 1.0:
+        for k in sd:
+            if "speech_encoder" in k and (".self_attn.q_proj." in k or ".self_attn.k_proj." in k):
+                sd[k] = sd[k] * f
+    return bf16_weights(sd)

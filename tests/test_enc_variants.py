@@ -1,0 +1,150 @@
+"""Encoder flag variants (agents/options.py:32-41): `--xpos 1` (xPos-scaled rotary
+embedding, patch_speech_encoder.py:631,823-824) and `--rope 0` (bf16 sinusoidal table added at the absolute
+frame index, patch_speech_encoder.py:448-461,488-493).
+
+The fixture tests/golden/ref_tiny_enc_variants.npz holds what the reference's own encoder code produced with
+those flags (tests/golden/make_ref_variant_pins.py).  CPU: the oracle reproduces it.  GPU: the CUDA path
+reproduces it (through the C-ABI) within the bf16 tolerance of tests/test_gpu_parity.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from infinisst_b200 import tiny_config
+from infinisst_b200.synthetic import make_audio
+from oracle import infinisst_oracle as O
+from parity_utils import ENC_VARIANTS, rel_l2, variant_state_dict
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PINS = os.path.join(HERE, "golden", "ref_tiny_enc_variants.npz")
+SEG = 15360
+VARIANTS = list(ENC_VARIANTS)
+# rel-L2 of the bf16 CUDA path against the fp32 reference features.  norope: the bound of test_gpu_parity.py.
+# xpos: the pins use 3x sharper encoder attention (parity_utils.variant_state_dict), under which the oracle's own
+# bf16-eager run sits at 0.035-0.055 from its fp32 run; the flag itself moves the features by >= 0.13 from chunk 1 on.
+FEAT_TOL = {"xpos": 7e-2, "norope": 3e-2}
+
+
+@pytest.fixture(scope="module")
+def pins():
+    return np.load(PINS)
+
+
+def _cfg(pins, name):
+    cfg = tiny_config(max_cache_size=int(pins["max_cache"]))
+    cfg.enc.xpos, cfg.enc.rope = ENC_VARIANTS[name][:2]
+    return cfg
+
+
+def _chunks(n):
+    audio = make_audio(n * SEG / 16000.0)
+    for c in range(n):
+        pcm = audio[c * SEG:(c + 1) * SEG][None].clone()
+        if c == 0:
+            pcm = torch.cat([torch.zeros(1, 399), pcm], 1)
+        yield c, pcm
+
+
+@pytest.mark.parametrize("name", VARIANTS)
+def test_oracle_reproduces_reference_variant(pins, name):
+    cfg = _cfg(pins, name)
+    sd = O.cast_state_dict(variant_state_dict(cfg, name), torch.float32)
+    cache = None
+    for c, pcm in _chunks(int(pins["n_chunks"])):
+        feats, cache = O.encode_speech(sd, cfg.enc, pcm, cache)
+        np.testing.assert_allclose(feats[0].numpy(), pins[f"{name}_c{c}_speech_feats"], atol=2e-5, rtol=1e-5)
+
+
+def test_variants_differ_from_the_default_encoder(pins):
+    """The flags change the result by far more than the parity tolerance (so the tests above and below cannot
+    pass by ignoring them): the same weights through the default encoder (--xpos 0 --rope 1) land >= 1.8x the GPU
+    tolerance away from the pinned features."""
+    for name in VARIANTS:
+        cfg = _cfg(pins, name)
+        cfg.enc.xpos, cfg.enc.rope = False, True
+        sd = O.cast_state_dict(variant_state_dict(cfg, name), torch.float32)
+        cache = None
+        for c, pcm in _chunks(int(pins["n_chunks"])):
+            feats, cache = O.encode_speech(sd, cfg.enc, pcm, cache)
+            d = rel_l2(feats[0], torch.from_numpy(pins[f"{name}_c{c}_speech_feats"]))
+            if c >= 1:
+                assert d > 1.8 * FEAT_TOL[name], (name, c, d)
+
+
+def test_sinusoidal_table_is_the_reference_bf16_arithmetic():
+    """patch_speech_encoder.py:448-461: positions are a bfloat16 arange, so above 256 neighbouring frames share
+    a table row - the restatement must keep that."""
+    t = O.sinusoidal_positional_embedding(300, 8, 64)
+    assert t.dtype == torch.bfloat16 and t.shape == (8, 64)
+    assert torch.equal(t[0], t[1])          # 300, 301 -> bf16 300, 300 (spacing 2 above 256)
+    assert not torch.equal(t[1], t[3])
+
+
+def test_xpos_scale_centres():
+    """get_scale is centred on len(t) // 2 of the slice it is given: the middle position has scale 1."""
+    cfg = tiny_config()
+    s = O.xpos_scale(cfg.enc, torch.arange(10.0), 64)
+    assert torch.allclose(s[5], torch.ones(64))
+    assert (s[0] > 1).all() and (s[9] < 1).all()        # base < 1: negative powers grow
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", VARIANTS)
+def test_cuda_reproduces_reference_variant(pins, name):
+    from infinisst_b200.engine import Engine
+    cfg = _cfg(pins, name)
+    sd = variant_state_dict(cfg, name)
+    eng = Engine(cfg, device=0, max_streams=2)
+    eng.load_state_dict(sd)
+    sid = eng.open_stream()
+    worst = 0.0
+    for c, pcm in _chunks(int(pins["n_chunks"])):
+        feats = eng.encode_chunk([sid], pcm, 1, return_feats=True)
+        e = rel_l2(feats[0].cpu(), torch.from_numpy(pins[f"{name}_c{c}_speech_feats"]))
+        worst = max(worst, e)
+        assert e < FEAT_TOL[name], f"{name} chunk {c}: speech features rel_l2 {e}"
+    print(f"{name}: worst speech-feature rel_l2 {worst:.4f}")
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", VARIANTS)
+def test_cuda_variant_batched_equals_single_and_long_stream(pins, name):
+    """Two streams in one batch (one delayed by a chunk) equal their single-stream runs bit for bit; 30 chunks
+    (1440 frames: the 96-frame window slides 28 times, positions pass 256 where the bf16 sinusoid quantises)
+    stay within tolerance of the oracle."""
+    from infinisst_b200.engine import Engine
+    cfg = _cfg(pins, name)
+    sd = variant_state_dict(cfg, name)
+    osd = O.cast_state_dict(sd, torch.float32)
+    eng = Engine(cfg, device=0, max_streams=4)
+    eng.load_state_dict(sd)
+    n = 30
+    chunks = [p for _, p in _chunks(n)]
+    a, b, solo = eng.open_stream(), eng.open_stream(), eng.open_stream()
+    cache = None
+    solo_feats = []
+    for c in range(n):
+        f = eng.encode_chunk([solo], chunks[c], 1, return_feats=True)[0].cpu()
+        solo_feats.append(f)
+        ref, cache = O.encode_speech(osd, cfg.enc, chunks[c], cache)
+        e = rel_l2(f, ref[0])
+        assert e < FEAT_TOL[name], f"{name} chunk {c}: rel_l2 {e} vs oracle"
+    # stream a starts at chunk 0, stream b one call later: after the first call they run as one batch
+    fa = [eng.encode_chunk([a], chunks[0], 1, return_feats=True)[0].cpu()]
+    fb = []
+    for c in range(1, 6):
+        if c == 1:
+            fb.append(eng.encode_chunk([b], chunks[0], 1, return_feats=True)[0].cpu())
+            fa.append(eng.encode_chunk([a], chunks[1], 1, return_feats=True)[0].cpu())
+            continue
+        both = eng.encode_chunk([a, b], torch.cat([chunks[c], chunks[c - 1]], 0), 1, return_feats=True).cpu()
+        fa.append(both[0])
+        fb.append(both[1])
+    for c in range(6):
+        assert torch.equal(fa[c], solo_feats[c]), (name, "a", c)
+    for c in range(5):
+        assert torch.equal(fb[c], solo_feats[c]), (name, "b", c)
+    eng.close()
