@@ -48,6 +48,12 @@ typedef struct isst_config {
   int max_kv_len;      /* largest logical KV length of one stream (RoPE table / page table size) */
   int max_prompt;      /* longest turn prompt in tokens */
   int max_new_tokens;  /* longest generation per call */
+  /* encoder position variants (agents/options.py:32-41; zero = production, scripts/infer/infinisst.sh:70-71):
+   *   enc_xpos    --xpos 1: xPos scaling of rotated q / k, RotaryEmbedding(use_xpos) at patch_speech_encoder.py:631,823-824
+   *   enc_no_rope --rope 0: no rotation; the bf16 sinusoidal table of patch_speech_encoder.py:448-461 is added to
+   *               the frames at their absolute index (:488-493) */
+  int enc_xpos;
+  int enc_no_rope;
 } isst_config;
 
 /* Greedy generation parameters: the kwargs of model.generate at agents/infinisst.py:307-332 that

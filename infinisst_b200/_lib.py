@@ -26,6 +26,7 @@ class IsstConfig(C.Structure):
         ("head_dim", C.c_int), ("ffn", C.c_int), ("vocab", C.c_int), ("rms_eps", C.c_float),
         ("max_streams", C.c_int), ("max_batch", C.c_int), ("max_multiplier", C.c_int), ("kv_pages", C.c_int),
         ("max_kv_len", C.c_int), ("max_prompt", C.c_int), ("max_new_tokens", C.c_int),
+        ("enc_xpos", C.c_int), ("enc_no_rope", C.c_int),
     ]
 
 

@@ -500,14 +500,20 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
 // (prefix + i) % cap.  Interleaved-pair RoPE (rotary_embedding_torch, patch_speech_encoder.py:823-824) at
 // the absolute frame index; `tab` = rope_table_kernel<true> output [n*T][HD/2] (cos, sin).
 // ----------------------------------------------------------------------------------------------
+// xPos (`xpos_base` != nullptr, --xpos 1): rotary_embedding_torch scales the rotated query at window index
+// kept + i by base_d^((kept + i - T/2) / 512) - `get_scale(seq[-q_len:])` is centred on q_len // 2 - with the
+// scale cast to the model dtype first; keys are stored rotated but un-scaled, their window-relative scale is
+// applied per call by enc_xpos_keys_kernel.
 __global__ void enc_rope_append_kernel(bf16* __restrict__ qkv, bf16* k_ring, bf16* v_ring,
                                        const int* __restrict__ slots, const int* __restrict__ prefix,
-                                       const float2* __restrict__ tab, int T, int H, int HD, int cap) {
+                                       const float2* __restrict__ tab, int T, int H, int HD, int cap,
+                                       const float* __restrict__ xpos_base, int max_cache, float xpos_inv_scale_base) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y;
   const int slot = slots[b];
   const int pre = prefix[b];   // per batch entry
+  const int kept = min(pre, max_cache);
   const int chunks = H * HD / 8;
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * chunks; u += gridDim.x * blockDim.x) {
     const int i = u / chunks, c = u % chunks;
@@ -516,13 +522,19 @@ __global__ void enc_rope_append_kernel(bf16* __restrict__ qkv, bf16* k_ring, bf1
     const float2* cs = tab + static_cast<size_t>(b * T + i) * (HD / 2) + d / 2;
     const float2 c0 = cs[0], c1 = cs[1], c2 = cs[2], c3 = cs[3];
     const float cc[4] = {c0.x, c1.x, c2.x, c3.x}, ss[4] = {c0.y, c1.y, c2.y, c3.y};
+    float qs[4] = {1.f, 1.f, 1.f, 1.f};
+    if (xpos_base) {
+      const float power = static_cast<float>(kept + i - T / 2) * xpos_inv_scale_base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qs[j] = bf16_round(powf(xpos_base[d / 2 + j], power));
+    }
     uint4 q = *reinterpret_cast<const uint4*>(row + c * 8);
     uint4 k = *reinterpret_cast<const uint4*>(row + H * HD + c * 8);
     uint32_t qw[4] = {q.x, q.y, q.z, q.w}, kw[4] = {k.x, k.y, k.z, k.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 x = unpack_bf16(qw[j]);
-      qw[j] = pack_bf16(x.x * cc[j] - x.y * ss[j], x.y * cc[j] + x.x * ss[j]);
+      qw[j] = pack_bf16((x.x * cc[j] - x.y * ss[j]) * qs[j], (x.y * cc[j] + x.x * ss[j]) * qs[j]);
       x = unpack_bf16(kw[j]);
       kw[j] = pack_bf16(x.x * cc[j] - x.y * ss[j], x.y * cc[j] + x.x * ss[j]);
     }
@@ -530,6 +542,62 @@ __global__ void enc_rope_append_kernel(bf16* __restrict__ qkv, bf16* k_ring, bf1
     const size_t dst = ((static_cast<size_t>(slot) * H + head) * cap + (pre + i) % cap) * HD + d;
     *reinterpret_cast<uint4*>(k_ring + dst) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
     *reinterpret_cast<uint4*>(v_ring + dst) = *reinterpret_cast<const uint4*>(row + 2 * H * HD + c * 8);
+  }
+}
+
+// xPos key scaling (--xpos 1; not on the production path).  The reference re-scales every cached key on every call
+// by get_scale(seq) ** -1 with seq = [0, L) the indices in the CURRENT window, centred on L // 2
+// (patch_speech_encoder.py:823-824 -> rotate_queries_with_cached_keys): the factor of a key changes as the window
+// slides, so it cannot be baked into the ring.  This pass writes the window's keys, scaled, into a scratch ring of
+// the same geometry (same slot index), which the attention kernel then reads instead of k_ring.
+//   scale = bf16(base_d ^ ((j - L/2) / 512));  k' = bf16(k_rot * bf16(1 / scale))
+__global__ void enc_xpos_keys_kernel(const bf16* __restrict__ k_ring, bf16* __restrict__ k_scaled,
+                                     const int* __restrict__ slots, const int* __restrict__ prefix, int T, int H, int HD,
+                                     int cap, int max_cache, const float* __restrict__ xpos_base, float inv_scale_base) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int slot = slots[b];
+  const int pre = prefix[b];
+  const int kept = min(pre, max_cache);
+  const int L = kept + T;
+  const int ring0 = (pre - kept) % cap;
+  const int cpr = HD / 8;                       // 16-byte chunks per key row
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < H * L * cpr; u += gridDim.x * blockDim.x) {
+    const int c = u % cpr, j = (u / cpr) % L, head = u / (cpr * L);
+    const float power = static_cast<float>(j - L / 2) * inv_scale_base;
+    const size_t off = ((static_cast<size_t>(slot) * H + head) * cap + (ring0 + j) % cap) * HD + c * 8;
+    const uint4 k = *reinterpret_cast<const uint4*>(k_ring + off);
+    uint32_t kw[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float sc = bf16_round(1.f / bf16_round(powf(xpos_base[c * 4 + p], power)));
+      const float2 x = unpack_bf16(kw[p]);
+      kw[p] = pack_bf16(x.x * sc, x.y * sc);
+    }
+    *reinterpret_cast<uint4*>(k_scaled + off) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+  }
+}
+
+// --rope 0 (not on the production path): x[b, i, :] += sinusoidal_positional_embedding(n_steps, T, D)[i]
+// (patch_speech_encoder.py:448-461, 488-493).  The reference forms the table entirely in bfloat16: frequencies
+// exp(bf16(arange(D/2)) * -(ln 1e4 / (D/2 - 1))), positions bf16(arange(n_steps, n_steps + T)) (exact only up to
+// 256), their product, sin | cos - each step rounded to bf16; the sum with the bf16 activations rounds once more.
+__global__ void enc_sinusoid_add_kernel(bf16* __restrict__ x, const int* __restrict__ prefix, int T, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int half = D / 2;
+  const float step = -(logf(10000.f) / static_cast<float>(half - 1));
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < T * D; u += gridDim.x * blockDim.x) {
+    const int i = u / D, d = u % D;
+    const int f = d < half ? d : d - half;
+    const float freq = bf16_round(expf(bf16_round(bf16_round(static_cast<float>(f)) * step)));
+    const float pos = bf16_round(static_cast<float>(prefix[b] + i));
+    const float ang = bf16_round(pos * freq);
+    const float e = bf16_round(d < half ? sinf(ang) : cosf(ang));
+    bf16* px = x + (static_cast<size_t>(b) * T + i) * D + d;
+    *px = __float2bfloat16_rn(__bfloat162float(*px) + e);
   }
 }
 

@@ -187,6 +187,8 @@ struct isst_ctx {
   std::vector<LlmLayerW> llm;
   bf16* embed = nullptr;
   float *enc_inv_freq = nullptr, *llm_inv_freq = nullptr;          // RoPE frequencies (fp32, like the reference modules)
+  float* enc_xpos_base = nullptr;   // --xpos 1: (2d + 0.4 hd) / (1.4 hd) per rotary pair
+  bf16* enc_kx = nullptr;           // --xpos 1: one layer of window keys with the per-call xPos scale applied
   float2 *enc_rope_tab = nullptr, *llm_rope_ring = nullptr, *llm_rope_sys = nullptr;   // (cos, sin) of the new rows
   bf16* lq_sys = nullptr;                                          // q rotated for the pinned prefix keys
   int* d_evicted = nullptr;
@@ -773,6 +775,11 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     ISST_TRY(gemm(ctx, st, plain_view(nxt, M, C), ctx->post_proj, D, ctx->ex, D, 0, e));
   }
   ISST_TRY(tap(ctx, st, "enc_post_proj", ctx->ex, static_cast<size_t>(M) * D * 2));
+  if (c.enc_no_rope) {   // patch_speech_encoder.py:488-493
+    ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * D * 2 * 2);
+    ISST_CUDA(launch_k(ctx, enc_sinusoid_add_kernel, dim3(ceil_div(frames * D, 256), n), dim3(256), 0, st, ctx->ex, d_prefix, frames, D));
+    LAUNCH_CHECK(ctx);
+  }
   // ---- 24 pre-LN layers (E4-E11) ----
   const int blocksize = c.block_size * multiplier;
   {
@@ -796,12 +803,20 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(n) * frames * D * 2 * 4);
       dim3 grid(ceil_div(frames * D / 8, 256), n);
-      ISST_CUDA(launch_k(ctx, enc_rope_append_kernel, grid, dim3(256), 0, st, ctx->eqkv, kr, vr, d_slots, d_prefix, ctx->enc_rope_tab, frames, H, HD, ctx->enc_cap));
+      const float inv_base = 1.f / 512.f;   // rotary_embedding_torch xpos_scale_base
+      ISST_CUDA(launch_k(ctx, enc_rope_append_kernel, grid, dim3(256), 0, st, ctx->eqkv, kr, vr, d_slots, d_prefix, ctx->enc_rope_tab, frames, H, HD, ctx->enc_cap,
+                         static_cast<const float*>(ctx->enc_xpos_base), c.max_cache_size, inv_base));
       LAUNCH_CHECK(ctx);
+      if (c.enc_xpos) {
+        dim3 gx(ceil_div((c.max_cache_size + frames) * D / 8, 256), n);
+        ISST_CUDA(launch_k(ctx, enc_xpos_keys_kernel, gx, dim3(256), 0, st, static_cast<const bf16*>(kr), ctx->enc_kx, d_slots, d_prefix, frames, H, HD,
+                           ctx->enc_cap, c.max_cache_size, static_cast<const float*>(ctx->enc_xpos_base), inv_base));
+        LAUNCH_CHECK(ctx);
+      }
     }
     {
       EncAttnParams ep{};
-      ep.qkv = ctx->eqkv; ep.out = ctx->eattn; ep.k_ring = kr; ep.v_ring = vr; ep.slots = d_slots;
+      ep.qkv = ctx->eqkv; ep.out = ctx->eattn; ep.k_ring = c.enc_xpos ? ctx->enc_kx : kr; ep.v_ring = vr; ep.slots = d_slots;
       ep.prefix = d_prefix;
       ep.T = frames; ep.H = H; ep.cap = ctx->enc_cap; ep.max_cache = c.max_cache_size; ep.blocksize = blocksize;
       LlmAttnParams lp{};
@@ -1282,6 +1297,14 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(alloc_w2d(ctx->lm_head, c.vocab, HID));
   ISST_TRY(dev_alloc(&ctx->embed, static_cast<size_t>(c.vocab) * HID));
   ISST_TRY(dev_alloc(&ctx->enc_inv_freq, D / c.enc_heads / 2));
+  ISST_CHECK(!(c.enc_xpos && c.enc_no_rope), "enc_xpos needs the rotary embedding (enc_no_rope = 0)");
+  if (c.enc_xpos) {
+    const int hd = D / c.enc_heads;
+    std::vector<float> base(hd / 2);
+    for (int d = 0; d < hd / 2; ++d) base[d] = (2.f * d + 0.4f * hd) / (1.4f * hd);   // rotary_embedding_torch `scale` buffer
+    ISST_TRY(dev_alloc(&ctx->enc_xpos_base, hd / 2));
+    ISST_CUDA(cudaMemcpy(ctx->enc_xpos_base, base.data(), base.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   ISST_TRY(dev_alloc(&ctx->llm_inv_freq, c.head_dim / 2));
 
   // ---- stream state ----
@@ -1290,6 +1313,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->enc_layer_elems = static_cast<size_t>(c.max_streams) * D * ctx->enc_cap;
   ISST_TRY(dev_alloc(&ctx->enc_k, ctx->enc_layer_elems * c.enc_layers));
   ISST_TRY(dev_alloc(&ctx->enc_v, ctx->enc_layer_elems * c.enc_layers));
+  if (c.enc_xpos) ISST_TRY(dev_alloc(&ctx->enc_kx, ctx->enc_layer_elems));
   ISST_TRY(dev_alloc(&ctx->d_enc_prefix, c.max_streams));
   // per-batch-entry KV tables (uploaded before every forward): a beam-search batch has streams x beams entries
   const size_t nt = static_cast<size_t>(std::max(c.max_streams, c.max_batch));
@@ -1366,6 +1390,7 @@ void isst_destroy(isst_ctx* ctx) {
   // the context owns every device allocation it made; release the big pools explicitly
   cudaFree(ctx->beam_ws); cudaFree(ctx->beam_count);
   cudaFree(ctx->kv_pool); cudaFree(ctx->enc_k); cudaFree(ctx->enc_v); cudaFree(ctx->embed);
+  cudaFree(ctx->enc_kx); cudaFree(ctx->enc_xpos_base);
   for (auto& w : ctx->llm) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.wgu.ptr); cudaFree(w.wd.ptr); cudaFree(w.rms1); cudaFree(w.rms2); }
   for (auto& w : ctx->enc) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.w1.ptr); cudaFree(w.w2.ptr);
     cudaFree(w.ln1_w); cudaFree(w.ln1_b); cudaFree(w.ln2_w); cudaFree(w.ln2_b); cudaFree(w.bqkv); cudaFree(w.bo); cudaFree(w.b1); cudaFree(w.b2); }
@@ -1408,6 +1433,8 @@ int isst_load_weight(isst_ctx* ctx, const char* name_c, const void* data, const 
     long long ne; numel(shape, ndim, &ne);
     ISST_CHECK(ne == half && dtype == ISST_DTYPE_F32, "inv_freq must be f32 [head_dim / 2]");
     ISST_CUDA(cudaMemcpy(enc ? ctx->enc_inv_freq : ctx->llm_inv_freq, data, half * sizeof(float), cudaMemcpyDefault));
+    // --rope 0: zero frequencies make every (cos, sin) = (1, 0), i.e. q and k pass through the append kernel unrotated
+    if (enc && c.enc_no_rope) ISST_CUDA(cudaMemset(ctx->enc_inv_freq, 0, half * sizeof(float)));
     return done();
   }
   if (starts_with(name, ENC + "feature_extractor.conv_layers.")) {

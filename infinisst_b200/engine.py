@@ -69,6 +69,8 @@ class Engine:
         c.head_dim, c.ffn, c.vocab, c.rms_eps = l.head_dim, l.ffn, l.vocab, l.rms_eps
         c.max_streams, c.max_batch, c.max_multiplier = max_streams, max_batch, max_multiplier
         c.kv_pages, c.max_kv_len, c.max_prompt, c.max_new_tokens = kv_pages, max_kv_len, max_prompt, max_new
+        # with --rope 0 the rotary embedding (and its xPos scaling) is never applied: patch_speech_encoder.py:823-824
+        c.enc_xpos, c.enc_no_rope = int(bool(e.xpos and e.rope)), int(not e.rope)
         self._c = c
         self.max_kv_len = max_kv_len
         self.max_multiplier = max_multiplier

@@ -193,3 +193,76 @@ def test_preprocess_tokenizer_assigns_reference_ids():
     cfg2, _ = _tiny_sd()
     with pytest.raises(ValueError, match="embedding table"):
         ck.preprocess_tokenizer(_ToyTokenizer(base), cfg2, max_multiplier=2)
+
+
+@pytest.mark.gpu
+def test_agent_loads_from_checkpoint_files_like_the_reference(tmp_path):
+    """agents/infinisst.py:130-183 end to end: `--state-dict-path` (an un-pruned Lightning dump), `--model-name`
+    (a directory with config.json + generation_config.json), a HF-style tokenizer that goes through `preprocess`
+    and `apply_chat_template` (+ the agent's `[:, :-1]` / `[:, 25:]` slicing).  No architecture is handed in: it is
+    read off the files.  The stream must equal the one of an agent built from the in-memory config."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_ref_pins import FakeTokenizer
+    from infinisst_b200.agent import InfiniSST
+    from infinisst_b200.synthetic import make_audio
+    from parity_utils import bf16_weights
+
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    torch.save({"model." + k: v.bfloat16() for k, v in sd.items()}, tmp_path / "pytorch_model.bin")
+    d = tmp_path / "Llama-3.1-tiny"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps({
+        "num_attention_heads": cfg.llm.heads, "num_key_value_heads": cfg.llm.kv_heads, "rms_norm_eps": cfg.llm.rms_eps,
+        "rope_theta": cfg.llm.rope_theta, "rope_scaling": dict(cfg.llm.rope_scaling, rope_type="llama3")}))
+    (d / "generation_config.json").write_text(json.dumps({"eos_token_id": cfg.gen.eos_token_ids}))
+
+    class Tok(FakeTokenizer):
+        names = {"<sp_patch>": cfg.tpl.sp_patch_id, "<sp_start>": cfg.tpl.sp_patch_id + 1, "<sp_end>": cfg.tpl.sp_patch_id + 2,
+                 "user": cfg.tpl.user_token_id, "assistant": cfg.tpl.assist_token_id,
+                 "<|start_header_id|>": cfg.tpl.start_header_id, "<|end_header_id|>": cfg.tpl.end_header_id,
+                 "<|eot_id|>": cfg.tpl.eot_id}
+
+        def add_tokens(self, toks, special_tokens=False):
+            return 0                                    # the synthetic vocabulary already holds the 7 speech tokens
+
+        def __len__(self):
+            return cfg.llm.vocab
+
+        def convert_tokens_to_ids(self, t):
+            return [self.names.get(x) for x in t] if isinstance(t, (list, tuple)) else self.names.get(t)
+
+    def make_args(**kw):
+        p = argparse.ArgumentParser()
+        InfiniSST.add_args(p)
+        a = p.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", "96", "--xpos", "0",
+                          "--latency-multiplier", "1", "--max-latency-multiplier", "4", "--max-new-tokens", "10",
+                          "--no-repeat-ngram-size", "5", "--max-llm-cache-size", "150", "--always-cache-system-prompt",
+                          "--beam", "1", "--length-shrink-cfg", "[(128,2,2)] * 2"])
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+
+    ref_agent = InfiniSST(make_args(model_config=cfg, state_dict=sd))
+    agent = InfiniSST(make_args(state_dict_path=str(tmp_path / "pytorch_model.bin"), model_name=str(d), tokenizer=Tok(cfg)))
+    got = agent.cfg
+    assert (got.llm.layers, got.llm.heads, got.llm.kv_heads, got.llm.head_dim, got.llm.vocab) == \
+        (cfg.llm.layers, cfg.llm.heads, cfg.llm.kv_heads, cfg.llm.head_dim, cfg.llm.vocab)
+    assert got.enc.conv_layers == [tuple(x) for x in cfg.enc.conv_layers] and got.gen.eos_token_ids == cfg.gen.eos_token_ids
+    assert (got.llm.user_token_id, got.llm.assist_token_id, got.llm.sp_patch_token_id) == \
+        (cfg.llm.user_token_id, cfg.llm.assist_token_id, cfg.llm.sp_patch_token_id)
+    seg, n = 15360, 8
+    audio = make_audio(n * seg / 16000.0)
+    sa, sb = ref_agent.build_states(), agent.build_states()
+    sa.source_sample_rate = sb.source_sample_rate = 16000
+    for c in range(n):
+        for st in (sa, sb):
+            st.source = audio[: (c + 1) * seg].tolist()
+            st.source_finished = c == n - 1
+        ra, rb = ref_agent.policy(sa), agent.policy(sb)
+        assert sa.target_ids == sb.target_ids, f"chunk {c}"
+        assert sa.past_key_values[0][0].size(2) == sb.past_key_values[0][0].size(2)
+        assert type(ra) is type(rb)
+    assert sb.system_prompt_size == len(cfg.tpl.system_ids) and len(sb.target_ids) > 20
+    assert sb.past_key_values[0][0].size(2) <= 150 + len(cfg.tpl.system_ids)      # the window slid
