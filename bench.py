@@ -249,7 +249,10 @@ def main_native(args, env):
 
     t0 = time.perf_counter()
     K = args.beam
-    eng = Engine(cfg, device=dev, max_streams=2 * S + 2, max_batch=S * K, max_prompt=64, max_beams=K)   # + scratch streams of the stand-alone kernel bench and the latency stream
+    # + scratch streams of the stand-alone kernel bench (skipped above 256 streams: state for 2 x 512 streams does
+    # not fit 180 GB) and the latency stream
+    S_alone = S if S <= 256 else 0
+    eng = Engine(cfg, device=dev, max_streams=S + S_alone + 2, max_batch=S * K, max_prompt=64, max_beams=K)
     sd = make_state_dict(cfg, seed=0, device=f"cuda:{dev}", dtype=torch.bfloat16)
     eng.load_state_dict(sd)
     del sd
@@ -408,6 +411,8 @@ def main_native(args, env):
     # ---- stand-alone decode attention (the HBM-bound kernel the north star names) ----
     dec = {}
     try:
+        if not S_alone:
+            raise RuntimeError("skipped: no scratch streams at this batch size")
         ms = eng.decode_attention_bench(S, 1000, 32)
         by = S * 1001 * cfg.llm.kv_heads * cfg.llm.head_dim * 2 * 2
         dec = {"streams": S, "kv_len": 1000, "ms": ms, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk["hbm_gbs"]}
