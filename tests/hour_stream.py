@@ -5,7 +5,7 @@ prompt, encoder window 576 frames).  Checks, for every chunk: the eviction (kept
 integer model of agents/infinisst.py:337-361 bit-exactly, the KV length stays bounded, the page pool does not
 leak; reports wall time, speech-s/s and chunk latency percentiles as one JSON line.
 
-    python tools/hour_stream.py [--seconds 3600] [--beam 1] > profiles/rNN_hour_stream.json
+    python tests/hour_stream.py [--seconds 3600] [--beam 1] > profiles/rNN_hour_stream.json
 Not a bench value (the oracle integer model is the checker here, tests-style); needs a B200."""
 import argparse
 import json
