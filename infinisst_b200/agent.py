@@ -183,6 +183,8 @@ class InfiniSST(SpeechToTextAgent):
         self.pseudo_batch_size = getattr(args, "pseudo_batch_size", 1)
         self.max_llm_cache_size = args.max_llm_cache_size
         self.always_cache_system_prompt = args.always_cache_system_prompt
+        self.dpo_sampling = getattr(args, "dpo_sampling", False)              # agents/infinisst.py:100-101
+        self.output_file = getattr(args, "output_file", "translations.json")
         self.chunk_latencies: List[float] = []
         self.args = args
         self.load_model(args)
@@ -353,6 +355,15 @@ class InfiniSST(SpeechToTextAgent):
         output_ids = sequence[input_len:-1]                                   # agents/infinisst.py:363
         states.target_ids.extend(output_ids)
         translation = self.tokenizer.decode(output_ids, skip_special_tokens=True).strip().replace("�", "")
+        if getattr(self, "dpo_sampling", False):                              # agents/infinisst.py:369-382
+            states.translations_list.append(f"'{translation}'" if translation else "''")
+            if states.source_finished:
+                try:
+                    with open(self.output_file, "a", encoding="utf-8") as f:
+                        f.write(f"[{', '.join(states.translations_list)}]" + "\n")
+                    states.translations_list = []
+                except Exception as e:  # noqa: BLE001 - the reference reports and carries on
+                    print(f"Error writing translations to file: {e}")
         states.segment_idx += 1
         if translation != "" or states.source_finished:
             return WriteAction(content=translation, finished=states.source_finished)

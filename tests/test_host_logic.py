@@ -153,3 +153,26 @@ def test_suppress_non_language_token_ids():
             return self.words[idx]
     assert non_language_token_ids(Tok(), 7) == [1, 2, 3]
     assert non_language_token_ids(TemplateTokenizer(tiny_config()), 16) == []
+
+
+def test_dpo_sampling_translation_log(tmp_path):
+    """agents/infinisst.py:363-394: drop-last output slice, quoted per-segment translations appended to
+    --output-file as one bracketed line when the source finishes, Read / Write action rule."""
+    from infinisst_b200.agent import InfiniSST, ReadAction, S2TAgentStates, WriteAction
+
+    class Tok:
+        def decode(self, ids, skip_special_tokens=True):
+            return " ".join(f"w{i}" for i in ids)
+
+    agent = InfiniSST.__new__(InfiniSST)                 # host logic only: no engine, no GPU
+    agent.tokenizer, agent.dpo_sampling, agent.output_file = Tok(), True, str(tmp_path / "translations.json")
+    st = S2TAgentStates()
+    a = agent._finish(st, 3, [9, 9, 9, 5, 6, 7])          # prompt of 3, generated 5 6 7: the last token is dropped
+    assert isinstance(a, WriteAction) and a.content == "w5 w6" and not a.finished and st.target_ids == [5, 6]
+    a = agent._finish(st, 3, [9, 9, 9, 7])                # a single generated token: nothing is emitted
+    assert isinstance(a, ReadAction) and st.translations_list == ["'w5 w6'", "''"] and st.segment_idx == 2
+    st.source_finished = True
+    a = agent._finish(st, 3, [9, 9, 9, 8, 1])
+    assert isinstance(a, WriteAction) and a.finished and a.content == "w8"
+    assert open(agent.output_file, encoding="utf-8").read() == "['w5 w6', '', 'w8']\n"
+    assert st.translations_list == []
