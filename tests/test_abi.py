@@ -30,12 +30,36 @@ def test_header_symbols_are_exported_and_bound():
     assert sorted(_lib.SYMBOLS) == declared
 
 
-def test_struct_layout_matches_header():
-    # isst_config: 4 + 3*8 + 4 + 2 + 1 + 3*8 + 7 ints + float + 7 ints, all 4-byte fields
-    n_fields = 1 + 3 * 8 + 4 + 2 + 1 + 3 * 8 + 7 + 1 + 7
-    assert C.sizeof(_lib.IsstConfig) == 4 * n_fields
-    # isst_gen_params: int, int, float, int, int[8], int, (pad), pointer, int, (pad)
-    assert C.sizeof(_lib.IsstGenParams) == 4 * 12 + 4 + 4 + 8 + 8 or C.sizeof(_lib.IsstGenParams) == 72
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every struct field as the C compiler lays out include/infinisst_b200.h, against the
+    ctypes mirrors in _lib.py (field names must match too)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"isst_config": _lib.IsstConfig, "isst_gen_params": _lib.IsstGenParams,
+               "isst_beam_follow": _lib.IsstBeamFollow, "isst_beam_trace": _lib.IsstBeamTrace}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)      # the header is plain C
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    # every field the header declares is mirrored (count the declarators of isst_config)
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct isst_config \{(.*?)\} isst_config;", hdr, flags=re.S).group(1)
+    names = re.findall(r"\b([a-z_0-9]+)(?:\[[A-Z_0-9]+\])?\s*[,;]", body)
+    assert names == [f for f, _ in _lib.IsstConfig._fields_]
 
 
 def test_library_is_sm100a_tcgen05_tma():
