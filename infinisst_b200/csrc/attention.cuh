@@ -429,7 +429,7 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       msafe[h] = (mx[h] == -INFINITY) ? 0.f : mx[h];
-      corr[h] = (m_run[h] == -INFINITY) ? 0.f : exp2f(m_run[h] - msafe[h]);
+      corr[h] = (m_run[h] == -INFINITY) ? 0.f : exp2_fast(m_run[h] - msafe[h]);
       m_run[h] = mx[h];
       l_run[h] *= corr[h];
     }
@@ -442,8 +442,8 @@ chunk_attention_kernel(const EncAttnParams ep, const LlmAttnParams lp) {
     float ls[2] = {0.f, 0.f};
 #pragma unroll
     for (int n = 0; n < KT / 8; ++n) {
-      const float p0 = exp2f(s[n][0] - msafe[0]), p1 = exp2f(s[n][1] - msafe[0]);
-      const float p2 = exp2f(s[n][2] - msafe[1]), p3 = exp2f(s[n][3] - msafe[1]);
+      const float p0 = exp2_fast(s[n][0] - msafe[0]), p1 = exp2_fast(s[n][1] - msafe[0]);
+      const float p2 = exp2_fast(s[n][2] - msafe[1]), p3 = exp2_fast(s[n][3] - msafe[1]);
       ls[0] += p0 + p1;
       ls[1] += p2 + p3;
       // C fragments of two adjacent n8 tiles form the A fragment of one k16 step
@@ -722,7 +722,7 @@ __global__ void decode_combine_kernel(const float* __restrict__ part_o, const fl
   for (int s = 0; s < splits; ++s) {
     const size_t pi = static_cast<size_t>(bh) * splits + s;
     const float pm = part_ml[pi * 2];
-    const float w = (pm == -INFINITY) ? 0.f : exp2f(pm - ms);
+    const float w = (pm == -INFINITY) ? 0.f : exp2_fast(pm - ms);
     ll += w * part_ml[pi * 2 + 1];
     if (d < HD) oo += w * part_o[pi * HD + d];
   }

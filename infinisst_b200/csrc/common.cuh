@@ -66,6 +66,13 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// 2^x for softmax probabilities: one MUFU.EX2 (ex2.approx.ftz) instead of exp2f's denormal-safe sequence; results
+// below 2^-126 flush to zero, -inf gives 0
+__device__ __forceinline__ float exp2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // start while its predecessor in the stream is still running; everything it does before pdl_wait() overlaps the

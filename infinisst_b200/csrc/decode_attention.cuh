@@ -333,10 +333,10 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     const float msafe = (mx == -INFINITY) ? 0.f : mx;
-    const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - msafe);
+    const float corr = (m_run == -INFINITY) ? 0.f : exp2_fast(m_run - msafe);
     m_run = mx;
-    const float p00 = exp2f(s[0][0] - msafe), p01 = exp2f(s[0][1] - msafe);
-    const float p10 = exp2f(s[1][0] - msafe), p11 = exp2f(s[1][1] - msafe);
+    const float p00 = exp2_fast(s[0][0] - msafe), p01 = exp2_fast(s[0][1] - msafe);
+    const float p10 = exp2_fast(s[1][0] - msafe), p11 = exp2_fast(s[1][1] - msafe);
     l_run = l_run * corr + (p00 + p01 + p10 + p11);
     const uint32_t pb0 = pack_bf16(p00, p01);     // P^T B fragment: keys 2*t4, 2*t4+1 of query g
     const uint32_t pb1 = pack_bf16(p10, p11);     //                 keys 8 + 2*t4, +1
@@ -390,7 +390,7 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float wm = sm_m[w * GROUP + hq];
-      const float wgt = (wm == -INFINITY) ? 0.f : exp2f(wm - ms);
+      const float wgt = (wm == -INFINITY) ? 0.f : exp2_fast(wm - ms);
       sm_w[w * GROUP + hq] = wgt;
       ll += wgt * sm_l[w * GROUP + hq];
     }

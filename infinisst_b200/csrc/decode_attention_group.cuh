@@ -206,10 +206,10 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       const float msafe = (mx == -INFINITY) ? 0.f : mx;
-      corr[h] = (m_run[h] == -INFINITY) ? 0.f : exp2f(m_run[h] - msafe);
+      corr[h] = (m_run[h] == -INFINITY) ? 0.f : exp2_fast(m_run[h] - msafe);
       m_run[h] = mx;
-      pr[h][0] = exp2f(s[0][2 * h] - msafe); pr[h][1] = exp2f(s[0][2 * h + 1] - msafe);
-      pr[h][2] = exp2f(s[1][2 * h] - msafe); pr[h][3] = exp2f(s[1][2 * h + 1] - msafe);
+      pr[h][0] = exp2_fast(s[0][2 * h] - msafe); pr[h][1] = exp2_fast(s[0][2 * h + 1] - msafe);
+      pr[h][2] = exp2_fast(s[1][2 * h] - msafe); pr[h][3] = exp2_fast(s[1][2 * h + 1] - msafe);
       l_run[h] = l_run[h] * corr[h] + ((pr[h][0] + pr[h][1]) + (pr[h][2] + pr[h][3]));
     }
     // P^T B fragments: keys (2*t4, 2*t4+1) and (8 + 2*t4, +1) of query g (tile 0) / g + 8 (tile 1)
@@ -265,7 +265,7 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float wm = sm_m[w * ROWS + r];
-      const float wgt = (wm == -INFINITY) ? 0.f : exp2f(wm - ms);
+      const float wgt = (wm == -INFINITY) ? 0.f : exp2_fast(wm - ms);
       sm_w[w * ROWS + r] = wgt;
       ll += wgt * sm_l[w * ROWS + r];
     }

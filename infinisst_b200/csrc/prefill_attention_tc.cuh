@@ -294,7 +294,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
       float corr = 1.f;
       const bool raise = mx > m_run + kPaRescaleThreshold || (m_run == -INFINITY && mx != -INFINITY);
       if (raise) {
-        corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - mx);
+        corr = (m_run == -INFINITY) ? 0.f : exp2_fast(m_run - mx);
         m_run = mx;
         l_run *= corr;
       }
@@ -324,8 +324,8 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           const int idx = c * 8 + e2 * 2;
-          const float p0 = exp2f(__uint_as_float(sr[idx >> 4][idx & 15]) - msafe);
-          const float p1 = exp2f(__uint_as_float(sr[(idx + 1) >> 4][(idx + 1) & 15]) - msafe);
+          const float p0 = exp2_fast(__uint_as_float(sr[idx >> 4][idx & 15]) - msafe);
+          const float p1 = exp2_fast(__uint_as_float(sr[(idx + 1) >> 4][(idx + 1) & 15]) - msafe);
           ls += p0 + p1;
           pk[e2] = pack_bf16(p0, p1);
         }
