@@ -22,9 +22,19 @@ ls -la $O
 if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:prefill_attention_tc -s 2 -c 2 -f -o $O/prof_prefill_attn python bench.py --ncu-step --warmup 1 > $O/ncu_pattn.log 2>&1; echo "ncu prefill attn exit=$?"
+  # tensor-bound GEMMs: the 4 GEMMs of one prefill layer (1408 tokens).  One step launches 106 gemm_sk kernels before
+  # the LLM prefill (6 conv + post_proj + 24 x 4 encoder + 2 adapter + proj); skip into prefill layer 1
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:gemm_sk -s 110 -c 4 -f -o $O/prof_gemm_prefill python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm_prefill.log 2>&1; echo "ncu gemm prefill exit=$?"
   timeout 600 python bench.py --timeline $O/timeline.txt --warmup 2 > $O/timeline.log 2>&1; echo "timeline exit=$?"
   # beam search (the reference's shipped decoding): bench line + full capture of the shared-prefix group attention
   timeout 600 python bench.py --beam 4 --steps 4 --warmup 3 --latency-chunks 10 --cpu-baseline-chunks 0 > $O/bench_beam4.json 2> $O/bench_beam4.err; echo "bench beam4 exit=$?"
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:decode_attention_group -s 32 -c 1 -f -o $O/prof_group_attn python bench.py --beam 4 --ncu-step --warmup 1 > $O/ncu_gattn.log 2>&1; echo "ncu group attn exit=$?"
 fi
+# digest on the box (the raw reports of a full round exceed the 64 MiB gpurun copies back), keep only the summaries
+if [ "${NCU:-1}" = "1" ]; then
+  PROF_OUT=$O/profiles python tools/make_profiles.py ${TAG:-round} > $O/make_profiles.log 2>&1; echo "digest exit=$?"
+  rm -f $O/*.ncu-rep
+fi
+du -sh $O

@@ -3,7 +3,8 @@
   <tag>_launch_list.txt         ncu launch list of one step, grouped by (kernel, grid)
   <tag>_ncu_full_<name>.txt     per-launch summary of the `ncu --set full` captures (time, DRAM bytes, throughput, occupancy limits)
   traffic.json                  measured DRAM bytes per launch of each captured kernel class (read by bench.py -> roofline.traffic)
-Usage: python tools/make_profiles.py r01h
+Usage: python tools/make_profiles.py r01h          (PROF_OUT=gpurun_out/profiles to digest on the GPU box: the raw
+                                                   .ncu-rep files of a full round exceed what gpurun copies back)
 """
 import csv
 import io
@@ -14,8 +15,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+PROF = os.environ.get("PROF_OUT") or os.path.join(ROOT, "profiles")     # PROF_OUT: digest on the GPU box into gpurun_out/
+WANT = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_uniform.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
         "launch__shared_mem_per_block", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
@@ -71,6 +73,7 @@ def main(tag):
         open(os.path.join(PROF, f"{tag}_launch_list.txt"), "w").write(txt)
     traffic = {}
     for rep, name, title, cls in [("prof_gemm_decode.ncu-rep", "gemm_decode", "weight-streaming GEMMs of two decode layers (o_proj, gate/up, down, qkv; 64 tokens)", "gemm_stream"),
+                                  ("prof_gemm_prefill.ncu-rep", "gemm_prefill", "tensor-bound GEMMs of one prefill layer (64 streams x 22 = 1408 tokens: o_proj / gate-up / down / qkv order as captured)", "gemm_tensor"),
                                   ("prof_decode_attn.ncu-rep", "decode_attention", "decode attention, 64 streams x kv_len ~1001, layers 0-1 of one decode forward", "attn_decode"),
                                   ("prof_prefill_attn.ncu-rep", "prefill_attention", "tcgen05 chunk-prefill attention, 64 streams x 22 tokens over kv_len ~1023", "attn_prefill"),
                                   ("prof_group_attn.ncu-rep", "beam_group_attention", "beam search shared-prefix decode attention, 64 sentences x 4 beams, prefix ~1010 keys + 4 private tails", "attn_decode_beam4")]:
