@@ -148,3 +148,42 @@ def test_cuda_variant_batched_equals_single_and_long_stream(pins, name):
     for c in range(5):
         assert torch.equal(fb[c], solo_feats[c]), (name, "b", c)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_agent_flags_reach_the_engine():
+    """`--xpos` defaults to 1 in the reference's argparse (agents/options.py:32-36) and `--rope 0` switches the
+    rotary embedding off: the agent must hand both to the library (isst_config.enc_xpos / enc_no_rope), and
+    `--xpos 1 --rope 0` is the sinusoidal encoder (the rotary module is never applied, patch_speech_encoder.py:823)."""
+    import argparse
+    from infinisst_b200.agent import InfiniSST
+
+    def build(extra):
+        cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+        p = argparse.ArgumentParser()
+        InfiniSST.add_args(p)
+        args = p.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", "96",
+                             "--latency-multiplier", "1", "--max-latency-multiplier", "1", "--max-new-tokens", "10",
+                             "--no-repeat-ngram-size", "5", "--max-llm-cache-size", "150", "--always-cache-system-prompt",
+                             "--beam", "1"] + extra)
+        args.model_config, args.state_dict = cfg, variant_state_dict(cfg, "xpos")
+        return InfiniSST(args)
+
+    seg = SEG
+    audio = make_audio(3 * seg / 16000.0)
+    outs = {}
+    for name, extra, want in [("default", [], (1, 0)), ("xpos0", ["--xpos", "0"], (0, 0)),
+                              ("norope", ["--rope", "0"], (0, 1))]:
+        agent = build(extra)
+        c = agent.model.engine._c
+        assert (c.enc_xpos, c.enc_no_rope) == want, name
+        st = agent.build_states()
+        st.source_sample_rate = 16000
+        for k in range(3):
+            st.source = audio[: (k + 1) * seg].tolist()
+            agent.policy(st)
+        outs[name] = list(st.target_ids)
+        st.reset()
+        agent.model.engine.close()
+    assert len(outs["default"]) > 10
+    assert outs["default"] != outs["xpos0"] or outs["default"] != outs["norope"]     # the flags change the stream
