@@ -6,8 +6,9 @@ agents/options.py:1-125).  Differences, each deliberate:
     reference's beam search with KV hand-back (patch_hf.py:43-302, 687-967) on the CUDA path;
   * `cache_checkpoints` and `system_prompt_size` live on the per-stream states (quirk Q3) so several
     streams can share one agent/engine;
-  * `policy_batch` advances many independent streams in lock-step (the reference can only tile one
-    stream, agents/infinisst.py:291-301).
+  * `policy_batch` advances many independent streams per call (the reference can only tile one
+    stream, agents/infinisst.py:291-301); streams may join a running batch at any call (their first chunk, with the
+    long system + turn prompt, shares the batch with later turns of the others: right-padded ids + attention_mask).
 SimulEval is imported when present; otherwise light stand-ins keep the agent usable and testable.
 """
 from __future__ import annotations
@@ -298,7 +299,7 @@ class InfiniSST(SpeechToTextAgent):
         parser.add_argument("--pseudo-batch-size", type=int, default=1)
 
     # ---------------------------------------------------------------- per-chunk pieces
-    def _prepare_speech(self, states) -> torch.Tensor:
+    def _prepare_speech(self, states, explicit_offset: bool = True) -> torch.Tensor:
         """agents/infinisst.py:200-223; returns float32 [1, n] on the host (the bf16 cast of :222
         happens on the device inside conv0)."""
         sp_seg_frame = int(self.args.block_size // 4 * 0.08 * 16000)
@@ -311,7 +312,7 @@ class InfiniSST(SpeechToTextAgent):
         if source.size(0) % seg != 0:
             n_pad = seg - source.size(0) % seg
             source = torch.cat([source, torch.zeros(n_pad)], dim=0)
-        if states.src_len == 0:
+        if states.src_len == 0 and explicit_offset:
             source = torch.cat([torch.zeros(79 + 320), source], dim=0)
         states.src_len = len(states.source)
         return source.unsqueeze(0)
@@ -393,29 +394,39 @@ class InfiniSST(SpeechToTextAgent):
         with synchronized_timer("generate", self.chunk_latencies):
             sts = [states_list[i] for i in run]
             first = [st.speech_cache is None for st in sts]
-            if any(first) != all(first):
-                raise ValueError("a lock-step batch must not mix first chunks with later chunks")
-            speech = torch.cat([self._prepare_speech(st) for st in sts], dim=0)
-            ids = torch.cat([self._prepare_inputs(st) for st in sts], dim=0)
+            mixed = any(first) != all(first)
+            # streams may join a running batch: a joining stream brings the long first-chunk prompt (system + turn)
+            # and its 79+320 zero offset is the library's zero carried tail, so every row has the same sample count
+            speech = torch.cat([self._prepare_speech(st, explicit_offset=not mixed) for st in sts], dim=0)
+            rows = [self._prepare_inputs(st)[0] for st in sts]
+            lens = [int(r.numel()) for r in rows]
+            ids = torch.full((len(rows), max(lens)), int(self.tokenizer.pad_token_id), dtype=torch.long)
+            mask = torch.zeros(len(rows), max(lens), dtype=torch.long)
+            for j, r in enumerate(rows):
+                ids[j, :lens[j]] = r
+                mask[j, :lens[j]] = 1
             enc = [st.target_ids[-self.no_repeat_ngram_lookback:] for st in sts]
+            sizes = {st.system_prompt_size for st in sts}
+            if self.always_cache_system_prompt and len(sizes) != 1:
+                raise ValueError("streams of one batch must share the system prompt length")
             pin = sts[0].system_prompt_size if self.always_cache_system_prompt else 0
-            outputs = self._generate(sts, ids, speech, enc, pin)
+            outputs = self._generate(sts, ids, speech, enc, pin, mask if min(lens) != max(lens) else None)
             for st in sts:
                 st.past_key_values = st.speech_cache
                 self._evict(st)
         for j, i in enumerate(run):
             seq = [t for t in outputs.sequences[j].tolist()]
             n_gen = self._n_generated[j]
-            seq = seq[: ids.shape[1] + n_gen]
-            actions[i] = self._finish(states_list[i], ids.shape[1], seq)
+            seq = seq[: lens[j] + n_gen]
+            actions[i] = self._finish(states_list[i], lens[j], seq)
         return actions
 
-    def _generate(self, sts, ids, speech, enc, pin):
+    def _generate(self, sts, ids, speech, enc, pin, attention_mask=None):
         """model.generate with the kwargs of agents/infinisst.py:307-332 (ragged `encoder_input_ids`
         are passed per stream instead of one padded tensor)."""
         enc_t = enc if any(len(e) for e in enc) else None
         out = self.model.generate(
-            attention_mask=None, input_ids=ids, speech_batch=speech, do_sample=False, top_p=1.0, top_k=0,
+            attention_mask=attention_mask, input_ids=ids, speech_batch=speech, do_sample=False, top_p=1.0, top_k=0,
             epsilon_cutoff=0.0, temperature=1.0, num_beams=self.beam, max_new_tokens=self.max_new_tokens,
             num_return_sequences=1, encoder_input_ids=enc_t, encoder_no_repeat_ngram_size=self.no_repeat_ngram_size,
             no_repeat_ngram_size=self.no_repeat_ngram_size, repetition_penalty=self.repetition_penalty,

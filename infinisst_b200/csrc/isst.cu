@@ -1609,12 +1609,14 @@ int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   ISST_CHECK(multiplier >= 1 && multiplier <= ctx->cfg.max_multiplier, "multiplier out of range");
   const int n_new = ctx->cfg.block_size * multiplier * ctx->total_stride;
-  bool fresh = ctx->streams[stream_ids[0]].enc_prefix == 0;
-  for (int b = 0; b < n; ++b)
-    ISST_CHECK((ctx->streams[stream_ids[b]].enc_prefix == 0) == fresh, "batch mixes fresh and running streams");
+  // A fresh stream's carried tail is zero (isst_stream_open), which IS the reference's 79+320 zero offset of the first
+  // chunk: fresh and running streams may share a batch as long as every row brings exactly n_new samples.  The
+  // explicit-offset form (n_new + 79+320 samples, as agents/infinisst.py:216-218 builds it) needs an all-fresh batch.
+  bool fresh = true;
+  for (int b = 0; b < n; ++b) fresh = fresh && ctx->streams[stream_ids[b]].enc_prefix == 0;
   const bool with_offset = fresh && n_samples == n_new + ctx->n_tail;
   ISST_CHECK(n_samples == n_new || with_offset,
-             "n_samples must be block_size*multiplier*320 (+ 79+320 on the first chunk of a stream)");
+             "n_samples must be block_size*multiplier*320 (+ 79+320 only when every stream of the batch is at its first chunk)");
   ISST_CUDA(cudaStreamSynchronize(st));   // the pinned metadata region below may still be in flight from a previous call
   MetaBuilder mb{ctx};
   const size_t o_slots = mb.alloc(n), o_prefix = mb.alloc(n);

@@ -190,7 +190,13 @@ class SpeechLlamaForCausalLM:
                                       "(agents/infinisst.py:319-320 passes the same value)")
         B = input_ids.shape[0]
         handles = self._handles(states, past_key_values, B)
-        ids = [input_ids[b].tolist() for b in range(B)]
+        if attention_mask is not None:
+            # ragged prompts, right-padded as the agent's tokenizer pads (padding_side="right", agents/infinisst.py:137):
+            # a stream at its first chunk (system + turn) next to streams in later turns
+            lens = attention_mask.to(torch.long).sum(dim=1).tolist()
+            ids = [input_ids[b, :lens[b]].tolist() for b in range(B)]
+        else:
+            ids = [input_ids[b].tolist() for b in range(B)]
         self.model.speech_encoder.set_blocksize(multiplier)
         self.engine.encode_chunk([h.sid for h in handles], speech_batch.float(), multiplier)
         enc = [[] for _ in range(B)]

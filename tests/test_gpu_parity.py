@@ -470,3 +470,123 @@ def test_profile_counters(op_engine):
     assert prof["attn_encoder"]["launches"] == cfg.enc.layers and prof["attn_prefill"]["launches"] == cfg.llm.layers
     assert all(v["ms"] >= 0 for v in prof.values())
     eng.close()
+
+
+def test_streams_join_a_running_batch():
+    """Continuous serving: streams arrive at different times and share the batched calls from then on - a joining
+    stream's first chunk (61-token system + turn prompt, 79+320 zero offset = the library's zero carried tail) runs
+    in the same batch as 22-token later turns of the others (right-padded ids + attention_mask through
+    `model.generate`).  Every stream is checked against ITS OWN oracle: teacher-forced tokens, step logits, KV
+    lengths, evictions - exactly as if it ran alone."""
+    from infinisst_b200.agent import S2TAgentStates, evict_plan
+    from infinisst_b200.model import SpeechLlamaForCausalLM
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=4)
+    eng.debug(True)
+    model = SpeechLlamaForCausalLM(cfg, engine=eng)
+    g = cfg.gen
+    n_calls, joins = 8, [0, 1, 3]
+    audios = [make_audio(n_calls * SEG / 16000.0, seed=100 + j) for j in range(len(joins))]
+    orcs = [OracleStream(cfg, sd) for _ in joins]
+    states = [S2TAgentStates() for _ in joins]
+    free0 = eng.pages_free()
+    evictions = 0
+    for call in range(n_calls):
+        live = [j for j, start in enumerate(joins) if call >= start]
+        recs, rows, forced = {}, [], []
+        for j in live:
+            c = call - joins[j]
+            recs[j] = orcs[j].chunk(audios[j][: (c + 1) * SEG].tolist())
+            ids = O.build_prompt(cfg.tpl, c == 0)
+            rows.append(ids)
+            forced.append(recs[j][1].sequences[0][len(ids):])
+            if c == 0:
+                states[j].system_prompt_size = len(cfg.tpl.system_ids)
+        width = max(len(r) for r in rows)
+        ids_t = torch.full((len(live), width), g.pad_token_id, dtype=torch.long)
+        mask = torch.zeros(len(live), width, dtype=torch.long)
+        for k, r in enumerate(rows):
+            ids_t[k, :len(r)] = torch.tensor(r)
+            mask[k, :len(r)] = 1
+        # every row brings exactly one chunk of samples: the joining stream's zero offset is its zero carried tail
+        pcm = torch.cat([audios[j][(call - joins[j]) * SEG:(call - joins[j] + 1) * SEG][None] for j in live], 0)
+        out = model.generate(attention_mask=mask, input_ids=ids_t, speech_batch=pcm, num_beams=1,
+                             max_new_tokens=g.max_new_tokens, encoder_input_ids=[states[j].target_ids[-100:] for j in live],
+                             encoder_no_repeat_ngram_size=g.no_repeat_ngram_size, no_repeat_ngram_size=g.no_repeat_ngram_size,
+                             repetition_penalty=g.repetition_penalty, pad_token_id=g.pad_token_id,
+                             states=[states[j] for j in live], multiplier=1, forced_tokens=forced,
+                             pin_prefix=len(cfg.tpl.system_ids))
+        logits = eng.read_tap("step_logits", torch.float32).view(g.max_new_tokens, len(live), cfg.llm.vocab)
+        for k, j in enumerate(live):
+            rec = recs[j][1]
+            assert out.generated[k] == forced[k], (call, j)
+            assert out.sequences[k, :len(rows[k]) + len(forced[k])].tolist() == rows[k] + forced[k]
+            for s_ in range(len(rec.step_logits)):
+                assert rel_l2(logits[s_, k], rec.step_logits[s_][0]) < LOGIT_TOL, (call, j, s_)
+            st = states[j]
+            st.target_ids.extend(recs[j][0])
+            st.past_key_values = st.speech_cache
+            cur = st.speech_cache.kv_len
+            plan = evict_plan(st, cur, g.max_llm_cache_size, g.always_cache_system_prompt)
+            if plan is not None:
+                eng.kv_evict(st.speech_cache.sid, plan[0], plan[1])
+                evictions += 1
+            log = orcs[j].st.kv_log[-1]
+            assert cur == log["cur"] and st.speech_cache.kv_len == log["after"], (call, j)
+            assert st.speech_cache.n_steps == orcs[j].st.enc_cache.n_steps
+    assert evictions >= 4
+    for st in states:
+        st.speech_cache.close()
+    assert eng.pages_free() == free0
+    eng.close()
+
+
+def test_agent_policy_batch_accepts_joining_streams():
+    """The agent-level form of the above: `policy_batch` with streams that start at different calls returns one
+    action per stream, keeps every KV window bounded and gives every page back."""
+    import argparse
+    from infinisst_b200.agent import InfiniSST
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    p = argparse.ArgumentParser()
+    InfiniSST.add_args(p)
+    args = p.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", "96", "--xpos", "0",
+                         "--latency-multiplier", "1", "--max-latency-multiplier", "1", "--max-new-tokens", "10",
+                         "--no-repeat-ngram-size", "5", "--max-llm-cache-size", "150", "--always-cache-system-prompt",
+                         "--beam", "1"])
+    args.model_config, args.state_dict, args.max_streams = cfg, sd, 4
+    agent = InfiniSST(args)
+    free0 = agent.model.engine.pages_free()
+    n_calls, joins = 8, [0, 1, 3]
+    audios = [make_audio(n_calls * SEG / 16000.0, seed=100 + j) for j in range(len(joins))]
+    states = [agent.build_states() for _ in joins]
+    solo_first = []
+    for j in range(len(joins)):          # each stream's first chunk alone (the explicit-offset form of the reference)
+        st = agent.build_states()
+        st.source_sample_rate = 16000
+        st.source = audios[j][:SEG].tolist()
+        agent.policy(st)
+        solo_first.append(list(st.target_ids))
+        st.reset()
+    for st in states:
+        st.source_sample_rate = 16000
+    for call in range(n_calls):
+        live = [j for j, start in enumerate(joins) if call >= start]
+        for j in live:
+            states[j].source = audios[j][: (call - joins[j] + 1) * SEG].tolist()
+            states[j].source_finished = call == n_calls - 1
+        acts = agent.policy_batch([states[j] for j in live])
+        assert len(acts) == len(live) and all(a is not None for a in acts)
+        for j in live:
+            if call == joins[j] and j > 0:
+                # joined a running batch: same emitted ids as alone up to the first near-tie (random weights)
+                a, b = states[j].target_ids, solo_first[j]
+                same = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+                assert same >= min(len(a), len(b)) - 3, (j, a, b)
+            assert states[j].past_key_values[0][0].size(2) <= 150 + 40
+    assert all(len(st.target_ids) > 20 for st in states)
+    for st in states:
+        st.reset()
+    assert agent.model.engine.pages_free() == free0
+    agent.model.engine.close()
