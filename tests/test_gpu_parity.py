@@ -542,9 +542,10 @@ def test_streams_join_a_running_batch():
     eng.close()
 
 
-def test_agent_policy_batch_accepts_joining_streams():
+@pytest.mark.parametrize("beam", [1, 4], ids=["greedy", "beam4"])
+def test_agent_policy_batch_accepts_joining_streams(beam):
     """The agent-level form of the above: `policy_batch` with streams that start at different calls returns one
-    action per stream, keeps every KV window bounded and gives every page back."""
+    action per stream, keeps every KV window bounded and gives every page back (greedy and the shipped `--beam 4`)."""
     import argparse
     from infinisst_b200.agent import InfiniSST
     cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
@@ -554,7 +555,7 @@ def test_agent_policy_batch_accepts_joining_streams():
     args = p.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", "96", "--xpos", "0",
                          "--latency-multiplier", "1", "--max-latency-multiplier", "1", "--max-new-tokens", "10",
                          "--no-repeat-ngram-size", "5", "--max-llm-cache-size", "150", "--always-cache-system-prompt",
-                         "--beam", "1"])
+                         "--beam", str(beam)])
     args.model_config, args.state_dict, args.max_streams = cfg, sd, 4
     agent = InfiniSST(args)
     free0 = agent.model.engine.pages_free()
