@@ -148,6 +148,13 @@ int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids
                  const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
                  void* cuda_stream);
 
+/* The same forward with the reference's own output shape: logits of EVERY position (model/llm.py:236-237 applies
+ * lm_head to all T rows; CausalLMOutputWithPast.logits is [B, T, vocab]), packed [sum(lens)][vocab] f32 in stream
+ * order.  For scoring / teacher-forced evaluation; generation only ever reads the last row (isst_forward). */
+int isst_forward_all(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                     const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
+                     void* cuda_stream);
+
 /* KV length (past_key_values[0][0].size(2), agents/infinisst.py:337) and sliding-window eviction
  * (agents/infinisst.py:354-361): drop the logical tokens [keep_prefix, drop_upto).  Page-table edit,
  * no data movement.  keep_prefix must be 0 or the stream's pinned prefix. */

@@ -68,6 +68,7 @@ SYMBOLS = {
                                 C.POINTER(IsstBeamFollow), _I32P, _IP, C.POINTER(C.c_float), C.POINTER(IsstBeamTrace),
                                 _P]),
     "isst_forward": (_I, [_P, _I, _IP, _I32P, _IP, _I32P, _P, _I, _P, _P]),
+    "isst_forward_all": (_I, [_P, _I, _IP, _I32P, _IP, _I32P, _P, _I, _P, _P]),
     "isst_kv_len": (_I, [_P, _I, _IP]),
     "isst_kv_evict": (_I, [_P, _I, _I, _I]),
     "isst_enc_steps": (_I, [_P, _I, _IP]),

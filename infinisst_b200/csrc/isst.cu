@@ -213,6 +213,8 @@ struct isst_ctx {
   int speech_rows_per_stream = 0;
   bf16 *lx = nullptr, *lh = nullptr, *lqkv = nullptr, *lattn = nullptr, *lgu = nullptr, *llast = nullptr;
   float* logits = nullptr;
+  float* logits_all = nullptr;      // isst_forward_all: [rows][vocab], grown on demand
+  size_t logits_all_rows = 0;
   SelectWs sel_ws{nullptr, nullptr, nullptr};
   float *part_o = nullptr, *part_ml = nullptr;
   int decode_splits = 1;
@@ -895,6 +897,7 @@ struct LlmBatch {
   const int* d_last_row = nullptr;
   const int* d_active = nullptr;   // may be null
   bool decode = false;
+  float* all_logits = nullptr;     // isst_forward_all: logits of EVERY position [M][vocab] instead of the last rows
   double kv_tokens = 0;            // sum over streams of the KV length attended to (profiling only)
   double qk_pairs = 0;             // sum over streams of T_b * L_b (profiling only)
   int max_L = 0;                   // longest KV length attended to in this batch (grid sizing)
@@ -1126,6 +1129,14 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
   LAUNCH_CHECK(ctx);
   // final norm + lm_head on the LAST position of each stream only (the reference computes and discards
   // the other T-1 rows, llm.py:236-237 / SURVEY §2.3 L9)
+  if (lb.all_logits) {
+    // the reference's own shape: final norm + lm_head over all T positions (model/llm.py:236-237)
+    ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, ctx->final_norm, nullptr, nullptr, M, D, c.rms_eps, pending));
+    Epilogue e;
+    e.out_f32 = 1;
+    ISST_TRY(gemm(ctx, st, plain_view(ctx->lh, M, D), ctx->lm_head, c.vocab, lb.all_logits, c.vocab, 0, e));
+    return 0;
+  }
   pending.x_out = nullptr;   // only the gathered last rows are completed; the residual stream is not needed any more
   ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->llast, ctx->final_norm, nullptr, lb.d_last_row, lb.n, D, c.rms_eps, pending));
   {
@@ -1390,7 +1401,7 @@ void isst_destroy(isst_ctx* ctx) {
   // the context owns every device allocation it made; release the big pools explicitly
   cudaFree(ctx->beam_ws); cudaFree(ctx->beam_count);
   cudaFree(ctx->kv_pool); cudaFree(ctx->enc_k); cudaFree(ctx->enc_v); cudaFree(ctx->embed);
-  cudaFree(ctx->enc_kx); cudaFree(ctx->enc_xpos_base);
+  cudaFree(ctx->enc_kx); cudaFree(ctx->enc_xpos_base); cudaFree(ctx->logits_all);
   for (auto& w : ctx->llm) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.wgu.ptr); cudaFree(w.wd.ptr); cudaFree(w.rms1); cudaFree(w.rms2); }
   for (auto& w : ctx->enc) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.w1.ptr); cudaFree(w.w2.ptr);
     cudaFree(w.ln1_w); cudaFree(w.ln1_b); cudaFree(w.ln2_w); cudaFree(w.ln2_b); cudaFree(w.bqkv); cudaFree(w.bo); cudaFree(w.b1); cudaFree(w.b2); }
@@ -1696,9 +1707,26 @@ static int setup_llm_batch(isst_ctx* ctx, cudaStream_t st, MetaBuilder& mb, int 
   return 0;
 }
 
+static int forward_impl(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                        const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
+                        void* cuda_stream, bool all_positions);
+
 int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
                  const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
                  void* cuda_stream) {
+  return forward_impl(ctx, n, stream_ids, ids, lens, speech_slot, embeds_override, pin_prefix, out_logits, cuda_stream, false);
+}
+
+int isst_forward_all(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                     const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
+                     void* cuda_stream) {
+  ISST_CHECK(out_logits, "null argument");
+  return forward_impl(ctx, n, stream_ids, ids, lens, speech_slot, embeds_override, pin_prefix, out_logits, cuda_stream, true);
+}
+
+static int forward_impl(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids, const int* lens,
+                        const int32_t* speech_slot, const void* embeds_override, int pin_prefix, float* out_logits,
+                        void* cuda_stream, bool all_positions) {
   ISST_TRY(check_batch(ctx, n, stream_ids));
   ISST_CHECK(lens && (ids || embeds_override), "null argument");
   ISST_CUDA(cudaSetDevice(ctx->device));
@@ -1718,8 +1746,19 @@ int isst_forward(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* ids
     LAUNCH_CHECK(ctx);
   }
   ISST_TRY(tap(ctx, st, "prompt_embeds", ctx->lx, static_cast<size_t>(lb.M) * ctx->cfg.hidden * 2));
+  if (all_positions) {
+    if (ctx->logits_all_rows < static_cast<size_t>(lb.M)) {       // not a hot path: grown on demand
+      ISST_CUDA(cudaStreamSynchronize(st));
+      cudaFree(ctx->logits_all);
+      ctx->logits_all = nullptr; ctx->logits_all_rows = 0;
+      ISST_TRY(dev_alloc(&ctx->logits_all, static_cast<size_t>(lb.M) * ctx->cfg.vocab));
+      ctx->logits_all_rows = lb.M;
+    }
+    lb.all_logits = ctx->logits_all;
+  }
   ISST_TRY(llm_forward(ctx, st, lb, true));
-  if (out_logits) ISST_CUDA(cudaMemcpyAsync(out_logits, ctx->logits, static_cast<size_t>(n) * ctx->cfg.vocab * 4, cudaMemcpyDefault, st));
+  if (all_positions) ISST_CUDA(cudaMemcpyAsync(out_logits, ctx->logits_all, static_cast<size_t>(lb.M) * ctx->cfg.vocab * 4, cudaMemcpyDefault, st));
+  else if (out_logits) ISST_CUDA(cudaMemcpyAsync(out_logits, ctx->logits, static_cast<size_t>(n) * ctx->cfg.vocab * 4, cudaMemcpyDefault, st));
   ISST_CUDA(cudaStreamSynchronize(st));
   prof_flush(ctx);
   for (int b = 0; b < n; ++b) ctx->streams[stream_ids[b]].kv_len += lens[b];

@@ -281,8 +281,9 @@ class Engine:
 
     def forward(self, sids: Sequence[int], ids: Optional[Sequence[Sequence[int]]], speech_slots=None,
                 embeds: Optional[torch.Tensor] = None, lens: Optional[Sequence[int]] = None,
-                pin_prefix: int = 0) -> torch.Tensor:
-        """Append tokens (or given embeddings) to the stream caches; last-position logits [n, vocab] f32."""
+                pin_prefix: int = 0, all_positions: bool = False) -> torch.Tensor:
+        """Append tokens (or given embeddings) to the stream caches; last-position logits [n, vocab] f32, or with
+        `all_positions` the logits of every position, packed [sum(lens), vocab] (the reference's forward shape)."""
         n = len(sids)
         if ids is not None:
             lens = [len(r) for r in ids]
@@ -296,9 +297,11 @@ class Engine:
         if embeds is not None:
             embeds = embeds.to(device=f"cuda:{self.device}", dtype=torch.bfloat16).contiguous()
             eptr = C.c_void_p(embeds.data_ptr())
-        out = torch.empty(n, self.cfg.llm.vocab, dtype=torch.float32, device=f"cuda:{self.device}")
-        _lib.check(self.lib.isst_forward(self.h, n, _ints(sids), flat, _ints(lens), slots, eptr, pin_prefix,
-                                         C.c_void_p(out.data_ptr()), self._stream_ptr()))
+        rows = sum(lens) if all_positions else n
+        out = torch.empty(rows, self.cfg.llm.vocab, dtype=torch.float32, device=f"cuda:{self.device}")
+        fn = self.lib.isst_forward_all if all_positions else self.lib.isst_forward
+        _lib.check(fn(self.h, n, _ints(sids), flat, _ints(lens), slots, eptr, pin_prefix,
+                      C.c_void_p(out.data_ptr()), self._stream_ptr()))
         return out
 
     # ------------------------------------------------------------------ per-kernel-class timing

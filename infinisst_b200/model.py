@@ -238,7 +238,10 @@ class SpeechLlamaForCausalLM:
     def forward(self, input_ids=None, text_input_ids=None, attention_mask=None, text_attention_mask=None,
                 past_key_values=None, inputs_embeds=None, labels=None, text_labels=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, speech_batch=None, src_lengths=None,
-                after_lens=None, return_dict=None, states=None, multiplier=1, pin_prefix=0, **_unused) -> CausalLMOutput:
+                after_lens=None, return_dict=None, states=None, multiplier=1, pin_prefix=0, last_only=False,
+                **_unused) -> CausalLMOutput:
+        """model/llm.py:192-270.  `logits` is [B, T, vocab] like the reference's (lm_head over every position, :236-237);
+        `last_only=True` (extension) computes the last position only, [B, 1, vocab] - all that generation reads."""
         if labels is not None:
             raise NotImplementedError("training loss (model/llm.py:239-258) is out of scope")
         B = input_ids.shape[0] if input_ids is not None else inputs_embeds.shape[0]
@@ -250,11 +253,13 @@ class SpeechLlamaForCausalLM:
         if inputs_embeds is not None:
             T = inputs_embeds.shape[1]
             logits = self.engine.forward(sids, None, embeds=inputs_embeds.reshape(B * T, -1), lens=[T] * B,
-                                         pin_prefix=pin_prefix)
+                                         pin_prefix=pin_prefix, all_positions=not last_only)
         else:
+            T = input_ids.shape[1]
             ids = [input_ids[b].tolist() for b in range(B)]
             slots = [self._slot_map(r) if speech_batch is not None else [-1] * len(r) for r in ids]
-            logits = self.engine.forward(sids, ids, slots, pin_prefix=pin_prefix)
-        return CausalLMOutput(logits=logits[:, None, :], past_key_values=handles[0] if B == 1 else handles)
+            logits = self.engine.forward(sids, ids, slots, pin_prefix=pin_prefix, all_positions=not last_only)
+        logits = logits[:, None, :] if last_only else logits.view(B, T, -1)
+        return CausalLMOutput(logits=logits, past_key_values=handles[0] if B == 1 else handles)
 
     __call__ = forward

@@ -591,3 +591,40 @@ def test_agent_policy_batch_accepts_joining_streams(beam):
         st.reset()
     assert agent.model.engine.pages_free() == free0
     agent.model.engine.close()
+
+
+def test_model_forward_returns_every_position_like_the_reference():
+    """`model.forward` (model/llm.py:192-270) applies lm_head to all T positions (:236-237): logits are
+    [B, T, vocab].  Two calls on one stream (first chunk with the spliced speech tokens, then a follow-up turn over
+    the cached KV), every position held against the oracle; `last_only=True` equals the last row."""
+    from infinisst_b200.model import SpeechLlamaForCausalLM
+    cfg = tiny_config()
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=3)
+    model = SpeechLlamaForCausalLM(cfg, engine=eng)
+    osd = O.cast_state_dict(sd, torch.float32)
+    audio = make_audio(2 * SEG / 16000.0)
+
+    class _St:
+        speech_cache = None
+    st_a, st_b = _St(), _St()
+    enc_cache, llm_cache = None, O.LlmCache.empty(cfg.llm.layers)
+    for c in range(2):
+        ids = O.build_prompt(cfg.tpl, c == 0)
+        pcm = _chunk_pcm(audio, c)
+        feats, enc_cache = O.encode_speech(osd, cfg.enc, pcm, enc_cache)
+        emb = O.splice_embeddings(osd, cfg.llm, torch.tensor([ids]), feats)
+        ref = O.llama_forward(osd, cfg.llm, emb, llm_cache)[0]                       # [T, V]
+        ids_t = torch.tensor([ids], dtype=torch.long)
+        out = model.forward(input_ids=ids_t, speech_batch=pcm, states=st_a, multiplier=1,
+                            pin_prefix=len(cfg.tpl.system_ids))
+        assert tuple(out.logits.shape) == (1, len(ids), cfg.llm.vocab)
+        got = out.logits[0].float().cpu()
+        worst = max(rel_l2(got[t], ref[t]) for t in range(len(ids)))
+        assert worst < LOGIT_TOL, (c, worst)
+        last = model.forward(input_ids=ids_t, speech_batch=pcm, states=st_b, multiplier=1,
+                             pin_prefix=len(cfg.tpl.system_ids), last_only=True)
+        assert tuple(last.logits.shape) == (1, 1, cfg.llm.vocab)
+        assert rel_l2(last.logits[0, 0].float().cpu(), got[-1]) < 1e-3
+        assert out.past_key_values[0][0].size(2) == llm_cache.length()
+    eng.close()
