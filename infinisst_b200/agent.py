@@ -181,6 +181,11 @@ class InfiniSST(SpeechToTextAgent):
         self.repetition_penalty = args.repetition_penalty
         self.suppress_non_language = args.suppress_non_language
         self.max_new_tokens = args.max_new_tokens
+        # sampling flags are handed to generate like the reference does (agents/infinisst.py:93-97, 311-315); the CUDA
+        # path implements the shipped modes (greedy, beam search) and refuses do_sample loudly instead of ignoring it
+        self.do_sample = getattr(args, "do_sample", False)
+        self.top_p, self.top_k = getattr(args, "top_p", 1.0), getattr(args, "top_k", 0)
+        self.epsilon_cutoff, self.temperature = getattr(args, "epsilon_cutoff", 0.0), getattr(args, "temperature", 1.0)
         self.pseudo_batch_size = getattr(args, "pseudo_batch_size", 1)
         self.max_llm_cache_size = args.max_llm_cache_size
         self.always_cache_system_prompt = args.always_cache_system_prompt
@@ -426,8 +431,8 @@ class InfiniSST(SpeechToTextAgent):
         are passed per stream instead of one padded tensor)."""
         enc_t = enc if any(len(e) for e in enc) else None
         out = self.model.generate(
-            attention_mask=attention_mask, input_ids=ids, speech_batch=speech, do_sample=False, top_p=1.0, top_k=0,
-            epsilon_cutoff=0.0, temperature=1.0, num_beams=self.beam, max_new_tokens=self.max_new_tokens,
+            attention_mask=attention_mask, input_ids=ids, speech_batch=speech, do_sample=self.do_sample, top_p=self.top_p,
+            top_k=self.top_k, epsilon_cutoff=self.epsilon_cutoff, temperature=self.temperature, num_beams=self.beam, max_new_tokens=self.max_new_tokens,
             num_return_sequences=1, encoder_input_ids=enc_t, encoder_no_repeat_ngram_size=self.no_repeat_ngram_size,
             no_repeat_ngram_size=self.no_repeat_ngram_size, repetition_penalty=self.repetition_penalty,
             pad_token_id=self.tokenizer.pad_token_id, return_dict_in_generate=True, return_legacy_cache=False,

@@ -176,3 +176,16 @@ def test_dpo_sampling_translation_log(tmp_path):
     assert isinstance(a, WriteAction) and a.finished and a.content == "w8"
     assert open(agent.output_file, encoding="utf-8").read() == "['w5 w6', '', 'w8']\n"
     assert st.translations_list == []
+
+
+def test_sampling_is_refused_not_ignored():
+    """`--do-sample` reaches `model.generate` (agents/infinisst.py:311-315) and is refused there: the CUDA path
+    implements the shipped decoding modes (greedy, beam search) and must not silently fall back to them."""
+    import inspect
+    from infinisst_b200.agent import InfiniSST
+    from infinisst_b200.model import SpeechLlamaForCausalLM
+    src = inspect.getsource(InfiniSST._generate)
+    assert "do_sample=self.do_sample" in src and "temperature=self.temperature" in src
+    model = SpeechLlamaForCausalLM.__new__(SpeechLlamaForCausalLM)       # no engine needed: the check comes first
+    with pytest.raises(NotImplementedError, match="do_sample"):
+        model.generate(input_ids=torch.zeros(1, 3, dtype=torch.long), do_sample=True)
