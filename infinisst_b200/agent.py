@@ -187,6 +187,10 @@ class InfiniSST(SpeechToTextAgent):
         self.top_p, self.top_k = getattr(args, "top_p", 1.0), getattr(args, "top_k", 0)
         self.epsilon_cutoff, self.temperature = getattr(args, "epsilon_cutoff", 0.0), getattr(args, "temperature", 1.0)
         self.pseudo_batch_size = getattr(args, "pseudo_batch_size", 1)
+        if self.pseudo_batch_size != 1:
+            # the reference tiles ONE stream B times to measure batched throughput (agents/infinisst.py:291-301); here
+            # batches are made of independent streams (policy_batch) - refuse instead of silently running B = 1
+            raise ValueError("--pseudo-batch-size > 1 is not supported: batch independent streams with policy_batch")
         self.max_llm_cache_size = args.max_llm_cache_size
         self.always_cache_system_prompt = args.always_cache_system_prompt
         self.dpo_sampling = getattr(args, "dpo_sampling", False)              # agents/infinisst.py:100-101
