@@ -244,6 +244,11 @@ def main_native(args, env):
     torch.cuda.set_device(dev)
     sp.init("nccl", device=dev)
     S = args.streams
+    if args.total_streams:
+        # BASELINE.json configs[4] literally: a fixed population of streams partitioned over the GPUs (strong scaling)
+        if args.total_streams % world:
+            raise SystemExit("--total-streams must be a multiple of the GPU count")
+        S = args.total_streams // world
     cfg = production_config()
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
 
@@ -454,7 +459,7 @@ def main_native(args, env):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": red["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": red["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if args.total_streams else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"BASELINE.json configs[2] per GPU ({S} concurrent streams, batched chunk-prefill + decode; "
                                f"x{world} GPUs = configs[4] partition): wav2vec2-large + Llama-3.1-8B bf16 random-init, "
@@ -510,6 +515,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="concurrent streams per GPU")
+    ap.add_argument("--total-streams", type=int, default=0, help="fixed stream population split over the GPUs (configs[4]: 512); overrides --streams")
     ap.add_argument("--beam", type=int, default=1, help="1 = greedy (the north-star workload); k > 1 = the reference's beam search")
     ap.add_argument("--prime", type=int, default=34, help="untimed chunks run first so both sliding windows are full")
     ap.add_argument("--latency-chunks", type=int, default=20, help="single-stream latency sample (0 = skip)")
