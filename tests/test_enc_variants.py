@@ -187,3 +187,29 @@ def test_agent_flags_reach_the_engine():
         agent.model.engine.close()
     assert len(outs["default"]) > 10
     assert outs["default"] != outs["xpos0"] or outs["default"] != outs["norope"]     # the flags change the stream
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", VARIANTS)
+def test_cuda_variant_latency_multiplier_2(pins, name):
+    """96-frame chunks (set_blocksize(2), speech_encoder.py:143-145): the xPos centres move with T and L, the
+    sinusoidal offsets advance by 96 - held against the oracle."""
+    from infinisst_b200.engine import Engine
+    cfg = _cfg(pins, name)
+    sd = variant_state_dict(cfg, name)
+    osd = O.cast_state_dict(sd, torch.float32)
+    eng = Engine(cfg, device=0, max_streams=2, max_multiplier=2)
+    eng.load_state_dict(sd)
+    sid = eng.open_stream()
+    audio = make_audio(4 * 2 * SEG / 16000.0)
+    cache = None
+    for c in range(4):
+        pcm = audio[c * 2 * SEG:(c + 1) * 2 * SEG][None].clone()
+        if c == 0:
+            pcm = torch.cat([torch.zeros(1, 399), pcm], 1)
+        ref, cache = O.encode_speech(osd, cfg.enc, pcm, cache, multiplier=2)
+        got = eng.encode_chunk([sid], pcm, 2, return_feats=True)[0].cpu()
+        assert got.shape == ref[0].shape
+        e = rel_l2(got, ref[0])
+        assert e < FEAT_TOL[name], f"{name} m=2 chunk {c}: rel_l2 {e}"
+    eng.close()

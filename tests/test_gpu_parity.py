@@ -628,3 +628,49 @@ def test_model_forward_returns_every_position_like_the_reference():
         assert rel_l2(last.logits[0, 0].float().cpu(), got[-1]) < 1e-3
         assert out.past_key_values[0][0].size(2) == llm_cache.length()
     eng.close()
+
+
+def test_error_convention_and_recovery():
+    """SURVEY §8b error convention: every misuse comes back as a non-zero status + isst_last_error() (raised as
+    IsstError by the shim), nothing is silently truncated, and the context keeps working afterwards."""
+    from infinisst_b200._lib import IsstError
+    cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = _engine(cfg, sd, max_streams=2)
+    a, b = eng.open_stream(), eng.open_stream()
+    with pytest.raises(IsstError, match="no free stream slot"):
+        eng.open_stream()
+    audio = make_audio(2 * SEG / 16000.0)
+    with pytest.raises(IsstError, match="n_samples"):
+        eng.encode_chunk([a], audio[None, :1000].clone(), 1)                  # not a whole chunk
+    with pytest.raises(IsstError, match="multiplier"):
+        eng.encode_chunk([a], audio[None, :2 * SEG].clone(), 2)              # engine built for multiplier 1
+    with pytest.raises(IsstError):
+        eng.encode_chunk([a, a], torch.cat([_chunk_pcm(audio, 0)] * 2, 0), 1)  # the same stream twice in a batch
+    with pytest.raises(IsstError):
+        eng.kv_len(7)                                                          # not an open stream
+    ids = O.build_prompt(cfg.tpl, True)
+    with pytest.raises(IsstError, match="prompt length"):
+        eng.generate([a], [ids * 4], [[-1] * (4 * len(ids))], [[]], cfg.gen, pin_prefix=len(cfg.tpl.system_ids))
+    # the context is intact: a normal chunk on both streams still matches the oracle
+    orc = OracleStream(cfg, sd)
+    out_o, rec, taps = orc.chunk(audio[:SEG].tolist())
+    forced = rec.sequences[0][len(ids):]
+    pcm = torch.cat([_chunk_pcm(audio, 0)] * 2, 0)
+    eng.encode_chunk([a, b], pcm, 1)
+    toks = eng.generate([a, b], [ids, ids], [slot_map(cfg, ids)] * 2, [[], []], cfg.gen,
+                        pin_prefix=len(cfg.tpl.system_ids), forced=[forced, forced])
+    assert toks[0] == forced and toks[1] == forced
+    assert eng.kv_len(a) == eng.kv_len(b) == orc.st.llm_cache.length()
+    with pytest.raises(IsstError, match="keep_prefix"):
+        eng.kv_evict(a, 3, 50)                                                 # not the stream's pinned prefix
+    cur = eng.kv_len(a)
+    with pytest.raises(IsstError):
+        eng.kv_evict(a, len(cfg.tpl.system_ids), cur + 5)                      # beyond the cache
+    assert eng.kv_len(a) == cur
+    eng.kv_evict(a, len(cfg.tpl.system_ids), len(cfg.tpl.system_ids) + 10)
+    assert eng.kv_len(a) == cur - 10
+    eng.close_stream(a)
+    c = eng.open_stream()                                                      # the slot is reusable
+    assert eng.kv_len(c) == 0 and eng.enc_steps(c) == 0
+    eng.close()
