@@ -674,3 +674,49 @@ def test_error_convention_and_recovery():
     c = eng.open_stream()                                                      # the slot is reusable
     assert eng.kv_len(c) == 0 and eng.enc_steps(c) == 0
     eng.close()
+
+
+def test_update_multiplier_mid_stream():
+    """`InfiniSST.update_multiplier` (agents/infinisst.py:125-128) may change the latency multiplier between policy
+    calls of one stream: chunk length, block size of the encoder mask (set_blocksize, speech_encoder.py:143-145),
+    speech tokens per turn and max_new_tokens all follow.  One stream through m = 1, 2, 2, 1, 4, 1, 2 against the
+    oracle (teacher-forced tokens, logits, features, KV lengths and evictions)."""
+    cfg = tiny_config(max_cache_size=192, max_llm_cache_size=300)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    pattern = [1, 2, 2, 1, 4, 1, 2]
+    eng = _engine(cfg, sd, max_streams=2, max_multiplier=4, max_prompt=64 + 12 * 4)
+    eng.debug(True)
+    audio = make_audio(sum(pattern) * SEG / 16000.0)
+    orc = OracleStream(cfg, sd)
+    sid = eng.open_stream()
+    target, ck, pos, evictions = [], O.EvictionState(), 0, 0
+    for c, m in enumerate(pattern):
+        cfg.gen.latency_multiplier, cfg.gen.max_new_tokens = m, 10 * m
+        n_new = SEG * m
+        out_o, rec, taps = orc.chunk(audio[: pos + n_new].tolist())
+        ids = O.build_prompt(cfg.tpl, c == 0, m)
+        forced = rec.sequences[0][len(ids):]
+        pcm = audio[pos:pos + n_new][None].clone()
+        if c == 0:
+            pcm = torch.cat([torch.zeros(1, 399), pcm], 1)
+        pos += n_new
+        feats = eng.encode_chunk([sid], pcm, m, return_feats=True)
+        assert feats.shape[1] == 12 * m
+        assert rel_l2(feats.cpu(), taps["speech_feats"]) < ENC_TOL, (c, m)
+        toks = eng.generate([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen,
+                            pin_prefix=len(cfg.tpl.system_ids), forced=[forced])[0]
+        assert toks == forced, (c, m)
+        logits = eng.read_tap("step_logits", torch.float32).view(-1, cfg.llm.vocab)
+        for s in range(len(rec.step_logits)):
+            assert rel_l2(logits[s], rec.step_logits[s][0]) < LOGIT_TOL, (c, m, s)
+        target.extend(out_o)
+        cur = eng.kv_len(sid)
+        assert cur == orc.st.kv_log[-1]["cur"]
+        kept = O.evict(ck, cur, cfg.gen.max_llm_cache_size, True, len(cfg.tpl.system_ids))
+        if kept is not None:
+            eng.kv_evict(sid, kept[0], cur - kept[1])
+            evictions += 1
+        assert eng.kv_len(sid) == orc.st.llm_cache.length()
+        assert eng.enc_steps(sid) == orc.st.enc_cache.n_steps
+    assert evictions >= 1
+    eng.close()
