@@ -246,6 +246,9 @@ class InfiniSST(SpeechToTextAgent):
             self.tokenizer = TemplateTokenizer(cfg)
         elif not isinstance(self.tokenizer, TemplateTokenizer) and hasattr(self.tokenizer, "add_tokens"):
             ck.preprocess_tokenizer(self.tokenizer, cfg, self.max_latency_multiplier)       # :177
+            if hasattr(self.tokenizer, "apply_chat_template"):
+                # the real system turn (agents/infinisst.py:229-241) sizes the pinned prefix / KV capacity
+                ck.template_from_tokenizer(self.tokenizer, cfg, self.source_lang, self.target_lang, self.latency_multiplier)
         self.bad_words_ids = list(getattr(args, "bad_words_ids", []) or [])
         if self.suppress_non_language and not self.bad_words_ids:
             n_vocab = len(self.tokenizer) if hasattr(self.tokenizer, "__len__") else cfg.llm.vocab
