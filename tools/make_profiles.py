@@ -89,6 +89,11 @@ def main(tag):
             alg = None
             if cls == "gemm_stream":      # o_proj, gate/up, down, qkv weights of a decode layer (bf16) - activations are < 2 %
                 alg = (4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336 + 6144 * 4096) * 2 / 4.0
+            elif cls == "gemm_tensor":    # the same four GEMMs at 1408 tokens: weights + activations in + outputs (+ residual reads)
+                M = 1408
+                w = (6144 * 4096 + 4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336) * 2
+                io = M * 2 * ((4096 + 6144) + (4096 + 2 * 4096) + (4096 + 14336) + (14336 + 2 * 4096))
+                alg = (w + io) / 4.0
             elif cls == "attn_decode_beam4":  # shared prefix once per sentence + one private page pair per beam (<= 32 keys)
                 alg = 64 * (1008 + 4 * 20) * 8 * 128 * 2 * 2
             elif cls in ("attn_decode", "attn_prefill"):   # K and V of 64 streams x ~1001-1023 tokens x 8 kv heads x 128 x bf16
