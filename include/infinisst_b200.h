@@ -94,7 +94,10 @@ int isst_stream_close(isst_ctx* ctx, int stream_id);
 /* SpeechEncoderW2V2RoPE.encode_speech (model/speech_encoder.py:219-236) for n streams in lock-step:
  * pcm [n][n_samples] f32 (host or device) -> speech features [n][n_samples/320/4][hidden] bf16, kept
  * in the context for the following isst_generate and optionally copied to out_feats (device or host
- * pointer, may be NULL).  A fresh stream takes 79+320 leading samples more (agents/infinisst.py:216-218). */
+ * pointer, may be NULL).  A fresh stream takes 79+320 leading samples more (agents/infinisst.py:216-218).
+ * n_samples = j * block_size * 320 with 1 <= j <= multiplier: a short final chunk is padded to whole
+ * segments of ONE block only (agents/infinisst.py:211-213) while the encoder mask keeps the block size of
+ * the multiplier (set_blocksize, model/speech_encoder.py:143-145); j segments give 12 * j speech rows. */
 int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* pcm, int n_samples,
                       int multiplier, void* out_feats, void* cuda_stream);
 
@@ -163,13 +166,23 @@ int isst_kv_evict(isst_ctx* ctx, int stream_id, int keep_prefix, int drop_upto);
 int isst_enc_steps(isst_ctx* ctx, int stream_id, int* n_steps);   /* W2V2RoPECache.n_steps */
 
 /* Introspection for tests / bench. */
-int isst_debug_enable(isst_ctx* ctx, int on);   /* keep per-step raw logits + encoder taps */
+/* bit 0: keep taps - encoder stages, "step_logits" (raw last-position logits per step, f32 [max_new][n][vocab]),
+ * "step_scores" (the same rows after the logits processors = what the device's arg-max saw) and "step_picked"
+ * (int32 [n][max_new]: the device's own arg-max at every step, also when `forced` overrides the token that is fed). */
+int isst_debug_enable(isst_ctx* ctx, int on);
 int isst_debug_read(isst_ctx* ctx, const char* name, void* dst_host, int64_t max_bytes, int64_t* n_bytes);
 /* Test hook: pretend `delta` more ring tokens were appended and evicted before now, i.e. move the stream's
  * absolute RoPE positions (a one-hour stream reaches ~1e5).  Scores only depend on position differences
  * (patch_llm.py:287-299), so results must not change. */
 int isst_debug_shift_positions(isst_ctx* ctx, int stream_id, int64_t delta);
 int64_t isst_launch_count(isst_ctx* ctx);       /* kernels launched so far */
+/* Launches so far of one kernel variant, by name ("prefill_attention_tc_unsplit", "decode_attention_direct",
+ * "gemm_sk_swap64_deferred", "decode_chain64", ...): parity tests assert that the variant they mean to cover ran. */
+int isst_path_count(isst_ctx* ctx, const char* name, int64_t* count);
+/* Per-context test / tuning options (no environment variables on the hot path): "pdl" 0/1 programmatic dependent
+ * launch, "decode_splits" fixed key-split count of decode attention (0 = automatic), "decode_chain" 0/1 the fused
+ * decode-layer kernel (0 = one kernel per operator). */
+int isst_debug_option(isst_ctx* ctx, const char* key, int value);
 /* Per-kernel-class device timing for the roofline leg of bench.py: while enabled every launch is
  * bracketed by CUDA events on the caller's stream.  isst_profile_read walks the classes by index
  * (returns 1 past the last one): launches, summed event time, and the ALGORITHMIC flops / bytes
@@ -182,10 +195,10 @@ int isst_profile_read(isst_ctx* ctx, int index, char* name, int name_cap, int64_
 int isst_pages_free(isst_ctx* ctx);
 
 /* Stand-alone operator entry points (device pointers) used by the parity tests and bench.py:
- * out[M,N] = act[M,K] . w[N,K]^T (+bias, gelu, +resid);  impl: 0 = tcgen05, 1 = CUDA-core validation. */
+ * out[M,N] = act[M,K] . w[N,K]^T (+bias, gelu, +resid) through the tcgen05 GEMM. */
 int isst_op_gemm(isst_ctx* ctx, const void* act_bf16, const void* w_bf16, int M, int N, int K,
                  const float* bias, int act_gelu, const void* resid_bf16, int dual, void* out, int out_f32,
-                 int impl, int force_swap, int force_splits, void* cuda_stream);
+                 int force_swap, int force_splits, void* cuda_stream);
 /* Decode attention over synthetic paged KV for `n` streams of length L (bench roofline leg). */
 int isst_op_decode_attention_bench(isst_ctx* ctx, int n, int L, int iters, float* ms_per_iter,
                                    void* cuda_stream);

@@ -81,7 +81,9 @@ SYMBOLS = {
     "isst_profile_reset": (_I, [_P]),
     "isst_profile_read": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-    "isst_op_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "isst_op_gemm": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "isst_path_count": (_I, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
+    "isst_debug_option": (_I, [_P, C.c_char_p, _I]),
     "isst_op_decode_attention_bench": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), _P]),
 }
 

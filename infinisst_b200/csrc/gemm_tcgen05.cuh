@@ -13,10 +13,8 @@
 //   kDual         : two weight tiles per k-block (rows f and f + dual_off) -> two accumulators;
 //                   epilogue writes silu(acc0) * acc1  (Llama gate/up)
 //
-// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).  Split-K: grid.z = batch * splits;
-// partials go to an fp32 workspace and the last-arriving CTA of a tile reduces them in split order
-// (deterministic) and applies the epilogue.
+// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM allocator,
+// warps 4-11 = epilogue (TMEM lane quarter = warp % 4, two column halves); see gemm_sk_kernel below.
 #pragma once
 #include "common.cuh"
 
@@ -26,8 +24,6 @@ namespace tc {
 constexpr int kBM = 128;       // rows of the 128-lane operand
 constexpr int kBK = 64;        // bf16 elements per k-block = 128 bytes = one swizzle atom row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;
 
 struct GemmParams {
   int M_tok;        // token rows per batch
@@ -148,23 +144,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-template <int kBN, bool kDual, bool kSwap>
-struct Cfg {
-  static constexpr int kActRows = kSwap ? kBN : kBM;
-  static constexpr int kWRows = kSwap ? kBM : kBN;
-  static constexpr int kNW = kDual ? 2 : 1;
-  static constexpr int kActBytes = kActRows * kBK * 2;
-  static constexpr int kWBytes = kWRows * kBK * 2;
-  static constexpr int kStageBytes = kActBytes + kNW * kWBytes;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kAccCols = kBN * kNW;
-  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
-  static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
-};
 
 // Final epilogue for 16 consecutive columns of one TMEM lane.
 //   normal: lane = token row, columns = features;  swap: lane = feature, columns = tokens.
@@ -336,187 +315,8 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, int b, int
   }
 }
 
-template <int kBN, bool kDual, bool kSwap>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
-                    const GemmParams p) {
-  using C = Cfg<kBN, kDual, kSwap>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* tmem_full_bar = empty_bar + C::kStages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  int* flag_smem = reinterpret_cast<int*>(tmem_ptr_smem + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tile_tok = blockIdx.x;    // token tile (128 rows normal, kBN rows swap)
-  const int tile_feat = blockIdx.y;   // feature tile (kBN normal, 128 swap)
-  const int b = blockIdx.z / p.splits;
-  const int split = blockIdx.z % p.splits;
-  const int num_kb = (p.K + kBK - 1) / kBK;
-  const int kb0 = static_cast<int>((static_cast<long long>(num_kb) * split) / p.splits);
-  const int kb1 = static_cast<int>((static_cast<long long>(num_kb) * (split + 1)) / p.splits);
-
-  if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_act)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
-    for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(static_cast<uint32_t>(C::kTmemCols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const int act_row0 = tile_tok * C::kActRows;
-  const int w_row0 = tile_feat * C::kWRows;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * C::kStageBytes;
-        uint8_t* sw = sa + C::kActBytes;
-        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-        // activation tensor map is 4-D {conv_c, conv_s, row_group, batch}: tap t of row r = (t % s, r + t / s)
-        const int k0 = kb * kBK;
-        const int tap = k0 / p.conv_c;
-        tma_load_4d(sa, &tm_act, &full_bar[stage], k0 - tap * p.conv_c, tap % p.conv_s, act_row0 + tap / p.conv_s, b);
-        tma_load_2d(sw, &tm_w, &full_bar[stage], kb * kBK, w_row0);
-        if (kDual) tma_load_2d(sw + C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, w_row0 + p.dual_off);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(kBM, kBN);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-        const uint32_t sw = sa + C::kActBytes;
-        const uint64_t d_act = make_smem_desc(sa);
-        const uint64_t d_w0 = make_smem_desc(sw);
-        const uint64_t d_w1 = make_smem_desc(sw + C::kWBytes);
-#pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-          const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-          if (!kSwap) {
-            umma_bf16(tmem_base, d_act + koff, d_w0 + koff, idesc, acc);
-            if (kDual) umma_bf16(tmem_base + kBN, d_act + koff, d_w1 + koff, idesc, acc);
-          } else {
-            umma_bf16(tmem_base, d_w0 + koff, d_act + koff, idesc, acc);
-            if (kDual) umma_bf16(tmem_base + kBN, d_w1 + koff, d_act + koff, idesc, acc);
-          }
-        }
-        umma_commit(&empty_bar[stage]);
-        if (kb == kb1 - 1) umma_commit(tmem_full_bar);
-      }
-      __syncwarp();
-      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-    }
-  } else if (warp >= 4) {
-    const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
-    const int r = q * 32 + lane;                  // TMEM lane == row of the 128-row operand
-    const int et = threadIdx.x - 128;             // 0..127 epilogue thread id
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int lane_idx = (kSwap ? tile_feat : tile_tok) * kBM + r;
-    const int col_base = (kSwap ? tile_tok : tile_feat) * kBN;
-    if (p.splits == 1) {
-      if (kSwap && kBN >= 32) {
-#pragma unroll 1
-        for (int c = 0; c < kBN; c += 32) {
-          float v0[32], v1[32];
-          tmem_ld16(taddr + c, v0);
-          tmem_ld16(taddr + c + 16, v0 + 16);
-          if (kDual) { tmem_ld16(taddr + kBN + c, v1); tmem_ld16(taddr + kBN + c + 16, v1 + 16); }
-          epilogue_store_swap<kDual, 32>(p, b, lane_idx, col_base + c, v0, v1);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < kBN; c += 16) {
-          float v0[16], v1[16];
-          tmem_ld16(taddr + c, v0);
-          if (kDual) tmem_ld16(taddr + kBN + c, v1);
-          epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
-        }
-      }
-    } else {
-      const int tiles_per_b = gridDim.x * gridDim.y;
-      const int tile_lin = (b * gridDim.y + tile_feat) * gridDim.x + tile_tok;
-      (void)tiles_per_b;
-      float* ws_tile = p.ws + static_cast<size_t>(tile_lin) * p.splits * (C::kAccCols * kBM);
-      float* mine = ws_tile + static_cast<size_t>(split) * (C::kAccCols * kBM);
-#pragma unroll 1
-      for (int c = 0; c < C::kAccCols; c += 16) {
-        float v[16];
-        tmem_ld16(taddr + c, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mine[(c + i) * kBM + r] = v[i];
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        const int prev = atomicAdd(&p.counters[tile_lin], 1);
-        *flag_smem = (prev == p.splits - 1) ? 1 : 0;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*flag_smem) {
-        __threadfence();
-        constexpr int NC = (kSwap && kBN >= 32) ? 32 : 16;
-#pragma unroll 1
-        for (int c = 0; c < kBN; c += NC) {
-          float v0[NC], v1[NC];
-#pragma unroll
-          for (int i = 0; i < NC; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
-#pragma unroll 2
-          for (int s = 0; s < p.splits; ++s) {
-            const float* src = ws_tile + static_cast<size_t>(s) * (C::kAccCols * kBM);
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-              v0[i] += __ldcg(&src[(c + i) * kBM + r]);
-              if (kDual) v1[i] += __ldcg(&src[(kBN + c + i) * kBM + r]);
-            }
-          }
-          if (kSwap && kBN >= 32) epilogue_store_swap<kDual, NC>(p, b, lane_idx, col_base + c, v0, v1);
-          else epilogue_store16<kDual, kSwap>(p, b, lane_idx, col_base + c, v0, v1);
-        }
-        if (et == 0) p.counters[tile_lin] = 0;
-      }
-    }
-    tcgen05_fence_before();
-  }
-  __syncthreads();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(C::kTmemCols))
-                 : "memory");
-  }
-}
-
-
 // =================================================================================================
-// Persistent data-parallel + stream-K variant (the product default).
+// Persistent data-parallel + stream-K kernel.
 //
 // G CTAs (G <= #SMs, one per SM) stay resident for the whole GEMM:
 //   * data-parallel part: the first floor(tiles / G) * G tiles are dealt round-robin (CTA c takes tiles

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <set>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -162,9 +163,11 @@ struct isst_ctx {
   int device = 0;
   int sm_count = 148;
   bool finalized = false;
-  bool simple_gemm = false;
-  bool pdl = true;          // ISST_PDL=0 disables programmatic dependent launch
-  bool gemm_v1 = false;     // ISST_GEMM=v1: one-tile-per-CTA tcgen05 kernel (previous generation, kept for A/B runs)
+  // per-context tuning / test options (isst_debug_option); nothing on the hot path reads the environment
+  bool pdl = true;          // "pdl" = 0: plain stream order instead of programmatic dependent launch
+  int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
+  std::set<const void*> smem_attr_done;      // kernels whose dynamic shared-memory limit was raised on this device
+  std::map<std::string, long long> paths;    // launches per kernel variant (isst_path_count; parity tests assert on them)
   unsigned long long* gemm_dbg = nullptr;   // optional phase stamps of the last stream-K launch
   int64_t launches = 0;
   bool debug = false;
@@ -308,20 +311,14 @@ struct Epilogue {
   int dual_off = 0;
 };
 
-template <int kBN, bool kDual, bool kSwap>
-static int launch_tc(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
-                     dim3 grid) {
-  using C = tc::Cfg<kBN, kDual, kSwap>;
-  static bool attr_set = false;
-  auto kern = tc::gemm_tcgen05_kernel<kBN, kDual, kSwap>;
-  if (!attr_set) {
-    ISST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+// Raises the dynamic shared-memory limit of a kernel once per context (= per device).
+template <typename F>
+static int ensure_smem(isst_ctx* ctx, F* kern, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (!ctx->smem_attr_done.count(key)) {
+    ISST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->smem_attr_done.insert(key);
   }
-  CUtensorMap amap;
-  ISST_TRY(make_act_map(&amap, v, C::kActRows));
-  kern<<<grid, tc::kThreads, C::kSmemBytes, st>>>(amap, w.map, p);
-  LAUNCH_CHECK(ctx);
   return 0;
 }
 
@@ -354,8 +351,7 @@ static void sk_plan(isst_ctx* ctx, int M_tok, int N_out, int K, int batch, int a
   // (~6 us: park partial, fence, wait, reduce) and wins only when it shortens the critical path by more than
   // that, i.e. when a whole tile is long compared with the reduction: `gain` units saved vs `r_units`.
   const long long rem = sk.tiles % G;
-  static const char* ru_env = getenv("ISST_SK_RUNITS");     // tuning aid
-  const long long r_units = ru_env ? atoi(ru_env) : ((swap && !dual) ? 16 : 24);
+  const long long r_units = (swap && !dual) ? 16 : 24;
   bool use_sk = rem > 0 && (sk.num_kb - ceil_div(static_cast<int>(rem * sk.num_kb), static_cast<int>(G))) > r_units;
   if (force_splits > 1) use_sk = rem > 0;
   sk.tiles_dp = use_sk ? sk.tiles - rem : sk.tiles;
@@ -384,12 +380,8 @@ template <int kBN, bool kDual, bool kSwap>
 static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
                      int force_splits) {
   using C = tc::SkCfg<kBN, kDual, kSwap>;
-  static bool attr_set = false;
   auto kern = tc::gemm_sk_kernel<kBN, kDual, kSwap>;
-  if (!attr_set) {
-    ISST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
-  }
+  ISST_TRY(ensure_smem(ctx, kern, C::kSmemBytes));
   tc::SkParams sk{};
   long long G = 0;
   int S = 0;
@@ -399,6 +391,8 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   pp.part_out = S ? ctx->defer_ws : nullptr;
   pp.part_splits = S;
   ctx->last_defer_splits = S;
+  if (kSwap) ctx->paths[std::string("gemm_sk_swap") + std::to_string(kBN) + (kDual ? "_dual" : "") + (S ? "_deferred" : "")]++;
+  else ctx->paths[std::string("gemm_sk_rows") + std::to_string(kBN) + (kDual ? "_dual" : "")]++;
   pp.counter_half = ctx->n_counters / 2;
   pp.counter_parity = ctx->gemm_parity;
   ctx->gemm_parity ^= 1;
@@ -414,7 +408,7 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
 
 static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, int n_out, void* out,
                 long long ldo, long long out_batch_stride, const Epilogue& e, int force_swap = -1,
-                int force_splits = 0, int force_simple = -1) {
+                int force_splits = 0) {
   tc::GemmParams p{};
   p.M_tok = v.rows;
   p.N_out = n_out;
@@ -439,7 +433,6 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
   p.part_splits = 0;
   ctx->last_defer_splits = 0;
   ISST_CHECK(v.K == w.K, "gemm: K mismatch");
-  const bool simple = force_simple >= 0 ? (force_simple != 0) : ctx->simple_gemm;
   // algorithmic work: every operand touched once (weights dominate when few tokens stream them)
   const double nw = e.dual ? 2.0 : 1.0;
   const double g_flops = 2.0 * v.rows * v.batch * static_cast<double>(n_out) * v.K * nw;
@@ -449,84 +442,36 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
                          static_cast<double>(v.rows) * v.batch * n_out * (e.out_f32 ? 4 : 2) * (e.resid ? 2 : 1);
   // M <= 128 tokens: weight streaming (HBM roofline); more: tensor-pipe roofline
   ProfScope ps(ctx, st, v.rows * v.batch <= 128 ? P_GEMM_STREAM : P_GEMM_TENSOR, g_flops, g_bytes);
-  if (simple) {
-    SimpleGemmExtra x{v.ptr, v.batch_stride, v.conv_c, v.conv_s, w.ptr, e.dual};
-    dim3 grid(ceil_div(n_out, 8), ceil_div(v.rows, 8), v.batch);
-    gemm_simple_kernel<<<grid, 256, 0, st>>>(p, x);
-    LAUNCH_CHECK(ctx);
-    return 0;
-  }
   ISST_CHECK(v.conv_c % tc::kBK == 0, "gemm: conv_c must be a multiple of 64");
   // weights on the 128-lane operand up to 64 token rows; measured at 128 / 256 rows (tests/gemm_bench_rows.py):
   // tokens on the 128-lane operand is as fast or faster (133 vs 137 us, 197 vs 210 us per decode layer)
   bool swap = (v.rows <= 64 && v.batch == 1);
   if (force_swap >= 0) swap = force_swap != 0;
   ISST_CHECK(!(swap && v.batch != 1), "gemm: swap mode needs batch == 1");
-  if (!ctx->gemm_v1) {
-    // persistent stream-K kernel: tile shape by mode, CTA count = SM count whatever the tile count
-    const int sbn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
+  // persistent stream-K kernel: tile shape by mode, CTA count = SM count whatever the tile count
+  const int sbn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
 #define ISST_SK(BN, DUAL, SWAP) return launch_sk<BN, DUAL, SWAP>(ctx, st, v, w, p, force_splits)
-    if (!swap) {
-      if (e.dual) ISST_SK(128, true, false);
-      if (n_out >= 256) ISST_SK(256, false, false);
-      ISST_SK(128, false, false);
-    }
-    if (e.dual) {
-      switch (sbn) {
-        case 16: ISST_SK(16, true, true);
-        case 32: ISST_SK(32, true, true);
-        case 64: ISST_SK(64, true, true);
-        default: ISST_SK(128, true, true);
-      }
-    }
-    switch (sbn) {
-      case 16: ISST_SK(16, false, true);
-      case 32: ISST_SK(32, false, true);
-      case 64: ISST_SK(64, false, true);
-      default: ISST_SK(128, false, true);
-    }
-#undef ISST_SK
-  }
-  const int num_kb = ceil_div(v.K, tc::kBK);
-  int bn = 128;
-  if (swap) bn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
-  const int tok_tiles = swap ? ceil_div(v.rows, bn) : ceil_div(v.rows, tc::kBM);
-  const int feat_tiles = swap ? ceil_div(n_out, tc::kBM) : ceil_div(n_out, bn);
-  const int tiles = tok_tiles * feat_tiles * v.batch;
-  int splits = 1;
-  if (tiles < ctx->sm_count) {
-    splits = std::max(1, ctx->sm_count / tiles);
-    splits = std::min(splits, std::max(1, num_kb / 4));
-    splits = std::min(splits, 16);
-  }
-  if (force_splits > 0) splits = std::min(force_splits, num_kb);
-  const size_t acc_cols = static_cast<size_t>(bn) * (e.dual ? 2 : 1);
-  if (splits > 1) {
-    const size_t need = static_cast<size_t>(tiles) * splits * acc_cols * tc::kBM;
-    if (need > ctx->gemm_ws_floats || tiles > ctx->n_counters) splits = 1;
-  }
-  p.splits = splits;
-  dim3 grid(tok_tiles, feat_tiles, v.batch * splits);
-#define ISST_TC(BN, DUAL, SWAP) return launch_tc<BN, DUAL, SWAP>(ctx, st, v, w, p, grid)
   if (!swap) {
-    if (e.dual) ISST_TC(128, true, false);
-    ISST_TC(128, false, false);
+    if (e.dual) ISST_SK(128, true, false);
+    if (n_out >= 256) ISST_SK(256, false, false);
+    ISST_SK(128, false, false);
   }
   if (e.dual) {
-    switch (bn) {
-      case 16: ISST_TC(16, true, true);
-      case 32: ISST_TC(32, true, true);
-      case 64: ISST_TC(64, true, true);
-      default: ISST_TC(128, true, true);
+    switch (sbn) {
+      case 16: ISST_SK(16, true, true);
+      case 32: ISST_SK(32, true, true);
+      case 64: ISST_SK(64, true, true);
+      default: ISST_SK(128, true, true);
     }
   }
-  switch (bn) {
-    case 16: ISST_TC(16, false, true);
-    case 32: ISST_TC(32, false, true);
-    case 64: ISST_TC(64, false, true);
-    default: ISST_TC(128, false, true);
+  switch (sbn) {
+    case 16: ISST_SK(16, false, true);
+    case 32: ISST_SK(32, false, true);
+    case 64: ISST_SK(64, false, true);
+    default: ISST_SK(128, false, true);
   }
-#undef ISST_TC
+#undef ISST_SK
+  return set_error("gemm: unreachable");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -768,7 +713,8 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
     T = To;
   }
   const int frames = T;   // new frames per stream
-  ISST_CHECK(frames == c.block_size * multiplier, "chunk does not produce block_size*multiplier frames");
+  ISST_CHECK(frames * ctx->total_stride == n_new && frames % c.block_size == 0 && frames <= c.block_size * multiplier,
+             "chunk does not produce a whole number of block_size-frame segments");
   const int M = n * frames;
   ISST_TRY(tap(ctx, st, "enc_conv", cur, static_cast<size_t>(M) * C * 2));
   // ---- LayerNorm(C) + post_extract_proj (E3) ----
@@ -833,11 +779,7 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
       constexpr int NS = 3;
       constexpr int smem = chunk_attn_smem_bytes<64, NW, NS>();
       ISST_CHECK(HD == 64, "encoder attention kernel is built for head_dim 64");
-      static bool enc_attr_set = false;
-      if (!enc_attr_set) {
-        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<64, true, NW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        enc_attr_set = true;
-      }
+      ISST_TRY(ensure_smem(ctx, chunk_attention_kernel<64, true, NW, NS>, smem));
       ISST_CUDA(launch_k(ctx, chunk_attention_kernel<64, true, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
     }
@@ -930,8 +872,7 @@ static PagedKV paged_kv(isst_ctx* ctx, int layer) {
 // Decode attention launch: split count from the longest stream so that the grid is a few waves of
 // 2 CTAs per SM; every split is a whole number of 64-key tiles.
 static int decode_splits_for(isst_ctx* ctx, int n, int max_L) {
-  static const char* force = getenv("ISST_DEC_SPLITS");          // tuning aid
-  if (force) return std::max(1, std::min(ctx->decode_splits, atoi(force)));
+  if (ctx->opt_dec_splits > 0) return std::max(1, std::min(ctx->decode_splits, ctx->opt_dec_splits));
   const int tiles_total = std::max(1, ceil_div(max_L, kDecTile) + 1);
   // long-lived CTAs stream best (measured: 1 split at 64 streams x 8 kv heads = 512 CTAs beats 2-3 splits by 10%)
   const int target = std::max(1, std::min(ctx->decode_splits, ceil_div(2 * ctx->sm_count, n * ctx->cfg.kv_heads)));
@@ -947,11 +888,8 @@ struct DecodeFuse {          // fused RoPE + KV append inside the decode attenti
 };
 static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* qkv, const PagedKV& kv, const int* d_slots,
                                    int n, int splits, float scale_log2, const DecodeFuse& fz = DecodeFuse{}) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ISST_CUDA(cudaFuncSetAttribute(decode_attention_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes));
-    attr_set = true;
-  }
+  ISST_TRY(ensure_smem(ctx, decode_attention_mma_kernel<4>, kDecSmemBytes));
+  ctx->paths[splits == 1 ? "decode_attention_direct" : "decode_attention_split"]++;
   DecodeParams2 dp{};
   dp.qkv = qkv; dp.q_sys = ctx->lq_sys; dp.kv = kv; dp.slots = d_slots;
   dp.out = ctx->lattn; dp.part_o = ctx->part_o; dp.part_ml = ctx->part_ml; dp.H = ctx->cfg.heads;
@@ -995,10 +933,8 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       qkv_splits = ctx->last_defer_splits;
     }
     PagedKV kv = paged_kv(ctx, l);
-    static const bool fuse_env = !(getenv("ISST_DEC_FUSE") && atoi(getenv("ISST_DEC_FUSE")) == 0);   // A/B aid
-    static const bool group_env = !(getenv("ISST_BEAM_GROUP") && atoi(getenv("ISST_BEAM_GROUP")) == 0);   // A/B aid
-    const bool grouped = lb.decode && lb.group == 4 && lb.d_key_hi && group_env;   // beam search: shared-prefix attention
-    const bool fuse_append = lb.decode && fuse_env && !grouped;    // decode: the attention kernel rotates and appends by itself
+    const bool grouped = lb.decode && lb.group == 4 && lb.d_key_hi;   // beam search: shared-prefix attention
+    const bool fuse_append = lb.decode && !grouped;    // decode: the attention kernel rotates and appends by itself
     if (!fuse_append) {
       ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
       dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
@@ -1011,67 +947,39 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       LlmAttnParams lp{};
       lp.qkv = ctx->lqkv; lp.q_sys = ctx->lq_sys; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
       lp.T = lb.d_T; lp.H = H; lp.scale_log2 = scale_log2;
-      EncAttnParams ep{};
-      constexpr int NW = 6;   // 96 query rows per CTA: the 4 x 22 rows of a steady-state turn in one CTA, 2 CTAs per SM
       ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
                    lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
-      static const bool pa_tc = !(getenv("ISST_PREFILL_TC") && atoi(getenv("ISST_PREFILL_TC")) == 0);   // tcgen05 prefill attention (ISST_PREFILL_TC=0: the mma.sync kernel, for A/B runs)
-      if (pa_tc) {
-        static bool pa_attr = false;
-        if (!pa_attr) {
-          ISST_CUDA(cudaFuncSetAttribute(prefill_attention_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
-          pa_attr = true;
-        }
-        // few streams: one CTA per (row tile, kv head, stream) leaves most SMs idle and walks the whole KV serially -
-        // cut the key range into splits (fp32 partials merged by decode_combine_kernel)
-        const int row_tiles = ceil_div(4 * lb.max_T, 128);
-        const int ctas = row_tiles * Hkv * lb.n;
-        const int key_tiles = ceil_div(lb.max_L, kPaKT) + 1;
-        int ks = 1;
-        static const bool ks_env = !(getenv("ISST_PREFILL_SPLITS") && atoi(getenv("ISST_PREFILL_SPLITS")) == 0);   // A/B aid
-        if (ks_env && 2 * ctas <= ctx->sm_count) ks = std::max(1, std::min({ctx->sm_count / ctas, key_tiles / 2, 8}));
-        const size_t part_cap = static_cast<size_t>(c.max_batch) * H * ctx->decode_splits;     // (row, head, split) slots of part_o
-        while (ks > 1 && static_cast<size_t>(M) * H * ks > part_cap) --ks;
-        lp.key_splits = ks; lp.part_o = ctx->part_o; lp.part_ml = ctx->part_ml;
-        if (ks > 1) {
-          static bool pas_attr = false;
-          if (!pas_attr) {
-            ISST_CUDA(cudaFuncSetAttribute(prefill_attention_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPaSmemBytes));
-            pas_attr = true;
-          }
-          ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, true>, dim3(row_tiles * ks, Hkv, lb.n), dim3(kPaThreads),
-                             kPaSmemBytes, st, lp));
-        } else {
-          ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, false>, dim3(row_tiles, Hkv, lb.n), dim3(kPaThreads),
-                             kPaSmemBytes, st, lp));
-        }
-        LAUNCH_CHECK(ctx);
-        if (ks > 1) {
-          ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(M * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, ks));
-          LAUNCH_CHECK(ctx);
-        }
+      ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, false>, kPaSmemBytes));
+      // few streams: one CTA per (row tile, kv head, stream) leaves most SMs idle and walks the whole KV serially -
+      // cut the key range into splits (fp32 partials merged by decode_combine_kernel)
+      const int row_tiles = ceil_div(4 * lb.max_T, 128);
+      const int ctas = row_tiles * Hkv * lb.n;
+      const int key_tiles = ceil_div(lb.max_L, kPaKT) + 1;
+      int ks = 1;
+      if (2 * ctas <= ctx->sm_count) ks = std::max(1, std::min({ctx->sm_count / ctas, key_tiles / 2, 8}));
+      const size_t part_cap = static_cast<size_t>(c.max_batch) * H * ctx->decode_splits;     // (row, head, split) slots of part_o
+      while (ks > 1 && static_cast<size_t>(M) * H * ks > part_cap) --ks;
+      lp.key_splits = ks; lp.part_o = ctx->part_o; lp.part_ml = ctx->part_ml;
+      ctx->paths[ks > 1 ? "prefill_attention_tc_keysplit" : "prefill_attention_tc_unsplit"]++;
+      if (ks > 1) {
+        ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, true>, kPaSmemBytes));
+        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, true>, dim3(row_tiles * ks, Hkv, lb.n), dim3(kPaThreads),
+                           kPaSmemBytes, st, lp));
       } else {
-      dim3 grid(ceil_div(4 * lb.max_T, NW * 16), Hkv, lb.n);
-      constexpr int NS = 3;
-      constexpr int smem = chunk_attn_smem_bytes<128, NW, NS>();
-      static bool attr_set = false;
-      if (!attr_set) {
-        ISST_CUDA(cudaFuncSetAttribute(chunk_attention_kernel<128, false, NW, NS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, false>, dim3(row_tiles, Hkv, lb.n), dim3(kPaThreads),
+                           kPaSmemBytes, st, lp));
       }
-      ISST_CUDA(launch_k(ctx, chunk_attention_kernel<128, false, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
+      if (ks > 1) {
+        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(M * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, ks));
+        LAUNCH_CHECK(ctx);
       }
     } else if (grouped) {
       // algorithmic bytes: the shared prefix once per sentence + every beam's private tail
       const double tok = lb.prefix_tokens + (lb.kv_tokens - lb.prefix_tokens * lb.group);
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, tok * Hkv * HD * 2 * 2);
-      static bool grp_attr = false;
-      if (!grp_attr) {
-        ISST_CUDA(cudaFuncSetAttribute(decode_attention_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpSmemBytes));
-        grp_attr = true;
-      }
+      ISST_TRY(ensure_smem(ctx, decode_attention_group_kernel, kGrpSmemBytes));
+      ctx->paths["decode_attention_group"]++;
       const int n_groups = lb.n / lb.group;
       const int splits_p = decode_splits_for(ctx, n_groups, std::max(lb.max_prefix, 1));
       DecodeGroupParams gp{};
@@ -1250,11 +1158,6 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->cfg = *cfg;
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  const char* g = getenv("ISST_GEMM");
-  ctx->simple_gemm = g && std::string(g) == "simple";
-  ctx->gemm_v1 = g && std::string(g) == "v1";
-  const char* pd = getenv("ISST_PDL");
-  ctx->pdl = !(pd && std::string(pd) == "0");
   const isst_config& c = ctx->cfg;
   ISST_CHECK(c.n_conv >= 2 && c.n_conv <= ISST_MAX_CONV && c.n_adapter >= 0 && c.n_adapter <= ISST_MAX_CONV, "bad conv config");
   ctx->C = c.conv_dim[0];
@@ -1387,7 +1290,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->n_counters = 4096;
   ISST_TRY(dev_alloc(&ctx->gemm_counters, ctx->n_counters));
   ISST_CUDA(cudaMemset(ctx->gemm_counters, 0, ctx->n_counters * sizeof(int)));
-  ctx->meta_ints = kEncMetaInts + static_cast<size_t>(nb) * (c.max_prompt * 4 + 256 + c.max_new_tokens * 4) + 4096;
+  ctx->meta_ints = kEncMetaInts + static_cast<size_t>(nb) * (c.max_prompt * 4 + 256 + c.max_new_tokens * 5) + 4096;
   ISST_TRY(dev_alloc(&ctx->d_meta, ctx->meta_ints));
   ISST_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_meta), ctx->meta_ints * sizeof(int)));
   ISST_CUDA(cudaEventCreateWithFlags(&ctx->ev_active, cudaEventDisableTiming));
@@ -1506,7 +1409,9 @@ int isst_load_weight(isst_ctx* ctx, const char* name_c, const void* data, const 
     if (leaf == "fc1.bias") LV(w.b1, F);
     if (leaf == "fc2.weight") LM(w.w2.ptr, D, F);
     if (leaf == "fc2.bias") LV(w.b2, D);
-    if (leaf == "self_attn.rotary_emb.freqs") return 0;   // the host passes layer 0's copy as rope.enc.inv_freq
+    // rotary_embedding_torch buffers (freqs: the host passes layer 0's copy as rope.enc.inv_freq; scale / dummy /
+    // cached_* are persistent in some versions of the library): recomputed here, ignored like unused modules
+    if (starts_with(leaf, "self_attn.rotary_emb.")) return 0;
     return set_error("unknown encoder layer key: " + name);
   }
   if (starts_with(name, SPE + "length_shrink.conv_layers.")) {
@@ -1541,6 +1446,7 @@ int isst_load_weight(isst_ctx* ctx, const char* name_c, const void* data, const 
     if (leaf == "mlp.down_proj.weight") LM(w.wd.ptr, HID, c.ffn);
     if (leaf == "input_layernorm.weight") LV(w.rms1, HID);
     if (leaf == "post_attention_layernorm.weight") LV(w.rms2, HID);
+    if (starts_with(leaf, "self_attn.rotary_emb.")) return 0;   // older HF checkpoints carry per-layer inv_freq buffers
     return set_error("unknown LLM layer key: " + name);
   }
 #undef LM
@@ -1622,7 +1528,16 @@ int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* 
   ISST_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   ISST_CHECK(multiplier >= 1 && multiplier <= ctx->cfg.max_multiplier, "multiplier out of range");
-  const int n_new = ctx->cfg.block_size * multiplier * ctx->total_stride;
+  // One call brings j whole segments of block_size frames, 1 <= j <= multiplier: the reference pads a short final
+  // chunk to a multiple of ONE segment only (agents/infinisst.py:211-213) while the encoder mask keeps the block size
+  // of the multiplier (set_blocksize, speech_encoder.py:143-145); fewer frames then give fewer speech rows.
+  const int seg_samples = ctx->cfg.block_size * ctx->total_stride;
+  int n_new = ctx->cfg.block_size * multiplier * ctx->total_stride;
+  {
+    const int body = n_samples >= ctx->n_tail && (n_samples - ctx->n_tail) % seg_samples == 0 && n_samples % seg_samples != 0
+                         ? n_samples - ctx->n_tail : n_samples;
+    if (body % seg_samples == 0 && body >= seg_samples && body <= n_new) n_new = body;
+  }
   // A fresh stream's carried tail is zero (isst_stream_open), which IS the reference's 79+320 zero offset of the first
   // chunk: fresh and running streams may share a batch as long as every row brings exactly n_new samples.  The
   // explicit-offset form (n_new + 79+320 samples, as agents/infinisst.py:216-218 builds it) needs an all-fresh batch.
@@ -1630,7 +1545,8 @@ int isst_encode_chunk(isst_ctx* ctx, int n, const int* stream_ids, const float* 
   for (int b = 0; b < n; ++b) fresh = fresh && ctx->streams[stream_ids[b]].enc_prefix == 0;
   const bool with_offset = fresh && n_samples == n_new + ctx->n_tail;
   ISST_CHECK(n_samples == n_new || with_offset,
-             "n_samples must be block_size*multiplier*320 (+ 79+320 only when every stream of the batch is at its first chunk)");
+             "n_samples must be j*block_size*320 with 1 <= j <= multiplier (+ 79+320 only when every stream of the batch is "
+             "at its first chunk); feed pending audio one policy call at a time");
   ISST_CUDA(cudaStreamSynchronize(st));   // the pinned metadata region below may still be in flight from a previous call
   MetaBuilder mb{ctx};
   const size_t o_slots = mb.alloc(n), o_prefix = mb.alloc(n);
@@ -1793,6 +1709,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   const size_t o_next = mb.alloc(n), o_forced = mb.alloc(forced ? static_cast<size_t>(n) * max_new : 0);
   const size_t o_sup = mb.alloc(gen->n_suppress), o_eos = mb.alloc(8);
   const size_t o_ones = mb.alloc(n), o_iota = mb.alloc(n);
+  const size_t o_picked = mb.alloc(static_cast<size_t>(n) * max_new);
   ISST_CHECK(mb.used <= ctx->meta_ints, "metadata buffer too small");
   int row = 0, eoff = 0;
   for (int b = 0; b < n; ++b) {
@@ -1809,6 +1726,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     mb.host(o_iota)[b] = b;
     for (int s = 0; s < max_new; ++s) {
       mb.host(o_out)[static_cast<size_t>(b) * max_new + s] = -1;
+      mb.host(o_picked)[static_cast<size_t>(b) * max_new + s] = -1;
       if (forced) mb.host(o_forced)[static_cast<size_t>(b) * max_new + s] = forced[static_cast<size_t>(b) * max_new + s];
     }
     row += lens[b];
@@ -1822,7 +1740,7 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
   GenState g{};
   g.ctx_ids = mb.dev(o_ctx); g.ctx_len = mb.dev(o_ctxlen); g.enc_ids = mb.dev(o_enc); g.enc_len = mb.dev(o_enclen);
   g.active = mb.dev(o_active); g.out_tokens = mb.dev(o_out); g.out_count = mb.dev(o_cnt); g.next_token = mb.dev(o_next);
-  g.forced = forced ? mb.dev(o_forced) : nullptr; g.suppress = mb.dev(o_sup); g.eos = mb.dev(o_eos);
+  g.forced = forced ? mb.dev(o_forced) : nullptr; g.picked = mb.dev(o_picked); g.suppress = mb.dev(o_sup); g.eos = mb.dev(o_eos);
   g.ctx_cap = ctx_cap; g.enc_cap = enc_cap; g.max_new = max_new; g.n_suppress = gen->n_suppress; g.n_eos = gen->n_eos;
   g.ngram = gen->no_repeat_ngram_size; g.penalty = gen->repetition_penalty;
 
@@ -1842,6 +1760,8 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
     ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(kSelParts, n), dim3(kSelThreads), 0, st, ctx->logits, c.vocab, g, ctx->sel_ws));
     LAUNCH_CHECK(ctx);
   }
+  // the select kernel applied the processors in place: `logits` now holds the scores the arg-max saw
+  ISST_TRY(tap(ctx, st, "step_scores", ctx->logits, lbytes, 0, lbytes * max_new));
   // ---- decode steps ----
   LlmBatch db = lb;
   db.M = n; db.max_T = 1; db.d_T = mb.dev(o_ones); db.d_tok_base = mb.dev(o_iota); db.d_last_row = mb.dev(o_iota);
@@ -1878,7 +1798,9 @@ int isst_generate(isst_ctx* ctx, int n, const int* stream_ids, const int32_t* id
       ISST_CUDA(launch_k(ctx, greedy_select_kernel, dim3(kSelParts, n), dim3(kSelThreads), 0, st, ctx->logits, c.vocab, g, ctx->sel_ws));
       LAUNCH_CHECK(ctx);
     }
+    ISST_TRY(tap(ctx, st, "step_scores", ctx->logits, lbytes, lbytes * step, lbytes * max_new));
   }
+  ISST_TRY(tap(ctx, st, "step_picked", mb.dev(o_picked), static_cast<size_t>(n) * max_new * sizeof(int)));
   ISST_CUDA(cudaMemcpyAsync(ctx->h_meta + o_out, mb.dev(o_out), static_cast<size_t>(n) * max_new * sizeof(int), cudaMemcpyDeviceToHost, st));
   ISST_CUDA(cudaMemcpyAsync(ctx->h_meta + o_cnt, mb.dev(o_cnt), n * sizeof(int), cudaMemcpyDeviceToHost, st));
   ISST_CUDA(cudaStreamSynchronize(st));
@@ -2415,10 +2337,26 @@ int isst_debug_shift_positions(isst_ctx* ctx, int stream_id, int64_t delta) {
 }
 
 int64_t isst_launch_count(isst_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int isst_path_count(isst_ctx* ctx, const char* name, int64_t* count) {
+  ISST_CHECK(ctx && name && count, "null argument");
+  auto it = ctx->paths.find(name);
+  *count = it == ctx->paths.end() ? 0 : it->second;
+  return 0;
+}
+
+int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
+  ISST_CHECK(ctx && key_c, "null argument");
+  const std::string key(key_c);
+  if (key == "pdl") ctx->pdl = value != 0;
+  else if (key == "decode_splits") ctx->opt_dec_splits = value;
+  else return set_error("unknown option: " + key);
+  return 0;
+}
 int isst_pages_free(isst_ctx* ctx) { return ctx ? static_cast<int>(ctx->free_pages.size()) : -1; }
 
 int isst_op_gemm(isst_ctx* ctx, const void* act_bf16, const void* w_bf16, int M, int N, int K, const float* bias,
-                 int act_gelu, const void* resid_bf16, int dual, void* out, int out_f32, int impl, int force_swap,
+                 int act_gelu, const void* resid_bf16, int dual, void* out, int out_f32, int force_swap,
                  int force_splits, void* cuda_stream) {
   ISST_CHECK(ctx && act_bf16 && w_bf16 && out, "null argument");
   ISST_CUDA(cudaSetDevice(ctx->device));
@@ -2431,7 +2369,7 @@ int isst_op_gemm(isst_ctx* ctx, const void* act_bf16, const void* w_bf16, int M,
   Epilogue e;
   e.bias = bias; e.act = act_gelu; e.resid = static_cast<const bf16*>(resid_bf16); e.ldr = N; e.out_f32 = out_f32;
   e.dual = dual; e.dual_off = dual ? N : 0;
-  return gemm(ctx, st, plain_view(static_cast<const bf16*>(act_bf16), M, K), w, N, out, N, 0, e, force_swap, force_splits, impl);
+  return gemm(ctx, st, plain_view(static_cast<const bf16*>(act_bf16), M, K), w, N, out, N, 0, e, force_swap, force_splits);
 }
 
 int isst_op_decode_attention_bench(isst_ctx* ctx, int n, int L, int iters, float* ms_per_iter, void* cuda_stream) {

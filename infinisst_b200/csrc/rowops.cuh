@@ -1,5 +1,5 @@
 // Memory-bound row kernels: conv0 + LayerNorm + GELU, LayerNorm / RMSNorm rows, embedding gather +
-// speech splice, logits processors + arg-max, and the CUDA-core validation GEMM.
+// speech splice, logits processors + arg-max.
 #pragma once
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
@@ -358,6 +358,7 @@ struct GenState {
   int* out_count;      // [n]
   int* next_token;     // [n] token to forward at the next decode step
   const int* forced;   // [n][max_new] or null (teacher forcing for parity tests)
+  int* picked;         // [n][max_new] or null: the arg-max of the processed scores at every step, whatever `forced` says
   const int* suppress; // [n_suppress]
   const int* eos;      // [n_eos]
   int ctx_cap, enc_cap, max_new, n_suppress, n_eos;
@@ -478,6 +479,7 @@ greedy_select_kernel(float* logits, int V, GenState g, SelectWs ws) {
   }
   ws.count[b] = 0;
   int tok = (bi == 0x7fffffff) ? 0 : bi;
+  if (g.picked) g.picked[static_cast<size_t>(b) * g.max_new + g.step] = tok;
   if (g.forced) tok = g.forced[static_cast<size_t>(b) * g.max_new + g.step];
   g.out_tokens[static_cast<size_t>(b) * g.max_new + g.step] = tok;
   g.out_count[b] = g.step + 1;
@@ -496,70 +498,6 @@ __global__ void advance_kv_len_kernel(int* kv_len, const int* __restrict__ slots
   pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < n && (!active || active[b])) kv_len[slots[b]] += Tn[b];
-}
-
-// ----------------------------------------------------------------------------------------------
-// CUDA-core validation GEMM (same contract as tc::gemm_tcgen05_kernel; selected with ISST_GEMM=simple).
-// It exists to separate "tcgen05 kernel wrong" from "everything else wrong" on the GPU box; the product
-// default is the tcgen05 kernel.  One warp = one output feature x 8 tokens.
-// Activation addressing covers the im2col-free conv view: element (tok, kidx) lives at
-//   act + b*act_batch_stride + ((tok*conv_s + kidx / conv_c) * conv_c + kidx % conv_c).
-// ----------------------------------------------------------------------------------------------
-struct SimpleGemmExtra {
-  const bf16* act;
-  long long act_batch_stride;
-  int conv_c, conv_s;
-  const bf16* w;     // [rows, K] row-major
-  int dual;
-};
-
-__global__ void __launch_bounds__(256)
-gemm_simple_kernel(const tc::GemmParams p, const SimpleGemmExtra x) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * 8 + warp;
-  const int t0 = blockIdx.y * 8;
-  const int b = blockIdx.z;
-  if (f >= p.N_out) return;
-  float acc0[8], acc1[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
-  const bf16* w0 = x.w + static_cast<size_t>(f) * p.K;
-  const bf16* w1 = x.w + static_cast<size_t>(f + p.dual_off) * p.K;
-  const bf16* a = x.act + static_cast<size_t>(b) * x.act_batch_stride;
-  for (int k = lane * 2; k < p.K; k += 64) {
-    const float2 wv = __bfloat1622float2(*reinterpret_cast<const bf162*>(w0 + k));
-    float2 uv = make_float2(0.f, 0.f);
-    if (x.dual) uv = __bfloat1622float2(*reinterpret_cast<const bf162*>(w1 + k));
-    const int kk = k / x.conv_c, c = k % x.conv_c;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int tok = t0 + i;
-      if (tok < p.M_tok) {
-        const float2 av = __bfloat1622float2(*reinterpret_cast<const bf162*>(
-            a + (static_cast<size_t>(tok) * x.conv_s + kk) * x.conv_c + c));
-        acc0[i] += av.x * wv.x + av.y * wv.y;
-        if (x.dual) acc1[i] += av.x * uv.x + av.y * uv.y;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    acc0[i] = warp_sum(acc0[i]);
-    if (x.dual) acc1[i] = warp_sum(acc1[i]);
-  }
-  if (lane == 0) {
-    for (int i = 0; i < 8; ++i) {
-      const int tok = t0 + i;
-      if (tok >= p.M_tok) break;
-      float v = acc0[i] + (p.bias ? p.bias[f] : 0.f);
-      if (x.dual) v = silu(v) * acc1[i];
-      if (p.act == 1) v = gelu_erf(v);
-      if (p.resid) v += __bfloat162float(p.resid[b * p.resid_batch_stride + static_cast<long long>(tok) * p.ldr + f]);
-      const long long oi = b * p.out_batch_stride + static_cast<long long>(tok) * p.ldo + f;
-      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = v;
-      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(v);
-    }
-  }
 }
 
 }  // namespace isst

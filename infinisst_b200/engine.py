@@ -154,6 +154,15 @@ class Engine:
     def launch_count(self) -> int:
         return self.lib.isst_launch_count(self.h)
 
+    def path_count(self, name: str) -> int:
+        """Launches so far of one kernel variant (isst_path_count)."""
+        v = C.c_int64()
+        _lib.check(self.lib.isst_path_count(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def option(self, key: str, value: int) -> None:
+        _lib.check(self.lib.isst_debug_option(self.h, key.encode(), int(value)))
+
     # ------------------------------------------------------------------ the per-chunk step
     def _stream_ptr(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -339,7 +348,7 @@ class Engine:
 
     # ------------------------------------------------------------------ stand-alone operators
     def op_gemm(self, act: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
-                resid: Optional[torch.Tensor] = None, dual: bool = False, out_f32: bool = False, impl: int = 0,
+                resid: Optional[torch.Tensor] = None, dual: bool = False, out_f32: bool = False,
                 force_swap: int = -1, force_splits: int = 0) -> torch.Tensor:
         M, K = act.shape
         N = w.shape[0] // (2 if dual else 1)
@@ -348,7 +357,7 @@ class Engine:
             self.h, C.c_void_p(act.data_ptr()), C.c_void_p(w.data_ptr()), M, N, K,
             C.c_void_p(bias.data_ptr()) if bias is not None else None, int(gelu),
             C.c_void_p(resid.data_ptr()) if resid is not None else None, int(dual), C.c_void_p(out.data_ptr()),
-            int(out_f32), impl, force_swap, force_splits, self._stream_ptr()))
+            int(out_f32), force_swap, force_splits, self._stream_ptr()))
         return out
 
     def decode_attention_bench(self, n: int, L: int, iters: int = 20) -> float:

@@ -1,5 +1,5 @@
 """GPU micro-benchmark of the GEMM kernels on the production shapes (not a pytest file).
-    python tests/gemm_bench.py            # stream-K kernel, plus the previous generation (ISST_GEMM=v1) for A/B
+    python tests/gemm_bench.py            # stream-K tcgen05 kernel
 Weights rotate over enough distinct buffers that no launch finds its weights in L2."""
 import os
 import sys
@@ -70,11 +70,7 @@ def stamps(eng, M, N, K, kw):
 
 def main():
     out = []
-    for mode in (["sk", "v1"] if "--ab" in sys.argv else ["sk"]):
-        if mode == "v1":
-            os.environ["ISST_GEMM"] = "v1"
-        else:
-            os.environ.pop("ISST_GEMM", None)
+    for mode in ["sk"]:
         eng = Engine(tiny_config(), device=0, max_streams=2)
         for (name, M, N, K, kw) in SHAPES:
             us, tf, gbs = bench(eng, name, M, N, K, kw)

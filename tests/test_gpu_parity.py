@@ -72,8 +72,7 @@ def op_engine():
     eng.close()
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "cuda_core"])
-def test_gemm_vs_torch_fp32(op_engine, impl):
+def test_gemm_vs_torch_fp32(op_engine):
     """out = act . W^T with every fused epilogue, against a plain PyTorch fp32 reference of the op.
     Inputs are bf16, accumulation fp32: the only error is the bf16 rounding of the output."""
     torch.manual_seed(0)
@@ -94,7 +93,7 @@ def test_gemm_vs_torch_fp32(op_engine, impl):
         if resid is not None:
             ref = ref + resid.float()
         out = op_engine.op_gemm(a, w, bias=bias, gelu=kw.get("gelu", False), resid=resid, dual=dual,
-                                out_f32=kw.get("out_f32", False), impl=impl, force_swap=kw.get("force_swap", -1),
+                                out_f32=kw.get("out_f32", False), force_swap=kw.get("force_swap", -1),
                                 force_splits=kw.get("force_splits", 0))
         torch.cuda.synchronize()
         tol = 2e-5 if kw.get("out_f32") else 4e-3            # fp32 out: accumulation order only; bf16 out: 2^-8 rounding
