@@ -97,6 +97,9 @@ class S2TAgentStates(AgentStates):
 
     def reset(self):
         super().reset()
+        for m in getattr(self, "_pseudo_mirrors", None) or []:
+            m.reset()
+        self._pseudo_mirrors = None
         if getattr(self, "speech_cache", None) is not None:
             self.speech_cache.close()        # give the stream slot and its KV pages back
         self.src_len = 0
@@ -186,11 +189,12 @@ class InfiniSST(SpeechToTextAgent):
         self.do_sample = getattr(args, "do_sample", False)
         self.top_p, self.top_k = getattr(args, "top_p", 1.0), getattr(args, "top_k", 0)
         self.epsilon_cutoff, self.temperature = getattr(args, "epsilon_cutoff", 0.0), getattr(args, "temperature", 1.0)
+        # --pseudo-batch-size B (agents/infinisst.py:291-301): the reference tiles ONE stream B times (audio, prompt, both
+        # caches) to measure batched throughput and reads row 0.  Here B engine streams mirror the stream: they are fed
+        # the same audio / prompt through one batched call, so the batched kernels run on B rows and row 0 is returned.
         self.pseudo_batch_size = getattr(args, "pseudo_batch_size", 1)
-        if self.pseudo_batch_size != 1:
-            # the reference tiles ONE stream B times to measure batched throughput (agents/infinisst.py:291-301); here
-            # batches are made of independent streams (policy_batch) - refuse instead of silently running B = 1
-            raise ValueError("--pseudo-batch-size > 1 is not supported: batch independent streams with policy_batch")
+        if self.pseudo_batch_size < 1:
+            raise ValueError("--pseudo-batch-size must be >= 1")
         self.max_llm_cache_size = args.max_llm_cache_size
         self.always_cache_system_prompt = args.always_cache_system_prompt
         self.dpo_sampling = getattr(args, "dpo_sampling", False)              # agents/infinisst.py:100-101
@@ -253,9 +257,26 @@ class InfiniSST(SpeechToTextAgent):
         if self.suppress_non_language and not self.bad_words_ids:
             n_vocab = len(self.tokenizer) if hasattr(self.tokenizer, "__len__") else cfg.llm.vocab
             self.bad_words_ids = non_language_token_ids(self.tokenizer, n_vocab)
+        # cfg.gen mirrors the flags the engine sizes itself from (the agent evicts with --max-llm-cache-size, so the KV
+        # capacity must follow it, not the config default)
+        cfg.gen.max_llm_cache_size = int(args.max_llm_cache_size)
+        cfg.gen.always_cache_system_prompt = bool(args.always_cache_system_prompt)
+        cfg.gen.no_repeat_ngram_size = int(args.no_repeat_ngram_size)
+        cfg.gen.no_repeat_ngram_lookback = int(args.no_repeat_ngram_lookback)
+        cfg.gen.repetition_penalty = float(args.repetition_penalty)
+        cfg.gen.latency_multiplier = int(self.latency_multiplier)
+        cfg.gen.beam = int(self.beam)
+        # engine capacities from the flags: first-chunk prompt = system + 9 header tokens + block_size//4 * m speech
+        # slots (agents/infinisst.py:225-260; 73 / 85 / 97 tokens at m = 2 / 3 / 4 with a 40-token system turn), longest
+        # generation = --max-new-tokens or 10 * m after update_multiplier (:125-128)
+        n_speech_max = args.block_size // 4 * max(self.max_latency_multiplier, self.latency_multiplier)
+        max_prompt = len(cfg.tpl.system_ids) + 10 + n_speech_max + 8
+        max_new = max(int(self.max_new_tokens), 10 * max(self.max_latency_multiplier, self.latency_multiplier))
         self.model = SpeechLlamaForCausalLM(
-            cfg, engine=getattr(args, "engine", None), max_streams=getattr(args, "max_streams", 8),
-            max_multiplier=self.max_latency_multiplier, max_beams=self.beam)
+            cfg, engine=getattr(args, "engine", None),
+            max_streams=max(getattr(args, "max_streams", 8), self.pseudo_batch_size),
+            max_multiplier=max(self.max_latency_multiplier, self.latency_multiplier), max_beams=self.beam,
+            max_prompt=max(64, max_prompt), max_new_tokens=max_new)
         if sd is not None:
             ck.check_state_dict(sd, cfg)
             self.model.load_state_dict(sd)
@@ -320,10 +341,14 @@ class InfiniSST(SpeechToTextAgent):
             states.source = states.source[-states.MAX_SRC_LEN:]
         src = states.source[states.src_len:]
         source = src.float() if isinstance(src, torch.Tensor) else torch.tensor(src, dtype=torch.float32)
-        seg = sp_seg_frame * self.latency_multiplier
-        if source.size(0) % seg != 0:
-            n_pad = seg - source.size(0) % seg
+        if source.size(0) % sp_seg_frame != 0:                                # :211-213: ONE segment, whatever m is
+            n_pad = sp_seg_frame - source.size(0) % sp_seg_frame
             source = torch.cat([source, torch.zeros(n_pad)], dim=0)
+        if source.size(0) > sp_seg_frame * self.latency_multiplier:
+            # more than m segments pending (e.g. --min-start-sec beyond one chunk): the reference would encode them all
+            # and splice only the first 12 * m features (model/llm.py:101-110); that silent truncation is refused here
+            raise ValueError(f"{source.size(0) // sp_seg_frame} audio segments are pending but one policy call takes at "
+                             f"most latency_multiplier = {self.latency_multiplier}; call policy once per source segment")
         if states.src_len == 0 and explicit_offset:
             source = torch.cat([torch.zeros(79 + 320), source], dim=0)
         states.src_len = len(states.source)
@@ -355,7 +380,10 @@ class InfiniSST(SpeechToTextAgent):
         input_ids = tok.apply_chat_template([messages], return_tensors="pt", padding=True, truncation=False,
                                             add_special_tokens=False)[:, :-1]
         if states.speech_cache is not None:
-            input_ids = input_ids[:, 25:]          # Llama-3.1 default system header (agents/infinisst.py:262-264)
+            if self.llama31:
+                input_ids = input_ids[:, 25:]      # Llama-3.1 default system header (agents/infinisst.py:262-264)
+            else:
+                input_ids[:, 0] = tok.eos_token_id  # llama-3-8B-instruct (:265-266)
         return input_ids
 
     def _evict(self, states) -> None:
@@ -377,6 +405,9 @@ class InfiniSST(SpeechToTextAgent):
                     states.translations_list = []
                 except Exception as e:  # noqa: BLE001 - the reference reports and carries on
                     print(f"Error writing translations to file: {e}")
+        # the reference's per-chunk log line (agents/infinisst.py:384): KV length and the words emitted so far
+        if getattr(getattr(self, "args", None), "log_chunks", True) and states.past_key_values is not None:
+            print(states.past_key_values[0][0].size(2), (" " if self.target_lang != "Chinese" else "").join(states.target))
         states.segment_idx += 1
         if translation != "" or states.source_finished:
             return WriteAction(content=translation, finished=states.source_finished)
@@ -386,6 +417,14 @@ class InfiniSST(SpeechToTextAgent):
     def policy(self, states: Optional[S2TAgentStates] = None):
         if states is None:
             states = self.states
+        if self.pseudo_batch_size > 1:
+            # agents/infinisst.py:291-301: B - 1 mirror streams receive the same audio and prompts, row 0 is the stream
+            mirrors = getattr(states, "_pseudo_mirrors", None)
+            if mirrors is None:
+                mirrors = states._pseudo_mirrors = [self.build_states() for _ in range(self.pseudo_batch_size - 1)]
+            for m in mirrors:
+                m.source, m.source_sample_rate, m.source_finished = states.source, states.source_sample_rate, states.source_finished
+            return self.policy_batch([states] + mirrors)[0]
         return self.policy_batch([states])[0]
 
     @torch.inference_mode()
@@ -405,6 +444,9 @@ class InfiniSST(SpeechToTextAgent):
             return actions
         with synchronized_timer("generate", self.chunk_latencies):
             sts = [states_list[i] for i in run]
+            for st in sts:
+                if st.source_finished:
+                    st.segment_idx = -1                                       # agents/infinisst.py:303-304
             first = [st.speech_cache is None for st in sts]
             mixed = any(first) != all(first)
             # streams may join a running batch: a joining stream brings the long first-chunk prompt (system + turn)

@@ -199,6 +199,13 @@ class SpeechLlamaForCausalLM:
             ids = [input_ids[b].tolist() for b in range(B)]
         self.model.speech_encoder.set_blocksize(multiplier)
         self.engine.encode_chunk([h.sid for h in handles], speech_batch.float(), multiplier)
+        # model/llm.py:101-110 splices `speech_features[i, index : index + a_p - u_p - 5]` between the headers with
+        # torch.cat: when the encoder produced FEWER features than the prompt has <sp_patch> slots (short final chunk at
+        # multiplier > 1) the spliced sequence is simply shorter.  Same here: the surplus slots are not fed to the LLM.
+        slot_maps = [self._slot_map(r) for r in ids]
+        n_feat = self.engine.speech_tokens
+        fed = [[t for t, sl in zip(r, sm) if sl < n_feat] for r, sm in zip(ids, slot_maps)]
+        fed_slots = [[sl for sl in sm if sl < n_feat] for sm in slot_maps]
         enc = [[] for _ in range(B)]
         if isinstance(encoder_input_ids, (list, tuple)):      # extension: ragged per-stream histories
             enc = [[int(t) for t in row] for row in encoder_input_ids]
@@ -217,13 +224,13 @@ class SpeechLlamaForCausalLM:
         if num_beams > 1:
             # beam search with KV hand-back (patch_hf.py:626-655, 687-967; agents/infinisst.py:334-336): `sequences`
             # is the best hypothesis (closing EOS appended when it fits), the handle continues from ITS cache
-            res = self.engine.generate_beam([h.sid for h in handles], ids, [self._slot_map(r) for r in ids], enc, g,
+            res = self.engine.generate_beam([h.sid for h in handles], fed, fed_slots, enc, g,
                                             num_beams, pin_prefix=pin_prefix, length_penalty=float(length_penalty),
                                             follow=beam_follow, want_trace=beam_trace)
             toks = res[0]
             extra = {"sequences_scores": torch.tensor(res[1]), "beam_trace": res[2] if beam_trace else None}
         else:
-            toks = self.engine.generate([h.sid for h in handles], ids, [self._slot_map(r) for r in ids], enc, g,
+            toks = self.engine.generate([h.sid for h in handles], fed, fed_slots, enc, g,
                                         pin_prefix=pin_prefix, forced=forced_tokens)
         pad = self.cfg.gen.pad_token_id if pad_token_id is None else pad_token_id
         width = max(len(r) + len(t) for r, t in zip(ids, toks))

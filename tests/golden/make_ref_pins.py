@@ -225,13 +225,23 @@ def main():
         out["m2_n_chunks"], out["m2_max_llm"] = np.int32(n_m), np.int32(200)
         for c in range(n_m):
             st_m.source = audio[: (c + 1) * seg * m].tolist()
+            if c == n_m - 1:
+                # short FINAL chunk at m = 2: the agent pads to ONE segment only
+                # (agents/infinisst.py:211-213): half a segment of new audio becomes 48 frames = 12 features for a
+                # prompt that still has 24 <sp_patch> slots; the splice (model/llm.py:101-110) then yields a SHORTER
+                # sequence, and states.source_finished sets segment_idx = -1 (:303-304)
+                st_m.source = audio[: c * seg * m + seg // 2].tolist()
+                st_m.source_finished = True
             kv_before = 0 if st_m.past_key_values is None else st_m.past_key_values[0][0].size(2)
             agent.policy(st_m)
             gen = taps["gen"]
             out[f"m2_c{c}_speech_feats"] = taps["speech_feats"][0].numpy().astype(np.float32)
             out[f"m2_c{c}_step_logits"] = torch.stack([x[0] for x in gen.step_logits]).numpy().astype(np.float32)
             out[f"m2_c{c}_sequence"] = gen.sequences[0].numpy().astype(np.int32)
-            out[f"m2_c{c}_kv"] = np.array([kv_before + gen.sequences.size(1) - 1, st_m.past_key_values[0][0].size(2)], dtype=np.int32)
+            # KV length right after generate = last-layer K rows of the returned cache (a short final chunk feeds
+            # fewer positions than `sequences` has prompt ids)
+            out[f"m2_c{c}_kv"] = np.array([gen.past_key_values_pre[0].size(2), st_m.past_key_values[0][0].size(2)], dtype=np.int32)
+            out[f"m2_c{c}_n_feats"] = np.int32(taps["speech_feats"].shape[1])
             print(f"m=2 chunk {c}: kv {kv_before} -> {out[f'm2_c{c}_kv'].tolist()}")
         agent.update_multiplier(1)
     # ---- eviction timelines: the agent's own eviction code (agents/infinisst.py:334-361) on a cache whose

@@ -64,3 +64,37 @@ def variant_state_dict(cfg, name: str, seed: int = 0) -> Dict[str, torch.Tensor]
             if "speech_encoder" in k and (".self_attn.q_proj." in k or ".self_attn.k_proj." in k):
                 sd[k] = sd[k] * f
     return bf16_weights(sd)
+
+
+def sharpen_lm_head(sd: Dict[str, torch.Tensor], cfg, n_gen: int = 2048, levels: int = 14, ratio: float = 0.85,
+                    embed_norm: float = 6400.0, seed: int = 4321) -> List[int]:
+    """Synthetic weights whose greedy margins are healthy (SURVEY §7 hard part 2, option (c)), in place.
+
+    With random weights the 128 263 last-position logits are nearly i.i.d.: the top-2 gap is below the bf16 error of
+    ANY implementation in ~20 % of the steps, so free-running token streams of two correct implementations part after
+    a few tokens.  Here a family of `n_gen` + 1 tokens (the "\\n\\n" that ends every turn prompt and `n_gen` plain
+    vocabulary ids) gets orthonormal embedding directions that dominate the residual stream, and lm_head row v is
+    sum_j ratio^j * direction(predecessor_j(v)): after token t the logits are ~64 * ratio^j on the j-th successor of t
+    and ~0 elsewhere (exactly 0 outside the family), i.e. well separated fall-back candidates.  Which candidate wins is
+    decided by the logits processors (repetition penalty, n-gram and encoder-n-gram bans fire in every chunk), so a
+    free-running stream exercises them on the device while staying comparable between implementations.
+    Returns the generating vocabulary."""
+    E, lm = sd["model.embed_tokens.weight"], sd["lm_head.weight"]
+    V, D = lm.shape
+    assert n_gen + 1 <= D
+    g = torch.Generator(device=lm.device).manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(D, D, device=lm.device, dtype=torch.float32, generator=g))
+    q = q.t().contiguous()[: n_gen + 1]                                   # orthonormal rows
+    gen_ids = [2000 + 37 * k for k in range(n_gen)]          # clear of the synthetic system prompt's filler ids
+    special = {cfg.tpl.user_token_id, cfg.tpl.assist_token_id, cfg.tpl.nl_id, cfg.tpl.eot_id}
+    assert gen_ids[-1] < min(V, 128000) and not special & set(gen_ids)
+    family = torch.tensor([cfg.tpl.nl_id] + gen_ids, device=lm.device)
+    E[family] = (embed_norm * q).to(E.dtype)
+    new = torch.zeros(V, D, device=lm.device, dtype=torch.float32)
+    idx = torch.arange(n_gen + 1, device=lm.device)
+    gen_t = torch.tensor(gen_ids, device=lm.device)
+    for j in range(levels):
+        succ = (idx + 1 + 97 * j) % n_gen                                 # j-th successor of family member i (a generating id)
+        new.index_add_(0, gen_t[succ], (ratio ** j) * q)
+    lm.copy_(new.to(lm.dtype))
+    return gen_ids

@@ -363,6 +363,62 @@ def test_agent_drop_in_api():
     agent.model.engine.close()
 
 
+@pytest.mark.parametrize("flags", [["--latency-multiplier", "2", "--max-new-tokens", "20"],
+                                   ["--latency-multiplier", "4", "--max-new-tokens", "40"],
+                                   ["--latency-multiplier", "3"],
+                                   ["--latency-multiplier", "2", "--max-new-tokens", "20", "--pseudo-batch-size", "3"]],
+                         ids=["m2", "m4", "m3_default_max_new_and_cache", "m2_pseudo_batch3"])
+def test_agent_sizes_its_engine_from_the_flags(flags):
+    """The agent's own flags size the engine (first-chunk prompt = 40 + 9 + 12 m tokens: 73 / 85 / 97 at m = 2 / 3 / 4;
+    `--max-new-tokens` defaults to 1000 and `--max-llm-cache-size` to 10000, agents/infinisst.py:185-198 +
+    agents/options.py).  m = 2 is held against the oracle (tokens up to the first near-tie, KV lengths); the default
+    flags must simply run: 1000 new tokens per call, a 10000-token window that never evicts here."""
+    import argparse
+    from infinisst_b200.agent import InfiniSST
+    cfg = tiny_config(max_cache_size=192, max_llm_cache_size=300)
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    p = argparse.ArgumentParser()
+    InfiniSST.add_args(p)
+    base = ["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", "192", "--xpos", "0", "--no-repeat-ngram-size", "5",
+            "--always-cache-system-prompt", "--beam", "1"]
+    defaults = "--max-new-tokens" not in flags
+    if not defaults:
+        base += ["--max-llm-cache-size", "300"]
+    args = p.parse_args(base + flags)
+    args.model_config, args.state_dict, args.log_chunks = cfg, sd, False
+    agent = InfiniSST(args)
+    m = args.latency_multiplier
+    states = agent.build_states()
+    states.source_sample_rate = 16000
+    n_calls = 2 if defaults else 5
+    audio = make_audio(n_calls * m * SEG / 16000.0)
+    cfg_o = tiny_config(max_cache_size=192, max_llm_cache_size=300)
+    cfg_o.gen.latency_multiplier, cfg_o.gen.max_new_tokens = m, args.max_new_tokens
+    orc = OracleStream(cfg_o, sd)
+    agree = not defaults
+    for c in range(n_calls):
+        states.source = audio[: (c + 1) * m * SEG].tolist()
+        states.source_finished = c == n_calls - 1
+        n_before = len(states.target_ids)
+        act = agent.policy(states)
+        assert not act.is_read()
+        kv = states.past_key_values[0][0].size(2)
+        if defaults:
+            assert len(states.target_ids) - n_before <= 999 and kv <= 10000 + 40
+            continue
+        out_o, rec, _ = orc.chunk(audio[: (c + 1) * m * SEG].tolist())
+        if agree and states.target_ids[n_before:] != out_o:
+            agree = False
+            margins = [float(s[0].max() - s[0].topk(2).values[1]) for s in rec.step_scores]
+            assert min(margins) < TIE_EPS, (c, margins)
+        if agree:
+            assert kv == orc.st.llm_cache.length()
+        assert kv <= 300 + 40 + 22 + 12 * m + 10 * m
+    assert act.finished and states.segment_idx == 0          # -1 on the last segment (agents/infinisst.py:303-304), then += 1
+    states.reset()
+    agent.model.engine.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # production widths
 # ----------------------------------------------------------------------------------------------

@@ -71,7 +71,12 @@ def test_oracle_reproduces_reference_stream_multiplier_2(pins):
     audio = make_audio(int(pins["n_chunks"]) * SEG / 16000.0)
     orc = OracleStream(cfg, sd)
     for c in range(n):
-        out_ids, rec, taps = orc.chunk(audio[: (c + 1) * SEG * m].tolist())
+        # the last call is a SHORT FINAL chunk: half a segment of new audio, padded by the agent to ONE segment
+        # (agents/infinisst.py:211-213) -> 12 features for a prompt with 24 <sp_patch> slots; the reference's splice
+        # (model/llm.py:101-110) then feeds a shorter sequence to the LLM
+        src = audio[: (c + 1) * SEG * m] if c < n - 1 else audio[: c * SEG * m + SEG // 2]
+        out_ids, rec, taps = orc.chunk(src.tolist())
+        assert taps["speech_feats"].shape[1] == int(pins[f"m2_c{c}_n_feats"]) == (24 if c < n - 1 else 12)
         np.testing.assert_allclose(taps["speech_feats"][0].numpy(), pins[f"m2_c{c}_speech_feats"], atol=1e-5, rtol=1e-5)
         got = torch.stack([l[0] for l in rec.step_logits]).numpy()
         np.testing.assert_allclose(got, pins[f"m2_c{c}_step_logits"], atol=2e-4, rtol=1e-4)
@@ -204,4 +209,58 @@ def test_cuda_path_reproduces_reference_stream(pins):
             eng.kv_evict(sid, plan[0], plan[1])
         assert eng.kv_len(sid) == after
         assert eng.enc_steps(sid) == int(pins[f"c{c}_enc_steps"])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_reference_stream_multiplier_2(pins):
+    """Latency multiplier 2 through `model.generate` (the reference-facing call), ending with the SHORT FINAL chunk
+    of the pins: 12 speech features for 24 <sp_patch> slots - the surplus slots are not fed (model/llm.py:101-110),
+    `sequences` still carries the whole prompt, the KV grows by the shorter sequence."""
+    from infinisst_b200.agent import S2TAgentStates, evict_plan
+    from infinisst_b200.engine import Engine
+    from infinisst_b200.model import SpeechLlamaForCausalLM
+    n, m = int(pins["m2_n_chunks"]), 2
+    cfg = tiny_config(max_cache_size=int(pins["max_cache"]), max_llm_cache_size=int(pins["m2_max_llm"]))
+    cfg.gen.latency_multiplier, cfg.gen.max_new_tokens = m, 10 * m
+    g = cfg.gen
+    sd = bf16_weights(make_state_dict(cfg, seed=0))
+    eng = Engine(cfg, device=0, max_streams=2, max_multiplier=m, max_prompt=64 + 12 * m)
+    eng.load_state_dict(sd)
+    eng.debug(True)
+    model = SpeechLlamaForCausalLM(cfg, engine=eng)
+    audio = make_audio(int(pins["n_chunks"]) * SEG / 16000.0)
+    st = S2TAgentStates()
+    st.system_prompt_size = len(cfg.tpl.system_ids)
+    for c in range(n):
+        last = c == n - 1
+        pcm = audio[c * SEG * m:(c + 1) * SEG * m] if not last else \
+            torch.cat([audio[c * SEG * m: c * SEG * m + SEG // 2], torch.zeros(SEG - SEG // 2)])
+        pcm = pcm[None].clone()
+        if c == 0:
+            pcm = torch.cat([torch.zeros(1, 399), pcm], 1)
+        seq = pins[f"m2_c{c}_sequence"].tolist()
+        ids = O.build_prompt(cfg.tpl, c == 0, m)
+        assert seq[:len(ids)] == ids
+        forced = seq[len(ids):]
+        out = model.generate(input_ids=torch.tensor([ids]), speech_batch=pcm, num_beams=1, max_new_tokens=g.max_new_tokens,
+                             encoder_input_ids=[st.target_ids[-100:]], encoder_no_repeat_ngram_size=g.no_repeat_ngram_size,
+                             no_repeat_ngram_size=g.no_repeat_ngram_size, repetition_penalty=g.repetition_penalty,
+                             pad_token_id=g.pad_token_id, states=st, multiplier=m, forced_tokens=[forced],
+                             pin_prefix=len(cfg.tpl.system_ids))
+        assert out.sequences[0].tolist() == seq                              # whole prompt + chosen tokens
+        assert eng.speech_tokens == int(pins[f"m2_c{c}_n_feats"])
+        feats = eng.read_tap("speech_feats").float().view(-1, cfg.llm.hidden)[: eng.speech_tokens]
+        assert rel_l2(feats, torch.from_numpy(pins[f"m2_c{c}_speech_feats"])) < 3e-2, c
+        logits = eng.read_tap("step_logits", torch.float32).view(g.max_new_tokens, cfg.llm.vocab)
+        ref = torch.from_numpy(pins[f"m2_c{c}_step_logits"])
+        for s_ in range(ref.shape[0]):
+            assert rel_l2(logits[s_], ref[s_]) < 5e-2, (c, s_)
+        st.target_ids.extend(forced[:-1])
+        cur, after = pins[f"m2_c{c}_kv"].tolist()
+        assert st.speech_cache.kv_len == cur, (c, st.speech_cache.kv_len, cur)
+        plan = evict_plan(st, cur, g.max_llm_cache_size, True)
+        if plan is not None:
+            eng.kv_evict(st.speech_cache.sid, plan[0], plan[1])
+        assert st.speech_cache.kv_len == after
     eng.close()
