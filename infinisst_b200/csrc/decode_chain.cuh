@@ -1,0 +1,433 @@
+// Fused decode-layer chain: ONE persistent kernel runs a sequence of weight-streaming GEMMs and RMSNorm row phases
+// of the Llama decode step (<= 64 token rows), separated by in-kernel grid barriers:
+//
+//     o_proj -> [+residual, RMSNorm] -> gate/up (SiLU * up) -> down_proj -> [+residual, RMSNorm] -> QKV of the next layer
+//     (last layer: ... -> down_proj -> [+residual, final RMSNorm on the last rows] -> lm_head)
+//
+// Replaces, per decode layer, the o_proj / gate / up / down / q / k / v nn.Linear calls and the two LlamaRMSNorm
+// modules of the reference (HF LlamaDecoderLayer as patched by model/patches/patch_llm.py:231-336; SURVEY §2.3 L1, L2,
+// L7, L8) - seven launches of the operator-per-kernel path - with one launch; decode attention stays its own kernel
+// between two chains (it consumes the QKV split partials the chain leaves and produces the o_proj input).
+//
+// Why: at 64 rows every GEMM is pure weight streaming (HBM-bound).  With one kernel per operator each launch pays
+// start-up (CTA launch, barrier init, TMEM allocation), accumulator drain and grid turnover of a 224 KB one-CTA-per-SM
+// kernel: ~7 us of the ~25-50 us a GEMM takes.  Here the CTAs stay resident, the TMA producer walks straight from the
+// last weight tile of one phase into the first weight tiles of the next (weights never depend on a previous phase), and
+// only the ACTIVATION loads of a phase wait for the grid barrier that closes the phase before it - the shared-memory
+// ring (9 x 24 KB per SM = 32 MB over the GPU, ~5 us of HBM time) keeps HBM busy across the barrier.
+//
+// Structure (384 threads, one CTA per SM, G = #SMs CTAs):
+//   warp 0      TMA producer: per unit (128-feature tile x k-range) and k-block one stage = [act tile BN x 64][weight tile
+//               128 x 64], both K-major SWIZZLE_128B; a gate/up k-block is two stages (gate rows, then up rows)
+//   warp 1      tcgen05.mma issuer: D[128 features x BN tokens] (+ second accumulator for `up`), fp32 in TMEM,
+//               double-buffered so the epilogue of a unit overlaps the MMAs of the next
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: fp32 split-K partials / SiLU(gate) * up in bf16 / fp32 logits; the RMSNorm row phases
+//               (sum of the split partials + residual -> residual stream, normalise, scale) - one row per CTA
+// Grid barrier: one monotonically increasing 64-bit counter PER PHASE INDEX in global memory (a CTA without work in a
+// phase runs ahead and arrives early for later phases - with a single counter those early arrivals would be mistaken for
+// the missing arrivals of the phase being waited for); every CTA arrives once per phase, waiters poll with
+// ld.acquire.gpu; readers of another CTA's generic-proxy stores through TMA add fence.proxy.async.
+// All CTAs are co-resident (grid <= #SMs, 1 CTA / SM), so spinning cannot deadlock; under programmatic dependent launch
+// the kernel may start while its predecessor drains (its weight prefetch then overlaps the predecessor's tail).
+// The k-ranges, accumulation order and the order in which the row phase sums the partials are those of the
+// operator-per-kernel path (gemm_sk_kernel deferred mode + norm_rows_kernel), so both paths give identical bits.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace isst {
+namespace chain {
+
+using namespace tc;
+
+constexpr int kMaxPhases = 8;
+constexpr int kMaxMaps = 4;
+enum { PH_GEMM = 0, PH_ROWS = 1 };
+enum { EPI_PART = 0, EPI_SILU = 1, EPI_F32 = 2 };
+
+struct Phase {
+  int kind;
+  // ---- PH_GEMM: out[tok, f] = act[tok, :] . W[f, :] over feature tiles of 128 rows ----
+  int wmap, amap;            // tensor map indices
+  int tiles;                 // ceil(n_out / 128)
+  int num_kb;                // K / 64
+  int splits;                // k-ranges per tile; units = tiles * splits
+  int dual;                  // 1: W holds [gate; up], rows f and dual_off + f -> silu(gate) * up
+  int dual_off;
+  int epi;                   // EPI_*
+  int n_out;
+  void* out;                 // EPI_PART: float [splits][n_tok][n_out]; EPI_SILU: bf16 [n_tok][n_out]; EPI_F32: float [n_tok][n_out]
+  // ---- PH_ROWS: x = bf16(x_in[src] + sum_s part[s][src]); x_out[src] = x; h_out[row] = w * bf16(x * rstd) ----
+  const bf16* x_in;
+  bf16* x_out;               // may be null
+  bf16* h_out;
+  const float* w;
+  const float* part;         // may be null (n_part = 0)
+  int n_part;
+  long long part_stride;
+  const int* gather;         // src row of row r, or null (identity)
+  int n_rows;
+  int C;
+  float eps;
+};
+
+struct Params {
+  CUtensorMap wmaps[kMaxMaps];
+  CUtensorMap amaps[kMaxMaps];
+  Phase ph[kMaxPhases];
+  int n_phases;
+  int n_wmaps, n_amaps;
+  int n_tok;
+  unsigned long long* bar;                    // [kMaxPhases] grid barrier counters, one per phase index
+  unsigned long long bar_base[kMaxPhases];    // their values when this launch starts
+};
+
+template <int kBN>
+struct Cfg {
+  static constexpr int kActBytes = kBN * kBK * 2;
+  static constexpr int kWBytes = kBM * kBK * 2;
+  static constexpr int kStageBytes = kActBytes + kWBytes;
+  static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
+  static constexpr int kAccCols = 2 * kBN;                    // gate | up
+  static constexpr int kTmemColsRaw = 2 * kAccCols;           // double-buffered
+  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : 256));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+  static constexpr int kEpiThreads = 256;
+  static constexpr int kThreads = 128 + kEpiThreads;
+  static constexpr int kEpiHalves = kBN >= 32 ? 2 : 1;
+  static constexpr int kHalfCols = kBN / kEpiHalves;
+  static_assert(kBN == 16 || kBN == 32 || kBN == 64, "token tile");
+  static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_wait(const Params& p, int phase_done, int G) {      // one thread
+  const unsigned long long target = p.bar_base[phase_done] + static_cast<unsigned long long>(G);
+  while (ld_acquire_u64(p.bar + phase_done) < target) __nanosleep(20);
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// unit u of a GEMM phase -> (tile, k-range); CTA c owns units c, c + G, ...
+__device__ __forceinline__ void unit_range(const Phase& ph, int u, int& tile, int& split, int& kb0, int& kb1) {
+  tile = u / ph.splits;
+  split = u - tile * ph.splits;
+  kb0 = static_cast<int>(static_cast<long long>(ph.num_kb) * split / ph.splits);
+  kb1 = static_cast<int>(static_cast<long long>(ph.num_kb) * (split + 1) / ph.splits);
+}
+
+template <int kBN>
+__global__ void __launch_bounds__(384, 1)
+decode_chain_kernel(const __grid_constant__ Params p) {
+  using C = Cfg<kBN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* red = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [16] row-phase reduction scratch (+ [1] result)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  pdl_launch_dependents();
+
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < p.n_wmaps; ++i)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.wmaps[i])) : "memory");
+      for (int i = 0; i < p.n_amaps; ++i)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.amaps[i])) : "memory");
+      for (int s = 0; s < C::kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull_bar[a], 1);
+        mbar_init(&tempty_bar[a], C::kEpiThreads);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("bar.arrive 2, %0;" ::"n"(C::kThreads) : "memory");
+  } else {
+    if (warp == 2) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(static_cast<uint32_t>(C::kTmemCols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(C::kThreads) : "memory");
+    tcgen05_fence_after();
+    tmem_base = *tmem_ptr_smem;
+  }
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first_dep = true;                          // nothing of the predecessor KERNEL has been waited for yet
+      for (int pi = 0; pi < p.n_phases; ++pi) {
+        const Phase& ph = p.ph[pi];
+        if (ph.kind != PH_GEMM) continue;
+        const CUtensorMap* wm = &p.wmaps[ph.wmap];
+        const CUtensorMap* am = &p.amaps[ph.amap];
+        const int units = ph.tiles * ph.splits;
+        const int nsub = ph.dual ? 2 : 1;
+        // Weights do not depend on earlier phases: weight tiles are requested as soon as ring stages free up; the
+        // activation tiles of those stages follow once the phase before this one is complete everywhere.
+        bool dep_ok = false;
+        int n_pend = 0;
+        int pend_stage[C::kStages], pend_k0[C::kStages];
+        auto resolve = [&]() {
+          if (pi == 0 || first_dep) pdl_wait();
+          first_dep = false;
+          if (pi > 0) grid_wait(p, pi - 1, G);
+          fence_proxy_async_all();                    // other CTAs' generic-proxy stores -> visible to TMA reads
+          for (int i = 0; i < n_pend; ++i)
+            tma_load_4d(smem + pend_stage[i] * C::kStageBytes, am, &full_bar[pend_stage[i]], pend_k0[i], 0, 0, 0);
+          n_pend = 0;
+          dep_ok = true;
+        };
+        for (int u = cta; u < units; u += G) {
+          int tile, split, kb0, kb1;
+          unit_range(ph, u, tile, split, kb0, kb1);
+          const int w_row0 = tile * kBM;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              if (!dep_ok && n_pend == C::kStages) resolve();
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * C::kStageBytes;
+              mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+              tma_load_2d(sa + C::kActBytes, wm, &full_bar[stage], kb * kBK, w_row0 + sub * ph.dual_off);
+              if (dep_ok) {
+                tma_load_4d(sa, am, &full_bar[stage], kb * kBK, 0, 0, 0);
+              } else {
+                pend_stage[n_pend] = stage; pend_k0[n_pend] = kb * kBK;
+                ++n_pend;
+              }
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        if (!dep_ok && n_pend > 0) resolve();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pi = 0; pi < p.n_phases; ++pi) {
+      const Phase& ph = p.ph[pi];
+      if (ph.kind != PH_GEMM) continue;
+      const int units = ph.tiles * ph.splits;
+      const int nsub = ph.dual ? 2 : 1;
+      for (int u = cta; u < units; u += G) {
+        int tile, split, kb0, kb1;
+        unit_range(ph, u, tile, split, kb0, kb1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + acc * C::kAccCols;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+              const uint64_t d_act = make_smem_desc(sa);
+              const uint64_t d_w = make_smem_desc(sa + C::kActBytes);
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                umma_bf16(tacc + sub * kBN, d_w + koff, d_act + koff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1 && sub == nsub - 1) umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue + row phases =================
+    pdl_wait();                                   // every buffer written below belongs to earlier kernels until now
+    const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
+    const int half = (warp - 4) >> 2;             // token-column half handled by this warp
+    const int r = q * 32 + lane;                  // TMEM lane == feature row of the tile
+    const int et = threadIdx.x - 128;             // 0..255
+    const bool works = half < C::kEpiHalves;
+    const int hc0 = half * C::kHalfCols;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pi = 0; pi < p.n_phases; ++pi) {
+      const Phase& ph = p.ph[pi];
+      if (ph.kind == PH_GEMM) {
+        const int units = ph.tiles * ph.splits;
+        for (int u = cta; u < units; u += G) {
+          int tile, split, kb0, kb1;
+          unit_range(ph, u, tile, split, kb0, kb1);
+          const int f = tile * kBM + r;
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + acc * C::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+          // tcgen05.ld is warp-collective (.sync.aligned): the condition around it must be warp-uniform (a partial
+          // last tile, e.g. the 7 valid rows of lm_head's tile 1002, guards the STORES per lane instead)
+          if (works && tile * kBM + q * 32 < ph.n_out) {
+            const bool row_ok = f < ph.n_out;
+            const int n_tok = p.n_tok - hc0;       // valid token columns from hc0 on
+            if (ph.epi == EPI_SILU) {
+              bf16* dst = reinterpret_cast<bf16*>(ph.out) + static_cast<size_t>(hc0) * ph.n_out + f;
+#pragma unroll 1
+              for (int c = 0; c < C::kHalfCols; c += 16) {
+                float g[16], up[16];
+                tmem_ld16(taddr + hc0 + c, g);
+                tmem_ld16(taddr + kBN + hc0 + c, up);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float x = __fdividef(g[i], 1.0f + __expf(-g[i])) * up[i];
+                  if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = __float2bfloat16_rn(x);
+                }
+              }
+            } else {
+              // EPI_PART: fp32 partial of this k-range [split][tok][feature]; EPI_F32: fp32 logits [tok][feature]
+              float* dst = reinterpret_cast<float*>(ph.out) +
+                           (static_cast<size_t>(ph.epi == EPI_PART ? split : 0) * p.n_tok + hc0) * ph.n_out + f;
+#pragma unroll 1
+              for (int c = 0; c < C::kHalfCols; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + hc0 + c, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = v[i];
+              }
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        // ---- row phase: one row per CTA (rows cta, cta + G, ...) ----
+        if (pi > 0) {
+          if (et == 0) grid_wait(p, pi - 1, G);
+          asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+        }
+        const int Cc = ph.C;
+        const int groups = Cc >> 3;                // 16-byte column groups; thread et owns groups et and et + 256
+        const int nvw = (groups + 31) >> 5;        // "virtual warps" of the one-group-per-thread layout (norm_rows_kernel)
+        for (int row = cta; row < ph.n_rows; row += G) {
+          const size_t src = ph.gather ? static_cast<size_t>(ph.gather[row]) : static_cast<size_t>(row);
+          const bf16* x = ph.x_in + src * Cc;
+          float v[2][8];
+          float sq[2] = {0.f, 0.f};
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int gi = it * C::kEpiThreads + et;
+            if (gi < groups) {
+              const int c0 = gi * 8;
+              uint4 raw = *reinterpret_cast<const uint4*>(x + c0);
+              if (ph.n_part > 0) {
+                float a8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+                const float* p0 = ph.part + src * Cc + c0;
+                float4 pa[8], pb[8];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                  if (sp < ph.n_part) {
+                    const float4* pp = reinterpret_cast<const float4*>(p0 + sp * ph.part_stride);
+                    pa[sp] = __ldcg(pp); pb[sp] = __ldcg(pp + 1);
+                  }
+                }
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                  if (sp < ph.n_part) {
+                    a8[0] += pa[sp].x; a8[1] += pa[sp].y; a8[2] += pa[sp].z; a8[3] += pa[sp].w;
+                    a8[4] += pb[sp].x; a8[5] += pb[sp].y; a8[6] += pb[sp].z; a8[7] += pb[sp].w;
+                  }
+                }
+                const uint32_t ru[4] = {raw.x, raw.y, raw.z, raw.w};
+                uint32_t nu[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f2 = unpack_bf16(ru[j]);
+                  nu[j] = pack_bf16(a8[2 * j] + f2.x, a8[2 * j + 1] + f2.y);
+                }
+                raw = make_uint4(nu[0], nu[1], nu[2], nu[3]);
+                if (ph.x_out) *reinterpret_cast<uint4*>(ph.x_out + src * Cc + c0) = raw;
+              }
+              const uint32_t uu[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f2 = unpack_bf16(uu[j]);
+                v[it][2 * j] = f2.x; v[it][2 * j + 1] = f2.y;
+                sq[it] += f2.x * f2.x + f2.y * f2.y;
+              }
+            }
+          }
+          // reduction in the order of norm_rows_kernel<.., 1>: warp tree per 32 groups, then the warps in sequence
+          const float s0 = warp_sum(sq[0]), s1 = warp_sum(sq[1]);
+          if (lane == 0) { red[et >> 5] = s0; red[8 + (et >> 5)] = s1; }
+          asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+          if (et == 0) {
+            float qsum = 0.f;
+            for (int i = 0; i < nvw; ++i) qsum += red[i];
+            red[16] = rsqrtf(qsum / Cc + ph.eps);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+          const float rstd = red[16];
+          bf16* o = ph.h_out + static_cast<size_t>(row) * Cc;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int gi = it * C::kEpiThreads + et;
+            if (gi < groups) {
+              const int c0 = gi * 8;
+              const float4 w0 = *reinterpret_cast<const float4*>(ph.w + c0), w1 = *reinterpret_cast<const float4*>(ph.w + c0 + 4);
+              const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                pk[j] = pack_bf16(wv[2 * j] * bf16_round(v[it][2 * j] * rstd), wv[2 * j + 1] * bf16_round(v[it][2 * j + 1] * rstd));
+              *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");      // `red` is reused by the next row
+        }
+      }
+      // ---- this CTA is done with phase pi ----
+      if (pi + 1 < p.n_phases) {
+        asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+        if (et == 0) {
+          __threadfence();
+          atomicAdd(p.bar + pi, 1ULL);
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(C::kTmemCols))
+                 : "memory");
+  }
+}
+
+}  // namespace chain
+}  // namespace isst

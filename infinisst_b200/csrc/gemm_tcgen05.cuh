@@ -676,7 +676,8 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
           // ---- deferred split reduction: this CTA's fp32 partial goes to part_out[split][tok][feature]; the
           //      consumer row kernel (norm / RoPE-append) sums the splits - no fence, counter or wait here ----
           const int split = cta % p.part_splits;
-          if (works && lane_idx < p.N_out) {
+          if (works && lane_idx - lane < p.N_out) {              // warp-uniform: tcgen05.ld is warp-collective
+            const bool row_ok = lane_idx < p.N_out;
             float* dst = p.part_out + (static_cast<size_t>(split) * p.M_tok + col_base + hc0) * p.N_out + lane_idx;
             const int n_tok = p.M_tok - col_base - hc0;          // valid token columns from hc0 on
 #pragma unroll 1
@@ -685,7 +686,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
               tmem_ld16(taddr + hc0 + c, v);
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (c + i < n_tok) dst[static_cast<size_t>(c + i) * p.N_out] = v[i];
+                if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * p.N_out] = v[i];
             }
           }
           tcgen05_fence_before();

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "decode_attention.cuh"
 #include "decode_attention_group.cuh"
+#include "decode_chain.cuh"
 #include "gemm_tcgen05.cuh"
 #include "prefill_attention_tc.cuh"
 #include "beam.cuh"
@@ -166,6 +167,9 @@ struct isst_ctx {
   // per-context tuning / test options (isst_debug_option); nothing on the hot path reads the environment
   bool pdl = true;          // "pdl" = 0: plain stream order instead of programmatic dependent launch
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
+  bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
+  unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
+  unsigned long long chain_base[chain::kMaxPhases] = {0};   // their values once every launch issued so far has completed
   std::set<const void*> smem_attr_done;      // kernels whose dynamic shared-memory limit was raised on this device
   std::map<std::string, long long> paths;    // launches per kernel variant (isst_path_count; parity tests assert on them)
   unsigned long long* gemm_dbg = nullptr;   // optional phase stamps of the last stream-K launch
@@ -901,8 +905,161 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused decode-layer chain (decode_chain.cuh): phase list builder + launcher
+// ------------------------------------------------------------------------------------------------
+struct ChainBuilder {
+  chain::Params p{};
+  int bn = 64;
+  double flops = 0, bytes = 0;
+  const void* amap_ptr[chain::kMaxMaps] = {nullptr, nullptr, nullptr, nullptr};
+  int amap_K[chain::kMaxMaps] = {0, 0, 0, 0};
+};
+static void chain_begin(ChainBuilder& cb, int n_tok) {
+  cb.p.n_tok = n_tok;
+  cb.bn = n_tok <= 16 ? 16 : (n_tok <= 32 ? 32 : 64);
+}
+// out = act[n_tok, K] . W^T; returns the number of k-splits (EPI_PART: partials [splits][n_tok][n_out] in `out`)
+static int chain_gemm(isst_ctx* ctx, ChainBuilder& cb, const bf16* act, const Weight2D& w, int n_out, int dual, int epi,
+                      void* out, int* splits_out) {
+  ISST_CHECK(cb.p.n_phases < chain::kMaxPhases && cb.p.n_wmaps < chain::kMaxMaps, "decode chain: too many phases");
+  ISST_CHECK(w.K % tc::kBK == 0, "decode chain: K must be a multiple of 64");
+  chain::Phase& ph = cb.p.ph[cb.p.n_phases++];
+  ph = chain::Phase{};
+  ph.kind = chain::PH_GEMM;
+  ph.wmap = cb.p.n_wmaps;
+  cb.p.wmaps[cb.p.n_wmaps++] = w.map;
+  int ai = -1;
+  for (int i = 0; i < cb.p.n_amaps; ++i)
+    if (cb.amap_ptr[i] == act && cb.amap_K[i] == w.K) ai = i;
+  if (ai < 0) {
+    ISST_CHECK(cb.p.n_amaps < chain::kMaxMaps, "decode chain: too many activation buffers");
+    ai = cb.p.n_amaps++;
+    ISST_TRY(get_act_map(ctx, &cb.p.amaps[ai], plain_view(act, cb.p.n_tok, w.K), cb.bn));
+    cb.amap_ptr[ai] = act; cb.amap_K[ai] = w.K;
+  }
+  ph.amap = ai;
+  ph.tiles = ceil_div(n_out, tc::kBM);
+  ph.num_kb = w.K / tc::kBK;
+  ph.dual = dual; ph.dual_off = dual ? n_out : 0;
+  ph.epi = epi; ph.n_out = n_out; ph.out = out;
+  int S = 1;
+  if (epi == chain::EPI_PART) {
+    // the split rule of the operator-per-kernel path (sk_plan, deferred mode): same k-ranges, same bits
+    const long long s = std::min<long long>(std::min<long long>(ctx->sm_count / std::max(ph.tiles, 1), 8), ph.num_kb / 8);
+    if (s >= 2 && static_cast<size_t>(s) * cb.p.n_tok * n_out <= ctx->defer_ws_floats) S = static_cast<int>(s);
+    ISST_CHECK(static_cast<size_t>(S) * cb.p.n_tok * n_out <= ctx->defer_ws_floats, "decode chain: partial workspace too small");
+  }
+  ph.splits = S;
+  if (splits_out) *splits_out = S;
+  const double nw = dual ? 2.0 : 1.0;
+  cb.flops += 2.0 * cb.p.n_tok * static_cast<double>(n_out) * w.K * nw;
+  cb.bytes += nw * n_out * static_cast<double>(w.K) * 2 + static_cast<double>(cb.p.n_tok) * w.K * 2 +
+              static_cast<double>(cb.p.n_tok) * n_out * (epi == chain::EPI_SILU ? 2 : 4) * S;
+  return 0;
+}
+static int chain_rows(ChainBuilder& cb, const bf16* x_in, bf16* x_out, bf16* h_out, const float* w, const float* part,
+                      int n_part, long long part_stride, const int* gather, int n_rows, int C, float eps) {
+  ISST_CHECK(cb.p.n_phases < chain::kMaxPhases, "decode chain: too many phases");
+  ISST_CHECK(C % 8 == 0 && C <= 4096 && n_part <= 8, "decode chain: unsupported row width / split count");
+  chain::Phase& ph = cb.p.ph[cb.p.n_phases++];
+  ph = chain::Phase{};
+  ph.kind = chain::PH_ROWS;
+  ph.x_in = x_in; ph.x_out = x_out; ph.h_out = h_out; ph.w = w; ph.part = n_part > 0 ? part : nullptr; ph.n_part = n_part;
+  ph.part_stride = part_stride; ph.gather = gather; ph.n_rows = n_rows; ph.C = C; ph.eps = eps;
+  cb.bytes += static_cast<double>(n_rows) * C * (4.0 + 4.0 * n_part);
+  return 0;
+}
+template <int kBN>
+static int chain_launch_bn(isst_ctx* ctx, cudaStream_t st, ChainBuilder& cb) {
+  using C = chain::Cfg<kBN>;
+  auto kern = chain::decode_chain_kernel<kBN>;
+  ISST_TRY(ensure_smem(ctx, kern, C::kSmemBytes));
+  const int G = ctx->sm_count;
+  cb.p.bar = ctx->chain_bar;
+  for (int i = 0; i + 1 < cb.p.n_phases; ++i) {       // every CTA arrives once at every phase but the last
+    cb.p.bar_base[i] = ctx->chain_base[i];
+    ctx->chain_base[i] += static_cast<unsigned long long>(G);
+  }
+  ProfScope ps(ctx, st, P_GEMM_STREAM, cb.flops, cb.bytes);
+  ISST_CUDA(launch_k(ctx, kern, dim3(G), dim3(C::kThreads), C::kSmemBytes, st, cb.p));
+  LAUNCH_CHECK(ctx);
+  ctx->paths[std::string("decode_chain") + std::to_string(kBN)]++;
+  return 0;
+}
+static int chain_launch(isst_ctx* ctx, cudaStream_t st, ChainBuilder& cb) {
+  ISST_CHECK(cb.p.n_phases >= 1, "decode chain: empty");
+  if (cb.bn == 16) return chain_launch_bn<16>(ctx, st, cb);
+  if (cb.bn == 32) return chain_launch_bn<32>(ctx, st, cb);
+  return chain_launch_bn<64>(ctx, st, cb);
+}
+
+// One decode forward (every stream advances by one token, <= 64 rows) on the fused chain: 2 launches per layer
+// (decode attention + chain) instead of 7.
+static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) {
+  const isst_config& c = ctx->cfg;
+  const int D = c.hidden, H = c.heads, Hkv = c.kv_heads, HD = c.head_dim, F = c.ffn;
+  const int QKV = (H + 2 * Hkv) * HD;
+  const int M = lb.M;
+  const float scale_log2 = 1.4426950408889634f / std::sqrt(static_cast<float>(HD));
+  ISST_CHECK(HD == 128 && H / Hkv == 4, "LLM attention kernels are built for head_dim 128 and 4:1 GQA");
+  {
+    ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (HD / 2) * 16);
+    ISST_CUDA(launch_k(ctx, rope_table_kernel<false>, dim3(ceil_div(lb.max_T * (HD / 2), 128), lb.n), dim3(128), 0, st,
+                       ctx->llm_rope_ring, ctx->llm_rope_sys, lb.d_tok_base, lb.d_T, ctx->d_kv_len, ctx->d_evicted, lb.d_active,
+                       ctx->llm_inv_freq, HD / 2, 0));
+    LAUNCH_CHECK(ctx);
+  }
+  int qkv_splits = 1;
+  {
+    ChainBuilder cb;
+    chain_begin(cb, M);
+    ISST_TRY(chain_rows(cb, ctx->lx, nullptr, ctx->lh, ctx->llm[0].rms1, nullptr, 0, 0, nullptr, M, D, c.rms_eps));
+    ISST_TRY(chain_gemm(ctx, cb, ctx->lh, ctx->llm[0].wqkv, QKV, 0, chain::EPI_PART, ctx->defer_ws, &qkv_splits));
+    ISST_TRY(chain_launch(ctx, st, cb));
+  }
+  for (int l = 0; l < c.layers; ++l) {
+    LlmLayerW& w = ctx->llm[l];
+    {
+      PagedKV kv = paged_kv(ctx, l);
+      ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
+      const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
+      DecodeFuse fz;
+      fz.on = true; fz.active = lb.d_active;
+      fz.part = ctx->defer_ws; fz.n_part = qkv_splits; fz.part_stride = static_cast<long long>(M) * QKV;
+      ISST_TRY(launch_decode_attention(ctx, st, ctx->lqkv, kv, lb.d_slots, lb.n, splits, scale_log2, fz));
+      if (splits > 1) {
+        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits));
+        LAUNCH_CHECK(ctx);
+      }
+    }
+    ChainBuilder cb;
+    chain_begin(cb, M);
+    int so = 1, sd = 1;
+    ISST_TRY(chain_gemm(ctx, cb, ctx->lattn, w.wo, D, 0, chain::EPI_PART, ctx->defer_ws, &so));
+    ISST_TRY(chain_rows(cb, ctx->lx, ctx->lx, ctx->lh, w.rms2, ctx->defer_ws, so, static_cast<long long>(M) * D, nullptr, M, D, c.rms_eps));
+    ISST_TRY(chain_gemm(ctx, cb, ctx->lh, w.wgu, F, 1, chain::EPI_SILU, ctx->lgu, nullptr));
+    ISST_TRY(chain_gemm(ctx, cb, ctx->lgu, w.wd, D, 0, chain::EPI_PART, ctx->defer_ws, &sd));
+    if (l + 1 < c.layers) {
+      ISST_TRY(chain_rows(cb, ctx->lx, ctx->lx, ctx->lh, ctx->llm[l + 1].rms1, ctx->defer_ws, sd, static_cast<long long>(M) * D, nullptr, M, D, c.rms_eps));
+      ISST_TRY(chain_gemm(ctx, cb, ctx->lh, ctx->llm[l + 1].wqkv, QKV, 0, chain::EPI_PART, ctx->defer_ws, &qkv_splits));
+    } else {
+      // final norm on the last row of every stream + lm_head (the reference computes and discards the other rows)
+      ISST_TRY(chain_rows(cb, ctx->lx, nullptr, ctx->llast, ctx->final_norm, ctx->defer_ws, sd, static_cast<long long>(M) * D, lb.d_last_row, lb.n, D, c.rms_eps));
+      ISST_TRY(chain_gemm(ctx, cb, ctx->llast, ctx->lm_head, c.vocab, 0, chain::EPI_F32, ctx->logits, nullptr));
+    }
+    ISST_TRY(chain_launch(ctx, st, cb));
+  }
+  ISST_CUDA(launch_k(ctx, advance_kv_len_kernel, dim3(ceil_div(lb.n, 128)), dim3(128), 0, st, ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n));
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool tap_layers) {
   const isst_config& c = ctx->cfg;
+  if (ctx->opt_chain && lb.decode && lb.M <= 64 && lb.M == lb.n && lb.group == 1 && !lb.all_logits && !tap_layers)
+    return llm_decode_chain(ctx, st, lb);
   const int D = c.hidden, H = c.heads, Hkv = c.kv_heads, HD = c.head_dim, F = c.ffn;
   const int QKV = (H + 2 * Hkv) * HD;
   const int M = lb.M;
@@ -1287,6 +1444,8 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->gemm_ws, ctx->gemm_ws_floats));
   ctx->defer_ws_floats = static_cast<size_t>(8) * 128 * std::max(QKV, HID);   // <= 8 splits x <= 128 tokens x widest deferred output
   ISST_TRY(dev_alloc(&ctx->defer_ws, ctx->defer_ws_floats));
+  ISST_TRY(dev_alloc(&ctx->chain_bar, chain::kMaxPhases));
+  ISST_CUDA(cudaMemset(ctx->chain_bar, 0, chain::kMaxPhases * sizeof(unsigned long long)));
   ctx->n_counters = 4096;
   ISST_TRY(dev_alloc(&ctx->gemm_counters, ctx->n_counters));
   ISST_CUDA(cudaMemset(ctx->gemm_counters, 0, ctx->n_counters * sizeof(int)));
@@ -1305,7 +1464,7 @@ void isst_destroy(isst_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   // the context owns every device allocation it made; release the big pools explicitly
-  cudaFree(ctx->beam_ws); cudaFree(ctx->beam_count);
+  cudaFree(ctx->beam_ws); cudaFree(ctx->beam_count); cudaFree(ctx->chain_bar);
   cudaFree(ctx->kv_pool); cudaFree(ctx->enc_k); cudaFree(ctx->enc_v); cudaFree(ctx->embed);
   cudaFree(ctx->enc_kx); cudaFree(ctx->enc_xpos_base); cudaFree(ctx->logits_all);
   for (auto& w : ctx->llm) { cudaFree(w.wqkv.ptr); cudaFree(w.wo.ptr); cudaFree(w.wgu.ptr); cudaFree(w.wd.ptr); cudaFree(w.rms1); cudaFree(w.rms2); }
@@ -2350,6 +2509,7 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   const std::string key(key_c);
   if (key == "pdl") ctx->pdl = value != 0;
   else if (key == "decode_splits") ctx->opt_dec_splits = value;
+  else if (key == "decode_chain") ctx->opt_chain = value != 0;
   else return set_error("unknown option: " + key);
   return 0;
 }

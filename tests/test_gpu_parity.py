@@ -775,3 +775,44 @@ def test_update_multiplier_mid_stream():
         assert eng.enc_steps(sid) == orc.st.enc_cache.n_steps
     assert evictions >= 1
     eng.close()
+
+
+@pytest.mark.parametrize("shape", ["tiny_1", "tiny_5", "prod_slice_64", "prod_slice_20"])
+def test_decode_chain_bit_identical_to_operator_path(shape):
+    """The fused decode-layer chain (decode_chain.cuh: o_proj -> RMSNorm -> gate/up -> down -> RMSNorm -> next QKV in
+    one persistent kernel with grid barriers) keeps the k-split ranges, the accumulation order and the partial-sum
+    order of the operator-per-kernel path: the raw step logits of both paths must be IDENTICAL bit for bit, for 1, 5,
+    20 and 64 rows (token tiles of 16, 32 and 64 columns), tiny and production widths."""
+    from infinisst_b200.runner import LockstepRunner
+    if shape.startswith("tiny"):
+        cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
+        sd = bf16_weights(make_state_dict(cfg, seed=0))
+        B, n_chunks = int(shape.split("_")[1]), 7
+    else:
+        cfg = _production(1, 3)
+        sd = make_state_dict(cfg, seed=0, device="cuda:0", dtype=torch.bfloat16)
+        B, n_chunks = int(shape.split("_")[2]), 3
+    audios = [make_audio(n_chunks * SEG / 16000.0, seed=300 + b) for b in range(B)]
+    res = []
+    for use_chain in (1, 0):
+        eng = _engine(cfg, sd, max_streams=B, max_batch=B)
+        eng.option("decode_chain", use_chain)
+        eng.debug(True)
+        run = LockstepRunner(eng, cfg, B)
+        rec = []
+        for c in range(n_chunks):
+            pcm = torch.cat([_chunk_pcm(a, c) for a in audios], 0)
+            forced = res[0][c][0] if res else None               # the second run is teacher-forced with the first run's tokens
+            run.step_device(pcm, forced=forced)
+            rec.append((run.last_tokens, eng.read_tap("step_logits", torch.float32).clone()))
+        bn = 16 if B <= 16 else (32 if B <= 32 else 64)
+        n_chain = eng.path_count(f"decode_chain{bn}")
+        assert (n_chain > 0) == bool(use_chain), (use_chain, n_chain)
+        if use_chain:
+            assert n_chain == n_chunks * (cfg.gen.max_new_tokens - 1) * (cfg.llm.layers + 1)
+        res.append(rec)
+        run.close()
+        eng.close()
+    for c, ((ta, la), (tb, lb)) in enumerate(zip(*res)):
+        assert ta == tb
+        assert torch.equal(la, lb), (c, float((la - lb).abs().max()))
