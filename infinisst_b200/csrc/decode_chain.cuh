@@ -78,6 +78,7 @@ struct Params {
   int n_phases;
   int n_wmaps, n_amaps;
   int n_tok;
+  unsigned long long* dbg;                    // optional [grid][32] %globaltimer stamps (phase analysis), may be null
   unsigned long long* bar;                    // [kMaxPhases] grid barrier counters, one per phase index
   unsigned long long bar_base[kMaxPhases];    // their values when this launch starts
 };
@@ -137,6 +138,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
   const int lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   pdl_launch_dependents();
+  if (p.dbg && threadIdx.x == 0) p.dbg[cta * 32] = gtimer();
 
   uint32_t tmem_base = 0;
   if (warp == 0) {
@@ -197,6 +199,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
             tma_load_4d(smem + pend_stage[i] * C::kStageBytes, am, &full_bar[pend_stage[i]], pend_k0[i], 0, 0, 0);
           n_pend = 0;
           dep_ok = true;
+          if (p.dbg) p.dbg[cta * 32 + 1 + 3 * pi] = gtimer();          // dependency of this phase resolved, activations requested
         };
         for (int u = cta; u < units; u += G) {
           int tile, split, kb0, kb1;
@@ -284,6 +287,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           const int f = tile * kBM + r;
           mbar_wait(&tfull_bar[acc], acc_phase);
           tcgen05_fence_after();
+          if (p.dbg && et == 0 && u == cta) p.dbg[cta * 32 + 2 + 3 * pi] = gtimer();   // first accumulator of the phase complete
           const uint32_t taddr = tmem_base + acc * C::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
           // tcgen05.ld is warp-collective (.sync.aligned): the condition around it must be warp-uniform (a partial
           // last tile, e.g. the 7 valid rows of lm_head's tile 1002, guards the STORES per lane instead)
@@ -327,6 +331,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           if (et == 0) grid_wait(p, pi - 1, G);
           asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
         }
+        if (p.dbg && et == 0) p.dbg[cta * 32 + 2 + 3 * pi] = gtimer();                 // row phase may start
         const int Cc = ph.C;
         const int groups = Cc >> 3;                // 16-byte column groups; thread et owns groups et and et + 256
         const int nvw = (groups + 31) >> 5;        // "virtual warps" of the one-group-per-thread layout (norm_rows_kernel)
@@ -410,6 +415,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         }
       }
       // ---- this CTA is done with phase pi ----
+      if (p.dbg && et == 0) p.dbg[cta * 32 + 3 + 3 * pi] = gtimer();                   // this CTA's part of the phase is done
       if (pi + 1 < p.n_phases) {
         asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
         if (et == 0) {

@@ -1049,6 +1049,7 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
       ISST_TRY(chain_rows(cb, ctx->lx, nullptr, ctx->llast, ctx->final_norm, ctx->defer_ws, sd, static_cast<long long>(M) * D, lb.d_last_row, lb.n, D, c.rms_eps));
       ISST_TRY(chain_gemm(ctx, cb, ctx->llast, ctx->lm_head, c.vocab, 0, chain::EPI_F32, ctx->logits, nullptr));
     }
+    if (l == 1) cb.p.dbg = ctx->gemm_dbg;             // phase stamps of a middle layer's chain ("gemm_stamps" tap, debug bit 1)
     ISST_TRY(chain_launch(ctx, st, cb));
   }
   ISST_CUDA(launch_k(ctx, advance_kv_len_kernel, dim3(ceil_div(lb.n, 128)), dim3(128), 0, st, ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n));
