@@ -147,12 +147,15 @@ def _aliased_state_dict(cfg):
     return sd
 
 
-def _steady_oracle_stream(cfg, sd, O):
+def _steady_oracle_stream(cfg, sd, O, device="cpu", dtype=torch.float32, seed=1):
     """A StreamState whose caches sit at the steady-state lengths (encoder window 576 frames + audio
     ring, LLM window just below the eviction threshold) with random contents: what a stream looks
     like after ~35 chunks, without paying 35 CPU chunks to get there."""
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(seed)
     e, l, gen = cfg.enc, cfg.llm, cfg.gen
+
+    def rnd(*shape, scale=0.5):
+        return (torch.randn(*shape, generator=g) * scale).to(device=device, dtype=dtype)
     st = O.StreamState()
     sys_n = len(cfg.tpl.system_ids)
     cur, chunks = 0, 0
@@ -164,15 +167,15 @@ def _steady_oracle_stream(cfg, sd, O):
             cur = kept[0] + kept[1]
             break
     st.system_size = sys_n
-    st.llm_cache = O.LlmCache([torch.randn(1, l.kv_heads, cur, l.head_dim, generator=g) * 0.5 for _ in range(l.layers)],
-                              [torch.randn(1, l.kv_heads, cur, l.head_dim, generator=g) * 0.5 for _ in range(l.layers)])
+    st.llm_cache = O.LlmCache([rnd(1, l.kv_heads, cur, l.head_dim) for _ in range(l.layers)],
+                              [rnd(1, l.kv_heads, cur, l.head_dim) for _ in range(l.layers)])
     st.enc_cache = O.new_enc_cache(e)
     st.enc_cache.n_steps = e.block_size * chunks
-    st.enc_cache.src = torch.randn(1, 79 + 320 + 320 * e.block_size, generator=g) * 0.1
+    st.enc_cache.src = rnd(1, 79 + 320 + 320 * e.block_size, scale=0.1)
     st.enc_cache.src_len = e.block_size
     for lc in st.enc_cache.layers:
-        lc.k = torch.randn(e.heads, e.max_cache_size, e.head_dim, generator=g) * 0.5
-        lc.v = torch.randn(e.heads, e.max_cache_size, e.head_dim, generator=g) * 0.5
+        lc.k = rnd(e.heads, e.max_cache_size, e.head_dim)
+        lc.v = rnd(e.heads, e.max_cache_size, e.head_dim)
     st.src_len = CHUNK * chunks
     st.target_ids = [1000 + (7 * i) % 5000 for i in range(9 * chunks)]
     return st, chunks, cur
@@ -203,8 +206,67 @@ def run_oracle_cpu(n_chunks: int, warm: int, threads: int):
     total = sum(times)
     desc = (f"oracle port (PyTorch eager fp32, reference operator sequence incl. cat-grown caches and per-call key "
             f"re-rotation), 1 stream x {n_chunks} steady-state chunks (LLM KV {cur} tokens, encoder window "
-            f"{cfg.enc.max_cache_size} frames), {threads} threads, setup {setup_s:.1f}s untimed")
+            f"{cfg.enc.max_cache_size} frames; timing-only weights: layers alias layer 0's tensors, cache contents random), "
+            f"{threads} threads, setup {setup_s:.1f}s untimed")
     return CHUNK_S * n_chunks / total, times, desc
+
+
+def run_oracle_gpu_eager(dev: int, n_chunks: int = 4, n_sub: int = 4, streams: int = 64):
+    """The "reference GPU path" stand-in of SURVEY §2.1 / §8d / BASELINE.md §3: the oracle - the reference's own operator
+    sequence in plain PyTorch (cat-grown caches, per-call re-rotation of every cached key, repeat_kv, lm_head over all
+    prompt positions) - executed in bf16 eager ON THE SAME B200, production dimensions, steady state.  It is a
+    PyTorch-eager restatement, NOT the reference (whose dependencies are absent); cuBLAS / ATen kernels
+    run here, none of this repo's.  Timed: one stream for `n_chunks` chunks, and `n_sub` distinct streams advanced one
+    after the other per chunk round (the reference has no batching across streams: SURVEY §0), scaled to `streams`."""
+    from infinisst_b200 import production_config
+    from infinisst_b200.synthetic import make_state_dict
+    from oracle import infinisst_oracle as O       # bench.py's reference legs may run the oracle
+    device = f"cuda:{dev}"
+    cfg = production_config()
+    sd = make_state_dict(cfg, seed=0, device=device, dtype=torch.bfloat16)
+    sts = []
+    for i in range(n_sub):
+        st, chunks0, cur = _steady_oracle_stream(cfg, sd, O, device=device, dtype=torch.bfloat16, seed=10 + i)
+        st.src_len = CHUNK                           # only source[src_len:] is read (agents/infinisst.py:208)
+        sts.append(st)
+    g = torch.Generator().manual_seed(3)
+
+    def chunk(st):
+        source = [0.0] * st.src_len + (0.1 * torch.randn(CHUNK, generator=g)).tolist()
+        O.policy_chunk(sd, cfg, st, source, torch.bfloat16)
+        st.src_len = CHUNK
+
+    with torch.inference_mode():
+        chunk(sts[0])                                 # warm-up (cuBLAS handles, allocator)
+        torch.cuda.synchronize()
+        one = []
+        for _ in range(n_chunks):
+            t0 = time.perf_counter()
+            chunk(sts[0])
+            torch.cuda.synchronize()
+            one.append(time.perf_counter() - t0)
+        for st in sts[1:]:
+            chunk(st)
+        torch.cuda.synchronize()
+        rounds = []
+        for _ in range(max(2, n_chunks // 2)):
+            t0 = time.perf_counter()
+            for st in sts:
+                chunk(st)
+            torch.cuda.synchronize()
+            rounds.append(time.perf_counter() - t0)
+    kv = sts[0].llm_cache.length()
+    del sd, sts
+    torch.cuda.empty_cache()
+    per_round = sum(rounds) / len(rounds)
+    return {"label": "PyTorch-eager restatement of the reference (oracle) in bf16 on this B200 - not the reference itself",
+            "one_stream": {"speech_s_per_s": CHUNK_S * len(one) / sum(one), "p50_ms": 1e3 * pct(one, 0.5), "chunks": len(one)},
+            "looped_streams": {"streams_timed": n_sub, "ms_per_round_of_timed_streams": 1e3 * per_round,
+                               "speech_s_per_s": CHUNK_S * n_sub / per_round,
+                               "note": f"streams advance one after the other (no cross-stream batching in the reference); "
+                                       f"{streams} streams would take {1e3 * per_round * streams / n_sub:.0f} ms per chunk round at "
+                                       f"the same rate"},
+            "kv_len": kv, "dtype": "bf16"}
 
 
 def main_reference(args, env):
@@ -447,6 +509,14 @@ def main_native(args, env):
                "kv_len": eng.kv_len(one.sids[0]), "speech_s_per_s": CHUNK_S / (sum(ts) / len(ts) / 1e3)}
         one.close()
     all_e2e = sp.gather_floats([1e3 * t for t in e2e_lat])
+    eager = None
+    if rank == 0 and world == 1 and args.eager_chunks > 0:
+        try:
+            eager = run_oracle_gpu_eager(dev, n_chunks=args.eager_chunks)
+            eager["native_over_eager_one_stream"] = lat.get("speech_s_per_s", 0.0) / eager["one_stream"]["speech_s_per_s"] if lat else None
+            eager["native_64_streams_over_eager_looped"] = e2e_value / eager["looped_streams"]["speech_s_per_s"]
+        except Exception as ex:          # noqa: BLE001
+            eager = {"error": str(ex)}
 
     if rank != 0:
         eng.close()
@@ -483,6 +553,8 @@ def main_native(args, env):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if eager is not None:
+        line["extra"] = {"reference_gpu_eager": eager}
     emit(line)
     eng.close()
     sp.shutdown()
@@ -522,6 +594,7 @@ def main():
     ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline of one step to this file and exit")
     ap.add_argument("--ncu-step", action="store_true", help="run ONE profiled step after priming and exit (for ncu)")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=3, help="oracle chunks timed on the host at N=1 (0 = skip)")
+    ap.add_argument("--eager-chunks", type=int, default=4, help="oracle chunks timed in bf16 eager on the GPU at N=1 (0 = skip)")
     args = ap.parse_args()
     from infinisst_b200 import stream_parallel as sp
     env = sp.env_world()

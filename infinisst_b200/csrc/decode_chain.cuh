@@ -14,13 +14,16 @@
 // kernel: ~7 us of the ~25-50 us a GEMM takes.  Here the CTAs stay resident, the TMA producer walks straight from the
 // last weight tile of one phase into the first weight tiles of the next (weights never depend on a previous phase), and
 // only the ACTIVATION loads of a phase wait for the grid barrier that closes the phase before it - the shared-memory
-// ring (9 x 24 KB per SM = 32 MB over the GPU, ~5 us of HBM time) keeps HBM busy across the barrier.
+// ring (5 x 40 KB per SM) keeps requests in flight across the barrier.
 //
 // Structure (384 threads, one CTA per SM, G = #SMs CTAs):
-//   warp 0      TMA producer: per unit (128-feature tile x k-range) and k-block one stage = [act tile BN x 64][weight tile
-//               128 x 64], both K-major SWIZZLE_128B; a gate/up k-block is two stages (gate rows, then up rows)
-//   warp 1      tcgen05.mma issuer: D[128 features x BN tokens] (+ second accumulator for `up`), fp32 in TMEM,
-//               double-buffered so the epilogue of a unit overlaps the MMAs of the next
+//   warp 0      TMA producer: per unit (TWO 128-feature tiles x k-range) and k-block one stage = [act tile BN x 64]
+//               [weight tile A 128 x 64][weight tile B 128 x 64], all K-major SWIZZLE_128B.  The two tiles are gate / up
+//               rows of the same features (SwiGLU) or two adjacent feature tiles: one activation tile serves 32 KB of
+//               weights - an SM ingests ~70 KB/us from L2/HBM whatever the mix (measured: 47 KB/us of weights with one
+//               8 KB activation tile per 16 KB weight tile), so the activation share decides how fast weights stream
+//   warp 1      tcgen05.mma issuer: two accumulators D[128 features x BN tokens], fp32 in TMEM, double-buffered so
+//               the epilogue of a unit overlaps the MMAs of the next
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue: fp32 split-K partials / SiLU(gate) * up in bf16 / fp32 logits; the RMSNorm row phases
 //               (sum of the split partials + residual -> residual stream, normalise, scale) - one row per CTA
@@ -49,11 +52,12 @@ struct Phase {
   int kind;
   // ---- PH_GEMM: out[tok, f] = act[tok, :] . W[f, :] over feature tiles of 128 rows ----
   int wmap, amap;            // tensor map indices
-  int tiles;                 // ceil(n_out / 128)
+  int tiles;                 // units of TWO weight tiles: rows [tile * tile_rows, +128) and the same + sub_off
+  int tile_rows;             // 128 (gate/up: second tile = `up` rows of the same features) or 256 (adjacent feature tiles)
+  int sub_off;               // row offset of the second tile: n_out (gate/up) or 128
   int num_kb;                // K / 64
-  int splits;                // k-ranges per tile; units = tiles * splits
-  int dual;                  // 1: W holds [gate; up], rows f and dual_off + f -> silu(gate) * up
-  int dual_off;
+  int splits;                // k-ranges per unit tile; units = tiles * splits
+  int dual;                  // 1: W holds [gate; up] -> silu(gate) * up
   int epi;                   // EPI_*
   int n_out;
   void* out;                 // EPI_PART: float [splits][n_tok][n_out]; EPI_SILU: bf16 [n_tok][n_out]; EPI_F32: float [n_tok][n_out]
@@ -87,7 +91,7 @@ template <int kBN>
 struct Cfg {
   static constexpr int kActBytes = kBN * kBK * 2;
   static constexpr int kWBytes = kBM * kBK * 2;
-  static constexpr int kStageBytes = kActBytes + kWBytes;
+  static constexpr int kStageBytes = kActBytes + 2 * kWBytes;
   static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static constexpr int kAccCols = 2 * kBN;                    // gate | up
@@ -184,9 +188,10 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         const CUtensorMap* wm = &p.wmaps[ph.wmap];
         const CUtensorMap* am = &p.amaps[ph.amap];
         const int units = ph.tiles * ph.splits;
-        const int nsub = ph.dual ? 2 : 1;
         // Weights do not depend on earlier phases: weight tiles are requested as soon as ring stages free up; the
         // activation tiles of those stages follow once the phase before this one is complete everywhere.
+        // (An L2 look-ahead beyond the ring - cp.async.bulk.prefetch.tensor for the next 8-64 tiles while waiting at
+        // the barrier - was measured: no gain, 64 tiles slower; phases are bound by SM ingest, not by HBM idling.)
         bool dep_ok = false;
         int n_pend = 0;
         int pend_stage[C::kStages], pend_k0[C::kStages];
@@ -204,22 +209,21 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         for (int u = cta; u < units; u += G) {
           int tile, split, kb0, kb1;
           unit_range(ph, u, tile, split, kb0, kb1);
-          const int w_row0 = tile * kBM;
+          const int w_row0 = tile * ph.tile_rows;
           for (int kb = kb0; kb < kb1; ++kb) {
-            for (int sub = 0; sub < nsub; ++sub) {
-              if (!dep_ok && n_pend == C::kStages) resolve();
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * C::kStageBytes;
-              mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-              tma_load_2d(sa + C::kActBytes, wm, &full_bar[stage], kb * kBK, w_row0 + sub * ph.dual_off);
-              if (dep_ok) {
-                tma_load_4d(sa, am, &full_bar[stage], kb * kBK, 0, 0, 0);
-              } else {
-                pend_stage[n_pend] = stage; pend_k0[n_pend] = kb * kBK;
-                ++n_pend;
-              }
-              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            if (!dep_ok && n_pend == C::kStages) resolve();
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            tma_load_2d(sa + C::kActBytes, wm, &full_bar[stage], kb * kBK, w_row0);
+            tma_load_2d(sa + C::kActBytes + C::kWBytes, wm, &full_bar[stage], kb * kBK, w_row0 + ph.sub_off);
+            if (dep_ok) {
+              tma_load_4d(sa, am, &full_bar[stage], kb * kBK, 0, 0, 0);
+            } else {
+              pend_stage[n_pend] = stage; pend_k0[n_pend] = kb * kBK;
+              ++n_pend;
             }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
         if (!dep_ok && n_pend > 0) resolve();
@@ -236,7 +240,6 @@ decode_chain_kernel(const __grid_constant__ Params p) {
       const Phase& ph = p.ph[pi];
       if (ph.kind != PH_GEMM) continue;
       const int units = ph.tiles * ph.splits;
-      const int nsub = ph.dual ? 2 : 1;
       for (int u = cta; u < units; u += G) {
         int tile, split, kb0, kb1;
         unit_range(ph, u, tile, split, kb0, kb1);
@@ -244,24 +247,25 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + acc * C::kAccCols;
         for (int kb = kb0; kb < kb1; ++kb) {
-          for (int sub = 0; sub < nsub; ++sub) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            if (lane == 0) {
-              const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-              const uint64_t d_act = make_smem_desc(sa);
-              const uint64_t d_w = make_smem_desc(sa + C::kActBytes);
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+            const uint64_t d_act = make_smem_desc(sa);
+            const uint64_t d_w0 = make_smem_desc(sa + C::kActBytes);
+            const uint64_t d_w1 = make_smem_desc(sa + C::kActBytes + C::kWBytes);
 #pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k) {
-                const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                umma_bf16(tacc + sub * kBN, d_w + koff, d_act + koff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              }
-              umma_commit(&empty_bar[stage]);
-              if (kb == kb1 - 1 && sub == nsub - 1) umma_commit(&tfull_bar[acc]);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              umma_bf16(tacc, d_w0 + koff, d_act + koff, idesc, accum);
+              umma_bf16(tacc + kBN, d_w1 + koff, d_act + koff, idesc, accum);
             }
-            __syncwarp();
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
           }
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -284,17 +288,17 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         for (int u = cta; u < units; u += G) {
           int tile, split, kb0, kb1;
           unit_range(ph, u, tile, split, kb0, kb1);
-          const int f = tile * kBM + r;
           mbar_wait(&tfull_bar[acc], acc_phase);
           tcgen05_fence_after();
           if (p.dbg && et == 0 && u == cta) p.dbg[cta * 32 + 2 + 3 * pi] = gtimer();   // first accumulator of the phase complete
           const uint32_t taddr = tmem_base + acc * C::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+          const int n_tok = p.n_tok - hc0;         // valid token columns from hc0 on
           // tcgen05.ld is warp-collective (.sync.aligned): the condition around it must be warp-uniform (a partial
           // last tile, e.g. the 7 valid rows of lm_head's tile 1002, guards the STORES per lane instead)
-          if (works && tile * kBM + q * 32 < ph.n_out) {
-            const bool row_ok = f < ph.n_out;
-            const int n_tok = p.n_tok - hc0;       // valid token columns from hc0 on
-            if (ph.epi == EPI_SILU) {
+          if (ph.epi == EPI_SILU) {
+            const int f = tile * kBM + r;
+            if (works && tile * kBM + q * 32 < ph.n_out) {
+              const bool row_ok = f < ph.n_out;
               bf16* dst = reinterpret_cast<bf16*>(ph.out) + static_cast<size_t>(hc0) * ph.n_out + f;
 #pragma unroll 1
               for (int c = 0; c < C::kHalfCols; c += 16) {
@@ -307,14 +311,22 @@ decode_chain_kernel(const __grid_constant__ Params p) {
                   if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = __float2bfloat16_rn(x);
                 }
               }
-            } else {
-              // EPI_PART: fp32 partial of this k-range [split][tok][feature]; EPI_F32: fp32 logits [tok][feature]
+            }
+          } else {
+            // EPI_PART: fp32 partial of this k-range [split][tok][feature]; EPI_F32: fp32 logits [tok][feature];
+            // the two accumulators are two adjacent feature tiles
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+              const int f0 = tile * ph.tile_rows + sub * ph.sub_off;
+              if (!(works && f0 + q * 32 < ph.n_out)) continue;
+              const int f = f0 + r;
+              const bool row_ok = f < ph.n_out;
               float* dst = reinterpret_cast<float*>(ph.out) +
                            (static_cast<size_t>(ph.epi == EPI_PART ? split : 0) * p.n_tok + hc0) * ph.n_out + f;
 #pragma unroll 1
               for (int c = 0; c < C::kHalfCols; c += 16) {
                 float v[16];
-                tmem_ld16(taddr + hc0 + c, v);
+                tmem_ld16(taddr + sub * kBN + hc0 + c, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                   if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = v[i];
@@ -339,7 +351,16 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           const size_t src = ph.gather ? static_cast<size_t>(ph.gather[row]) : static_cast<size_t>(row);
           const bf16* x = ph.x_in + src * Cc;
           float v[2][8];
+          float4 wq[2][2];                           // norm weights: independent of the row, fetched ahead of the reduction
           float sq[2] = {0.f, 0.f};
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int gi = it * C::kEpiThreads + et;
+            if (gi < groups) {
+              wq[it][0] = __ldg(reinterpret_cast<const float4*>(ph.w + gi * 8));
+              wq[it][1] = __ldg(reinterpret_cast<const float4*>(ph.w + gi * 8 + 4));
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             const int gi = it * C::kEpiThreads + et;
@@ -402,7 +423,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
             const int gi = it * C::kEpiThreads + et;
             if (gi < groups) {
               const int c0 = gi * 8;
-              const float4 w0 = *reinterpret_cast<const float4*>(ph.w + c0), w1 = *reinterpret_cast<const float4*>(ph.w + c0 + 4);
+              const float4 w0 = wq[it][0], w1 = wq[it][1];
               const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
               uint32_t pk[4];
 #pragma unroll

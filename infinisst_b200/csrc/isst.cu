@@ -168,6 +168,7 @@ struct isst_ctx {
   bool pdl = true;          // "pdl" = 0: plain stream order instead of programmatic dependent launch
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
+  bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
   unsigned long long chain_base[chain::kMaxPhases] = {0};   // their values once every launch issued so far has completed
   std::set<const void*> smem_attr_done;      // kernels whose dynamic shared-memory limit was raised on this device
@@ -315,6 +316,15 @@ struct Epilogue {
   int dual_off = 0;
 };
 
+// k-splits of a weight-streaming GEMM in the fused decode chain: units of TWO 128-row weight tiles (they share one
+// activation tile), cut into S k-ranges so that units x S fills the SMs.
+static int chain_splits(int sm_count, int n_out, int num_kb, bool dual) {
+  const int tiles = ceil_div(n_out, tc::kBM);
+  const int units = dual ? tiles : ceil_div(tiles, 2);
+  const long long s = std::min<long long>(std::min<long long>(sm_count / std::max(units, 1), 8), num_kb / 8);
+  return s >= 2 ? static_cast<int>(s) : 1;
+}
+
 // Raises the dynamic shared-memory limit of a kernel once per context (= per device).
 template <typename F>
 static int ensure_smem(isst_ctx* ctx, F* kern, int bytes) {
@@ -366,7 +376,10 @@ static void sk_plan(isst_ctx* ctx, int M_tok, int N_out, int K, int batch, int a
   if (want_defer) {
     // Deferred split reduction: every tile is cut into S equal k-ranges (one CTA each, tiles * S <= #SMs) and the
     // partials are summed by the consumer row kernel; falls back to the in-kernel schemes when S would be 1.
-    const long long S = std::min<long long>(std::min<long long>(ctx->sm_count / std::max<long long>(sk.tiles, 1), 8), sk.num_kb / 8);
+    long long S = std::min<long long>(std::min<long long>(ctx->sm_count / std::max<long long>(sk.tiles, 1), 8), sk.num_kb / 8);
+    // test option: the k-ranges of the fused decode chain (its units are tile pairs), so that both paths sum the same
+    // partials in the same order; the grid may then exceed the SM count (no CTA of this mode waits for another)
+    if (ctx->opt_defer_as_chain && swap && batch == 1) S = chain_splits(ctx->sm_count, N_out, sk.num_kb, false);
     if (swap && batch == 1 && S >= 2 && force_splits == 0 &&
         static_cast<size_t>(S) * M_tok * N_out <= ctx->defer_ws_floats) {
       G = sk.tiles * S;
@@ -940,15 +953,19 @@ static int chain_gemm(isst_ctx* ctx, ChainBuilder& cb, const bf16* act, const We
     cb.amap_ptr[ai] = act; cb.amap_K[ai] = w.K;
   }
   ph.amap = ai;
-  ph.tiles = ceil_div(n_out, tc::kBM);
+  // a unit streams TWO weight tiles against one activation tile: gate / up rows of the same 128 features, or two
+  // adjacent 128-feature tiles
+  const int tiles128 = ceil_div(n_out, tc::kBM);
+  ph.tiles = dual ? tiles128 : ceil_div(tiles128, 2);
+  ph.tile_rows = dual ? tc::kBM : 2 * tc::kBM;
+  ph.sub_off = dual ? n_out : tc::kBM;
   ph.num_kb = w.K / tc::kBK;
-  ph.dual = dual; ph.dual_off = dual ? n_out : 0;
+  ph.dual = dual;
   ph.epi = epi; ph.n_out = n_out; ph.out = out;
   int S = 1;
   if (epi == chain::EPI_PART) {
-    // the split rule of the operator-per-kernel path (sk_plan, deferred mode): same k-ranges, same bits
-    const long long s = std::min<long long>(std::min<long long>(ctx->sm_count / std::max(ph.tiles, 1), 8), ph.num_kb / 8);
-    if (s >= 2 && static_cast<size_t>(s) * cb.p.n_tok * n_out <= ctx->defer_ws_floats) S = static_cast<int>(s);
+    S = chain_splits(ctx->sm_count, n_out, ph.num_kb, false);
+    while (S > 1 && static_cast<size_t>(S) * cb.p.n_tok * n_out > ctx->defer_ws_floats) --S;
     ISST_CHECK(static_cast<size_t>(S) * cb.p.n_tok * n_out <= ctx->defer_ws_floats, "decode chain: partial workspace too small");
   }
   ph.splits = S;
@@ -2511,6 +2528,7 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   if (key == "pdl") ctx->pdl = value != 0;
   else if (key == "decode_splits") ctx->opt_dec_splits = value;
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
+  else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
   else return set_error("unknown option: " + key);
   return 0;
 }

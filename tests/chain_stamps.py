@@ -29,7 +29,7 @@ def main():
         pcm = 0.1 * torch.randn(B, SEG + (399 if c == 0 else 0), device="cuda:0", generator=g)
         r.step_device(pcm)
     torch.cuda.synchronize()
-    for use_chain in (1, 0, 1):
+    for use_chain, pref in ((1, 0), (0, 0), (1, 0), (0, 0)):
         eng.option("decode_chain", use_chain)
         ts = []
         for _ in range(4):
@@ -40,7 +40,8 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        print(f"chain={use_chain}: step ms {['%.2f' % t for t in ts]} (enc 1 + llm {layers} layers, {B} streams, kv {eng.kv_len(r.sids[0])})", flush=True)
+        print(f"chain={use_chain} prefetch={pref}: step ms {['%.2f' % t for t in ts]} (enc 1 + llm {layers} layers, {B} streams, kv {eng.kv_len(r.sids[0])})", flush=True)
+    eng.option("decode_chain", 1)
     eng.debug(2)
     pcm = 0.1 * torch.randn(B, SEG, device="cuda:0", generator=g)
     r.step_device(pcm)

@@ -797,6 +797,7 @@ def test_decode_chain_bit_identical_to_operator_path(shape):
     for use_chain in (1, 0):
         eng = _engine(cfg, sd, max_streams=B, max_batch=B)
         eng.option("decode_chain", use_chain)
+        eng.option("defer_splits_as_chain", 1)                   # operator path: the chain's k-ranges (its units are tile pairs)
         eng.debug(True)
         run = LockstepRunner(eng, cfg, B)
         rec = []
