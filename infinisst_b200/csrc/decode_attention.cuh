@@ -210,12 +210,14 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
       cs[k] = p.tab_sys[static_cast<size_t>(b) * 64 + dd[k]];
     }
     if (p.part) {
-      float va[3][4], vb[3][4];
+      // all partial loads of the thread's three items are issued before the first use (<= 8 k-splits; the sum runs in
+      // split order like the row kernels')
+      float va[3][8], vb[3][8];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float* p0 = p.part + static_cast<size_t>(b) * ldq + col[k] + dd[k];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           va[k][q] = 0.f; vb[k][q] = 0.f;
           if (q < p.n_part) { va[k][q] = __ldcg(p0 + q * p.part_stride); vb[k][q] = __ldcg(p0 + q * p.part_stride + 64); }
         }
@@ -223,8 +225,11 @@ decode_attention_mma_kernel(const DecodeParams2 p) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float sa = ((va[k][0] + va[k][1]) + va[k][2]) + va[k][3], sb = ((vb[k][0] + vb[k][1]) + vb[k][2]) + vb[k][3];
+#pragma unroll
+        for (int q = 4; q < 8; ++q)
+          if (q < p.n_part) { sa += va[k][q]; sb += vb[k][q]; }
         const float* p0 = p.part + static_cast<size_t>(b) * ldq + col[k] + dd[k];
-        for (int q = 4; q < p.n_part; ++q) { sa += __ldcg(p0 + q * p.part_stride); sb += __ldcg(p0 + q * p.part_stride + 64); }
+        for (int q = 8; q < p.n_part; ++q) { sa += __ldcg(p0 + q * p.part_stride); sb += __ldcg(p0 + q * p.part_stride + 64); }
         a[k] = bf16_round(sa); bb[k] = bf16_round(sb);             // the projection output is a bf16 tensor in the reference
       }
     } else {

@@ -342,9 +342,13 @@ struct SkParams {
 };
 
 
-template <int kBN, bool kDual, bool kSwap>
+// kMT (row mode only): 128-row token tiles per CTA tile.  A tensor-bound GEMM is limited by what an SM can ingest from
+// L2 (~74 KB/us measured: 959 TFLOP/s with 48 KB per 128 x 256 x 64 k-block); with kMT = 2 a k-block of 256 tokens x 256
+// features moves 64 KB for twice the flops (131 instead of 87 flop per byte).  The two token tiles own all 512 TMEM
+// columns, so the accumulator is not double-buffered there (the epilogue of a tile is exposed: a few us per ~60 us tile).
+template <int kBN, bool kDual, bool kSwap, int kMT = 1>
 struct SkCfg {
-  static constexpr int kActRows = kSwap ? kBN : kBM;
+  static constexpr int kActRows = kSwap ? kBN : kBM * kMT;
   static constexpr int kWRows = kSwap ? kBM : kBN;
   static constexpr int kNW = kDual ? 2 : 1;
   static constexpr int kActBytes = kActRows * kBK * 2;
@@ -352,8 +356,10 @@ struct SkCfg {
   static constexpr int kStageBytes = kActBytes + kNW * kWBytes;
   static constexpr int kStagesRaw = (224 * 1024) / kStageBytes;     // 227 KB per CTA minus barriers / alignment slack
   static constexpr int kStages = kStagesRaw > 10 ? 10 : kStagesRaw;
-  static constexpr int kAccCols = kBN * kNW;
-  static constexpr int kTmemColsRaw = 2 * kAccCols;
+  static constexpr int kAccCols = kBN * kNW;                      // per 128-row token tile
+  static constexpr int kAccAll = kAccCols * kMT;
+  static constexpr int kAccBufs = (2 * kAccAll <= 512) ? 2 : 1;
+  static constexpr int kTmemColsRaw = kAccBufs * kAccAll;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue: 8 warps (2 column halves) for the big
@@ -366,7 +372,8 @@ struct SkCfg {
   static constexpr int kHalfCols = kBN / kEpiHalves;
   static constexpr int kNC = (kSwap && !kDual && kHalfCols >= 32) ? 32 : 16;   // columns per epilogue step
   static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
-  static_assert(kTmemColsRaw <= 512, "two accumulators must fit TMEM");
+  static_assert(kTmemColsRaw <= 512, "the accumulators must fit TMEM");
+  static_assert(kMT == 1 || (!kSwap && kMT == 2), "token-tile pairs exist in row mode only");
   static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
 };
 
@@ -430,11 +437,11 @@ struct SkWalker {
   }
 };
 
-template <int kBN, bool kDual, bool kSwap>
+template <int kBN, bool kDual, bool kSwap, int kMT = 1>
 __global__ void __launch_bounds__(384) __maxnreg__(kSwap ? 128 : 168)
 gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const GemmParams p, const SkParams sk) {
-  using C = SkCfg<kBN, kDual, kSwap>;
+  using C = SkCfg<kBN, kDual, kSwap, kMT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -558,7 +565,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     while (w.next(tile, kb_begin, kb_end)) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + acc * C::kAccCols;
+      const uint32_t tacc = tmem_base + acc * C::kAccAll;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -573,8 +580,12 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
             const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
             if (!kSwap) {
-              umma_bf16(tacc, d_act + koff, d_w0 + koff, idesc, accum);
-              if (kDual) umma_bf16(tacc + kBN, d_act + koff, d_w1 + koff, idesc, accum);
+#pragma unroll
+              for (int mt = 0; mt < kMT; ++mt) {          // token tile mt: rows [128 mt, 128 mt + 128) of the activation box
+                const uint64_t aoff = koff + static_cast<uint64_t>((mt * kBM * kBK * 2) >> 4);
+                umma_bf16(tacc + mt * C::kAccCols, d_act + aoff, d_w0 + koff, idesc, accum);
+                if (kDual) umma_bf16(tacc + mt * C::kAccCols + kBN, d_act + aoff, d_w1 + koff, idesc, accum);
+              }
             } else {
               umma_bf16(tacc, d_w0 + koff, d_act + koff, idesc, accum);
               if (kDual) umma_bf16(tacc + kBN, d_w1 + koff, d_act + koff, idesc, accum);
@@ -586,7 +597,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================= epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =================
@@ -603,7 +614,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
       p.counters[(p.counter_parity ? 0 : p.counter_half) + i] = 0;
     const int hc0 = half * C::kHalfCols;          // first column of this warp's half
     constexpr int NC = C::kNC;
-    constexpr size_t kSlot = static_cast<size_t>(C::kAccCols) * kBM;
+    constexpr size_t kSlot = static_cast<size_t>(C::kAccAll) * kBM;
     int acc = 0;
     uint32_t acc_phase = 0;
     SkWalker w(sk, G, cta);
@@ -614,16 +625,21 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
     bool first_seg = true;
     while (w.next(tile, kb_begin, kb_end)) {
       const SkTile t = sk_tile(tile, sk);
-      const int lane_idx = (kSwap ? t.tf : t.tt) * kBM + r;
       const int col_base = (kSwap ? t.tt : t.tf) * kBN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       if (first_seg && sk.dbg && et == 0) sk.dbg[cta * 8 + 2] = gtimer();
       first_seg = false;
-      const uint32_t taddr = tmem_base + acc * C::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr0 = tmem_base + acc * C::kAccAll + (static_cast<uint32_t>(q * 32) << 16);
+      int lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + r;
+      uint32_t taddr = taddr0;
       if (kb_begin == 0 && kb_end == nkb) {
         // ---- the whole k-range of this tile was accumulated here: final epilogue straight from TMEM ----
-        if (works) {
+#pragma unroll 1
+        for (int mt = 0; mt < kMT; ++mt) {
+        lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + mt * kBM + r;
+        taddr = taddr0 + mt * C::kAccCols;
+        if (works && (kSwap || t.tt * C::kActRows + mt * kBM < p.M_tok)) {
 #pragma unroll 1
           for (int c = hc0; c < hc0 + C::kHalfCols; c += (kSwap ? NC : 32)) {
             if (!kSwap) {
@@ -669,6 +685,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
           }
         }
+        }
         tcgen05_fence_before();
         mbar_arrive(&tempty_bar[acc]);
       } else {
@@ -691,7 +708,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
           }
           tcgen05_fence_before();
           mbar_arrive(&tempty_bar[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1; }
           continue;
         }
         // ---- partial tile: park the fp32 partial and announce it; the reduction happens after the walk ----
@@ -700,11 +717,11 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         float* mine = p.ws + static_cast<size_t>(cta == c_first ? G + cta : cta) * kSlot;
         if (works) {
 #pragma unroll 1
-          for (int cc = 0; cc < C::kNW; ++cc)
+          for (int cc = 0; cc < C::kNW * kMT; ++cc)            // accumulator blocks of kBN columns: (token tile, gate | up)
 #pragma unroll 1
             for (int c = hc0; c < hc0 + C::kHalfCols; c += 16) {
               float v[16];
-              tmem_ld16(taddr + cc * kBN + c, v);
+              tmem_ld16(taddr0 + cc * kBN + c, v);
 #pragma unroll
               for (int i = 0; i < 16; ++i) mine[(cc * kBN + c + i) * kBM + r] = v[i];
             }
@@ -716,7 +733,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         if (et == 0) atomicAdd(const_cast<int*>(&counters[c_first]), 1);
         part_tile[n_part++] = tile;
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
     if (sk.dbg && et == 0) sk.dbg[cta * 8 + 3] = gtimer();
     // ---- reduce the shared tiles: every contributor takes its share of the 16-column chunks ----
@@ -731,22 +748,24 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
       }
       asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
       const SkTile t = sk_tile(tl, sk);
-      const int lane_idx = (kSwap ? t.tf : t.tt) * kBM + r;
       const int col_base = (kSwap ? t.tt : t.tf) * kBN;
-      // chunk list: kBN / 16 chunks dealt to (contributor, half) pairs
-      constexpr int kChunks = kBN / 16;
+      // chunk list: kMT * kBN / 16 chunks (token tile, 16 columns) dealt to (contributor, half) pairs
+      constexpr int kChunks = kMT * kBN / 16;
       const int workers = nc * C::kEpiHalves;
       const int me = (cta - c_first) * C::kEpiHalves + half;
       const int ch0 = kChunks * me / workers, ch1 = kChunks * (me + 1) / workers;
 #pragma unroll 1
       for (int ch = ch0; ch < ch1; ++ch) {
-        const int c = ch * 16;
+        const int mt = ch / (kBN / 16);
+        const int c = (ch - mt * (kBN / 16)) * 16;
+        const int lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + mt * kBM + r;
+        const size_t moff = static_cast<size_t>(mt) * C::kAccCols * kBM;      // this token tile's block in a parked partial
         float v0[16], v1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
 #pragma unroll 4
         for (int cc = c_first; cc <= c_last; ++cc) {
-          const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot;
+          const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot + moff;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             v0[i] += __ldcg(&src[(c + i) * kBM + r]);

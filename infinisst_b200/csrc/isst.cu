@@ -168,6 +168,7 @@ struct isst_ctx {
   bool pdl = true;          // "pdl" = 0: plain stream order instead of programmatic dependent launch
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
+  bool opt_tiles_x2 = true;          // "gemm_tiles_x2" = 0: 128-token tiles for the tensor-bound GEMMs (A/B)
   bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
   unsigned long long chain_base[chain::kMaxPhases] = {0};   // their values once every launch issued so far has completed
@@ -393,11 +394,11 @@ static void sk_plan(isst_ctx* ctx, int M_tok, int N_out, int K, int batch, int a
   *G_out = G;
 }
 
-template <int kBN, bool kDual, bool kSwap>
+template <int kBN, bool kDual, bool kSwap, int kMT = 1>
 static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
                      int force_splits) {
-  using C = tc::SkCfg<kBN, kDual, kSwap>;
-  auto kern = tc::gemm_sk_kernel<kBN, kDual, kSwap>;
+  using C = tc::SkCfg<kBN, kDual, kSwap, kMT>;
+  auto kern = tc::gemm_sk_kernel<kBN, kDual, kSwap, kMT>;
   ISST_TRY(ensure_smem(ctx, kern, C::kSmemBytes));
   tc::SkParams sk{};
   long long G = 0;
@@ -409,11 +410,11 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   pp.part_splits = S;
   ctx->last_defer_splits = S;
   if (kSwap) ctx->paths[std::string("gemm_sk_swap") + std::to_string(kBN) + (kDual ? "_dual" : "") + (S ? "_deferred" : "")]++;
-  else ctx->paths[std::string("gemm_sk_rows") + std::to_string(kBN) + (kDual ? "_dual" : "")]++;
+  else ctx->paths[std::string("gemm_sk_rows") + std::to_string(kBN) + (kDual ? "_dual" : "") + (kMT == 2 ? "_x2" : "")]++;
   pp.counter_half = ctx->n_counters / 2;
   pp.counter_parity = ctx->gemm_parity;
   ctx->gemm_parity ^= 1;
-  const size_t slot = static_cast<size_t>(C::kAccCols) * tc::kBM;
+  const size_t slot = static_cast<size_t>(C::kAccAll) * tc::kBM;
   ISST_CHECK(2 * static_cast<size_t>(G) * slot <= ctx->gemm_ws_floats && G <= ctx->n_counters / 2,
              "gemm: stream-K workspace too small");
   CUtensorMap amap;
@@ -469,8 +470,17 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
   const int sbn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
 #define ISST_SK(BN, DUAL, SWAP) return launch_sk<BN, DUAL, SWAP>(ctx, st, v, w, p, force_splits)
   if (!swap) {
-    if (e.dual) ISST_SK(128, true, false);
-    if (n_out >= 256) ISST_SK(256, false, false);
+    // more than one 128-row token tile: 256-token tiles (two accumulators sets) halve the operand bytes an SM has to
+    // ingest per flop - the bound of these GEMMs (SkCfg); strided-conv views (batch > 1) keep the 128-row tiles
+    // ... where that pays (measured, tests/gemm_bench.py --ab): a 256 x 256 tile owns all of TMEM, its epilogue is
+    // exposed (raw 1290 vs 1160 TFLOP/s), and fewer, larger tiles quantise worse - so only when the 256-token tiling
+    // is (nearly) exactly one wave of whole tiles (prefill / encoder QKV: 144 tiles; +21 %) or a single token tile
+    // (beam-search gate/up at 129-256 rows: every weight tile is then fetched once instead of twice; +29 %)
+    const long long t2 = static_cast<long long>(ceil_div(v.rows, 256)) * ceil_div(n_out, e.dual ? 128 : 256);
+    const bool one_wave = t2 <= ctx->sm_count && 10 * t2 >= 9 * ctx->sm_count;
+    const bool x2 = ctx->opt_tiles_x2 && v.rows > 128 && v.batch == 1 && (one_wave || (v.rows <= 256 && e.dual)) && v.K >= 2048;
+    if (e.dual) { if (x2) return launch_sk<128, true, false, 2>(ctx, st, v, w, p, force_splits); ISST_SK(128, true, false); }
+    if (n_out >= 256) { if (x2) return launch_sk<256, false, false, 2>(ctx, st, v, w, p, force_splits); ISST_SK(256, false, false); }
     ISST_SK(128, false, false);
   }
   if (e.dual) {
@@ -1458,7 +1468,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ctx->decode_splits = 32;
   ISST_TRY(dev_alloc(&ctx->part_o, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * c.head_dim));
   ISST_TRY(dev_alloc(&ctx->part_ml, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * 2));
-  ctx->gemm_ws_floats = static_cast<size_t>(16) << 20;   // 64 MB
+  ctx->gemm_ws_floats = static_cast<size_t>(24) << 20;   // 96 MB: two parked 256 x 256 fp32 partial tiles per CTA
   ISST_TRY(dev_alloc(&ctx->gemm_ws, ctx->gemm_ws_floats));
   ctx->defer_ws_floats = static_cast<size_t>(8) * 128 * std::max(QKV, HID);   // <= 8 splits x <= 128 tokens x widest deferred output
   ISST_TRY(dev_alloc(&ctx->defer_ws, ctx->defer_ws_floats));
@@ -2529,6 +2539,7 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   else if (key == "decode_splits") ctx->opt_dec_splits = value;
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
   else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
+  else if (key == "gemm_tiles_x2") ctx->opt_tiles_x2 = value != 0;
   else return set_error("unknown option: " + key);
   return 0;
 }

@@ -21,6 +21,7 @@ SHAPES = [
     ("pre gateup", 1408, 14336, 4096, {"dual": True}), ("pre down", 1408, 4096, 14336, {"resid": True}),
     ("enc qkv", 3072, 3072, 1024, {"bias": True}), ("enc out", 3072, 1024, 1024, {"bias": True, "resid": True}),
     ("enc fc1", 3072, 4096, 1024, {"bias": True, "gelu": True}), ("enc fc2", 3072, 1024, 4096, {"bias": True, "resid": True}),
+    ("beam qkv", 256, 6144, 4096, {}), ("beam gateup", 256, 14336, 4096, {"dual": True}), ("beam down", 256, 4096, 14336, {"resid": True}),
 ]
 
 
@@ -70,12 +71,16 @@ def stamps(eng, M, N, K, kw):
 
 def main():
     out = []
-    for mode in ["sk"]:
+    for mode in (["x2", "x1"] if "--ab" in sys.argv else ["sk"]):
         eng = Engine(tiny_config(), device=0, max_streams=2)
+        if mode == "x1":
+            eng.option("gemm_tiles_x2", 0)          # 128-token tiles for the tensor-bound GEMMs (A/B against 256-token tiles)
         for (name, M, N, K, kw) in SHAPES:
+            if mode != "sk" and M <= 128:
+                continue
             us, tf, gbs = bench(eng, name, M, N, K, kw)
             line = f"[{mode}] {name:12s} M={M:5d} N={N:6d} K={K:5d}  {us:8.1f} us  {tf:7.1f} TFLOP/s  {gbs:7.1f} GB/s"
-            if mode == "sk":
+            if mode == "sk" and "--stamps" in sys.argv:
                 line += "  stamps(start, first_tma, first_acc, walk_done, reduce_done, exit) mean/max us: " + " ".join(stamps(eng, M, N, K, kw))
             print(line, flush=True)
         eng.close()
