@@ -368,17 +368,19 @@ class InfiniSST(SpeechToTextAgent):
             else:
                 ids = [self.cfg.tpl.eot_id] + tok.turn_ids(n_speech)
             return torch.tensor([ids], dtype=torch.long)
+        def chat_ids(msgs):
+            # transformers >= 5 returns a BatchEncoding here, 4.47 (the reference's pin) the id tensor itself
+            out = tok.apply_chat_template([msgs], return_tensors="pt", padding=True, truncation=False, add_special_tokens=False)
+            return out["input_ids"] if hasattr(out, "keys") else out
         messages = []
         if states.speech_cache is None:
             latency_token = DEFAULT_LATENCY_TOKEN.format(self.latency_multiplier)
             messages.append({"role": "system", "content": f"Translate the following speech from {self.source_lang} "
                                                           f"to {self.target_lang} with latency {latency_token}."})
-            states.system_prompt_size = tok.apply_chat_template([messages], return_tensors="pt", padding=True,
-                                                                truncation=False, add_special_tokens=False).size(1)
+            states.system_prompt_size = chat_ids(messages).size(1)
         messages.append({"role": "user", "content": n_speech * DEFAULT_SPEECH_PATCH_TOKEN})
         messages.append({"role": "assistant", "content": ""})
-        input_ids = tok.apply_chat_template([messages], return_tensors="pt", padding=True, truncation=False,
-                                            add_special_tokens=False)[:, :-1]
+        input_ids = chat_ids(messages)[:, :-1]
         if states.speech_cache is not None:
             if self.llama31:
                 input_ids = input_ids[:, 25:]      # Llama-3.1 default system header (agents/infinisst.py:262-264)

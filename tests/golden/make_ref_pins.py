@@ -87,7 +87,9 @@ class FakeTokenizer:
         return " ".join(str(i) for i in ids)
 
 
-def build_reference_agent(cfg, sd, xpos=0, rope=1):
+def build_reference_agent(cfg, sd, xpos=0, rope=1, tokenizer=None, model_name="synthetic-llama-3.1"):
+    """`tokenizer`: a real HF tokenizer to hand to the agent (then the reference's OWN `preprocess`, model/llm.py:149-190,
+    runs on it); default: the FakeTokenizer over the synthetic template with a stand-in `preprocess`."""
     RS.install()
     import transformers
     from transformers import LlamaConfig
@@ -121,7 +123,8 @@ def build_reference_agent(cfg, sd, xpos=0, rope=1):
         self.config.user_token_id = l.user_token_id
         self.config.assist_token_id = l.assist_token_id
         self.config.start_header_id = l.start_header_id
-    ref_llm.SpeechLlamaForCausalLM.preprocess = preprocess
+    if tokenizer is None:
+        ref_llm.SpeechLlamaForCausalLM.preprocess = preprocess
 
     def _load_w2v2(self, path, finetuned):
         # fairseq checkpoint loading is third-party; the container classes come from the stand-in, their
@@ -130,7 +133,7 @@ def build_reference_agent(cfg, sd, xpos=0, rope=1):
         return Wav2Vec2Model(e.conv_layers, e.embed_dim, e.ffn_dim, e.heads, e.layers), e.embed_dim, e.layers
     ref_se.SpeechEncoderW2V2RoPE._load_w2v2 = _load_w2v2
 
-    transformers.AutoTokenizer.from_pretrained = staticmethod(lambda *a, **k: FakeTokenizer(cfg))
+    transformers.AutoTokenizer.from_pretrained = staticmethod(lambda *a, **k: tokenizer if tokenizer is not None else FakeTokenizer(cfg))
 
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         torch.save({k: v.clone() for k, v in sd.items()}, f.name)
@@ -144,7 +147,7 @@ def build_reference_agent(cfg, sd, xpos=0, rope=1):
         suppress_non_language=False, max_len_a=1, max_len_b=256, max_new_tokens=g.max_new_tokens, do_sample=False,
         top_p=1.0, top_k=0, epsilon_cutoff=0.0, temperature=1.0, pseudo_batch_size=1,
         max_llm_cache_size=g.max_llm_cache_size, always_cache_system_prompt=g.always_cache_system_prompt,
-        dpo_sampling=False, model_name="synthetic-llama-3.1", w2v2_path="synthetic", ctc_finetuned=True,
+        dpo_sampling=False, model_name=model_name, w2v2_path="synthetic", ctc_finetuned=True,
         w2v2_type="w2v2", length_shrink_cfg=adapter, block_size=e.block_size, max_cache_size=e.max_cache_size,
         xpos=xpos, rope=rope, state_dict_path=sd_path)
     # torch.cuda device placement: the agent moves tensors to model.device, which is the CPU here

@@ -266,3 +266,24 @@ def test_agent_loads_from_checkpoint_files_like_the_reference(tmp_path):
         assert type(ra) is type(rb)
     assert sb.system_prompt_size == len(cfg.tpl.system_ids) and len(sb.target_ids) > 20
     assert sb.past_key_values[0][0].size(2) <= 150 + len(cfg.tpl.system_ids)      # the window slid
+
+
+@pytest.mark.gpu
+def test_engine_ignores_rotary_buffers_some_checkpoints_carry():
+    """A `--xpos 1` checkpoint saved with a rotary_embedding_torch version whose `scale` buffer is persistent, or an
+    older HF checkpoint with per-layer `rotary_emb.inv_freq`, passes the strict key check AND loads: those buffers are
+    recomputed by the library."""
+    from infinisst_b200.engine import Engine
+    from parity_utils import bf16_weights
+    cfg, sd = _tiny_sd()
+    sd = bf16_weights(sd)
+    extra = dict(sd)
+    extra[ck.ENC + "encoder.layers.0.self_attn.rotary_emb.scale"] = torch.ones(cfg.enc.head_dim // 2)
+    extra[ck.ENC + "encoder.layers.1.self_attn.rotary_emb.dummy"] = torch.zeros(1)
+    extra["model.layers.0.self_attn.rotary_emb.inv_freq"] = torch.ones(cfg.llm.head_dim // 2)
+    ck.check_state_dict(extra, cfg)
+    eng = Engine(cfg, device=0, max_streams=1)
+    eng.load_state_dict(extra)
+    sid = eng.open_stream()
+    assert eng.kv_len(sid) == 0
+    eng.close()
