@@ -96,6 +96,8 @@ struct LlmAttnParams {
   int key_splits;
   float* part_o;
   float* part_ml;
+  int l2_ahead;           // K/V tiles asked into L2 ahead of the shared-memory ring (prefill_attention_tc_kernel)
+  int kv_row0;            // first row of this layer in the pool-wide KV tensor map (rows of head_dim elements)
 };
 
 __device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, int src_bytes) {

@@ -168,6 +168,7 @@ struct isst_ctx {
   bool pdl = true;          // "pdl" = 0: plain stream order instead of programmatic dependent launch
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
+  int opt_pa_l2_ahead = 1;           // "prefill_l2_ahead": K/V tiles the prefill attention asks into L2 ahead of its ring
   bool opt_tiles_x2 = true;          // "gemm_tiles_x2" = 0: 128-token tiles for the tensor-bound GEMMs (A/B)
   bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
@@ -212,6 +213,7 @@ struct isst_ctx {
   int *d_enc_prefix = nullptr, *d_page_table = nullptr, *d_kv_len = nullptr, *d_sys_len = nullptr,
       *d_ring_start = nullptr;
   bf16* kv_pool = nullptr;
+  CUtensorMap kv_map;        // the whole LLM KV pool as [rows][head_dim]: boxes of one page x 64 dims (prefill attention)
   size_t kv_layer_elems = 0, enc_layer_elems = 0;
 
   // workspaces
@@ -1145,14 +1147,16 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       const size_t part_cap = static_cast<size_t>(c.max_batch) * H * ctx->decode_splits;     // (row, head, split) slots of part_o
       while (ks > 1 && static_cast<size_t>(M) * H * ks > part_cap) --ks;
       lp.key_splits = ks; lp.part_o = ctx->part_o; lp.part_ml = ctx->part_ml;
+      lp.kv_row0 = static_cast<int>(static_cast<size_t>(l) * (ctx->kv_layer_elems / HD));
+      lp.l2_ahead = ctx->opt_pa_l2_ahead;
       ctx->paths[ks > 1 ? "prefill_attention_tc_keysplit" : "prefill_attention_tc_unsplit"]++;
       if (ks > 1) {
         ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, true>, kPaSmemBytes));
         ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, true>, dim3(row_tiles * ks, Hkv, lb.n), dim3(kPaThreads),
-                           kPaSmemBytes, st, lp));
+                           kPaSmemBytes, st, ctx->kv_map, lp));
       } else {
         ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, false>, dim3(row_tiles, Hkv, lb.n), dim3(kPaThreads),
-                           kPaSmemBytes, st, lp));
+                           kPaSmemBytes, st, ctx->kv_map, lp));
       }
       LAUNCH_CHECK(ctx);
       if (ks > 1) {
@@ -1433,6 +1437,19 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->kv_pool, ctx->kv_layer_elems * c.layers));
   ISST_CUDA(cudaMemset(ctx->kv_pool, 0, ctx->kv_layer_elems * c.layers * sizeof(bf16)));   // masked rows must hold finite values
   for (int p = c.kv_pages - 1; p >= 0; --p) ctx->free_pages.push_back(p);
+  {
+    // pool layout [layer][page][K|V][kv_head][16 tokens][head_dim]: every (page, K|V, head) is 16 consecutive rows
+    const unsigned long long rows = static_cast<unsigned long long>(ctx->kv_layer_elems / c.head_dim) * c.layers;
+    ISST_CHECK(c.head_dim == 128 && rows < (1ULL << 31), "KV pool too large for one tensor map");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(c.head_dim), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(c.head_dim) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kPageTokens)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&ctx->kv_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ctx->kv_pool, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ISST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(kv pool) failed: " + std::to_string(static_cast<int>(r)));
+  }
 
   // ---- workspaces ----
   const int nb = c.max_batch;
@@ -2540,6 +2557,7 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
   else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
   else if (key == "gemm_tiles_x2") ctx->opt_tiles_x2 = value != 0;
+  else if (key == "prefill_l2_ahead") ctx->opt_pa_l2_ahead = value;
   else return set_error("unknown option: " + key);
   return 0;
 }

@@ -9,9 +9,15 @@
 //     O[128 x 128] += P[128 x 64] V          tcgen05.mma, A = P (K-major), B = V ([key][dim] = MN-major), O stays in TMEM
 // The running maximum is only raised when it grows by more than 2^8 (then O in TMEM is rescaled in place), so P may
 // reach 256 instead of 1 - exact in the same relative precision - and almost every tile skips the correction.
-// Roles: warps 0-3 softmax / output, warp 4 MMA issuer (+ TMEM allocation), warps 5-6 K/V loaders (cp.async into the
-// 128-byte-swizzled layout the UMMA descriptors expect, 2-stage ring with full / empty mbarriers).  112 KB of shared
-// memory, 256 TMEM columns and < 128 registers per thread: two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
+// Roles: warps 0-3 softmax / output, warp 4 MMA issuer (+ TMEM allocation), warp 5 TMA producer.  K / V tiles are
+// TMA-staged straight from the paged pool: the pool of all layers is ONE 2-D tensor [rows of 128 dims] whose row
+// coordinate encodes (layer, page, K|V, kv head, token in page); a 64-key tile is 4 pages x (K, V) x two 64-dim halves =
+// 16 boxes of 16 rows x 128 B, written by the TMA unit in the SWIZZLE_128B layout the UMMA descriptors expect (no
+// generic-proxy stores, no proxy fence) into a 2-stage ring with full / empty mbarriers.  Tiles are aligned to pages in
+// SLOT space (the ring region starts at an arbitrary token offset after evictions): columns that fall before the ring
+// start, behind the last key or in the unused tail of the pinned prefix's last page are masked in the softmax.
+// 112 KB of shared memory, 256 TMEM columns and < 128 registers per thread: two CTAs per SM, so one CTA's softmax
+// overlaps the other's MMAs.
 // Keys are stored rotated at their absolute index (attention.cuh header): tiles of the pinned system prompt use the
 // q_sys query variant, tiles of the sliding part the ring variant; the softmax warps swap the variant in shared memory
 // at the boundary.
@@ -54,11 +60,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int GROUP, bool kSplit = false>
 __global__ void __launch_bounds__(kPaThreads, 2)
-prefill_attention_tc_kernel(const LlmAttnParams lp) {
+prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_kv, const LlmAttnParams lp) {
   using namespace tc;
   pdl_launch_dependents();
   pdl_wait();
@@ -68,7 +78,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
   uint8_t* sQ = smem;                                   // [half][128 rows][128 B]: the query variant in use
   uint8_t* sStage = smem + kPaQBytes;                   // [NS][K h0 | K h1 | V h0 | V h1][64][128 B]
   uint8_t* sP = sStage + NS * kPaStageBytes;            // [128 rows][128 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sP + kPaPBytes);   // [NS] tile landed (64 loader lanes arrive)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sP + kPaPBytes);   // [NS] tile landed (TMA transaction bytes)
   uint64_t* empty_bar = full_bar + NS;                  // [NS] tile consumed (tcgen05.commit after P V)
   uint64_t* s_bar = empty_bar + NS;                     // [2]  S buffer ready (tcgen05.commit after Q K^T)
   uint64_t* p_bar = s_bar + 2;                          // P written (128 softmax threads arrive)
@@ -94,7 +104,11 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
   const int key_end = L - T + i_hi + 1;
   const int sys_end = min(sys_len, key_end);
   const int n_sys_tiles = (sys_end + KT - 1) / KT;
-  const int n_tiles_all = n_sys_tiles + (key_end - sys_end + KT - 1) / KT;
+  // ring part: logical keys [sys_len, key_end) live in slots [ring_start, ring_slot_end); tiles of 64 slots start at the
+  // page that holds ring_start
+  const int ring_slot_end = ring_start + (key_end - sys_end);
+  const int sb0 = (ring_start >> 4) << 4;
+  const int n_tiles_all = n_sys_tiles + (key_end > sys_end ? (ring_slot_end - sb0 + KT - 1) / KT : 0);
   // this CTA's key tiles: [t_lo, t_lo + n_tiles); u = t - t_lo indexes ring stages / barrier phases
   const int tiles_per = (n_tiles_all + KS - 1) / KS;
   const int t_lo = kSplit ? min(n_tiles_all, split * tiles_per) : 0;
@@ -109,12 +123,16 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     }
     return;
   }
-  auto tile_k0 = [&](int t) { return t < n_sys_tiles ? t * KT : sys_end + (t - n_sys_tiles) * KT; };
-  auto tile_k1 = [&](int t) { return t < n_sys_tiles ? min(sys_end, t * KT + KT) : min(key_end, sys_end + (t - n_sys_tiles + 1) * KT); };
+  // tile t: slot of column 0, logical key index of column 0 (may lie before the first valid key), valid key range
+  auto tile_sb = [&](int t) { return t < n_sys_tiles ? t * KT : sb0 + (t - n_sys_tiles) * KT; };
+  auto tile_jbase = [&](int t) { return t < n_sys_tiles ? t * KT : sb0 + (t - n_sys_tiles) * KT - ring_start + sys_len; };
+  auto tile_jlo = [&](int t) { return t < n_sys_tiles ? t * KT : max(sys_len, tile_jbase(t)); };
+  auto tile_jhi = [&](int t) { return t < n_sys_tiles ? min(sys_end, t * KT + KT) : min(key_end, tile_jbase(t) + KT); };
 
   // ---- set-up: barriers, TMEM, both query variants (generic stores into the swizzled K-major layout) ----
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 64); mbar_init(&empty_bar[s], 1); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_kv)) : "memory");
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
     mbar_init(p_bar, 128);
     mbar_init(pv_bar, 1);
@@ -153,63 +171,43 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp >= 5) {
-    // ================= K / V loaders: 64 lanes, each tile = 64 keys x (K 256 B + V 256 B) =================
-    // lane (grp = l / 16, chunk = l % 16) copies chunk `chunk` of the keys 8*g .. 8*g+7 for g = 4*pass + grp.
-    const int l64 = tid - 160;
-    const int grp = l64 >> 4, chunk = l64 & 15;
-    const int hh = chunk >> 3, cc = chunk & 7;
-    const size_t page_elems = static_cast<size_t>(2) * lp.kv.kv_heads * kPageTokens * HD;
-    const bf16* head_base = lp.kv.pool + static_cast<size_t>(head) * kPageTokens * HD + chunk * 8;
-    const size_t v_off = static_cast<size_t>(lp.kv.kv_heads) * kPageTokens * HD;
-    auto issue = [&](int u) {
-      const int stage = u % NS;
-      const int t = t_lo + u;
-      uint8_t* dK = sStage + stage * kPaStageBytes + hh * (64 * 128);
-      uint8_t* dV = dK + 2 * (64 * 128);
-      const int k0 = tile_k0(t), k1 = tile_k1(t);
+    // ================= TMA producer: one lane; a tile = 4 pages x (K h0, K h1, V h0, V h1) boxes of 16 rows x 128 B =====
+    if (warp == 5 && lane == 0) {
+      const int Hkv = lp.kv.kv_heads;
+      // L2 look-ahead: the ring holds one tile beyond the one in use (two CTAs of 112 KB per SM), i.e. 32 KB per CTA in
+      // flight - at HBM latency that is ~20 KB/us per SM; tiles u+2 .. are therefore asked into L2 ahead of their turn
+      auto prefetch_tile = [&](int u) {
+        const int pg0 = tile_sb(t_lo + u) >> 4;
 #pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int g = 4 * ps + grp;
-        const int jg = min(k0 + 8 * g, L - 1);
-        const int s0 = kv_slot(jg, sys_len, ring_start);
-        const int last = kv_slot(min(jg + 7, k1 - 1 > jg ? k1 - 1 : jg), sys_len, ring_start);
-        const bf16* base_a = head_base + static_cast<size_t>(table[s0 >> 4]) * page_elems;
-        const bf16* base_b = head_base + static_cast<size_t>(table[last >> 4]) * page_elems;
-        const int n_ok = k1 - (k0 + 8 * g);
+        for (int pp = 0; pp < KT / kPageTokens; ++pp) {
+          const int page = table[min(pg0 + pp, lp.kv.pages_per_stream - 1)];
+          const int rk = lp.kv_row0 + ((page * 2) * Hkv + head) * kPageTokens;
+          const int rv = rk + Hkv * kPageTokens;
+          tma_prefetch_l2_2d(&tm_kv, 0, rk); tma_prefetch_l2_2d(&tm_kv, 64, rk);
+          tma_prefetch_l2_2d(&tm_kv, 0, rv); tma_prefetch_l2_2d(&tm_kv, 64, rv);
+        }
+      };
+      for (int u = 2; u < min(n_tiles, 2 + lp.l2_ahead); ++u) prefetch_tile(u);
+      for (int u = 0; u < n_tiles; ++u) {
+        if (lp.l2_ahead > 0 && u + 2 + lp.l2_ahead - 1 < n_tiles) prefetch_tile(u + 2 + lp.l2_ahead - 1);
+        const int stage = u % NS;
+        if (u >= NS) mbar_wait(&empty_bar[stage], ((u / NS) - 1) & 1);      // P V of the tile that used this stage is done
+        uint8_t* dK = sStage + stage * kPaStageBytes;
+        mbar_expect_tx(&full_bar[stage], kPaStageBytes);
+        const int pg0 = tile_sb(t_lo + u) >> 4;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int kr = 8 * g + it;
-          const int sl = s0 + it;
-          const bf16* src = (((sl ^ s0) & ~15) == 0 ? base_a : base_b) + (sl & 15) * HD;
-          const bool ok = it < n_ok;
-          if (!ok) src = lp.kv.pool;
-          const int off = kr * 128 + ((cc ^ (kr & 7)) << 4);
-          cpa16(dK + off, src, ok ? 16 : 0);            // invalid keys: zero fill
-          cpa16(dV + off, src + v_off, ok ? 16 : 0);
+        for (int pp = 0; pp < KT / kPageTokens; ++pp) {
+          // pages past the stream's table hold masked columns only: any valid page will do
+          const int page = table[min(pg0 + pp, lp.kv.pages_per_stream - 1)];
+          const int rk = lp.kv_row0 + ((page * 2) * Hkv + head) * kPageTokens;
+          const int rv = rk + Hkv * kPageTokens;
+          uint8_t* d = dK + pp * (kPageTokens * 128);
+          tma_load_2d(d, &tm_kv, &full_bar[stage], 0, rk);
+          tma_load_2d(d + 64 * 128, &tm_kv, &full_bar[stage], 64, rk);
+          tma_load_2d(d + 2 * (64 * 128), &tm_kv, &full_bar[stage], 0, rv);
+          tma_load_2d(d + 3 * (64 * 128), &tm_kv, &full_bar[stage], 64, rv);
         }
       }
-      cpa_commit();
-    };
-    // classic multi-stage cp.async pipeline inside the loader: tile t is published (proxy fence + arrive) once its
-    // group has landed, while the next NS-1 tiles are already in flight
-    // Tile t+NS-1 is requested as soon as its slot is free (P V of tile t-1 done), then tile t is published once
-    // this thread's copies of it have landed: NS-1 tiles stay in flight.  (The MMA warp finishes tile t-1 without
-    // needing tile t, so waiting for the slot before publishing cannot deadlock.)
-    for (int t = 0; t < NS - 1; ++t) {
-      if (t < n_tiles) issue(t);
-      else cpa_commit();                                 // keep the group count uniform
-    }
-    for (int t = 0; t < n_tiles; ++t) {
-      const int nt = t + NS - 1;
-      if (nt < n_tiles) {
-        if (nt >= NS) mbar_wait(&empty_bar[nt % NS], ((nt / NS) - 1) & 1);
-        issue(nt);
-      } else {
-        cpa_commit();
-      }
-      cpa_wait<NS - 1>();                                // tile t landed (this thread's copies)
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[t % NS]);
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -234,8 +232,14 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
       }
       __syncwarp();
     };
+    // Software-pipelined by one tile: S(t+1) = Q K(t+1)^T is issued BEFORE the softmax of tile t is awaited (S is
+    // double-buffered in TMEM), so the softmax warps find their next S tile ready and run back to back; without it every
+    // tile serialises S MMA -> softmax -> P V MMA.
+    // Buffer safety: S(t+1) overwrites the buffer of S(t-1), whose softmax finished before P(t-1) was announced (waited
+    // for in the previous iteration); K(t+1) sits in the other ring stage than K(t) / V(t).
+    if (n_tiles > 0) mma_s(0);
     for (int t = 0; t < n_tiles; ++t) {
-      mma_s(t);                                                // (the other CTA on this SM fills the tensor pipe meanwhile)
+      if (t + 1 < n_tiles) mma_s(t + 1);
       mbar_wait(p_bar, t & 1);
       tcgen05_fence_after();
       if (lane == 0) {
@@ -262,7 +266,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < n_tiles; ++t) {                        // t: local tile index
-      const int k0 = tile_k0(t_lo + t), k1 = min(tile_k1(t_lo + t), qhi);
+      const int jb = tile_jbase(t_lo + t), jlo = tile_jlo(t_lo + t), jhi = min(tile_jhi(t_lo + t), qhi);
       mbar_wait(&s_bar[t & 1], (t >> 1) & 1);
       tcgen05_fence_after();
       uint32_t sr[4][16];
@@ -270,7 +274,7 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
       for (int q4 = 0; q4 < 4; ++q4) tmem_ld16_issue(tmem_base + lane_addr + (t & 1) * KT + q4 * 16, sr[q4]);
       tmem_ld_wait();
       float mx = -INFINITY;
-      if (k0 + KT <= k1) {                                     // interior tile for this row: no mask
+      if (jb >= jlo && jb + KT <= jhi) {                       // interior tile for this row: no mask
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
 #pragma unroll
@@ -284,8 +288,8 @@ prefill_attention_tc_kernel(const LlmAttnParams lp) {
         for (int q4 = 0; q4 < 4; ++q4)
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int j = k0 + q4 * 16 + e;
-            const float sv = (j < k1) ? __uint_as_float(sr[q4][e]) * lp.scale_log2 : -INFINITY;
+            const int j = jb + q4 * 16 + e;
+            const float sv = (j >= jlo && j < jhi) ? __uint_as_float(sr[q4][e]) * lp.scale_log2 : -INFINITY;
             sr[q4][e] = __float_as_uint(sv);
             mx = fmaxf(mx, sv);
           }

@@ -106,9 +106,12 @@ def test_cuda_agent_from_tokenizer_files_reproduces_reference_stream(pins, tmp_p
     import transformers
     tok0 = transformers.AutoTokenizer.from_pretrained(TOK_DIR)
     eos = [int(tok0.convert_tokens_to_ids(t)) for t in ("<|end_of_text|>", "<|eom_id|>", "<|eot_id|>")]
-    (d / "config.json").write_text(json.dumps({
-        "num_attention_heads": cfg.llm.heads, "num_key_value_heads": cfg.llm.kv_heads, "rms_norm_eps": cfg.llm.rms_eps,
-        "rope_theta": cfg.llm.rope_theta, "rope_scaling": dict(cfg.llm.rope_scaling, rope_type="llama3")}))
+    (d / "config.json").write_text(json.dumps({            # the fields of a Llama config.json (AutoTokenizer reads it too)
+        "model_type": "llama", "architectures": ["LlamaForCausalLM"], "hidden_size": cfg.llm.hidden,
+        "intermediate_size": cfg.llm.ffn, "num_hidden_layers": cfg.llm.layers, "vocab_size": 512,
+        "max_position_embeddings": 131072, "num_attention_heads": cfg.llm.heads, "num_key_value_heads": cfg.llm.kv_heads,
+        "rms_norm_eps": cfg.llm.rms_eps, "rope_theta": cfg.llm.rope_theta,
+        "rope_scaling": dict(cfg.llm.rope_scaling, rope_type="llama3")}))
     (d / "generation_config.json").write_text(json.dumps({"eos_token_id": eos}))
     p = argparse.ArgumentParser()
     InfiniSST.add_args(p)
