@@ -94,15 +94,17 @@ struct Cfg {
   static constexpr int kStageBytes = kActBytes + 2 * kWBytes;
   static constexpr int kStagesRaw = (222 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
-  static constexpr int kAccCols = 2 * kBN;                    // gate | up
-  static constexpr int kTmemColsRaw = 2 * kAccCols;           // double-buffered
-  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : 256));
+  static constexpr int kAccCols = 2 * kBN;                    // two weight tiles: gate | up, or two adjacent feature tiles
+  static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;   // double-buffered up to 128 token columns
+  static constexpr int kTmemColsRaw = kAccBufs * kAccCols;
+  static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
   static constexpr int kEpiThreads = 256;
   static constexpr int kThreads = 128 + kEpiThreads;
   static constexpr int kEpiHalves = kBN >= 32 ? 2 : 1;
   static constexpr int kHalfCols = kBN / kEpiHalves;
-  static_assert(kBN == 16 || kBN == 32 || kBN == 64, "token tile");
+  static_assert(kBN == 16 || kBN == 32 || kBN == 64 || kBN == 128 || kBN == 256, "token tile");
+  static_assert(kStages >= 3, "ring too shallow");
   static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
 };
 
@@ -267,7 +269,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -335,7 +337,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           }
           tcgen05_fence_before();
           mbar_arrive(&tempty_bar[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1; }
         }
       } else {
         // ---- row phase: one row per CTA (rows cta, cta + G, ...) ----

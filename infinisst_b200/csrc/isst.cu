@@ -943,7 +943,7 @@ struct ChainBuilder {
 };
 static void chain_begin(ChainBuilder& cb, int n_tok) {
   cb.p.n_tok = n_tok;
-  cb.bn = n_tok <= 16 ? 16 : (n_tok <= 32 ? 32 : 64);
+  cb.bn = n_tok <= 16 ? 16 : (n_tok <= 32 ? 32 : (n_tok <= 64 ? 64 : (n_tok <= 128 ? 128 : 256)));
 }
 // out = act[n_tok, K] . W^T; returns the number of k-splits (EPI_PART: partials [splits][n_tok][n_out] in `out`)
 static int chain_gemm(isst_ctx* ctx, ChainBuilder& cb, const bf16* act, const Weight2D& w, int n_out, int dual, int epi,
@@ -1021,7 +1021,9 @@ static int chain_launch(isst_ctx* ctx, cudaStream_t st, ChainBuilder& cb) {
   ISST_CHECK(cb.p.n_phases >= 1, "decode chain: empty");
   if (cb.bn == 16) return chain_launch_bn<16>(ctx, st, cb);
   if (cb.bn == 32) return chain_launch_bn<32>(ctx, st, cb);
-  return chain_launch_bn<64>(ctx, st, cb);
+  if (cb.bn == 64) return chain_launch_bn<64>(ctx, st, cb);
+  if (cb.bn == 128) return chain_launch_bn<128>(ctx, st, cb);
+  return chain_launch_bn<256>(ctx, st, cb);
 }
 
 // One decode forward (every stream advances by one token, <= 64 rows) on the fused chain: 2 launches per layer
@@ -1040,6 +1042,7 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
                        ctx->llm_inv_freq, HD / 2, 0));
     LAUNCH_CHECK(ctx);
   }
+  const bool grouped = lb.group == 4 && lb.d_key_hi != nullptr;   // beam search: shared-prefix attention
   int qkv_splits = 1;
   {
     ChainBuilder cb;
@@ -1050,8 +1053,35 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
   }
   for (int l = 0; l < c.layers; ++l) {
     LlmLayerW& w = ctx->llm[l];
-    {
-      PagedKV kv = paged_kv(ctx, l);
+    PagedKV kv = paged_kv(ctx, l);
+    if (grouped) {
+      // beam search: rows come in groups of 4 beams that share their sentence's prompt pages.  RoPE + append (summing the
+      // QKV split partials) is its own kernel here; the shared prefix is attended to once per group
+      {
+        ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
+        dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
+        ISST_CUDA(launch_k(ctx, llm_rope_append_kernel, grid, dim3(128), 0, st, ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T,
+                           lb.d_active, ctx->llm_rope_ring, ctx->llm_rope_sys, H, static_cast<const float*>(ctx->defer_ws), qkv_splits,
+                           static_cast<long long>(M) * QKV));
+        LAUNCH_CHECK(ctx);
+      }
+      const double tok = lb.prefix_tokens + (lb.kv_tokens - lb.prefix_tokens * lb.group);
+      ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, tok * Hkv * HD * 2 * 2);
+      ISST_TRY(ensure_smem(ctx, decode_attention_group_kernel, kGrpSmemBytes));
+      ctx->paths["decode_attention_group"]++;
+      const int n_groups = lb.n / lb.group;
+      const int splits_p = decode_splits_for(ctx, n_groups, std::max(lb.max_prefix, 1));
+      DecodeGroupParams gp{};
+      gp.qkv = ctx->lqkv; gp.q_sys = ctx->lq_sys; gp.kv = kv; gp.slots = lb.d_slots; gp.key_hi = lb.d_key_hi;
+      gp.tail_page = lb.d_tail_page; gp.out = ctx->lattn;
+      gp.part_o = ctx->part_o; gp.part_ml = ctx->part_ml; gp.H = H; gp.splits = splits_p; gp.scale_log2 = scale_log2;
+      ISST_CUDA(launch_k(ctx, decode_attention_group_kernel, dim3(splits_p, Hkv, n_groups), dim3(kDecThreads), kGrpSmemBytes, st, gp));
+      LAUNCH_CHECK(ctx);
+      if (splits_p > 1) {
+        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(lb.n * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, splits_p));
+        LAUNCH_CHECK(ctx);
+      }
+    } else {
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, lb.kv_tokens * Hkv * HD * 2 * 2);
       const int splits = decode_splits_for(ctx, lb.n, lb.max_L);
       DecodeFuse fz;
@@ -1088,7 +1118,8 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
 
 static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool tap_layers) {
   const isst_config& c = ctx->cfg;
-  if (ctx->opt_chain && lb.decode && lb.M <= 64 && lb.M == lb.n && lb.group == 1 && !lb.all_logits && !tap_layers)
+  if (ctx->opt_chain && lb.decode && lb.M <= 256 && lb.M == lb.n && (lb.group == 1 || (lb.group == 4 && lb.d_key_hi)) &&
+      !lb.all_logits && !tap_layers)
     return llm_decode_chain(ctx, st, lb);
   const int D = c.hidden, H = c.heads, Hkv = c.kv_heads, HD = c.head_dim, F = c.ffn;
   const int QKV = (H + 2 * Hkv) * HD;
@@ -1487,7 +1518,7 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->part_ml, static_cast<size_t>(nb) * c.heads * ctx->decode_splits * 2));
   ctx->gemm_ws_floats = static_cast<size_t>(24) << 20;   // 96 MB: two parked 256 x 256 fp32 partial tiles per CTA
   ISST_TRY(dev_alloc(&ctx->gemm_ws, ctx->gemm_ws_floats));
-  ctx->defer_ws_floats = static_cast<size_t>(8) * 128 * std::max(QKV, HID);   // <= 8 splits x <= 128 tokens x widest deferred output
+  ctx->defer_ws_floats = static_cast<size_t>(8) * std::min(std::max(nb, 128), 256) * std::max(QKV, HID);   // <= 8 splits x <= 256 token rows x widest deferred output
   ISST_TRY(dev_alloc(&ctx->defer_ws, ctx->defer_ws_floats));
   ISST_TRY(dev_alloc(&ctx->chain_bar, chain::kMaxPhases));
   ISST_CUDA(cudaMemset(ctx->chain_bar, 0, chain::kMaxPhases * sizeof(unsigned long long)));

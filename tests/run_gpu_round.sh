@@ -13,8 +13,9 @@ tail -3 $O/bench.err; cat $O/bench.json
 if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
       --log-file $O/launches.csv python bench.py --ncu-step --warmup 1 > $O/ncu_launches.log 2>&1; echo "ncu launches exit=$?"
+  # the fused decode-layer chain: one launch = o_proj -> RMSNorm -> gate/up -> down -> RMSNorm -> next QKV (33 per decode forward)
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:gemm_sk -s 300 -c 4 -f -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit=$?"
+      -k regex:decode_chain -s 40 -c 3 -f -o $O/prof_gemm_decode python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm.log 2>&1; echo "ncu chain exit=$?"
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:decode_attention -s 32 -c 2 -f -o $O/prof_decode_attn python bench.py --ncu-step --warmup 1 > $O/ncu_attn.log 2>&1; echo "ncu attn exit=$?"
 fi
@@ -23,7 +24,8 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:prefill_attention_tc -s 2 -c 2 -f -o $O/prof_prefill_attn python bench.py --ncu-step --warmup 1 > $O/ncu_pattn.log 2>&1; echo "ncu prefill attn exit=$?"
   # tensor-bound GEMMs: the 4 GEMMs of one prefill layer (1408 tokens).  One step launches 106 gemm_sk kernels before
-  # the LLM prefill (6 conv + post_proj + 24 x 4 encoder + 2 adapter + proj); skip into prefill layer 1
+  # the LLM prefill (6 conv + post_proj + 24 x 4 encoder + 2 adapter + proj); skip into prefill layer 1 (decode GEMMs
+  # are decode_chain launches, so every gemm_sk launch of a step is a tensor-bound one except the prefill lm_head)
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:gemm_sk -s 110 -c 4 -f -o $O/prof_gemm_prefill python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm_prefill.log 2>&1; echo "ncu gemm prefill exit=$?"
   timeout 600 python bench.py --timeline $O/timeline.txt --warmup 2 > $O/timeline.log 2>&1; echo "timeline exit=$?"

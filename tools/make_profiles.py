@@ -72,7 +72,7 @@ def main(tag):
                              capture_output=True, text=True).stdout
         open(os.path.join(PROF, f"{tag}_launch_list.txt"), "w").write(txt)
     traffic = {}
-    for rep, name, title, cls in [("prof_gemm_decode.ncu-rep", "gemm_decode", "weight-streaming GEMMs of two decode layers (o_proj, gate/up, down, qkv; 64 tokens)", "gemm_stream"),
+    for rep, name, title, cls in [("prof_gemm_decode.ncu-rep", "decode_chain", "fused decode-layer chain, 64 token rows: one launch = o_proj -> RMSNorm -> gate/up -> down -> RMSNorm -> QKV of the next layer (436 MB of weights)", "gemm_stream"),
                                   ("prof_gemm_prefill.ncu-rep", "gemm_prefill", "tensor-bound GEMMs of one prefill layer (64 streams x 22 = 1408 tokens: o_proj / gate-up / down / qkv order as captured)", "gemm_tensor"),
                                   ("prof_decode_attn.ncu-rep", "decode_attention", "decode attention, 64 streams x kv_len ~1001, layers 0-1 of one decode forward", "attn_decode"),
                                   ("prof_prefill_attn.ncu-rep", "prefill_attention", "tcgen05 chunk-prefill attention, 64 streams x 22 tokens over kv_len ~1023", "attn_prefill"),
@@ -87,8 +87,8 @@ def main(tag):
         if tot:
             # algorithmic bytes of the SAME captured launches (production dims), so that traffic can be compared like with like
             alg = None
-            if cls == "gemm_stream":      # o_proj, gate/up, down, qkv weights of a decode layer (bf16) - activations are < 2 %
-                alg = (4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336 + 6144 * 4096) * 2 / 4.0
+            if cls == "gemm_stream":      # o_proj, gate/up, down, qkv weights of a decode layer (bf16) per chain launch
+                alg = (4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336 + 6144 * 4096) * 2
             elif cls == "gemm_tensor":    # the same four GEMMs at 1408 tokens: weights + activations in + outputs (+ residual reads)
                 M = 1408
                 w = (6144 * 4096 + 4096 * 4096 + 2 * 14336 * 4096 + 4096 * 14336) * 2
