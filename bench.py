@@ -324,6 +324,9 @@ def main_native(args, env):
     eng.load_state_dict(sd)
     del sd
     torch.cuda.empty_cache()
+    for kv in args.engine_opt:                       # A/B aid: per-context options of the library (isst_debug_option)
+        k, v = kv.split("=")
+        eng.option(k, int(v))
     log(f"[bench] model ready in {time.perf_counter() - t0:.1f}s")
 
     run = LockstepRunner(eng, cfg, S, beam=K)
@@ -594,6 +597,7 @@ def main():
     ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline of one step to this file and exit")
     ap.add_argument("--ncu-step", action="store_true", help="run ONE profiled step after priming and exit (for ncu)")
     ap.add_argument("--cpu-baseline-chunks", type=int, default=3, help="oracle chunks timed on the host at N=1 (0 = skip)")
+    ap.add_argument("--engine-opt", action="append", default=[], help="key=value per-context option (A/B runs), e.g. decode_splits=4")
     ap.add_argument("--eager-chunks", type=int, default=4, help="oracle chunks timed in bf16 eager on the GPU at N=1 (0 = skip)")
     args = ap.parse_args()
     from infinisst_b200 import stream_parallel as sp

@@ -117,7 +117,7 @@ __device__ __forceinline__ void grid_wait(const Params& p, int phase_done, int G
   const unsigned long long target = p.bar_base[phase_done] + static_cast<unsigned long long>(G);
   while (ld_acquire_u64(p.bar + phase_done) < target) __nanosleep(20);
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // unit u of a GEMM phase -> (tile, k-range); CTA c owns units c, c + G, ...
 __device__ __forceinline__ void unit_range(const Phase& ph, int u, int& tile, int& split, int& kb0, int& kb1) {
@@ -139,6 +139,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* red = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [16] row-phase reduction scratch (+ [1] result)
+  volatile int* rows_done = reinterpret_cast<volatile int*>(red + 20);   // 1 + index of the last row phase this CTA finished
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,6 +162,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         mbar_init(&tfull_bar[a], 1);
         mbar_init(&tempty_bar[a], C::kEpiThreads);
       }
+      *rows_done = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -197,6 +199,10 @@ decode_chain_kernel(const __grid_constant__ Params p) {
         bool dep_ok = false;
         int n_pend = 0;
         int pend_stage[C::kStages], pend_k0[C::kStages];
+        // a CTA that owns rows of the row phase before this one leaves the SM's ingest path to them: refilling the ring
+        // with 160 KB of weights at the same time stretched the slowest rows from ~2.5 to ~6 us (the phase waits for them)
+        if (pi > 0 && p.ph[pi - 1].kind == PH_ROWS && cta < p.ph[pi - 1].n_rows)
+          while (*rows_done < pi) __nanosleep(32);
         auto resolve = [&]() {
           if (pi == 0 || first_dep) pdl_wait();
           first_dep = false;
@@ -302,14 +308,21 @@ decode_chain_kernel(const __grid_constant__ Params p) {
             if (works && tile * kBM + q * 32 < ph.n_out) {
               const bool row_ok = f < ph.n_out;
               bf16* dst = reinterpret_cast<bf16*>(ph.out) + static_cast<size_t>(hc0) * ph.n_out + f;
+              // 32 token columns per step: the four TMEM loads of a step are in flight together (one wait)
+              constexpr int kStep = C::kHalfCols >= 32 ? 32 : 16;
 #pragma unroll 1
-              for (int c = 0; c < C::kHalfCols; c += 16) {
-                float g[16], up[16];
-                tmem_ld16(taddr + hc0 + c, g);
-                tmem_ld16(taddr + kBN + hc0 + c, up);
+              for (int c = 0; c < C::kHalfCols; c += kStep) {
+                uint32_t g[kStep], up[kStep];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float x = __fdividef(g[i], 1.0f + __expf(-g[i])) * up[i];
+                for (int j = 0; j < kStep; j += 16) {
+                  tmem_ld16_issue(taddr + hc0 + c + j, g + j);
+                  tmem_ld16_issue(taddr + kBN + hc0 + c + j, up + j);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < kStep; ++i) {
+                  const float gv = __uint_as_float(g[i]);
+                  const float x = __fdividef(gv, 1.0f + __expf(-gv)) * __uint_as_float(up[i]);
                   if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = __float2bfloat16_rn(x);
                 }
               }
@@ -317,21 +330,32 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           } else {
             // EPI_PART: fp32 partial of this k-range [split][tok][feature]; EPI_F32: fp32 logits [tok][feature];
             // the two accumulators are two adjacent feature tiles
+            // both tiles' columns of a step are loaded from TMEM together (one wait), then stored
+            const int fa = tile * ph.tile_rows, fb = fa + ph.sub_off;
+            const bool warp_a = works && fa + q * 32 < ph.n_out, warp_b = works && fb + q * 32 < ph.n_out;
+            if (warp_a) {
+              const bool ok_a = fa + r < ph.n_out, ok_b = fb + r < ph.n_out;
+              float* dst_a = reinterpret_cast<float*>(ph.out) +
+                             (static_cast<size_t>(ph.epi == EPI_PART ? split : 0) * p.n_tok + hc0) * ph.n_out + fa + r;
+              float* dst_b = dst_a + ph.sub_off;
+              constexpr int kStep = C::kHalfCols >= 32 ? 32 : 16;
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-              const int f0 = tile * ph.tile_rows + sub * ph.sub_off;
-              if (!(works && f0 + q * 32 < ph.n_out)) continue;
-              const int f = f0 + r;
-              const bool row_ok = f < ph.n_out;
-              float* dst = reinterpret_cast<float*>(ph.out) +
-                           (static_cast<size_t>(ph.epi == EPI_PART ? split : 0) * p.n_tok + hc0) * ph.n_out + f;
-#pragma unroll 1
-              for (int c = 0; c < C::kHalfCols; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + sub * kBN + hc0 + c, v);
+              for (int c = 0; c < C::kHalfCols; c += kStep) {
+                uint32_t va[kStep], vb[kStep];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = v[i];
+                for (int j = 0; j < kStep; j += 16) {
+                  tmem_ld16_issue(taddr + hc0 + c + j, va + j);
+                  if (warp_b) tmem_ld16_issue(taddr + kBN + hc0 + c + j, vb + j);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < kStep; ++i)
+                  if (ok_a && c + i < n_tok) dst_a[static_cast<size_t>(c + i) * ph.n_out] = __uint_as_float(va[i]);
+                if (warp_b) {
+#pragma unroll
+                  for (int i = 0; i < kStep; ++i)
+                    if (ok_b && c + i < n_tok) dst_b[static_cast<size_t>(c + i) * ph.n_out] = __uint_as_float(vb[i]);
+                }
               }
             }
           }
@@ -436,6 +460,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           }
           asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");      // `red` is reused by the next row
         }
+        if (et == 0) *rows_done = pi + 1;
       }
       // ---- this CTA is done with phase pi ----
       if (p.dbg && et == 0) p.dbg[cta * 32 + 3 + 3 * pi] = gtimer();                   // this CTA's part of the phase is done
