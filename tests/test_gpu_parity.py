@@ -497,8 +497,9 @@ def test_production_widths_vs_oracle(layers):
           f"(bf16-eager oracle vs fp32 oracle: {flips16}/{steps})")
     # 128 263 near-iid random logits: the top-2 gap is below the bf16 error for a few percent of the steps
     # (SURVEY §7 hard part 2); every flip was checked above to be such a near-tie, and the CUDA path must not
-    # flip more often than the reference's own bf16-eager numerics do against the fp32 oracle
-    assert flips <= max(flips16 + 2, 0.1 * steps + 1)
+    # flip more often than the reference's own bf16-eager numerics do against the fp32 oracle (measured: 1 / 30 and
+    # 2 / 30 against 1 / 30 and 6 / 30; token-level agreement over long streams: tests/test_gpu_headline.py)
+    assert flips <= max(flips16 + 1, 3)
     eng.close()
 
 
