@@ -10,6 +10,6 @@ for opt in "$@"; do
 import json, sys
 d = json.load(open(sys.argv[2]))
 k = d["kernel_classes"]
-print(f"{sys.argv[1]:32s} {d['value']:7.1f} speech-s/s {d['ms_per_step']:6.2f} ms  lat p50 {d['latency'].get('p50_ms', 0):5.1f} ms  attn_decode {k['attn_decode']['ms_per_step']:5.2f}  gemm_stream {k['gemm_stream']['ms_per_step']:5.2f}  attn_prefill {k['attn_prefill']['ms_per_step']:4.2f}  sm {d['clocks']['sm_mhz']}")
+print(f"{sys.argv[1]:32s} {d['value']:7.1f} speech-s/s {d['ms_per_step']:6.2f} ms  lat p50 {d['latency'].get('p50_ms', 0):5.1f} ms  attn_decode {k['attn_decode']['ms_per_step']:5.2f}  gemm_stream {k['gemm_stream']['ms_per_step']:5.2f}  attn_prefill {k['attn_prefill']['ms_per_step']:4.2f}  attn_enc {k['attn_encoder']['ms_per_step']:4.2f}  sm {d['clocks']['sm_mhz']}")
 PY
 done
