@@ -25,7 +25,6 @@
 #include "decode_attention.cuh"
 #include "decode_attention_group.cuh"
 #include "decode_chain.cuh"
-#include "encoder_attention_tc.cuh"
 #include "gemm_tcgen05.cuh"
 #include "prefill_attention_tc.cuh"
 #include "beam.cuh"
@@ -170,7 +169,6 @@ struct isst_ctx {
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
   int opt_pa_l2_ahead = 1;           // "prefill_l2_ahead": K/V tiles the prefill attention asks into L2 ahead of its ring
-  bool opt_enc_tc = true;            // "enc_attention_tc" = 0: the mma.sync encoder attention (A/B)
   bool opt_tiles_x2 = true;          // "gemm_tiles_x2" = 0: 128-token tiles for the tensor-bound GEMMs (A/B)
   bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
@@ -215,8 +213,6 @@ struct isst_ctx {
   int *d_enc_prefix = nullptr, *d_page_table = nullptr, *d_kv_len = nullptr, *d_sys_len = nullptr,
       *d_ring_start = nullptr;
   bf16* kv_pool = nullptr;
-  CUtensorMap enc_k_map, enc_v_map, enc_kx_map;   // encoder KV rings as [rows][64 dims]: boxes of 16 ring slots
-  bool enc_maps_ok = false;  // ring capacity a multiple of 16 and head_dim 64: the tcgen05 encoder attention applies
   CUtensorMap kv_map;        // the whole LLM KV pool as [rows][head_dim]: boxes of one page x 64 dims (prefill attention)
   size_t kv_layer_elems = 0, enc_layer_elems = 0;
 
@@ -808,30 +804,13 @@ static int encode_chunk(isst_ctx* ctx, cudaStream_t st, int n, const int* slots_
       double keys = 0;
       for (int b = 0; b < n; ++b) keys += std::min(ctx->streams[slots_h[b]].enc_prefix, c.max_cache_size) + frames;
       ProfScope ps(ctx, st, P_ATTN_ENC, 4.0 * frames * keys * D, keys * D * 2 * 2 + static_cast<double>(M) * D * 2 * 2);
-      if (ctx->enc_maps_ok && ctx->opt_enc_tc) {
-        // tcgen05 / TMEM attention with TMA-staged K / V boxes from the rings
-        EncAttnTcParams tp{};
-        tp.qkv = ctx->eqkv; tp.out = ctx->eattn; tp.slots = d_slots; tp.prefix = d_prefix;
-        tp.T = frames; tp.H = H; tp.cap = ctx->enc_cap; tp.max_cache = c.max_cache_size; tp.blocksize = blocksize;
-        const int rows_layer = static_cast<int>(ctx->enc_layer_elems / 64);
-        tp.k_row0 = c.enc_xpos ? 0 : l * rows_layer;
-        tp.v_row0 = l * rows_layer;
-        tp.rows_per_slot = H * ctx->enc_cap;
-        ISST_TRY(ensure_smem(ctx, encoder_attention_tc_kernel, kEaSmemBytes));
-        ctx->paths["encoder_attention_tc"]++;
-        ISST_CUDA(launch_k(ctx, encoder_attention_tc_kernel, dim3(ceil_div(frames, 128), H, n), dim3(kEaThreads), kEaSmemBytes, st,
-                           c.enc_xpos ? ctx->enc_kx_map : ctx->enc_k_map, ctx->enc_v_map, tp));
-        LAUNCH_CHECK(ctx);
-      } else {
       dim3 grid(ceil_div(frames, NW * 16), H, n);
       constexpr int NS = 3;
       constexpr int smem = chunk_attn_smem_bytes<64, NW, NS>();
       ISST_CHECK(HD == 64, "encoder attention kernel is built for head_dim 64");
       ISST_TRY(ensure_smem(ctx, chunk_attention_kernel<64, true, NW, NS>, smem));
-      ctx->paths["encoder_attention_mma_sync"]++;
       ISST_CUDA(launch_k(ctx, chunk_attention_kernel<64, true, NW, NS>, grid, dim3(NW * 32), smem, st, ep, lp));
       LAUNCH_CHECK(ctx);
-      }
     }
     {
       Epilogue e;
@@ -1472,25 +1451,6 @@ int isst_create(const isst_config* cfg, int device, isst_ctx** out) {
   ISST_TRY(dev_alloc(&ctx->enc_k, ctx->enc_layer_elems * c.enc_layers));
   ISST_TRY(dev_alloc(&ctx->enc_v, ctx->enc_layer_elems * c.enc_layers));
   if (c.enc_xpos) ISST_TRY(dev_alloc(&ctx->enc_kx, ctx->enc_layer_elems));
-  if (D / c.enc_heads == 64 && ctx->enc_cap % 16 == 0) {
-    // rings [layer][stream slot][head][cap][64]: one tensor map per buffer, a box = 16 ring slots x 64 dims
-    auto ring_map = [&](CUtensorMap* m, bf16* base, unsigned long long rows) -> int {
-      ISST_CHECK(rows < (1ULL << 31), "encoder KV ring too large for one tensor map");
-      cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(rows)};
-      cuuint64_t strides[1] = {128};
-      cuuint32_t box[2] = {64, 16};
-      cuuint32_t estr[2] = {1, 1};
-      CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      ISST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(encoder ring) failed: " + std::to_string(static_cast<int>(r)));
-      return 0;
-    };
-    const unsigned long long rows_layer = ctx->enc_layer_elems / 64;
-    ISST_TRY(ring_map(&ctx->enc_k_map, ctx->enc_k, rows_layer * c.enc_layers));
-    ISST_TRY(ring_map(&ctx->enc_v_map, ctx->enc_v, rows_layer * c.enc_layers));
-    if (c.enc_xpos) ISST_TRY(ring_map(&ctx->enc_kx_map, ctx->enc_kx, rows_layer));
-    ctx->enc_maps_ok = true;
-  }
   ISST_TRY(dev_alloc(&ctx->d_enc_prefix, c.max_streams));
   // per-batch-entry KV tables (uploaded before every forward): a beam-search batch has streams x beams entries
   const size_t nt = static_cast<size_t>(std::max(c.max_streams, c.max_batch));
@@ -2628,7 +2588,6 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
   else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
   else if (key == "gemm_tiles_x2") ctx->opt_tiles_x2 = value != 0;
-  else if (key == "enc_attention_tc") ctx->opt_enc_tc = value != 0;
   else if (key == "prefill_l2_ahead") ctx->opt_pa_l2_ahead = value;
   else return set_error("unknown option: " + key);
   return 0;
