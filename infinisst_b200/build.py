@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libinfinisst_b200.so")
 SOURCES = ["isst.cu"]
-HEADERS = ["common.cuh", "beam.cuh", "decode_attention_group.cuh", "decode_chain.cuh", "gemm_tcgen05.cuh", "attention.cuh", "decode_attention.cuh", "prefill_attention_tc.cuh", "rowops.cuh", "../../include/infinisst_b200.h"]
+HEADERS = ["common.cuh", "beam.cuh", "decode_attention_group.cuh", "decode_chain.cuh", "gemm_tcgen05.cuh", "gemm_pair.cuh", "attention.cuh", "decode_attention.cuh", "prefill_attention_tc.cuh", "rowops.cuh", "../../include/infinisst_b200.h"]
 
 
 def needs_build() -> bool:

@@ -26,6 +26,7 @@
 #include "decode_attention_group.cuh"
 #include "decode_chain.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_pair.cuh"
 #include "prefill_attention_tc.cuh"
 #include "beam.cuh"
 #include "rowops.cuh"
@@ -59,7 +60,8 @@ static int dev_alloc(T** p, size_t count) {
 struct Weight2D {
   bf16* ptr = nullptr;
   int rows = 0, K = 0;
-  CUtensorMap map;
+  CUtensorMap map;          // 128-row boxes
+  CUtensorMap map64;        // 64-row boxes (gate / up halves of a CTA-pair tile)
 };
 
 static int make_weight_map(Weight2D& w) {
@@ -71,6 +73,11 @@ static int make_weight_map(Weight2D& w) {
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ISST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: " + std::to_string(static_cast<int>(r)));
+  cuuint32_t box64[2] = {tc::kBK, 64};
+  r = g_encode_tiled(&w.map64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.ptr, dims, strides, box64, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ISST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight, 64 rows) failed: " + std::to_string(static_cast<int>(r)));
   return 0;
 }
 
@@ -170,6 +177,7 @@ struct isst_ctx {
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
   int opt_pa_l2_ahead = 1;           // "prefill_l2_ahead": K/V tiles the prefill attention asks into L2 ahead of its ring
   bool opt_tiles_x2 = true;          // "gemm_tiles_x2" = 0: 128-token tiles for the tensor-bound GEMMs (A/B)
+  bool opt_pair = true;              // "gemm_pair" = 0: one CTA per tile instead of CTA pairs (cta_group::2) above 128 rows (A/B)
   bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
   unsigned long long chain_base[chain::kMaxPhases] = {0};   // their values once every launch issued so far has completed
@@ -426,6 +434,58 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   return 0;
 }
 
+// CTA-pair kernel (gemm_pair.cuh): 256 features (gate/up: 128) x tile_tok tokens per pair of SMs.
+// tile_tok (any multiple of 16 up to 256) and the remainder policy come from a small cost model fitted to the phase
+// stamps of the kernel (tests/gemm_bench.py --stamps): a k-block costs what the SM needs to ingest its 16 KB of weights
+// and tile_tok / 2 token rows at ~43 B / clk; whole rounds of tiles (data-parallel) are compared with cutting the last
+// partial round stream-K style, which evens the load out but pays the fp32 park + reduce (~12 us).
+template <bool kDual>
+static int launch_pair(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p) {
+  using C = tc::PairCfg<kDual>;
+  auto kern = tc::gemm_pair_kernel<kDual>;
+  ISST_TRY(ensure_smem(ctx, kern, C::kSmemBytes));
+  const long long pairs = ctx->sm_count / 2;
+  const int tiles_feat = ceil_div(p.N_out, C::kFeatTile);
+  const int num_kb = ceil_div(p.K, tc::kBK);
+  int tile_tok = 0;
+  bool use_sk = false;
+  double best = 0.0;
+  for (int tt = 16; tt <= C::kCapN; tt += 16) {
+    const double kb_cycles = (16384.0 + 64.0 * tt) / 43.0;
+    const long long tiles = static_cast<long long>(ceil_div(p.M_tok, tt)) * tiles_feat;
+    const double dp = static_cast<double>(ceil_div(static_cast<int>(tiles), static_cast<int>(pairs))) * num_kb * kb_cycles;
+    const double sk = static_cast<double>(tiles) * num_kb / pairs * kb_cycles + 25000.0;
+    if (tile_tok == 0 || dp < best) { best = dp; tile_tok = tt; use_sk = false; }
+    if (tiles % pairs != 0 && sk < best) { best = sk; tile_tok = tt; use_sk = true; }
+  }
+  tc::SkParams sk{};
+  sk.tiles_tok = ceil_div(p.M_tok, tile_tok);
+  sk.tiles_feat = tiles_feat;
+  sk.num_kb = num_kb;
+  sk.tiles = static_cast<long long>(sk.tiles_tok) * tiles_feat;
+  long long G = std::min<long long>(pairs, use_sk ? sk.tiles * num_kb : sk.tiles);
+  sk.tiles_dp = use_sk ? sk.tiles - sk.tiles % G : sk.tiles;
+  sk.units_sk = (sk.tiles - sk.tiles_dp) * num_kb;
+  sk.g_sk = static_cast<int>(std::min<long long>(G, sk.units_sk));
+  sk.dbg = ctx->gemm_dbg;
+  tc::GemmParams pp = p;
+  pp.part_out = nullptr;
+  pp.part_splits = 0;
+  ctx->paths[std::string("gemm_pair") + (kDual ? "_dual" : "")]++;
+  pp.counter_half = ctx->n_counters / 2;
+  pp.counter_parity = ctx->gemm_parity;
+  ctx->gemm_parity ^= 1;
+  const size_t slot = static_cast<size_t>(C::kAccAll) * tc::kBM;
+  ISST_CHECK(2 * static_cast<size_t>(2 * G) * slot <= ctx->gemm_ws_floats && 2 * G <= ctx->n_counters / 2,
+             "gemm: stream-K workspace too small");
+  CUtensorMap amap;
+  ISST_TRY(get_act_map(ctx, &amap, v, tile_tok / 2));
+  ISST_CUDA(launch_k(ctx, kern, dim3(static_cast<unsigned>(2 * G)), dim3(C::kThreadsTotal), C::kSmemBytes, st, amap,
+                     kDual ? w.map64 : w.map, pp, sk, tile_tok));
+  LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, int n_out, void* out,
                 long long ldo, long long out_batch_stride, const Epilogue& e, int force_swap = -1,
                 int force_splits = 0) {
@@ -471,6 +531,11 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
   // persistent stream-K kernel: tile shape by mode, CTA count = SM count whatever the tile count
   const int sbn = v.rows <= 16 ? 16 : (v.rows <= 32 ? 32 : (v.rows <= 64 ? 64 : 128));
 #define ISST_SK(BN, DUAL, SWAP) return launch_sk<BN, DUAL, SWAP>(ctx, st, v, w, p, force_splits)
+  if (!swap && ctx->opt_pair && v.rows > 128 && v.batch == 1 && v.conv_c == v.K && v.K >= 256 && force_splits == 0) {
+    // tensor-bound regime: one tile per CTA pair (cta_group::2) - a third less operand traffic per SM and flop
+    if (e.dual) return launch_pair<true>(ctx, st, v, w, p);
+    return launch_pair<false>(ctx, st, v, w, p);
+  }
   if (!swap) {
     // more than one 128-row token tile: 256-token tiles (two accumulators sets) halve the operand bytes an SM has to
     // ingest per flop - the bound of these GEMMs (SkCfg); strided-conv views (batch > 1) keep the 128-row tiles
@@ -2588,6 +2653,7 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
   else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
   else if (key == "gemm_tiles_x2") ctx->opt_tiles_x2 = value != 0;
+  else if (key == "gemm_pair") ctx->opt_pair = value != 0;
   else if (key == "prefill_l2_ahead") ctx->opt_pa_l2_ahead = value;
   else return set_error("unknown option: " + key);
   return 0;

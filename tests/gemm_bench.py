@@ -73,6 +73,8 @@ def main():
     out = []
     for mode in (["x2", "x1"] if "--ab" in sys.argv else ["sk"]):
         eng = Engine(tiny_config(), device=0, max_streams=2)
+        if "--no-pair" in sys.argv:
+            eng.option("gemm_pair", 0)              # one CTA per tile above 128 rows (A/B against the CTA-pair kernel)
         if mode == "x1":
             eng.option("gemm_tiles_x2", 0)          # 128-token tiles for the tensor-bound GEMMs (A/B against 256-token tiles)
         for (name, M, N, K, kw) in SHAPES:

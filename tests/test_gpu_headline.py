@@ -154,7 +154,8 @@ def test_cfg2_batch64_production_widths():
     if chain == 0:
         assert deferred == n_chunks * (mn - 1) * layers * 3               # QKV, o_proj, down_proj with deferred partials
         assert eng.path_count("gemm_sk_swap64_dual") == n_chunks * (mn - 1) * layers
-    assert eng.path_count("gemm_sk_rows256") > 0 and eng.path_count("gemm_sk_rows128_dual") >= (n_chunks - 1) * layers
+    # tensor-bound GEMMs (prefill of 64 x 22 rows, encoder of 64 x 48 frames): the CTA-pair kernel
+    assert eng.path_count("gemm_pair") > 0 and eng.path_count("gemm_pair_dual") >= (n_chunks - 1) * layers
     run.close()
     eng.close()
 
