@@ -23,11 +23,11 @@ ls -la $O
 if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:prefill_attention_tc -s 2 -c 2 -f -o $O/prof_prefill_attn python bench.py --ncu-step --warmup 1 > $O/ncu_pattn.log 2>&1; echo "ncu prefill attn exit=$?"
-  # tensor-bound GEMMs: the 4 GEMMs of one prefill layer (1408 tokens).  One step launches 106 gemm_sk kernels before
-  # the LLM prefill (6 conv + post_proj + 24 x 4 encoder + 2 adapter + proj); skip into prefill layer 1 (decode GEMMs
-  # are decode_chain launches, so every gemm_sk launch of a step is a tensor-bound one except the prefill lm_head)
+  # tensor-bound GEMMs: the 4 GEMMs of one prefill layer (1408 tokens) on the CTA-pair kernel.  One step launches ~100
+  # gemm_pair kernels before the LLM prefill (post_proj + 24 x 4 encoder + proj; the strided conv views stay on gemm_sk);
+  # skip into prefill layer 1-2 (32 x 4 launches), any 4 consecutive launches there are one layer's o / gate-up / down / qkv
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:gemm_sk -s 110 -c 4 -f -o $O/prof_gemm_prefill python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm_prefill.log 2>&1; echo "ncu gemm prefill exit=$?"
+      -k regex:gemm_pair -s 104 -c 4 -f -o $O/prof_gemm_prefill python bench.py --ncu-step --warmup 1 --prime 3 > $O/ncu_gemm_prefill.log 2>&1; echo "ncu gemm prefill exit=$?"
   timeout 600 python bench.py --timeline $O/timeline.txt --warmup 2 > $O/timeline.log 2>&1; echo "timeline exit=$?"
   # beam search (the reference's shipped decoding): bench line + full capture of the shared-prefix group attention
   timeout 600 python bench.py --beam 4 --steps 4 --warmup 3 --latency-chunks 10 --cpu-baseline-chunks 0 > $O/bench_beam4.json 2> $O/bench_beam4.err; echo "bench beam4 exit=$?"
