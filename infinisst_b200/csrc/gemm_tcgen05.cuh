@@ -342,13 +342,9 @@ struct SkParams {
 };
 
 
-// kMT (row mode only): 128-row token tiles per CTA tile.  A tensor-bound GEMM is limited by what an SM can ingest from
-// L2 (~74 KB/us measured: 959 TFLOP/s with 48 KB per 128 x 256 x 64 k-block); with kMT = 2 a k-block of 256 tokens x 256
-// features moves 64 KB for twice the flops (131 instead of 87 flop per byte).  The two token tiles own all 512 TMEM
-// columns, so the accumulator is not double-buffered there (the epilogue of a tile is exposed: a few us per ~60 us tile).
-template <int kBN, bool kDual, bool kSwap, int kMT = 1>
+template <int kBN, bool kDual, bool kSwap>
 struct SkCfg {
-  static constexpr int kActRows = kSwap ? kBN : kBM * kMT;
+  static constexpr int kActRows = kSwap ? kBN : kBM;
   static constexpr int kWRows = kSwap ? kBM : kBN;
   static constexpr int kNW = kDual ? 2 : 1;
   static constexpr int kActBytes = kActRows * kBK * 2;
@@ -356,8 +352,7 @@ struct SkCfg {
   static constexpr int kStageBytes = kActBytes + kNW * kWBytes;
   static constexpr int kStagesRaw = (224 * 1024) / kStageBytes;     // 227 KB per CTA minus barriers / alignment slack
   static constexpr int kStages = kStagesRaw > 10 ? 10 : kStagesRaw;
-  static constexpr int kAccCols = kBN * kNW;                      // per 128-row token tile
-  static constexpr int kAccAll = kAccCols * kMT;
+  static constexpr int kAccAll = kBN * kNW;                       // accumulator columns of one tile
   static constexpr int kAccBufs = (2 * kAccAll <= 512) ? 2 : 1;
   static constexpr int kTmemColsRaw = kAccBufs * kAccAll;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
@@ -373,7 +368,6 @@ struct SkCfg {
   static constexpr int kNC = (kSwap && !kDual && kHalfCols >= 32) ? 32 : 16;   // columns per epilogue step
   static_assert(kBN % 16 == 0 && kBN >= 16 && kBN <= 256, "UMMA N");
   static_assert(kTmemColsRaw <= 512, "the accumulators must fit TMEM");
-  static_assert(kMT == 1 || (!kSwap && kMT == 2), "token-tile pairs exist in row mode only");
   static_assert(kActBytes % 1024 == 0 && kWBytes % 1024 == 0, "tiles must keep 1024B alignment");
 };
 
@@ -437,11 +431,11 @@ struct SkWalker {
   }
 };
 
-template <int kBN, bool kDual, bool kSwap, int kMT = 1>
+template <int kBN, bool kDual, bool kSwap>
 __global__ void __launch_bounds__(384) __maxnreg__(kSwap ? 128 : 168)
 gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
                const GemmParams p, const SkParams sk) {
-  using C = SkCfg<kBN, kDual, kSwap, kMT>;
+  using C = SkCfg<kBN, kDual, kSwap>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -580,12 +574,8 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
             const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
             if (!kSwap) {
-#pragma unroll
-              for (int mt = 0; mt < kMT; ++mt) {          // token tile mt: rows [128 mt, 128 mt + 128) of the activation box
-                const uint64_t aoff = koff + static_cast<uint64_t>((mt * kBM * kBK * 2) >> 4);
-                umma_bf16(tacc + mt * C::kAccCols, d_act + aoff, d_w0 + koff, idesc, accum);
-                if (kDual) umma_bf16(tacc + mt * C::kAccCols + kBN, d_act + aoff, d_w1 + koff, idesc, accum);
-              }
+              umma_bf16(tacc, d_act + koff, d_w0 + koff, idesc, accum);
+              if (kDual) umma_bf16(tacc + kBN, d_act + koff, d_w1 + koff, idesc, accum);
             } else {
               umma_bf16(tacc, d_w0 + koff, d_act + koff, idesc, accum);
               if (kDual) umma_bf16(tacc + kBN, d_w1 + koff, d_act + koff, idesc, accum);
@@ -631,15 +621,11 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
       if (first_seg && sk.dbg && et == 0) sk.dbg[cta * 8 + 2] = gtimer();
       first_seg = false;
       const uint32_t taddr0 = tmem_base + acc * C::kAccAll + (static_cast<uint32_t>(q * 32) << 16);
-      int lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + r;
-      uint32_t taddr = taddr0;
+      const int lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + r;
+      const uint32_t taddr = taddr0;
       if (kb_begin == 0 && kb_end == nkb) {
         // ---- the whole k-range of this tile was accumulated here: final epilogue straight from TMEM ----
-#pragma unroll 1
-        for (int mt = 0; mt < kMT; ++mt) {
-        lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + mt * kBM + r;
-        taddr = taddr0 + mt * C::kAccCols;
-        if (works && (kSwap || t.tt * C::kActRows + mt * kBM < p.M_tok)) {
+        if (works) {
 #pragma unroll 1
           for (int c = hc0; c < hc0 + C::kHalfCols; c += (kSwap ? NC : 32)) {
             if (!kSwap) {
@@ -685,7 +671,6 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
             }
           }
         }
-        }
         tcgen05_fence_before();
         mbar_arrive(&tempty_bar[acc]);
       } else {
@@ -717,7 +702,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         float* mine = p.ws + static_cast<size_t>(cta == c_first ? G + cta : cta) * kSlot;
         if (works) {
 #pragma unroll 1
-          for (int cc = 0; cc < C::kNW * kMT; ++cc)            // accumulator blocks of kBN columns: (token tile, gate | up)
+          for (int cc = 0; cc < C::kNW; ++cc)                  // accumulator blocks of kBN columns: gate | up
 #pragma unroll 1
             for (int c = hc0; c < hc0 + C::kHalfCols; c += 16) {
               float v[16];
@@ -749,23 +734,21 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
       asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
       const SkTile t = sk_tile(tl, sk);
       const int col_base = (kSwap ? t.tt : t.tf) * kBN;
-      // chunk list: kMT * kBN / 16 chunks (token tile, 16 columns) dealt to (contributor, half) pairs
-      constexpr int kChunks = kMT * kBN / 16;
+      // chunk list: kBN / 16 chunks of 16 columns dealt to (contributor, half) pairs
+      constexpr int kChunks = kBN / 16;
       const int workers = nc * C::kEpiHalves;
       const int me = (cta - c_first) * C::kEpiHalves + half;
       const int ch0 = kChunks * me / workers, ch1 = kChunks * (me + 1) / workers;
 #pragma unroll 1
       for (int ch = ch0; ch < ch1; ++ch) {
-        const int mt = ch / (kBN / 16);
-        const int c = (ch - mt * (kBN / 16)) * 16;
-        const int lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + mt * kBM + r;
-        const size_t moff = static_cast<size_t>(mt) * C::kAccCols * kBM;      // this token tile's block in a parked partial
+        const int c = ch * 16;
+        const int lane_idx = (kSwap ? t.tf * kBM : t.tt * C::kActRows) + r;
         float v0[16], v1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { v0[i] = 0.f; v1[i] = 0.f; }
 #pragma unroll 4
         for (int cc = c_first; cc <= c_last; ++cc) {
-          const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot + moff;
+          const float* src = p.ws + static_cast<size_t>(cc == c_first ? G + cc : cc) * kSlot;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             v0[i] += __ldcg(&src[(c + i) * kBM + r]);

@@ -176,7 +176,6 @@ struct isst_ctx {
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
   int opt_pa_l2_ahead = 1;           // "prefill_l2_ahead": K/V tiles the prefill attention asks into L2 ahead of its ring
-  bool opt_tiles_x2 = true;          // "gemm_tiles_x2" = 0: 128-token tiles for the tensor-bound GEMMs (A/B)
   bool opt_pair = true;              // "gemm_pair" = 0: one CTA per tile instead of CTA pairs (cta_group::2) above 128 rows (A/B)
   bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
@@ -404,11 +403,11 @@ static void sk_plan(isst_ctx* ctx, int M_tok, int N_out, int K, int batch, int a
   *G_out = G;
 }
 
-template <int kBN, bool kDual, bool kSwap, int kMT = 1>
+template <int kBN, bool kDual, bool kSwap>
 static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D& w, const tc::GemmParams& p,
                      int force_splits) {
-  using C = tc::SkCfg<kBN, kDual, kSwap, kMT>;
-  auto kern = tc::gemm_sk_kernel<kBN, kDual, kSwap, kMT>;
+  using C = tc::SkCfg<kBN, kDual, kSwap>;
+  auto kern = tc::gemm_sk_kernel<kBN, kDual, kSwap>;
   ISST_TRY(ensure_smem(ctx, kern, C::kSmemBytes));
   tc::SkParams sk{};
   long long G = 0;
@@ -420,7 +419,7 @@ static int launch_sk(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Wei
   pp.part_splits = S;
   ctx->last_defer_splits = S;
   if (kSwap) ctx->paths[std::string("gemm_sk_swap") + std::to_string(kBN) + (kDual ? "_dual" : "") + (S ? "_deferred" : "")]++;
-  else ctx->paths[std::string("gemm_sk_rows") + std::to_string(kBN) + (kDual ? "_dual" : "") + (kMT == 2 ? "_x2" : "")]++;
+  else ctx->paths[std::string("gemm_sk_rows") + std::to_string(kBN) + (kDual ? "_dual" : "")]++;
   pp.counter_half = ctx->n_counters / 2;
   pp.counter_parity = ctx->gemm_parity;
   ctx->gemm_parity ^= 1;
@@ -537,17 +536,9 @@ static int gemm(isst_ctx* ctx, cudaStream_t st, const ActView& v, const Weight2D
     return launch_pair<false>(ctx, st, v, w, p);
   }
   if (!swap) {
-    // more than one 128-row token tile: 256-token tiles (two accumulators sets) halve the operand bytes an SM has to
-    // ingest per flop - the bound of these GEMMs (SkCfg); strided-conv views (batch > 1) keep the 128-row tiles
-    // ... where that pays (measured, tests/gemm_bench.py --ab): a 256 x 256 tile owns all of TMEM, its epilogue is
-    // exposed (raw 1290 vs 1160 TFLOP/s), and fewer, larger tiles quantise worse - so only when the 256-token tiling
-    // is (nearly) exactly one wave of whole tiles (prefill / encoder QKV: 144 tiles; +21 %) or a single token tile
-    // (beam-search gate/up at 129-256 rows: every weight tile is then fetched once instead of twice; +29 %)
-    const long long t2 = static_cast<long long>(ceil_div(v.rows, 256)) * ceil_div(n_out, e.dual ? 128 : 256);
-    const bool one_wave = t2 <= ctx->sm_count && 10 * t2 >= 9 * ctx->sm_count;
-    const bool x2 = ctx->opt_tiles_x2 && v.rows > 128 && v.batch == 1 && (one_wave || (v.rows <= 256 && e.dual)) && v.K >= 2048;
-    if (e.dual) { if (x2) return launch_sk<128, true, false, 2>(ctx, st, v, w, p, force_splits); ISST_SK(128, true, false); }
-    if (n_out >= 256) { if (x2) return launch_sk<256, false, false, 2>(ctx, st, v, w, p, force_splits); ISST_SK(256, false, false); }
+    // one CTA per 128-token tile: strided-conv views (batch > 1), and the A/B arm of the CTA-pair kernel
+    if (e.dual) ISST_SK(128, true, false);
+    if (n_out >= 256) ISST_SK(256, false, false);
     ISST_SK(128, false, false);
   }
   if (e.dual) {
@@ -2652,7 +2643,6 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   else if (key == "decode_splits") ctx->opt_dec_splits = value;
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
   else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
-  else if (key == "gemm_tiles_x2") ctx->opt_tiles_x2 = value != 0;
   else if (key == "gemm_pair") ctx->opt_pair = value != 0;
   else if (key == "prefill_l2_ahead") ctx->opt_pa_l2_ahead = value;
   else return set_error("unknown option: " + key);

@@ -71,12 +71,10 @@ def stamps(eng, M, N, K, kw):
 
 def main():
     out = []
-    for mode in (["x2", "x1"] if "--ab" in sys.argv else ["sk"]):
+    for mode in (["pair", "single"] if "--ab" in sys.argv else ["sk"]):
         eng = Engine(tiny_config(), device=0, max_streams=2)
-        if "--no-pair" in sys.argv:
+        if "--no-pair" in sys.argv or mode == "single":
             eng.option("gemm_pair", 0)              # one CTA per tile above 128 rows (A/B against the CTA-pair kernel)
-        if mode == "x1":
-            eng.option("gemm_tiles_x2", 0)          # 128-token tiles for the tensor-bound GEMMs (A/B against 256-token tiles)
         for (name, M, N, K, kw) in SHAPES:
             if mode != "sk" and M <= 128:
                 continue
