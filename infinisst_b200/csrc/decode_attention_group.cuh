@@ -4,8 +4,9 @@
 // of it each step.  Here the beams of a sentence share the prompt's KV pages, so the prefix is read ONCE per
 // (sentence, kv head): the 4 beams x 4 query heads are exactly the 16 rows of mma.sync m16n8k16 (the per-row kernel
 // in decode_attention.cuh leaves 12 of those rows as padding).  The private tails (<= 4 pages = 64 keys per beam) follow
-// as one extra tile per beam in which only that beam's 4 rows are unmasked, so one launch replaces k per-row
-// attentions; with one key split the kernel writes the attention output itself (no combine pass).
+// packed into shared tiles: 16 keys of each beam side by side, each beam's 4 rows unmasked on its own 16 columns only
+// (one extra tile while the tails are <= 16 keys); one launch replaces k per-row attentions, and with one key split the
+// kernel writes the attention output itself (no combine pass).
 // Same loader (4 warps, cp.async ring, mbarriers), same rotate-at-write key convention (q_sys variant for the pinned
 // prefix tiles, ring variant after it).  HBM-bound: 4096 * prefix_len bytes per layer per SENTENCE.
 #pragma once
@@ -67,9 +68,14 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
     return;
   }
   const int n_pre = t_hi - t_lo;                     // shared-prefix tiles of this split
-  const int n_tiles = n_pre + (tails ? BEAMS : 0);   // + one tile per beam: its private keys [L, kv_len + 1)
-  const int tail_slot0 = p.tail_page[grp] * kPageTokens;
+  // private keys [L, kv_len + 1) of the 4 beams, packed: tail tile u holds keys [16 u, 16 u + 16) of beam w in the
+  // 16-key slice that compute warp w works on (a page per beam), so the usual <= 16 private keys cost ONE tile
   auto tail_len = [&](int beam) { return min(TILE, p.kv.kv_len[p.slots[b0 + beam]] + 1 - L); };
+  int max_tail = 0;
+#pragma unroll
+  for (int bm = 0; bm < BEAMS; ++bm) max_tail = max(max_tail, tail_len(bm));
+  const int n_tiles = n_pre + (tails ? (max_tail + 15) / 16 : 0);
+  const int tail_slot0 = p.tail_page[grp] * kPageTokens;
   auto tile_j0 = [&](int t) { return t < n_sys_tiles ? t * TILE : sys_len + (t - n_sys_tiles) * TILE; };
   auto tile_j1 = [&](int t) { return t < n_sys_tiles ? min(sys_len, t * TILE + TILE) : min(L, sys_len + (t - n_sys_tiles + 1) * TILE); };
 
@@ -101,11 +107,12 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
           nx_pb[ps] = table[last >> 4];
           nx_ok[ps] = tile_j1(t) - (tile_j0(t) + 8 * gi);
         } else {
-          // private tail of beam ti - n_pre: key i sits in slot tail_slot0 + i of that row's own pages (page aligned)
-          const int beam = ti - n_pre;
+          // packed tail tile u: key group gi = keys [8 (gi & 1), +8) of round u of beam gi >> 1; key i of a beam sits
+          // in slot tail_slot0 + i of that row's own pages (page aligned)
+          const int beam = gi >> 1, off = 16 * (ti - n_pre) + 8 * (gi & 1);
           const int* tb = p.kv.page_table + static_cast<size_t>(p.slots[b0 + beam]) * p.kv.pages_per_stream;
-          nx_ok[ps] = tail_len(beam) - 8 * gi;
-          nx_s0[ps] = tail_slot0 + 8 * gi;
+          nx_ok[ps] = tail_len(beam) - off;
+          nx_s0[ps] = tail_slot0 + off;
           nx_pa[ps] = nx_pb[ps] = nx_ok[ps] > 0 ? tb[nx_s0[ps] >> 4] : 0;
         }
       }
@@ -164,8 +171,7 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
 
   for (int ti = 0; ti < n_tiles; ++ti) {
     const int t = t_lo + ti;
-    const bool is_tail = ti >= n_pre;
-    const int tail_beam = ti - n_pre;                // tail tiles: only rows of this beam attend
+    const bool is_tail = ti >= n_pre;                // packed tail tile: this warp's 16 keys belong to beam `warp`
     dec_mbar_wait(&full_bar[ti % kDecStages], (ti / kDecStages) & 1);
     const bf16* sK = stage_base + (ti % kDecStages) * kDecStageElems;
     const bf16* sV = sK + TILE * LDS;
@@ -188,13 +194,13 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
       }
     }
     // ---- online softmax on rows g (elements 0, 1) and g + 8 (elements 2, 3) ----
-    const int jw = (is_tail ? 0 : tile_j0(t)) + 16 * warp;
-    const int j1 = is_tail ? tail_len(tail_beam) : tile_j1(t);
+    const int jw = is_tail ? 16 * (ti - n_pre) : tile_j0(t) + 16 * warp;
+    const int j1 = is_tail ? tail_len(warp) : tile_j1(t);
     float corr[2], pr[2][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float mx = m_run[h];
-      const bool row_on = !is_tail || ((g + 8 * h) >> 2) == tail_beam;
+      const bool row_on = !is_tail || ((g + 8 * h) >> 2) == warp;
 #pragma unroll
       for (int n = 0; n < 2; ++n)
 #pragma unroll
