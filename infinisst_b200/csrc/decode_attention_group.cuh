@@ -27,11 +27,22 @@ struct DecodeGroupParams {
   int H;
   int splits;               // key splits; the last one also takes the private tails
   float scale_log2;
+  // ---- fused RoPE + KV append (decode step of the chain path): the kernel completes the q rows of its 16 (beam, head)
+  //      pairs from the QKV GEMM's fp32 split partials and rotates them (both variants); the CTA that owns the tails also
+  //      completes, rotates and appends the new token's K / V of its kv head for the 4 beams before it reads the tails.
+  //      llm_rope_append_kernel is then not launched.  fuse == 0: q / q_sys / cache were prepared by that kernel.
+  int fuse;
+  const float* part;        // [n_part][n rows][(H + 2 Hkv) * HD] fp32
+  int n_part;
+  long long part_stride;
+  const float2* tab_ring;   // [n rows][HD / 2] (cos, sin) at the absolute position
+  const float2* tab_sys;    // [n rows][HD / 2] at the prefix-convention position
+  const int* active;        // [n rows] or null: rows that append
 };
 
 constexpr int kGrpRows = 16;                       // 4 beams x 4 query heads of one kv head
 constexpr int kGrpQLds = 128 + 8;
-constexpr int kGrpSmemBytes = kDecStages * kDecStageElems * 2 + 2 * kGrpRows * kGrpQLds * 2 + 2 * kDecStages * 8;
+constexpr int kGrpSmemBytes = kDecStages * kDecStageElems * 2 + 2 * kGrpRows * kGrpQLds * 2 + 2 * kDecStages * 8 + 8;
 
 __global__ void __launch_bounds__(kDecThreads, 2)
 decode_attention_group_kernel(const DecodeGroupParams p) {
@@ -43,6 +54,7 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
   bf16* qbuf = stage_base + kDecStages * kDecStageElems;       // [2 variants][16 rows][QL]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(qbuf + 2 * ROWS * QL);
   uint64_t* empty_bar = full_bar + kDecStages;
+  uint64_t* app_bar = empty_bar + kDecStages;                  // fused mode: the new token's K / V are in the pool
 
   const int split = blockIdx.x, head = blockIdx.y, grp = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -81,6 +93,7 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
 
   if (tid == 0) {
     for (int s0 = 0; s0 < kDecStages; ++s0) { dec_mbar_init(&full_bar[s0], 32 * kDecLoaders); dec_mbar_init(&empty_bar[s0], 4); }
+    dec_mbar_init(app_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -121,6 +134,7 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
     for (int ti = 0; ti < n_tiles; ++ti) {
       const int stage = ti % kDecStages;
       if (ti >= kDecStages) dec_mbar_wait(&empty_bar[stage], ((ti / kDecStages) - 1) & 1);
+      if (p.fuse && ti == n_pre) dec_mbar_wait(app_bar, 0);      // first tail tile: the compute warps have appended the new token
 #pragma unroll
       for (int ps = 0; ps < kPass; ++ps) {
         const int gi = 2 * (pass0 + ps) + g2;
@@ -148,7 +162,86 @@ decode_attention_group_kernel(const DecodeGroupParams p) {
   }
 
   // ---- compute warps: stage the 2 x 16 query rows (both RoPE variants) ----
-  {
+  if (p.fuse) {
+    const int ldq = (p.H + 2 * p.kv.kv_heads) * HD;
+    // split partials of elements (col + d .. d + 3) and (col + d + 64 .. + 67) of one row, summed in split order and
+    // rounded like the bf16 projection output; all (<= 16) 16-byte loads of a call are in flight together
+    auto quad_sum = [&](int row, int col, int d, float* a, float* bb) {
+      const float* p0 = p.part + static_cast<size_t>(row) * ldq + col + d;
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        va[q] = make_float4(0.f, 0.f, 0.f, 0.f); vb[q] = va[q];
+        if (q < p.n_part) {
+          va[q] = __ldcg(reinterpret_cast<const float4*>(p0 + q * p.part_stride));
+          vb[q] = __ldcg(reinterpret_cast<const float4*>(p0 + q * p.part_stride + 64));
+        }
+      }
+      float sa[4] = {((va[0].x + va[1].x) + va[2].x) + va[3].x, ((va[0].y + va[1].y) + va[2].y) + va[3].y,
+                     ((va[0].z + va[1].z) + va[2].z) + va[3].z, ((va[0].w + va[1].w) + va[2].w) + va[3].w};
+      float sb[4] = {((vb[0].x + vb[1].x) + vb[2].x) + vb[3].x, ((vb[0].y + vb[1].y) + vb[2].y) + vb[3].y,
+                     ((vb[0].z + vb[1].z) + vb[2].z) + vb[3].z, ((vb[0].w + vb[1].w) + vb[2].w) + vb[3].w};
+#pragma unroll
+      for (int q = 4; q < 8; ++q)
+        if (q < p.n_part) {
+          sa[0] += va[q].x; sa[1] += va[q].y; sa[2] += va[q].z; sa[3] += va[q].w;
+          sb[0] += vb[q].x; sb[1] += vb[q].y; sb[2] += vb[q].z; sb[3] += vb[q].w;
+        }
+      for (int q = 8; q < p.n_part; ++q) {
+        const float4 xa = __ldcg(reinterpret_cast<const float4*>(p0 + q * p.part_stride));
+        const float4 xb = __ldcg(reinterpret_cast<const float4*>(p0 + q * p.part_stride + 64));
+        sa[0] += xa.x; sa[1] += xa.y; sa[2] += xa.z; sa[3] += xa.w;
+        sb[0] += xb.x; sb[1] += xb.y; sb[2] += xb.z; sb[3] += xb.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] = bf16_round(sa[j]); bb[j] = bf16_round(sb[j]); }
+    };
+    auto store4 = [](bf16* dst, float x0, float x1, float x2, float x3) {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+    };
+    // q: 16 rows x 16 groups of 4 (d, d + 64) pairs over the 128 compute threads
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int item = it * 128 + tid;
+      const int r = item >> 4, d = (item & 15) * 4;
+      const int row = b0 + (r >> 2);
+      float a[4], bb[4];
+      const float4* tr = reinterpret_cast<const float4*>(p.tab_ring + static_cast<size_t>(row) * 64 + d);
+      const float4* ts = reinterpret_cast<const float4*>(p.tab_sys + static_cast<size_t>(row) * 64 + d);
+      const float4 r01 = tr[0], r23 = tr[1], s01 = ts[0], s23 = ts[1];      // (cos, sin) of d, d + 1 | d + 2, d + 3
+      quad_sum(row, (head * GROUP + (r & 3)) * HD, d, a, bb);
+      const float crc[4] = {r01.x, r01.z, r23.x, r23.z}, crs[4] = {r01.y, r01.w, r23.y, r23.w};
+      const float csc[4] = {s01.x, s01.z, s23.x, s23.z}, css[4] = {s01.y, s01.w, s23.y, s23.w};
+      store4(qbuf + r * QL + d, a[0] * crc[0] - bb[0] * crs[0], a[1] * crc[1] - bb[1] * crs[1], a[2] * crc[2] - bb[2] * crs[2], a[3] * crc[3] - bb[3] * crs[3]);
+      store4(qbuf + r * QL + d + 64, bb[0] * crc[0] + a[0] * crs[0], bb[1] * crc[1] + a[1] * crs[1], bb[2] * crc[2] + a[2] * crs[2], bb[3] * crc[3] + a[3] * crs[3]);
+      store4(qbuf + (ROWS + r) * QL + d, a[0] * csc[0] - bb[0] * css[0], a[1] * csc[1] - bb[1] * css[1], a[2] * csc[2] - bb[2] * css[2], a[3] * csc[3] - bb[3] * css[3]);
+      store4(qbuf + (ROWS + r) * QL + d + 64, bb[0] * csc[0] + a[0] * css[0], bb[1] * csc[1] + a[1] * css[1], bb[2] * csc[2] + a[2] * css[2], bb[3] * csc[3] + a[3] * css[3]);
+    }
+    if (tails) {
+      // the new token's K (rotated) and V of this kv head, for the 4 beams: 2 x 4 x 16 groups = one item per thread
+      const int is_v = tid >> 6, beam = (tid >> 4) & 3, d = (tid & 15) * 4;
+      const int row = b0 + beam;
+      float a[4], bb[4];
+      quad_sum(row, (p.H + is_v * p.kv.kv_heads + head) * HD, d, a, bb);
+      if (!p.active || p.active[row]) {
+        const int sl = p.slots[row];
+        const int L_old = p.kv.kv_len[sl];
+        const int* tb = p.kv.page_table + static_cast<size_t>(sl) * p.kv.pages_per_stream;
+        const size_t off = kv_offset(p.kv, tb, kv_slot(L_old, p.kv.sys_len[sl], p.kv.ring_start[sl]), is_v, head);
+        if (is_v) {
+          store4(p.kv.pool + off + d, a[0], a[1], a[2], a[3]);
+          store4(p.kv.pool + off + d + 64, bb[0], bb[1], bb[2], bb[3]);
+        } else {
+          const float4* tc = reinterpret_cast<const float4*>((L_old < p.kv.sys_len[sl] ? p.tab_sys : p.tab_ring) + static_cast<size_t>(row) * 64 + d);
+          const float4 c01 = tc[0], c23 = tc[1];
+          const float cc[4] = {c01.x, c01.z, c23.x, c23.z}, sn[4] = {c01.y, c01.w, c23.y, c23.w};
+          store4(p.kv.pool + off + d, a[0] * cc[0] - bb[0] * sn[0], a[1] * cc[1] - bb[1] * sn[1], a[2] * cc[2] - bb[2] * sn[2], a[3] * cc[3] - bb[3] * sn[3]);
+          store4(p.kv.pool + off + d + 64, bb[0] * cc[0] + a[0] * sn[0], bb[1] * cc[1] + a[1] * sn[1], bb[2] * cc[2] + a[2] * sn[2], bb[3] * cc[3] + a[3] * sn[3]);
+        }
+      }
+      dec_mbar_arrive(app_bar);
+    }
+  } else {
     const int ldq = (p.H + 2 * p.kv.kv_heads) * HD;
     // 2 variants x 16 rows x 16 chunks of 16 bytes = 512 chunks over 128 threads
     for (int c = tid; c < 2 * ROWS * 16; c += 128) {

@@ -1111,16 +1111,8 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
     LlmLayerW& w = ctx->llm[l];
     PagedKV kv = paged_kv(ctx, l);
     if (grouped) {
-      // beam search: rows come in groups of 4 beams that share their sentence's prompt pages.  RoPE + append (summing the
-      // QKV split partials) is its own kernel here; the shared prefix is attended to once per group
-      {
-        ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
-        dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
-        ISST_CUDA(launch_k(ctx, llm_rope_append_kernel, grid, dim3(128), 0, st, ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T,
-                           lb.d_active, ctx->llm_rope_ring, ctx->llm_rope_sys, H, static_cast<const float*>(ctx->defer_ws), qkv_splits,
-                           static_cast<long long>(M) * QKV));
-        LAUNCH_CHECK(ctx);
-      }
+      // beam search: rows come in groups of 4 beams that share their sentence's prompt pages; the shared prefix is
+      // attended to once per group.  The kernel completes (QKV split partials), rotates and appends by itself
       const double tok = lb.prefix_tokens + (lb.kv_tokens - lb.prefix_tokens * lb.group);
       ProfScope ps(ctx, st, P_ATTN_DECODE, 4.0 * lb.kv_tokens * H * HD, tok * Hkv * HD * 2 * 2);
       ISST_TRY(ensure_smem(ctx, decode_attention_group_kernel, kGrpSmemBytes));
@@ -1131,6 +1123,9 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
       gp.qkv = ctx->lqkv; gp.q_sys = ctx->lq_sys; gp.kv = kv; gp.slots = lb.d_slots; gp.key_hi = lb.d_key_hi;
       gp.tail_page = lb.d_tail_page; gp.out = ctx->lattn;
       gp.part_o = ctx->part_o; gp.part_ml = ctx->part_ml; gp.H = H; gp.splits = splits_p; gp.scale_log2 = scale_log2;
+      gp.fuse = 1; gp.part = static_cast<const float*>(ctx->defer_ws); gp.n_part = qkv_splits;
+      gp.part_stride = static_cast<long long>(M) * QKV;
+      gp.tab_ring = ctx->llm_rope_ring; gp.tab_sys = ctx->llm_rope_sys; gp.active = lb.d_active;
       ISST_CUDA(launch_k(ctx, decode_attention_group_kernel, dim3(splits_p, Hkv, n_groups), dim3(kDecThreads), kGrpSmemBytes, st, gp));
       LAUNCH_CHECK(ctx);
       if (splits_p > 1) {
