@@ -26,6 +26,7 @@ struct BeamSel {
   const int* suppress;       // [n_suppress]
   int n_suppress, ctx_cap, enc_cap, ngram;
   float penalty;
+  int write_back;            // 1: leave the processed log-probs in `logits` (teacher-forced parity runs read them back)
   int rows_per_group;        // live beams per sentence (1 at the first step: patch_hf.py:772-774)
   int n_keep;                // candidates per sentence
   float* part_max;           // [R][kSelParts]
@@ -37,7 +38,9 @@ struct BeamSel {
   int* out_i;                // [G][n_keep] row_in_group * V + token
 };
 
-// (max, sum exp) of one vocabulary slice of one row
+// (max, sum exp) of one vocabulary slice of one row.  The slice (V / 16 elements: 31.3 per thread at V = 128 256) is
+// read ONCE into registers; a slice longer than kLseRegs x 256 takes the remainder in a second sweep.
+constexpr int kLseRegs = 32;
 __global__ void __launch_bounds__(kSelThreads)
 beam_lse_kernel(const float* __restrict__ logits, int V, BeamSel s) {
   pdl_launch_dependents();
@@ -46,8 +49,15 @@ beam_lse_kernel(const float* __restrict__ logits, int V, BeamSel s) {
   const float* lg = logits + static_cast<size_t>(r) * V;
   const int per = (V + kSelParts - 1) / kSelParts;
   const int lo = part * per, hi = min(V, lo + per);
+  float x[kLseRegs];
   float m = -INFINITY;
-  for (int i = lo + tid; i < hi; i += kSelThreads) m = fmaxf(m, lg[i]);
+#pragma unroll
+  for (int k = 0; k < kLseRegs; ++k) {
+    const int i = lo + tid + k * kSelThreads;
+    x[k] = i < hi ? __ldg(lg + i) : -INFINITY;
+    m = fmaxf(m, x[k]);
+  }
+  for (int i = lo + tid + kLseRegs * kSelThreads; i < hi; i += kSelThreads) m = fmaxf(m, lg[i]);
   __shared__ float red[kSelThreads / 32];
   m = warp_max(m);
   if ((tid & 31) == 0) red[tid >> 5] = m;
@@ -57,8 +67,11 @@ beam_lse_kernel(const float* __restrict__ logits, int V, BeamSel s) {
   for (int w = 1; w < kSelThreads / 32; ++w) m = fmaxf(m, red[w]);
   __syncthreads();
   float sum = 0.f;
-  if (m > -INFINITY)
-    for (int i = lo + tid; i < hi; i += kSelThreads) sum += expf(lg[i] - m);
+  if (m > -INFINITY) {
+#pragma unroll
+    for (int k = 0; k < kLseRegs; ++k) sum += expf(x[k] - m);          // exp(-inf) = 0 for the padding
+    for (int i = lo + tid + kLseRegs * kSelThreads; i < hi; i += kSelThreads) sum += expf(lg[i] - m);
+  }
   sum = warp_sum(sum);
   if ((tid & 31) == 0) red[tid >> 5] = sum;
   __syncthreads();
@@ -114,16 +127,39 @@ __device__ __forceinline__ void block_top_n(int count, int n_keep, Get get, Put 
   }
 }
 
-// log-probs of one slice in place, processors, slice top-n; the last CTA of a sentence merges.
+// The same selection in ONE round for items that sit in shared memory: every item counts the items that come before it
+// in (value desc, key asc) order; that count is its output position.  `put` must have been pre-filled with (-inf, -1)
+// for the positions no item claims.  count^2 / 256 broadcast reads per thread instead of n_keep block-wide reductions.
+template <typename Put>
+__device__ __forceinline__ void block_rank_top_n(const float* v, const int* k, int count, int n_keep, Put put) {
+  for (int i = threadIdx.x; i < count; i += kSelThreads) {
+    const float vi = v[i];
+    const int ki = k[i];
+    if (ki < 0 || vi != vi) continue;
+    int rank = 0;
+    for (int j = 0; j < count; ++j) {
+      const float vj = v[j];
+      const int kj = k[j];
+      rank += (kj >= 0 && vj == vj && (vj > vi || (vj == vi && kj < ki))) ? 1 : 0;
+    }
+    if (rank < n_keep) put(rank, vi, ki);
+  }
+}
+constexpr int kBeamMergeCap = 1024;  // candidates of a sentence merged in shared memory (rows x 16 slices x n_keep)
+
+// log-probs of one slice, processors, slice top-n; the last CTA of a sentence merges.  The slice is read from global
+// memory once and lives in (dynamic) shared memory from then on: `lg` is that copy, indexed by token id.
 __global__ void __launch_bounds__(kSelThreads)
 beam_topk_kernel(float* logits, int V, BeamSel s) {
   pdl_launch_dependents();
   pdl_wait();
+  extern __shared__ float beam_slice[];
   const int part = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
   const int g = r / s.rows_per_group, rg = r - g * s.rows_per_group;
-  float* lg = logits + static_cast<size_t>(r) * V;
+  float* lg_global = logits + static_cast<size_t>(r) * V;
   const int per = (V + kSelParts - 1) / kSelParts;
   const int lo = part * per, hi = min(V, lo + per);
+  float* lg = beam_slice - lo;
   // log-sum-exp of the row from the slice partials
   float M = -INFINITY;
 #pragma unroll
@@ -135,7 +171,7 @@ beam_topk_kernel(float* logits, int V, BeamSel s) {
     if (pm > -INFINITY) S += s.part_sum[r * kSelParts + p] * expf(pm - M);
   }
   const float lse = M + logf(S);
-  for (int i = lo + tid; i < hi; i += kSelThreads) lg[i] -= lse;
+  for (int i = lo + tid; i < hi; i += kSelThreads) lg[i] = __ldg(lg_global + i) - lse;
   __syncthreads();
   const int n_ctx = s.ctx_len[r];
   const int* enc = s.enc_ids + static_cast<size_t>(g) * s.enc_cap;
@@ -179,25 +215,54 @@ beam_topk_kernel(float* logits, int V, BeamSel s) {
     if (id >= lo && id < hi) lg[id] = -INFINITY;
   }
   __syncthreads();
+  if (s.write_back)
+    for (int i = lo + tid; i < hi; i += kSelThreads) lg_global[i] = lg[i];
   const float bs = s.beam_score[r];
   float* cs = s.cand_s + (static_cast<size_t>(r) * kSelParts + part) * s.n_keep;
   int* ci = s.cand_i + (static_cast<size_t>(r) * kSelParts + part) * s.n_keep;
-  // Slice top-n in two levels: the n-th largest of the 256 per-thread maxima is a lower bound T of the slice's n-th
-  // largest score, so only elements >= T (a few dozen) enter the exact selection; ties that overflow the candidate
-  // list fall back to selecting over the whole slice.
-  __shared__ float tmax_s[kSelThreads];
-  __shared__ float cand_v[kBeamCandCap];
-  __shared__ int cand_k[kBeamCandCap];
+  // Slice top-n in two levels: a cheap lower bound T of the slice's n-th largest score first, so that only elements
+  // >= T (a few dozen) enter the exact selection; ties that overflow the candidate list fall back to selecting over the
+  // whole slice.
+  __shared__ float tmax_s[kSelThreads / 32];
+  __shared__ float cand_v[kBeamMergeCap];          // slice candidates (kBeamCandCap), later the sentence's merge list
+  __shared__ int cand_k[kBeamMergeCap];
   __shared__ float thr_s;
   __shared__ int cand_n;
   float tmax = -INFINITY;
   for (int i = lo + tid; i < hi; i += kSelThreads) tmax = fmaxf(tmax, lg[i] + bs);
-  tmax_s[tid] = tmax;
-  if (tid == 0) { thr_s = -INFINITY; cand_n = 0; }
+  // Lower bound of the slice's n_keep-th largest score: every warp takes the ceil(n_keep / 8) largest of its 32 thread
+  // maxima (shuffles only); these are 8 x ceil(n_keep / 8) >= n_keep distinct elements, so the smallest of them bounds
+  // the n_keep-th largest from below.  A warp with fewer finite values than that makes the bound -inf (exact fallback).
+  {
+    const int lane = tid & 31;
+    float mv = tmax;
+    bool live = tmax > -INFINITY;
+    float last = INFINITY;
+    const int rounds = (s.n_keep + 7) >> 3;
+    for (int t = 0; t < rounds; ++t) {
+      float bv = live ? mv : -INFINITY;
+      int bk = live ? lane : 64;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+      }
+      last = bv;                                            // -inf when the warp has run out of finite values
+      if (lane == bk) live = false;
+    }
+    if (lane == 0) tmax_s[tid >> 5] = last;
+  }
+  if (tid == 0) cand_n = 0;
+  for (int t = tid; t < s.n_keep; t += kSelThreads) { cs[t] = -INFINITY; ci[t] = -1; }
   __syncthreads();
-  block_top_n(kSelThreads, s.n_keep,
-              [&](int i, float* v, long long* k) { *v = tmax_s[i]; *k = tmax_s[i] > -INFINITY ? i : -1; },
-              [&](int t, float v, long long k) { if (t == s.n_keep - 1) thr_s = k >= 0 ? v : -INFINITY; });
+  if (tid == 0) {
+    float t = tmax_s[0];
+#pragma unroll
+    for (int w = 1; w < kSelThreads / 32; ++w) t = fminf(t, tmax_s[w]);
+    thr_s = t;
+  }
+  __syncthreads();
   const float thr = thr_s;
   for (int i = lo + tid; i < hi; i += kSelThreads) {
     const float v = lg[i] + bs;
@@ -208,9 +273,7 @@ beam_topk_kernel(float* logits, int V, BeamSel s) {
   }
   __syncthreads();
   if (cand_n <= kBeamCandCap) {
-    block_top_n(cand_n, s.n_keep,
-                [&](int i, float* v, long long* k) { *v = cand_v[i]; *k = cand_k[i]; },
-                [&](int t, float v, long long k) { cs[t] = v; ci[t] = static_cast<int>(k); });
+    block_rank_top_n(cand_v, cand_k, cand_n, s.n_keep, [&](int t, float v, int k) { cs[t] = v; ci[t] = k; });
   } else {
     block_top_n(hi - lo, s.n_keep,
                 [&](int i, float* v, long long* k) { *v = lg[lo + i] + bs; *k = lo + i; },
@@ -228,16 +291,29 @@ beam_topk_kernel(float* logits, int V, BeamSel s) {
   const float* gs = s.cand_s + static_cast<size_t>(g) * s.rows_per_group * kSelParts * s.n_keep;
   const int* gi = s.cand_i + static_cast<size_t>(g) * s.rows_per_group * kSelParts * s.n_keep;
   const int per_row = kSelParts * s.n_keep;
-  block_top_n(n_c, s.n_keep,
-              [&](int i, float* v, long long* k) {
-                const int tok = __ldcg(gi + i);
-                *v = __ldcg(gs + i);
-                *k = tok < 0 ? -1LL : static_cast<long long>(i / per_row) * V + tok;
-              },
-              [&](int t, float v, long long k) {
-                s.out_s[g * s.n_keep + t] = v;
-                s.out_i[g * s.n_keep + t] = static_cast<int>(k);
-              });
+  if (n_c <= kBeamMergeCap) {
+    for (int i = tid; i < n_c; i += kSelThreads) {
+      const int tok = __ldcg(gi + i);
+      cand_v[i] = __ldcg(gs + i);
+      cand_k[i] = tok < 0 ? -1 : (i / per_row) * V + tok;
+    }
+    for (int t = tid; t < s.n_keep; t += kSelThreads) { s.out_s[g * s.n_keep + t] = -INFINITY; s.out_i[g * s.n_keep + t] = -1; }
+    __syncthreads();
+    block_rank_top_n(cand_v, cand_k, n_c, s.n_keep,
+                     [&](int t, float v, int k) { s.out_s[g * s.n_keep + t] = v; s.out_i[g * s.n_keep + t] = k; });
+    __syncthreads();
+  } else {
+    block_top_n(n_c, s.n_keep,
+                [&](int i, float* v, long long* k) {
+                  const int tok = __ldcg(gi + i);
+                  *v = __ldcg(gs + i);
+                  *k = tok < 0 ? -1LL : static_cast<long long>(i / per_row) * V + tok;
+                },
+                [&](int t, float v, long long k) {
+                  s.out_s[g * s.n_keep + t] = v;
+                  s.out_i[g * s.n_keep + t] = static_cast<int>(k);
+                });
+  }
   if (tid == 0) s.count[g] = 0;
   (void)rg;
 }

@@ -2282,7 +2282,10 @@ int isst_generate_beam(isst_ctx* ctx, int n, const int* stream_ids, const int32_
     ProfScope ps(ctx, st, P_SELECT, 0.0, static_cast<double>(rows) * V * 4 * 3);
     ISST_CUDA(launch_k(ctx, beam_lse_kernel, dim3(kSelParts, rows), dim3(kSelThreads), 0, st, static_cast<const float*>(ctx->logits), V, sel));
     LAUNCH_CHECK(ctx);
-    ISST_CUDA(launch_k(ctx, beam_topk_kernel, dim3(kSelParts, rows), dim3(kSelThreads), 0, st, ctx->logits, V, sel));
+    const int slice_bytes = ceil_div(V, kSelParts) * 4;            // the kernel keeps its vocabulary slice in shared memory
+    ISST_TRY(ensure_smem(ctx, beam_topk_kernel, std::max(slice_bytes, 64 * 1024)));
+    sel.write_back = follow ? 1 : 0;
+    ISST_CUDA(launch_k(ctx, beam_topk_kernel, dim3(kSelParts, rows), dim3(kSelThreads), slice_bytes, st, ctx->logits, V, sel));
     LAUNCH_CHECK(ctx);
     ISST_CUDA(cudaMemcpyAsync(h_res_s, sel.out_s, static_cast<size_t>(n) * n_keep * sizeof(float), cudaMemcpyDeviceToHost, st));
     ISST_CUDA(cudaMemcpyAsync(h_res_i, sel.out_i, static_cast<size_t>(n) * n_keep * sizeof(int), cudaMemcpyDeviceToHost, st));
