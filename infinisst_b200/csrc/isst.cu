@@ -175,6 +175,7 @@ struct isst_ctx {
   bool pdl = true;          // "pdl" = 0: plain stream order instead of programmatic dependent launch
   int opt_dec_splits = 0;   // "decode_splits" > 0: fixed key-split count of decode attention (micro-benchmarks)
   bool opt_chain = true;    // "decode_chain" = 0: one kernel per operator instead of the fused decode-layer chain
+  bool tap_llm_layers = false;   // "tap_llm_layers" = 1: per-layer residual taps of the LLM prefill (operator path only)
   int opt_pa_l2_ahead = 1;           // "prefill_l2_ahead": K/V tiles the prefill attention asks into L2 ahead of its ring
   bool opt_pair = true;              // "gemm_pair" = 0: one CTA per tile instead of CTA pairs (cta_group::2) above 128 rows (A/B)
   bool opt_defer_as_chain = false;   // "defer_splits_as_chain" (tests): the operator-per-kernel path cuts K like the chain does
@@ -993,6 +994,7 @@ static int launch_decode_attention(isst_ctx* ctx, cudaStream_t st, const bf16* q
 struct ChainBuilder {
   chain::Params p{};
   int bn = 64;
+  bool prefill = false;      // path accounting only
   double flops = 0, bytes = 0;
   const void* amap_ptr[chain::kMaxMaps] = {nullptr, nullptr, nullptr, nullptr};
   int amap_K[chain::kMaxMaps] = {0, 0, 0, 0};
@@ -1070,7 +1072,7 @@ static int chain_launch_bn(isst_ctx* ctx, cudaStream_t st, ChainBuilder& cb) {
   ProfScope ps(ctx, st, P_GEMM_STREAM, cb.flops, cb.bytes);
   ISST_CUDA(launch_k(ctx, kern, dim3(G), dim3(C::kThreads), C::kSmemBytes, st, cb.p));
   LAUNCH_CHECK(ctx);
-  ctx->paths[std::string("decode_chain") + std::to_string(kBN)]++;
+  ctx->paths[std::string(cb.prefill ? "prefill_chain" : "decode_chain") + std::to_string(kBN)]++;
   return 0;
 }
 static int chain_launch(isst_ctx* ctx, cudaStream_t st, ChainBuilder& cb) {
@@ -1082,8 +1084,50 @@ static int chain_launch(isst_ctx* ctx, cudaStream_t st, ChainBuilder& cb) {
   return chain_launch_bn<256>(ctx, st, cb);
 }
 
-// One decode forward (every stream advances by one token, <= 64 rows) on the fused chain: 2 launches per layer
-// (decode attention + chain) instead of 7.
+// Chunk-prefill attention of layer l over the paged KV (q / q_sys rotated and K / V appended by llm_rope_append_kernel).
+static int launch_prefill_attention(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, int l, const PagedKV& kv, float scale_log2) {
+  const isst_config& c = ctx->cfg;
+  const int H = c.heads, Hkv = c.kv_heads, HD = c.head_dim;
+  const int M = lb.M;
+  {
+      LlmAttnParams lp{};
+      lp.qkv = ctx->lqkv; lp.q_sys = ctx->lq_sys; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
+      lp.T = lb.d_T; lp.H = H; lp.scale_log2 = scale_log2;
+      ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
+                   lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
+      ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, false>, kPaSmemBytes));
+      // few streams: one CTA per (row tile, kv head, stream) leaves most SMs idle and walks the whole KV serially -
+      // cut the key range into splits (fp32 partials merged by decode_combine_kernel)
+      const int row_tiles = ceil_div(4 * lb.max_T, 128);
+      const int ctas = row_tiles * Hkv * lb.n;
+      const int key_tiles = ceil_div(lb.max_L, kPaKT) + 1;
+      int ks = 1;
+      if (2 * ctas <= ctx->sm_count) ks = std::max(1, std::min({ctx->sm_count / ctas, key_tiles / 2, 8}));
+      const size_t part_cap = static_cast<size_t>(c.max_batch) * H * ctx->decode_splits;     // (row, head, split) slots of part_o
+      while (ks > 1 && static_cast<size_t>(M) * H * ks > part_cap) --ks;
+      lp.key_splits = ks; lp.part_o = ctx->part_o; lp.part_ml = ctx->part_ml;
+      lp.kv_row0 = static_cast<int>(static_cast<size_t>(l) * (ctx->kv_layer_elems / HD));
+      lp.l2_ahead = ctx->opt_pa_l2_ahead;
+      ctx->paths[ks > 1 ? "prefill_attention_tc_keysplit" : "prefill_attention_tc_unsplit"]++;
+      if (ks > 1) {
+        ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, true>, kPaSmemBytes));
+        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, true>, dim3(row_tiles * ks, Hkv, lb.n), dim3(kPaThreads),
+                           kPaSmemBytes, st, ctx->kv_map, lp));
+      } else {
+        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, false>, dim3(row_tiles, Hkv, lb.n), dim3(kPaThreads),
+                           kPaSmemBytes, st, ctx->kv_map, lp));
+      }
+      LAUNCH_CHECK(ctx);
+      if (ks > 1) {
+        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(M * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, ks));
+        LAUNCH_CHECK(ctx);
+      }
+  }
+  return 0;
+}
+
+// One LLM forward on the fused chain: per layer one attention launch (decode: fused RoPE / append; chunk-prefill of up
+// to 128 rows: RoPE-append + tensor-core prefill attention) + ONE chain launch instead of five GEMM / norm launches.
 static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) {
   const isst_config& c = ctx->cfg;
   const int D = c.hidden, H = c.heads, Hkv = c.kv_heads, HD = c.head_dim, F = c.ffn;
@@ -1103,6 +1147,7 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
   {
     ChainBuilder cb;
     chain_begin(cb, M);
+    cb.prefill = !lb.decode;
     ISST_TRY(chain_rows(cb, ctx->lx, nullptr, ctx->lh, ctx->llm[0].rms1, nullptr, 0, 0, nullptr, M, D, c.rms_eps));
     ISST_TRY(chain_gemm(ctx, cb, ctx->lh, ctx->llm[0].wqkv, QKV, 0, chain::EPI_PART, ctx->defer_ws, &qkv_splits));
     ISST_TRY(chain_launch(ctx, st, cb));
@@ -1110,7 +1155,18 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
   for (int l = 0; l < c.layers; ++l) {
     LlmLayerW& w = ctx->llm[l];
     PagedKV kv = paged_kv(ctx, l);
-    if (grouped) {
+    if (!lb.decode) {
+      // chunk-prefill: RoPE + append of the new rows (summing the QKV split partials), then tensor-core prefill attention
+      {
+        ProfScope ps(ctx, st, P_APPEND, 0.0, static_cast<double>(M) * (2.0 * H + 4.0 * Hkv) * HD * 2);
+        dim3 grid(ceil_div(lb.max_T * (H + 2 * Hkv) * (HD / 16), 128), lb.n);
+        ISST_CUDA(launch_k(ctx, llm_rope_append_kernel, grid, dim3(128), 0, st, ctx->lqkv, ctx->lq_sys, kv, lb.d_slots, lb.d_tok_base, lb.d_T,
+                           lb.d_active, ctx->llm_rope_ring, ctx->llm_rope_sys, H, static_cast<const float*>(ctx->defer_ws), qkv_splits,
+                           static_cast<long long>(M) * QKV));
+        LAUNCH_CHECK(ctx);
+      }
+      ISST_TRY(launch_prefill_attention(ctx, st, lb, l, kv, scale_log2));
+    } else if (grouped) {
       // beam search: rows come in groups of 4 beams that share their sentence's prompt pages; the shared prefix is
       // attended to once per group.  The kernel completes (QKV split partials), rotates and appends by itself
       const double tok = lb.prefix_tokens + (lb.kv_tokens - lb.prefix_tokens * lb.group);
@@ -1146,6 +1202,7 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
     }
     ChainBuilder cb;
     chain_begin(cb, M);
+    cb.prefill = !lb.decode;
     int so = 1, sd = 1;
     ISST_TRY(chain_gemm(ctx, cb, ctx->lattn, w.wo, D, 0, chain::EPI_PART, ctx->defer_ws, &so));
     ISST_TRY(chain_rows(cb, ctx->lx, ctx->lx, ctx->lh, w.rms2, ctx->defer_ws, so, static_cast<long long>(M) * D, nullptr, M, D, c.rms_eps));
@@ -1157,10 +1214,17 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
     } else {
       // final norm on the last row of every stream + lm_head (the reference computes and discards the other rows)
       ISST_TRY(chain_rows(cb, ctx->lx, nullptr, ctx->llast, ctx->final_norm, ctx->defer_ws, sd, static_cast<long long>(M) * D, lb.d_last_row, lb.n, D, c.rms_eps));
-      ISST_TRY(chain_gemm(ctx, cb, ctx->llast, ctx->lm_head, c.vocab, 0, chain::EPI_F32, ctx->logits, nullptr));
+      // decode: one row per stream, lm_head is the chain's last phase; chunk-prefill: the chain's token columns are the
+      // M prompt rows while lm_head sees the n gathered rows only - it runs as its own GEMM below
+      if (lb.decode) ISST_TRY(chain_gemm(ctx, cb, ctx->llast, ctx->lm_head, c.vocab, 0, chain::EPI_F32, ctx->logits, nullptr));
     }
     if (l == 1) cb.p.dbg = ctx->gemm_dbg;             // phase stamps of a middle layer's chain ("gemm_stamps" tap, debug bit 1)
     ISST_TRY(chain_launch(ctx, st, cb));
+  }
+  if (!lb.decode) {
+    Epilogue e;
+    e.out_f32 = 1;
+    ISST_TRY(gemm(ctx, st, plain_view(ctx->llast, lb.n, D), ctx->lm_head, c.vocab, ctx->logits, c.vocab, 0, e));
   }
   ISST_CUDA(launch_k(ctx, advance_kv_len_kernel, dim3(ceil_div(lb.n, 128)), dim3(128), 0, st, ctx->d_kv_len, lb.d_slots, lb.d_T, lb.d_active, lb.n));
   LAUNCH_CHECK(ctx);
@@ -1169,8 +1233,10 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
 
 static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool tap_layers) {
   const isst_config& c = ctx->cfg;
-  if (ctx->opt_chain && lb.decode && lb.M <= 256 && lb.M == lb.n && (lb.group == 1 || (lb.group == 4 && lb.d_key_hi)) &&
-      !lb.all_logits && !tap_layers)
+  // the fused chain: decode forwards up to 256 rows, chunk-prefill up to 128 rows (beyond that the GEMMs are tensor-bound
+  // and go to the CTA-pair kernel); the per-layer debug taps exist on the operator path only
+  if (ctx->opt_chain && !lb.all_logits && !(tap_layers && ctx->tap_llm_layers) &&
+      (lb.decode ? (lb.M <= 256 && lb.M == lb.n && (lb.group == 1 || (lb.group == 4 && lb.d_key_hi))) : lb.M <= 128))
     return llm_decode_chain(ctx, st, lb);
   const int D = c.hidden, H = c.heads, Hkv = c.kv_heads, HD = c.head_dim, F = c.ffn;
   const int QKV = (H + 2 * Hkv) * HD;
@@ -1213,38 +1279,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       LAUNCH_CHECK(ctx);
     }
     if (!lb.decode) {
-      LlmAttnParams lp{};
-      lp.qkv = ctx->lqkv; lp.q_sys = ctx->lq_sys; lp.out = ctx->lattn; lp.kv = kv; lp.slots = lb.d_slots; lp.tok_base = lb.d_tok_base;
-      lp.T = lb.d_T; lp.H = H; lp.scale_log2 = scale_log2;
-      ProfScope ps(ctx, st, P_ATTN_PREFILL, 4.0 * lb.qk_pairs * H * HD,
-                   lb.kv_tokens * Hkv * HD * 2 * 2 + static_cast<double>(M) * H * HD * 2 * 2);
-      ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, false>, kPaSmemBytes));
-      // few streams: one CTA per (row tile, kv head, stream) leaves most SMs idle and walks the whole KV serially -
-      // cut the key range into splits (fp32 partials merged by decode_combine_kernel)
-      const int row_tiles = ceil_div(4 * lb.max_T, 128);
-      const int ctas = row_tiles * Hkv * lb.n;
-      const int key_tiles = ceil_div(lb.max_L, kPaKT) + 1;
-      int ks = 1;
-      if (2 * ctas <= ctx->sm_count) ks = std::max(1, std::min({ctx->sm_count / ctas, key_tiles / 2, 8}));
-      const size_t part_cap = static_cast<size_t>(c.max_batch) * H * ctx->decode_splits;     // (row, head, split) slots of part_o
-      while (ks > 1 && static_cast<size_t>(M) * H * ks > part_cap) --ks;
-      lp.key_splits = ks; lp.part_o = ctx->part_o; lp.part_ml = ctx->part_ml;
-      lp.kv_row0 = static_cast<int>(static_cast<size_t>(l) * (ctx->kv_layer_elems / HD));
-      lp.l2_ahead = ctx->opt_pa_l2_ahead;
-      ctx->paths[ks > 1 ? "prefill_attention_tc_keysplit" : "prefill_attention_tc_unsplit"]++;
-      if (ks > 1) {
-        ISST_TRY(ensure_smem(ctx, prefill_attention_tc_kernel<4, true>, kPaSmemBytes));
-        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, true>, dim3(row_tiles * ks, Hkv, lb.n), dim3(kPaThreads),
-                           kPaSmemBytes, st, ctx->kv_map, lp));
-      } else {
-        ISST_CUDA(launch_k(ctx, prefill_attention_tc_kernel<4, false>, dim3(row_tiles, Hkv, lb.n), dim3(kPaThreads),
-                           kPaSmemBytes, st, ctx->kv_map, lp));
-      }
-      LAUNCH_CHECK(ctx);
-      if (ks > 1) {
-        ISST_CUDA(launch_k(ctx, decode_combine_kernel, dim3(M * H), dim3(128), 0, st, ctx->part_o, ctx->part_ml, ctx->lattn, H, HD, ks));
-        LAUNCH_CHECK(ctx);
-      }
+      ISST_TRY(launch_prefill_attention(ctx, st, lb, l, kv, scale_log2));
     } else if (grouped) {
       // algorithmic bytes: the shared prefix once per sentence + every beam's private tail
       const double tok = lb.prefix_tokens + (lb.kv_tokens - lb.prefix_tokens * lb.group);
@@ -1299,7 +1334,7 @@ static int llm_forward(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb, bool 
       ISST_TRY(gemm(ctx, st, plain_view(ctx->lgu, M, F), w.wd, D, ctx->lx, D, 0, e));
       if (ctx->last_defer_splits) pending = DeferredSum{ctx->defer_ws, ctx->last_defer_splits, static_cast<long long>(M) * D, ctx->lx};
     }
-    if (tap_layers && ctx->debug) {
+    if (tap_layers && ctx->debug && ctx->tap_llm_layers) {
       if (pending.part) {   // materialise the layer output for the tap (debug only)
         ISST_TRY(norm_rows(ctx, st, true, false, ctx->lx, ctx->lh, w.rms1, nullptr, nullptr, M, D, c.rms_eps, pending));
         pending = DeferredSum{nullptr, 0, 0, nullptr};
@@ -2640,6 +2675,7 @@ int isst_debug_option(isst_ctx* ctx, const char* key_c, int value) {
   if (key == "pdl") ctx->pdl = value != 0;
   else if (key == "decode_splits") ctx->opt_dec_splits = value;
   else if (key == "decode_chain") ctx->opt_chain = value != 0;
+  else if (key == "tap_llm_layers") ctx->tap_llm_layers = value != 0;
   else if (key == "defer_splits_as_chain") ctx->opt_defer_as_chain = value != 0;
   else if (key == "gemm_pair") ctx->opt_pair = value != 0;
   else if (key == "prefill_l2_ahead") ctx->opt_pa_l2_ahead = value;
