@@ -61,6 +61,10 @@ GEMM_CASES = [
     (22, 768, 512, {"dual": True}), (1, 14336, 4096, {"dual": True}), (1408, 14336, 4096, {"dual": True}),
     (64, 14336, 4096, {"dual": True, "force_splits": 2}), (100, 256, 512, {"force_swap": 1}),
     (30, 256, 512, {"force_swap": 0}),
+    # CTA-pair kernel (more than 128 rows): ragged token / feature tiles, stream-K remainder, gate/up with ragged tiles
+    (129, 128, 256, {}), (200, 384, 512, {}), (513, 520, 256, {"out_f32": True}), (1408, 6144, 4096, {}),
+    (1408, 4096, 14336, {"resid": True}), (4000, 256, 320, {"bias": True}), (300, 768, 512, {"dual": True}),
+    (400, 640, 1024, {"dual": True}),
 ]
 
 
@@ -92,10 +96,14 @@ def test_gemm_vs_torch_fp32(op_engine):
             ref = torch.nn.functional.gelu(ref)
         if resid is not None:
             ref = ref + resid.float()
+        pair0 = op_engine.path_count("gemm_pair") + op_engine.path_count("gemm_pair_dual")
         out = op_engine.op_gemm(a, w, bias=bias, gelu=kw.get("gelu", False), resid=resid, dual=dual,
                                 out_f32=kw.get("out_f32", False), force_swap=kw.get("force_swap", -1),
                                 force_splits=kw.get("force_splits", 0))
         torch.cuda.synchronize()
+        # above 128 rows a plain GEMM runs on CTA pairs (cta_group::2) unless the test forces the one-CTA kernel
+        took_pair = op_engine.path_count("gemm_pair") + op_engine.path_count("gemm_pair_dual") - pair0
+        assert took_pair == int(M > 128 and K >= 256 and not kw.get("force_splits") and kw.get("force_swap", -1) != 1), (M, N, K, kw)
         tol = 2e-5 if kw.get("out_f32") else 4e-3            # fp32 out: accumulation order only; bf16 out: 2^-8 rounding
         assert rel_l2(out, ref) < tol, (M, N, K, kw, rel_l2(out, ref))
 
