@@ -45,6 +45,7 @@ using namespace tc;
 
 constexpr int kMaxPhases = 8;
 constexpr int kMaxMaps = 4;
+constexpr int kMaxTiles = 64;          // tile pairs of a fold_reduce GEMM (n_out <= 16384)
 enum { PH_GEMM = 0, PH_ROWS = 1 };
 enum { EPI_PART = 0, EPI_SILU = 1, EPI_F32 = 2 };
 
@@ -73,6 +74,16 @@ struct Phase {
   int n_rows;
   int C;
   float eps;
+  // ---- folded RMSNorm (decode): the row phase between two GEMMs and its grid barrier disappear ----
+  // PH_GEMM, EPI_PART with fold_reduce: once every k-split of a tile pair has parked its partial (a counter per tile), the
+  //   split CTAs share the tile's tokens: x = bf16(x_in + sum_s part[s]) -> x_out, h_out = bf16(x * w) (NOT normalised),
+  //   sq_out[tile][tok] = sum of x^2 over the tile's 256 features.  Uses x_in / x_out / h_out / w above.
+  // PH_GEMM with sq_in: the accumulators are multiplied by rstd[tok] = rsqrt(sum_t sq_in[t][tok] / C + eps) in the epilogue
+  //   (the GEMM is linear in its activation rows, so normalising after it is the same sum).
+  int fold_reduce;
+  float* sq_out;
+  const float* sq_in;
+  int n_sq;                  // tiles summed per token
 };
 
 struct Params {
@@ -85,6 +96,8 @@ struct Params {
   unsigned long long* dbg;                    // optional [grid][32] %globaltimer stamps (phase analysis), may be null
   unsigned long long* bar;                    // [kMaxPhases] grid barrier counters, one per phase index
   unsigned long long bar_base[kMaxPhases];    // their values when this launch starts
+  int* tile_ctr;                              // fold_reduce arrival counters [2 halves][kMaxPhases * kMaxTiles]: alternate
+  int ctr_parity;                             //   launches use alternate halves; a launch re-arms the other half
 };
 
 template <int kBN>
@@ -98,7 +111,7 @@ struct Cfg {
   static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;   // double-buffered up to 128 token columns
   static constexpr int kTmemColsRaw = kAccBufs * kAccCols;
   static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : (kTmemColsRaw <= 64 ? 64 : (kTmemColsRaw <= 128 ? 128 : (kTmemColsRaw <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512 + 1024;   // + rstd[256]
   static constexpr int kEpiThreads = 256;
   static constexpr int kThreads = 128 + kEpiThreads;
   static constexpr int kEpiHalves = kBN >= 32 ? 2 : 1;
@@ -127,7 +140,73 @@ __device__ __forceinline__ void unit_range(const Phase& ph, int u, int& tile, in
   kb1 = static_cast<int>(static_cast<long long>(ph.num_kb) * (split + 1) / ph.splits);
 }
 
-template <int kBN>
+// fold_reduce of one (tile pair, k-split) unit: this CTA's share of the tile's tokens (see Phase).  Kept out of line: the
+// epilogue around the call site is at the register limit of a 384-thread CTA.
+template <int kEpiThreads>
+__device__ __noinline__ void fold_reduce_tokens(const Phase& ph, int n_tok, int tile, int split, int et) {
+  const float* part = reinterpret_cast<const float*>(ph.out);
+  const int lane = et & 31;
+  const int t0 = n_tok * split / ph.splits, t1 = n_tok * (split + 1) / ph.splits;
+  // one warp per token, a lane owns 8 consecutive features of the tile pair's 256 (16-byte loads), the squared sum is
+  // one warp reduction - no block barrier
+  const int f0 = tile * ph.tile_rows + lane * 8;
+  const bool f_ok = f0 + 8 <= ph.n_out;                      // n_out is a multiple of 8 (checked on the host)
+  const size_t pstride = static_cast<size_t>(n_tok) * ph.n_out;
+  float wv[8];
+  {
+    const float4 w0 = f_ok ? __ldg(reinterpret_cast<const float4*>(ph.w + f0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w1 = f_ok ? __ldg(reinterpret_cast<const float4*>(ph.w + f0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+  }
+#pragma unroll 1
+  for (int t = t0 + (et >> 5); t < t1; t += kEpiThreads / 32) {
+    const size_t o = static_cast<size_t>(t) * ph.n_out + f0;
+    float a8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+    float sq = 0.f;
+    if (f_ok) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(ph.x_in + o);
+#pragma unroll 1
+      for (int sp0 = 0; sp0 < ph.splits; sp0 += 4) {         // four splits' loads in flight (eight measured slower
+        float4 pa[4], pb[4];                                 // at 64 rows: 77.1 vs 75.9 ms per step); split order
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (sp0 + q4 < ph.splits) {
+            const float4* pp = reinterpret_cast<const float4*>(part + (sp0 + q4) * pstride + o);
+            pa[q4] = __ldcg(pp); pb[q4] = __ldcg(pp + 1);
+          }
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (sp0 + q4 < ph.splits) {
+            a8[0] += pa[q4].x; a8[1] += pa[q4].y; a8[2] += pa[q4].z; a8[3] += pa[q4].w;
+            a8[4] += pb[q4].x; a8[5] += pb[q4].y; a8[6] += pb[q4].z; a8[7] += pb[q4].w;
+          }
+        }
+      }
+      const uint32_t ru[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t nu[4], hu[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f2 = unpack_bf16(ru[j]);
+        const float x0 = bf16_round(a8[2 * j] + f2.x), x1 = bf16_round(a8[2 * j + 1] + f2.y);
+        nu[j] = pack_bf16(x0, x1);
+        hu[j] = pack_bf16(x0 * wv[2 * j], x1 * wv[2 * j + 1]);
+        sq += x0 * x0 + x1 * x1;
+      }
+      if (ph.x_out) *reinterpret_cast<uint4*>(ph.x_out + o) = make_uint4(nu[0], nu[1], nu[2], nu[3]);
+      *reinterpret_cast<uint4*>(ph.h_out + o) = make_uint4(hu[0], hu[1], hu[2], hu[3]);
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) ph.sq_out[static_cast<size_t>(tile) * n_tok + t] = sq;
+  }
+}
+
+// kFold = false: GEMM phases + RMSNorm row phases (the head chain, chunk-prefill, `chain_fold` = 0).
+// kFold = true : GEMM phases with the folded RMSNorm (fold_reduce / sq_in) and NO row-phase code - the layer chains of a
+//                decode forward.  Two instantiations keep either variant inside the register budget of a 384-thread CTA.
+template <int kBN, bool kFold>
 __global__ void __launch_bounds__(384, 1)
 decode_chain_kernel(const __grid_constant__ Params p) {
   using C = Cfg<kBN>;
@@ -140,6 +219,7 @@ decode_chain_kernel(const __grid_constant__ Params p) {
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* red = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [16] row-phase reduction scratch (+ [1] result)
   volatile int* rows_done = reinterpret_cast<volatile int*>(red + 20);   // 1 + index of the last row phase this CTA finished
+  float* rstd_s = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 512);   // [256] per-token 1 / rms (sq_in phases)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,12 +367,29 @@ decode_chain_kernel(const __grid_constant__ Params p) {
     const int et = threadIdx.x - 128;             // 0..255
     const bool works = half < C::kEpiHalves;
     const int hc0 = half * C::kHalfCols;
+    int* ctr = p.tile_ctr + (p.ctr_parity ? kMaxPhases * kMaxTiles : 0);
+    if (kFold) {
+      for (int i = cta * C::kEpiThreads + et; i < kMaxPhases * kMaxTiles; i += G * C::kEpiThreads)
+        p.tile_ctr[(p.ctr_parity ? 0 : kMaxPhases * kMaxTiles) + i] = 0;     // the next folded launch's half (its last user is complete)
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int pi = 0; pi < p.n_phases; ++pi) {
       const Phase& ph = p.ph[pi];
       if (ph.kind == PH_GEMM) {
         const int units = ph.tiles * ph.splits;
+        const bool scaled = kFold && ph.sq_in != nullptr;
+        if (scaled) {
+          // 1 / rms of every token row from the squared sums the phase before left per feature tile
+          if (et == 0) grid_wait(p, pi - 1, G);
+          asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+          if (et < p.n_tok) {
+            float qs = 0.f;
+            for (int t = 0; t < ph.n_sq; ++t) qs += __ldcg(ph.sq_in + static_cast<size_t>(t) * p.n_tok + et);
+            rstd_s[et] = rsqrtf(qs / ph.C + ph.eps);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+        }
         for (int u = cta; u < units; u += G) {
           int tile, split, kb0, kb1;
           unit_range(ph, u, tile, split, kb0, kb1);
@@ -321,8 +418,9 @@ decode_chain_kernel(const __grid_constant__ Params p) {
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < kStep; ++i) {
-                  const float gv = __uint_as_float(g[i]);
-                  const float x = __fdividef(gv, 1.0f + __expf(-gv)) * __uint_as_float(up[i]);
+                  const float rs = scaled ? rstd_s[hc0 + c + i] : 1.0f;
+                  const float gv = __uint_as_float(g[i]) * rs;
+                  const float x = __fdividef(gv, 1.0f + __expf(-gv)) * (__uint_as_float(up[i]) * rs);
                   if (row_ok && c + i < n_tok) dst[static_cast<size_t>(c + i) * ph.n_out] = __float2bfloat16_rn(x);
                 }
               }
@@ -350,11 +448,13 @@ decode_chain_kernel(const __grid_constant__ Params p) {
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < kStep; ++i)
-                  if (ok_a && c + i < n_tok) dst_a[static_cast<size_t>(c + i) * ph.n_out] = __uint_as_float(va[i]);
+                  if (ok_a && c + i < n_tok)
+                    dst_a[static_cast<size_t>(c + i) * ph.n_out] = scaled ? __uint_as_float(va[i]) * rstd_s[hc0 + c + i] : __uint_as_float(va[i]);
                 if (warp_b) {
 #pragma unroll
                   for (int i = 0; i < kStep; ++i)
-                    if (ok_b && c + i < n_tok) dst_b[static_cast<size_t>(c + i) * ph.n_out] = __uint_as_float(vb[i]);
+                    if (ok_b && c + i < n_tok)
+                      dst_b[static_cast<size_t>(c + i) * ph.n_out] = scaled ? __uint_as_float(vb[i]) * rstd_s[hc0 + c + i] : __uint_as_float(vb[i]);
                 }
               }
             }
@@ -363,7 +463,22 @@ decode_chain_kernel(const __grid_constant__ Params p) {
           mbar_arrive(&tempty_bar[acc]);
           if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1; }
         }
-      } else {
+        if (kFold && ph.fold_reduce) {
+          // ---- folded residual + RMSNorm statistics: the k-split CTAs of a tile pair share its tokens ----
+          for (int u = cta; u < units; u += G) {
+            int tile, split, kb0, kb1;
+            unit_range(ph, u, tile, split, kb0, kb1);
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");      // this CTA's partials are out
+            if (et == 0) {
+              atomicAdd(&ctr[pi * kMaxTiles + tile], 1);
+              while (ld_acquire(&ctr[pi * kMaxTiles + tile]) < ph.splits) __nanosleep(20);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+            fold_reduce_tokens<C::kEpiThreads>(ph, p.n_tok, tile, split, et);
+          }
+        }
+      } else if (!kFold) {
         // ---- row phase: one row per CTA (rows cta, cta + G, ...) ----
         if (pi > 0) {
           if (et == 0) grid_wait(p, pi - 1, G);

@@ -72,6 +72,8 @@ def test_library_is_sm100a_tcgen05_tma():
     sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    # the CTA-pair GEMM: cta_group::2 MMAs, pair-wide TMA loads, commits multicast to both CTAs' barriers
+    assert "UTCHMMA.2CTA" in sass and "UTMALDG.2D.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
