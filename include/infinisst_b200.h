@@ -181,7 +181,10 @@ int64_t isst_launch_count(isst_ctx* ctx);       /* kernels launched so far */
 int isst_path_count(isst_ctx* ctx, const char* name, int64_t* count);
 /* Per-context test / tuning options (no environment variables on the hot path): "pdl" 0/1 programmatic dependent
  * launch, "decode_splits" fixed key-split count of decode attention (0 = automatic), "decode_chain" 0/1 the fused
- * decode-layer kernel (0 = one kernel per operator). */
+ * layer kernel (0 = one kernel per operator), "chain_fold" 0/1 RMSNorms folded into the decode GEMMs (default 0: the
+ * reference's rounding points), "gemm_pair" 0/1 CTA-pair GEMM above 128 token rows (0 = one CTA per tile),
+ * "prefill_l2_ahead" K/V tiles the prefill attention asks into L2 ahead of its ring, "defer_splits_as_chain" and
+ * "tap_llm_layers" (parity tests: operator path with the chain's k-ranges; per-layer residual taps). */
 int isst_debug_option(isst_ctx* ctx, const char* key, int value);
 /* Per-kernel-class device timing for the roofline leg of bench.py: while enabled every launch is
  * bracketed by CUDA events on the caller's stream.  isst_profile_read walks the classes by index
