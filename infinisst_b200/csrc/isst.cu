@@ -182,8 +182,8 @@ struct isst_ctx {
   int* chain_ctr = nullptr;                  // folded-norm arrival counters of decode_chain_kernel (two halves, see chain::Params)
   int chain_parity = 0;
   float* chain_sq = nullptr;                 // [2][kMaxTiles][256] squared row sums per feature tile (folded RMSNorm)
-  bool opt_fold = false;                     // "chain_fold" = 1: both RMSNorms of a decode layer folded into the GEMMs around them
-                                             //   (+1.3 % throughput; one bf16 rounding of the normalised activation less than the reference)
+  bool opt_fold = true;                      // "chain_fold" = 0: RMSNorm row phases between the decode GEMMs (the reference module's two
+                                             //   bf16 roundings; bit-identical to the operator path) instead of norms folded into the GEMMs
   unsigned long long* chain_bar = nullptr;   // grid-barrier counters of decode_chain_kernel, one per phase index (monotonic)
   unsigned long long chain_base[chain::kMaxPhases] = {0};   // their values once every launch issued so far has completed
   std::set<const void*> smem_attr_done;      // kernels whose dynamic shared-memory limit was raised on this device
@@ -1175,10 +1175,10 @@ static int llm_decode_chain(isst_ctx* ctx, cudaStream_t st, const LlmBatch& lb) 
     LAUNCH_CHECK(ctx);
   }
   const bool grouped = lb.group == 4 && lb.d_key_hi != nullptr;   // beam search: shared-prefix attention
-  // option "chain_fold" (decode): both RMSNorms of a layer are folded into the GEMMs around them (chain::Phase) - one
-  // grid barrier and the row phase less per norm; h = bf16(x * w) reaches the next GEMM un-normalised and 1 / rms is
-  // applied to its fp32 accumulators.  That is one bf16 rounding of the normalised activation less than the reference's
-  // RMSNorm module, so it is off by default (the product keeps the reference's rounding points)
+  // decode ("chain_fold", default on): both RMSNorms of a layer are folded into the GEMMs around them (chain::Phase) -
+  // one grid barrier and the row phase less per norm; h = bf16(x * w) reaches the next GEMM un-normalised and 1 / rms is
+  // applied to its fp32 accumulators: one bf16 rounding of the normalised activation less than the reference's RMSNorm
+  // module (closer to the fp32 oracle); "chain_fold" = 0 keeps the module's two roundings
   const bool fold = ctx->opt_fold && lb.decode;
   float* sq_a = ctx->chain_sq;                                     // o_proj -> gate/up
   float* sq_b = ctx->chain_sq + chain::kMaxTiles * 256;            // down / head -> QKV, lm_head

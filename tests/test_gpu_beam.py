@@ -142,9 +142,12 @@ def test_cuda_beam_search_follows_reference(pins, name):
 
 
 def test_cuda_beam_search_free_running(pins):
-    """No teacher forcing: the agent-level stream (SimulEval agent mirror, `--beam 4`) must emit the reference's
-    tokens on most chunks; once a near-tie flips a beam the KV history differs, so later chunks are only
-    required to keep the integer invariants."""
+    """No teacher forcing: the agent-level stream (SimulEval agent mirror, `--beam 4`) emits the reference's tokens
+    until a near-tie between hypotheses flips (random weights: the four beams of a sentence end within ~0.2 of each
+    other in cumulative log-prob, which bf16 noise reorders); at the first chunk whose ids differ the device's best
+    score must still agree with the reference restatement's best score within the tolerance of the teacher-forced
+    tests - a different winner among near-equal hypotheses, not a different distribution.  Once it has flipped the KV
+    history differs, so later chunks are only required to keep the integer invariants."""
     from infinisst_b200.agent import S2TAgentStates, evict_plan
     name = "plain"
     n, k = int(pins[f"{name}_n_chunks"]), int(pins["beam"])
@@ -157,13 +160,19 @@ def test_cuda_beam_search_free_running(pins):
     st = S2TAgentStates()
     st.system_prompt_size = len(cfg.tpl.system_ids)
     target, same, diverged = [], 0, False
+    cfg.gen.beam = k
+    ost = O.StreamState()                                                       # the reference restatement (fp32, CPU): best scores
     for c in range(n):
         p = f"{name}_c{c}_"
+        o_ids, o_rec = (None, None)
+        if not diverged:
+            o_ids, o_rec = O.policy_chunk(sd, cfg, ost, audio[: (c + 1) * SEG].tolist(), torch.float32)
+            assert o_ids == pins[p + "output_ids"].tolist()                         # (the oracle is pinned on the reference run)
         eng.encode_chunk([sid], _pcm(audio, c), 1)
         ids = O.build_prompt(cfg.tpl, c == 0)
         kv0 = eng.kv_len(sid)
-        toks, scores = eng.generate_beam([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen, k,
-                                         pin_prefix=len(cfg.tpl.system_ids))
+        toks, scores, dtrace = eng.generate_beam([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen, k,
+                                                 pin_prefix=len(cfg.tpl.system_ids), want_trace=True)
         out = toks[0][:-1]                                                      # agents/infinisst.py:363
         assert eng.kv_len(sid) == kv0 + len(ids) + len(out)                     # hand-back: prompt + forwarded tokens
         ref = pins[p + "output_ids"].tolist()
@@ -171,13 +180,26 @@ def test_cuda_beam_search_free_running(pins):
             same += 1
         elif not diverged:
             diverged = True
-            print(f"free-running beam search diverged at chunk {c}: cuda {out} ref {ref}")
+            # the FIRST decision that differs must be a near-tie in the reference restatement's own scores (after it
+            # the two searches explore different beams, so later scores are not comparable)
+            step = next((i for i, (d, o) in enumerate(zip(dtrace[0], o_rec.trace)) if d["next"] != o["next"]), None)
+            if step is None:                                                    # same search, another winner among the hypotheses
+                assert abs(scores[0] - o_rec.score) < 0.05 + 0.02 * abs(o_rec.score), (c, scores[0], o_rec.score)
+                print(f"free-running beam search: chunk {c}: same beams, hypotheses tie: cuda {scores[0]:.4f} ref {o_rec.score:.4f}")
+            else:
+                o = o_rec.trace[step]
+                o_score = {(par, tok): sc for (sc, par, tok) in o["cand"]}
+                for j, cand in enumerate(dtrace[0][step]["next"]):
+                    assert cand in o_score, (c, step, cand, "not among the reference's 2k candidates")
+                    gap = abs(o_score[cand] - o["scores"][j])
+                    assert gap < 0.05 + 0.02 * abs(o["scores"][j]), (c, step, j, cand, o_score[cand], o["scores"][j])
+                print(f"free-running beam search: near-tie at chunk {c} step {step}: cuda beams {dtrace[0][step]['next']} ref beams "
+                      f"{o['next']} ref scores {[round(x, 4) for x in o['scores']]}")
         target.extend(out)
         plan = evict_plan(st, eng.kv_len(sid), cfg.gen.max_llm_cache_size, True)
         if plan is not None:
             eng.kv_evict(sid, plan[0], plan[1])
-    print(f"free-running beam search: {same}/{n} chunks identical to the reference before the first divergence")
-    assert same >= 2
+    print(f"free-running beam search: {same}/{n} chunks identical to the reference before the first near-tie")
     eng.close_stream(sid)
     assert eng.pages_free() == free0
     eng.close()
@@ -218,13 +240,34 @@ def test_beam_batched_streams(pins):
 
 def test_agent_drop_in_api_with_beam(pins):
     """The SimulEval-facing agent with the reference's shipped `--beam 4`: same flags / methods as
-    agents/infinisst.py; emitted ids and KV lengths equal the reference agent's up to the first near-tie."""
+    agents/infinisst.py.  Every chunk's emitted ids and the KV length after hand-back + eviction must equal what the
+    engine-level stream of `test_cuda_beam_search_free_running` produces for the same audio (that test holds the
+    engine-level stream against the reference: identical until the first near-tie, which it verifies in the
+    reference's own scores); the chunks that also equal the reference agent's pins are reported."""
     import argparse
-    from infinisst_b200.agent import InfiniSST
+    from infinisst_b200.agent import InfiniSST, S2TAgentStates, evict_plan
     name = "plain"
     n, k = int(pins[f"{name}_n_chunks"]), int(pins["beam"])
     cfg = tiny_config(max_cache_size=int(pins["max_cache"]), max_llm_cache_size=int(pins["max_llm"]))
     sd = beam_weights(cfg, 1.0)
+    audio = make_audio(n * SEG / 16000.0)
+    # engine-level stream (encode_chunk + generate_beam + kv_evict), the sequence of calls the agent must make
+    eng = _engine(cfg, sd, k)
+    sid = eng.open_stream()
+    st = S2TAgentStates()
+    st.system_prompt_size = len(cfg.tpl.system_ids)
+    want, target = [], []
+    for c in range(n):
+        eng.encode_chunk([sid], _pcm(audio, c), 1)
+        ids = O.build_prompt(cfg.tpl, c == 0)
+        toks, _ = eng.generate_beam([sid], [ids], [slot_map(cfg, ids)], [target[-100:]], cfg.gen, k, pin_prefix=len(cfg.tpl.system_ids))
+        out = toks[0][:-1]
+        target.extend(out)
+        plan = evict_plan(st, eng.kv_len(sid), cfg.gen.max_llm_cache_size, True)
+        if plan is not None:
+            eng.kv_evict(sid, plan[0], plan[1])
+        want.append((out, eng.kv_len(sid)))
+    eng.close()
     ap = argparse.ArgumentParser()
     InfiniSST.add_args(ap)
     args = ap.parse_args(["--w2v2-type", "w2v2", "--block-size", "48", "--max-cache-size", str(int(pins["max_cache"])),
@@ -235,8 +278,7 @@ def test_agent_drop_in_api_with_beam(pins):
     agent = InfiniSST(args)
     states = agent.build_states()
     states.source_sample_rate = 16000
-    audio = make_audio(n * SEG / 16000.0)
-    same = 0
+    same_ref, ref_on = 0, True
     for c in range(n):
         p = f"{name}_c{c}_"
         states.source = audio[: (c + 1) * SEG].tolist()
@@ -244,12 +286,15 @@ def test_agent_drop_in_api_with_beam(pins):
         n_before = len(states.target_ids)
         act = agent.policy(states)
         assert not act.is_read()
-        if states.target_ids[n_before:] != pins[p + "output_ids"].tolist():
-            break
-        assert states.past_key_values[0][0].size(2) == int(pins[p + "kv"][2])      # after hand-back + eviction
-        same += 1
-    print(f"agent --beam {k}: {same}/{n} chunks identical to the reference agent before the first divergence")
-    assert same >= 2
+        got = states.target_ids[n_before:]
+        assert got == want[c][0], (c, got, want[c][0])
+        assert states.past_key_values[0][0].size(2) == want[c][1]                  # after hand-back + eviction
+        ref_on = ref_on and got == pins[p + "output_ids"].tolist()
+        if ref_on:
+            assert states.past_key_values[0][0].size(2) == int(pins[p + "kv"][2])
+            same_ref += 1
+    print(f"agent --beam {k}: {n}/{n} chunks identical to the engine-level stream, {same_ref}/{n} identical to the reference "
+          f"agent before the first near-tie")
     agent.model.engine.close()
 
 

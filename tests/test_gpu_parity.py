@@ -644,8 +644,10 @@ def test_agent_policy_batch_accepts_joining_streams(beam):
         acts = agent.policy_batch([states[j] for j in live])
         assert len(acts) == len(live) and all(a is not None for a in acts)
         for j in live:
-            if call == joins[j] and j > 0:
-                # joined a running batch: same emitted ids as alone up to the first near-tie (random weights)
+            if call == joins[j] and j > 0 and beam == 1:
+                # joined a running batch: same emitted ids as alone up to the first near-tie (random weights; the fp32
+                # sums of the attention key splits depend on the batch).  Not asserted for beam search, where one flip
+                # among near-equal hypotheses replaces the whole sequence (tests/test_gpu_beam.py checks those by score)
                 a, b = states[j].target_ids, solo_first[j]
                 same = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
                 assert same >= min(len(a), len(b)) - 3, (j, a, b)
@@ -792,8 +794,8 @@ def test_decode_chain_bit_identical_to_operator_path(shape):
     one persistent kernel with grid barriers) keeps the k-split ranges, the accumulation order and the partial-sum
     order of the operator-per-kernel path: with the RMSNorms as row phases (`chain_fold` = 0) the raw step logits of both
     paths must be IDENTICAL bit for bit, for 1, 5, 20 and 64 rows (token tiles of 16, 32 and 64 columns), tiny and
-    production widths - that is the product default; the `chain_fold` option (norms folded into the GEMMs) must stay
-    within bf16 noise of them."""
+    production widths; the product default (`chain_fold` = 1: norms folded into the decode GEMMs) must stay within bf16
+    noise of them."""
     from infinisst_b200.runner import LockstepRunner
     if shape.startswith("tiny"):
         cfg = tiny_config(max_cache_size=96, max_llm_cache_size=150)
@@ -806,7 +808,7 @@ def test_decode_chain_bit_identical_to_operator_path(shape):
         B, n_chunks = int(shape.split("_")[2]), 3
     audios = [make_audio(n_chunks * SEG / 16000.0, seed=300 + b) for b in range(B)]
     res = []
-    # (chain, folded norms): the `chain_fold` option, the product default (RMSNorm row phases), the operator-per-kernel path
+    # (chain, folded norms): the product default, the chain with RMSNorm row phases, the operator-per-kernel path
     for use_chain, fold in ((1, 1), (1, 0), (0, 0)):
         eng = _engine(cfg, sd, max_streams=B, max_batch=B)
         eng.option("decode_chain", use_chain)
