@@ -29,8 +29,9 @@ def main():
         pcm = 0.1 * torch.randn(B, SEG + (399 if c == 0 else 0), device="cuda:0", generator=g)
         r.step_device(pcm)
     torch.cuda.synchronize()
-    for use_chain, pref in ((1, 0), (0, 0), (1, 0), (0, 0)):
+    for use_chain, pref in ((1, 1), (1, 0), (1, 1), (1, 0)):      # (chain, folded norms)
         eng.option("decode_chain", use_chain)
+        eng.option("chain_fold", pref)
         ts = []
         for _ in range(4):
             pcm = 0.1 * torch.randn(B, SEG, device="cuda:0", generator=g)
@@ -40,8 +41,9 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        print(f"chain={use_chain} prefetch={pref}: step ms {['%.2f' % t for t in ts]} (enc 1 + llm {layers} layers, {B} streams, kv {eng.kv_len(r.sids[0])})", flush=True)
+        print(f"chain={use_chain} fold={pref}: step ms {['%.2f' % t for t in ts]} (enc 1 + llm {layers} layers, {B} streams, kv {eng.kv_len(r.sids[0])})", flush=True)
     eng.option("decode_chain", 1)
+    eng.option("chain_fold", int(os.environ.get("FOLD", "1")))
     eng.debug(2)
     pcm = 0.1 * torch.randn(B, SEG, device="cuda:0", generator=g)
     r.step_device(pcm)
@@ -49,7 +51,8 @@ def main():
     t = eng.read_tap("gemm_stamps", torch.int64).view(-1, 32)[:148].double()
     t0 = t[:, 0].min()
     rel = (t - t0) / 1e3
-    names = ["o_proj", "rows", "gate_up", "down", "rows", "qkv"]
+    fold = int(os.environ.get("FOLD", "1"))
+    names = ["o_proj+reduce", "gate_up", "down+reduce", "qkv"] if fold else ["o_proj", "rows", "gate_up", "down", "rows", "qkv"]
     print("CTA start: mean %.2f max %.2f us" % (rel[:, 0].mean(), rel[:, 0].max()))
     for pi, nm in enumerate(names):
         cols = rel[:, 1 + 3 * pi: 4 + 3 * pi]
