@@ -387,20 +387,20 @@ def _free_running_beam(enc_layers, llm_layers, n_chunks, beam=4, engine_opts=())
     return same
 
 
-@pytest.mark.parametrize("fold", [0, 1], ids=["default", "chain_fold"])
+@pytest.mark.parametrize("fold", [1, 0], ids=["default", "row_phases"])
 def test_free_running_beam4_sharpened_lm_head(fold):
     """`--beam 4` (the reference's shipped decoding) without teacher forcing at production widths, 8 + 8 layers: emitted
     ids, handed-back KV length and evictions equal the fp32 oracle's chunk by chunk up to the first near-tie between
     hypotheses, and the best hypothesis' score agrees with the oracle's within bf16 noise at every compared chunk -
-    for the product default and for the `chain_fold` option (RMSNorms folded into the decode GEMMs)."""
+    for the product default (RMSNorms folded into the decode GEMMs) and with `chain_fold` = 0 (row phases)."""
     assert _free_running_beam(8, 8, 40, engine_opts=(("chain_fold", fold),)) >= 3
 
 
-@pytest.mark.parametrize("fold", [0, 1], ids=["default", "chain_fold"])
+@pytest.mark.parametrize("fold", [1, 0], ids=["default", "row_phases"])
 def test_free_running_sharpened_lm_head(fold):
     """north_star: "greedy token streams identical in at least 99 % of chunks, with divergences logged" - 110 chunks
-    of the full wav2vec2-large + Llama-3.1-8B sized model, no teacher forcing; the product default and the
-    `chain_fold` option."""
+    of the full wav2vec2-large + Llama-3.1-8B sized model, no teacher forcing; the product default (RMSNorms folded
+    into the decode GEMMs) and `chain_fold` = 0 (row phases, the reference module's rounding points)."""
     n_evict = _free_running(24, 32, 110, 55, 0.99, engine_opts=(("chain_fold", fold),))
     assert n_evict >= 70
 
