@@ -1071,6 +1071,8 @@ static int chain_fold_reduce(ChainBuilder& cb, const bf16* x_in, bf16* x_out, bf
                  ph.n_out % 8 == 0,
              "decode chain: this phase cannot reduce in place");
   ph.fold_reduce = 1; ph.x_in = x_in; ph.x_out = x_out; ph.h_out = h_out; ph.w = w; ph.sq_out = sq_out;
+  // the same algorithmic row work as the RMSNorm row phase it replaces (partials + residual in, residual + activation out)
+  cb.bytes += static_cast<double>(cb.p.n_tok) * ph.n_out * (4.0 + 4.0 * ph.splits);
   return 0;
 }
 static void chain_scale(ChainBuilder& cb, const float* sq_in, int n_sq, int C, float eps) {
